@@ -1,0 +1,98 @@
+// encode.cu -- K1: ASCII k-mers -> 2-bit packed uint64 + N mask.
+//
+// Replaces the per-row string handling of score_seqs / compute_score_seq
+// (src/grafimo/score_sequences.py:279,286,375-386): letters are case-insensitive, 'N' marks the
+// row as "score = min_val"; any other symbol is undefined in the reference and is flagged (and
+// masked like N) here.
+//
+// A CTA stages the contiguous byte range of its 256 rows in shared memory with 16-byte loads
+// (rows are w bytes, usually an odd stride, so per-thread byte loads from HBM would waste sectors),
+// then each thread packs its own row from shared memory.  One warp ballot produces the mask word.
+#include "internal.cuh"
+
+#define ENC_ROWS 256
+
+__device__ __forceinline__ uint32_t base_code(uint32_t c)
+{
+    // 0..3 = A,C,G,T (either case), 4 = 'N', 5 = anything else
+    const uint32_t u = c & 0xDFu;  // upper-case
+    const uint32_t t = (u >> 1) & 3u;
+    const uint32_t code = t ^ (t >> 1);  // A->0 C->1 G->2 T->3
+    const bool acgt = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
+    return acgt ? code : (c == 'N' ? 4u : 5u);
+}
+
+__global__ void __launch_bounds__(ENC_ROWS) gb2_encode_kernel(const uint8_t *__restrict__ ascii, int64_t n, int w,
+                                                             int64_t stride, uint64_t *__restrict__ packed,
+                                                             uint32_t *__restrict__ nmask,
+                                                             unsigned long long *__restrict__ counts)
+{
+    extern __shared__ __align__(16) uint8_t stage[];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * ENC_ROWS;
+    const int64_t rows = min((int64_t)ENC_ROWS, n - row0);
+    // byte range of this CTA's rows, widened to 16-byte alignment
+    const uintptr_t gbeg = (uintptr_t)ascii + (uintptr_t)(row0 * stride);
+    const uintptr_t gend = gbeg + (uintptr_t)((rows - 1) * stride + w);
+    const uintptr_t abeg = gbeg & ~(uintptr_t)15;
+    const int head = (int)(gbeg - abeg);
+    const int nvec = (int)((gend - abeg + 15) >> 4);
+    // the last vector may run past the caller's buffer by up to 15 bytes; fall back to bytes there
+    const uintptr_t buf_end = (uintptr_t)ascii + (uintptr_t)((n - 1) * stride + w);
+    for (int i = tid; i < nvec; i += ENC_ROWS) {
+        const uintptr_t a = abeg + ((uintptr_t)i << 4);
+        if (a >= (uintptr_t)ascii && a + 16 <= buf_end) {
+            reinterpret_cast<uint4 *>(stage)[i] = __ldg(reinterpret_cast<const uint4 *>(a));
+        } else {
+            for (int b = 0; b < 16; ++b) {
+                const uintptr_t q = a + b;
+                stage[(i << 4) + b] = (q >= (uintptr_t)ascii && q < buf_end) ? __ldg(reinterpret_cast<const uint8_t *>(q)) : (uint8_t)'A';
+            }
+        }
+    }
+    __syncthreads();
+
+    uint64_t x = 0;
+    uint32_t flag = 0;  // bit0: masked (N or bad), bit1: bad symbol
+    if (tid < rows) {
+        const uint8_t *s = stage + head + (int64_t)tid * stride;
+        for (int i = 0; i < w; ++i) {
+            const uint32_t code = base_code(s[i]);
+            x |= (uint64_t)(code & 3u) << (2 * i);
+            flag |= (code >= 4u ? 1u : 0u) | (code == 5u ? 2u : 0u);
+        }
+        if (flag) x = 0;
+        packed[row0 + tid] = x;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, flag & 1u);
+    const unsigned mb = __ballot_sync(0xFFFFFFFFu, flag & 2u);
+    if ((tid & 31) == 0) {
+        const int64_t wrow = row0 + tid;
+        if (wrow < n) nmask[wrow >> 5] = m;
+        if (counts) {
+            if (m) atomicAdd(counts + 0, (unsigned long long)__popc(m));
+            if (mb) atomicAdd(counts + 1, (unsigned long long)__popc(mb));
+        }
+    }
+}
+
+extern "C" int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int64_t stride,
+                                uint64_t *d_packed, uint32_t *d_nmask, uint64_t *d_counts)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n >= 0, "gb2_encode_kmers: negative row count");
+    GB2_REQUIRE(ctx, w >= 1 && w <= GB2_MAX_WIDTH, "gb2_encode_kmers: width %d outside [1,%d]", w, GB2_MAX_WIDTH);
+    GB2_REQUIRE(ctx, stride >= w && stride <= 512, "gb2_encode_kmers: stride %lld outside [w,512]", (long long)stride);
+    if (n == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_ascii && d_packed && d_nmask, "gb2_encode_kmers: null buffer");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)ENC_ROWS * (size_t)stride + 48;
+    if (smem > 48 * 1024)
+        GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = gb2_div_up(n, ENC_ROWS);
+    GB2_REQUIRE(ctx, blocks < ((int64_t)1 << 31), "gb2_encode_kmers: too many rows for one launch");
+    gb2_encode_kernel<<<(unsigned)blocks, ENC_ROWS, smem, ctx->stream>>>(d_ascii, n, w, stride, d_packed, d_nmask,
+                                                                        (unsigned long long *)d_counts);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}

@@ -1,0 +1,79 @@
+// internal.cuh -- shared definitions of the grafimo_b200 CUDA library (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "grafimo_b200.h"
+
+struct gb2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D staging stream of gb2_scan_host
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // reusable device scratch (CUB temp storage, sort keys, ...)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned host mailbox for small device->host reads
+    uint64_t *h_mail = nullptr;
+};
+
+struct gb2_motif {
+    int device = 0;
+    int w = 0;
+    int n_chunks = 0;
+    int replicas = 0;
+    int monotone = 0;
+    int64_t lo = 0, hi = 0, span = 0;
+    int64_t min_val = 0, scale = 0;
+    double offset = 0.0, total = 0.0;
+    int64_t smem_bytes = 0;
+    uint32_t *d_lut = nullptr;     // [n_chunks][256]  (rc_rel << 16 | fwd_rel)
+    double *d_ptab = nullptr;      // [span]  p-value of score lo+k
+    uint32_t *d_bitmap = nullptr;  // [ceil(span/32)] hit bitmap for non-monotone tables
+    std::vector<double> h_ptab;    // host copy of d_ptab
+};
+
+#define GB2_SET_ERR(ctx, ...)                                          \
+    do {                                                               \
+        if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    } while (0)
+
+#define GB2_CUDA(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            GB2_SET_ERR(ctx, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return e__ == cudaErrorMemoryAllocation ? GB2_ERR_NOMEM : GB2_ERR_CUDA;                 \
+        }                                                                                           \
+    } while (0)
+
+#define GB2_LAUNCH_CHECK(ctx)                \
+    do {                                     \
+        (ctx)->launches++;                   \
+        GB2_CUDA(ctx, cudaGetLastError());   \
+    } while (0)
+
+#define GB2_REQUIRE(ctx, cond, ...)      \
+    do {                                 \
+        if (!(cond)) {                   \
+            GB2_SET_ERR(ctx, __VA_ARGS__); \
+            return GB2_ERR_ARG;          \
+        }                                \
+    } while (0)
+
+// grows the context scratch buffer (stream-ordered free of the old one)
+int gb2_scratch_reserve(gb2_ctx *ctx, size_t bytes);
+
+// kernels launched from other translation units
+int gb2_launch_ptable(gb2_ctx *ctx, const double *d_pval_mat, int64_t lo, int64_t span, double *d_ctab,
+                      double *d_ptab);
+
+static inline int64_t gb2_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,317 @@
+// qvalue.cu -- K5 (Benjamini-Hochberg from the score histogram), K6 (finalize hits: filter, CUB radix
+// sort, numeric columns) and the haplotype tally (sort + run-length segmented reduction).
+//
+//   K5  src/grafimo/score_sequences.py:401-428 (statsmodels fdr_bh on every scored row).  The p-value
+//       is a function of the integer score, so the multiset of p-values IS the histogram:
+//       sort bins by p ascending, C = running count, raw = p / (C / float(N)), q = reverse running
+//       minimum clipped at 1.  Tied p-values (several bins, or many rows in one bin) take the value of
+//       the last tied rank, exactly like the row-wise formula.  Integer prefix sums and min-scans are
+//       exact in any order, so they run as block scans; the two fp64 divisions are IEEE (div.rn).
+//   K6  src/grafimo/resultsTmp.py:303-313 (+ score_sequences.py:393 for the log-odds column).
+#include <math_constants.h>
+
+#include <cub/cub.cuh>
+
+#include "internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K5
+// ---------------------------------------------------------------------------------------------
+__global__ void gb2_bh_keys_kernel(const double *__restrict__ ptab, uint32_t span, double *__restrict__ keys,
+                                   uint32_t *__restrict__ bins)
+{
+    // input order = descending score (ascending p for a monotone table; ties stay in this order)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > span) return;
+    if (i == span) {  // N rows: score = min_val, p = 1
+        keys[i] = 1.0;
+        bins[i] = span;
+    } else {
+        const uint32_t b = span - 1u - i;
+        keys[i] = ptab[b];
+        bins[i] = b;
+    }
+}
+
+#define BH_THREADS 1024
+// Single CTA: <= 32002 bins.  Each thread owns a contiguous run of sorted bins.
+__global__ void __launch_bounds__(BH_THREADS) gb2_bh_kernel(const double *__restrict__ sorted_p,
+                                                            const uint32_t *__restrict__ sorted_bins,
+                                                            const unsigned long long *__restrict__ hist, uint32_t nbins,
+                                                            double *__restrict__ qtab, uint32_t *__restrict__ rank,
+                                                            unsigned long long *__restrict__ total_out)
+{
+    typedef cub::BlockScan<unsigned long long, BH_THREADS> ScanU64;
+    typedef cub::BlockScan<double, BH_THREADS> ScanF64;
+    __shared__ union {
+        typename ScanU64::TempStorage u;
+        typename ScanF64::TempStorage f;
+    } tmp;
+    __shared__ unsigned long long s_total;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
+    const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
+
+    // rank of every bin in p-ascending order
+    for (uint32_t i = beg; i < end; ++i) rank[sorted_bins[i]] = i;
+    if (hist == nullptr) return;  // rank-only call (no q-values wanted)
+
+    unsigned long long local = 0;
+    for (uint32_t i = beg; i < end; ++i) local += hist[sorted_bins[i]];
+    unsigned long long prefix, total;
+    ScanU64(tmp.u).ExclusiveSum(local, prefix, total);
+    if (tid == 0) { s_total = total; *total_out = total; }
+    __syncthreads();
+    const double dn = (double)s_total;
+
+    // reverse running minimum of raw = p / (C / N): thread t's run is reduced right-to-left, runs are
+    // combined with an inclusive min-scan over reversed thread order.
+    double run_min = CUDART_INF;
+    {
+        unsigned long long c = prefix;
+        // first pass: cumulative counts forward to get each raw; store raw temporarily in qtab by position
+        for (uint32_t i = beg; i < end; ++i) {
+            const unsigned long long cnt = hist[sorted_bins[i]];
+            c += cnt;
+            double raw = CUDART_INF;
+            if (cnt != 0ull) raw = __ddiv_rn(sorted_p[i], __ddiv_rn((double)c, dn));
+            run_min = fmin(run_min, raw);
+        }
+    }
+    // suffix-min over threads: reverse the thread order and take an inclusive min-scan
+    __shared__ double s_run[BH_THREADS];
+    s_run[BH_THREADS - 1 - tid] = run_min;
+    __syncthreads();
+    double rev = s_run[tid];
+    double scanned;
+    ScanF64(tmp.f).InclusiveScan(rev, scanned, cub::Min());
+    __syncthreads();
+    s_run[tid] = scanned;  // s_run[j] = min over original threads >= BH_THREADS-1-j
+    __syncthreads();
+    // minimum over all runs strictly to the right of this thread's run
+    double right = (tid + 1 < BH_THREADS) ? s_run[BH_THREADS - 2 - tid] : CUDART_INF;
+    {
+        // second pass right-to-left inside the run
+        unsigned long long c = prefix;
+        for (uint32_t i = beg; i < end; ++i) c += hist[sorted_bins[i]];
+        double m = right;
+        for (uint32_t i = end; i > beg; --i) {
+            const uint32_t k = i - 1;
+            const unsigned long long cnt = hist[sorted_bins[k]];
+            double raw = CUDART_INF;
+            if (cnt != 0ull) raw = __ddiv_rn(sorted_p[k], __ddiv_rn((double)c, dn));
+            m = fmin(m, raw);
+            qtab[sorted_bins[k]] = m > 1.0 ? 1.0 : m;
+            c -= cnt;
+        }
+    }
+}
+
+extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_hist, double *d_qtab,
+                                     uint32_t *d_rank, uint64_t *d_total)
+{
+    if (!ctx || !m) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, d_rank != nullptr, "gb2_qvalues_from_hist: null rank buffer");
+    GB2_REQUIRE(ctx, d_hist == nullptr || (d_qtab && d_total), "gb2_qvalues_from_hist: histogram given without q/total buffers");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t span = (uint32_t)m->span, nb = span + 1;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const double *)nullptr, (double *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)nb, 0, 64, ctx->stream);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = align(cub_bytes) + 2 * align(nb * sizeof(double)) + 2 * align(nb * sizeof(uint32_t));
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    double *k_in = (double *)base; base += align(nb * sizeof(double));
+    double *k_out = (double *)base; base += align(nb * sizeof(double));
+    uint32_t *v_in = (uint32_t *)base; base += align(nb * sizeof(uint32_t));
+    uint32_t *v_out = (uint32_t *)base;
+    gb2_bh_keys_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(m->d_ptab, span, k_in, v_in);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, (int)nb, 0, 64, ctx->stream));
+    ctx->launches += 1;
+    gb2_bh_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(k_out, v_out, (const unsigned long long *)d_hist, nb, d_qtab, d_rank,
+                                                     (unsigned long long *)d_total);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6
+// ---------------------------------------------------------------------------------------------
+__global__ void gb2_hit_keys_kernel(const gb2_hit *__restrict__ hits, uint64_t n, int32_t lo,
+                                    const double *__restrict__ qtab, const uint32_t *__restrict__ rank, int q_filter,
+                                    double q_thr, unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx,
+                                    unsigned long long *__restrict__ n_kept)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        const gb2_hit h = hits[i];
+        const uint32_t bin = (uint32_t)(h.score - lo);
+        keep = !q_filter || qtab[bin] < q_thr;  // strict, resultsTmp.py:305
+        // (p rank, row, strand): p ascending, then a deterministic order among equal p
+        unsigned long long key = ((unsigned long long)rank[bin] << 48) | ((h.row & 0x7FFFFFFFFFFFull) << 1) | (h.strand & 1u);
+        keys[i] = keep ? key : ~0ull;
+        idx[i] = (uint32_t)i;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_kept, (unsigned long long)__popc(m));
+}
+
+__global__ void gb2_hit_gather_kernel(const gb2_hit *__restrict__ hits, const uint32_t *__restrict__ order,
+                                      const unsigned long long *__restrict__ n_kept, int32_t lo, int w, double scale,
+                                      double offset, const double *__restrict__ ptab, const double *__restrict__ qtab,
+                                      uint64_t *__restrict__ o_row, uint8_t *__restrict__ o_strand,
+                                      int32_t *__restrict__ o_iscore, double *__restrict__ o_score,
+                                      double *__restrict__ o_p, double *__restrict__ o_q)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_kept) return;
+    const gb2_hit h = hits[order[i]];
+    const uint32_t bin = (uint32_t)(h.score - lo);
+    o_row[i] = h.row;
+    o_strand[i] = (uint8_t)h.strand;
+    o_iscore[i] = h.score;
+    // logodds = (score / scale) + (width * offset)            score_sequences.py:393
+    o_score[i] = __dadd_rn(__ddiv_rn((double)h.score, scale), __dmul_rn((double)w, offset));
+    o_p[i] = ptab[bin];
+    if (o_q != nullptr && qtab != nullptr) o_q[i] = qtab[bin];
+}
+
+extern "C" int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *m, const gb2_hit *d_hits, uint64_t n_hits,
+                                 const double *d_qtab, const uint32_t *d_rank, int q_filter, double q_threshold,
+                                 uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p,
+                                 double *d_q, uint64_t *d_n_out)
+{
+    if (!ctx || !m) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, d_n_out != nullptr && d_rank != nullptr, "gb2_finalize_hits: null counter or rank table");
+    GB2_REQUIRE(ctx, !q_filter || d_qtab != nullptr, "gb2_finalize_hits: q filter needs the q table");
+    GB2_REQUIRE(ctx, n_hits < ((uint64_t)1 << 31), "gb2_finalize_hits: at most 2^31-1 hits per call");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB2_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), ctx->stream));
+    if (n_hits == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_hits && d_row && d_strand && d_iscore && d_score && d_p, "gb2_finalize_hits: null buffer");
+    const int n = (int)n_hits;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 64, ctx->stream);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = align(cub_bytes) + 2 * align((size_t)n * 8) + 2 * align((size_t)n * 4);
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    unsigned long long *k_in = (unsigned long long *)base; base += align((size_t)n * 8);
+    unsigned long long *k_out = (unsigned long long *)base; base += align((size_t)n * 8);
+    uint32_t *v_in = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *v_out = (uint32_t *)base;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)gb2_div_up(n, threads);
+    gb2_hit_keys_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, n_hits, (int32_t)m->lo, d_qtab, d_rank, q_filter,
+                                                            q_threshold, k_in, v_in, (unsigned long long *)d_n_out);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, n, 0, 64, ctx->stream));
+    ctx->launches += 1;
+    gb2_hit_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, v_out, (const unsigned long long *)d_n_out,
+                                                              (int32_t)m->lo, m->w, (double)m->scale, m->offset, m->d_ptab,
+                                                              d_qtab, d_row, d_strand, d_iscore, d_score, d_p, d_q);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// haplotype tally
+// ---------------------------------------------------------------------------------------------
+__global__ void gb2_tally_heads_kernel(const unsigned long long *__restrict__ pos,
+                                       const unsigned long long *__restrict__ packed, int64_t n,
+                                       uint32_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || pos[i] != pos[i - 1] || packed[i] != packed[i - 1]) ? 1u : 0u;
+}
+
+__global__ void gb2_tally_emit_kernel(const unsigned long long *__restrict__ pos,
+                                      const unsigned long long *__restrict__ packed, int64_t n,
+                                      const uint32_t *__restrict__ flags, const unsigned long long *__restrict__ scan,
+                                      const unsigned long long *__restrict__ ref, unsigned long long pos_base,
+                                      int64_t n_ref, unsigned long long *__restrict__ u_pos,
+                                      unsigned long long *__restrict__ u_packed, unsigned long long *__restrict__ heads,
+                                      uint8_t *__restrict__ u_isref, unsigned long long *__restrict__ n_unique)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) {
+        const unsigned long long u = scan[i] - 1ull;
+        u_pos[u] = pos[i];
+        u_packed[u] = packed[i];
+        heads[u] = (unsigned long long)i;
+        uint8_t isref = 0;
+        if (ref != nullptr && pos[i] >= pos_base && (int64_t)(pos[i] - pos_base) < n_ref)
+            isref = ref[pos[i] - pos_base] == packed[i];
+        u_isref[u] = isref;
+    }
+    if (i == n - 1) *n_unique = scan[i];
+}
+
+__global__ void gb2_tally_freq_kernel(const unsigned long long *__restrict__ heads,
+                                      const unsigned long long *__restrict__ n_unique, int64_t n,
+                                      uint32_t *__restrict__ freq)
+{
+    const unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nu = *n_unique;
+    if (u >= nu) return;
+    const unsigned long long next = (u + 1 < nu) ? heads[u + 1] : (unsigned long long)n;
+    freq[u] = (uint32_t)(next - heads[u]);
+}
+
+extern "C" int gb2_tally_haplotypes(gb2_ctx *ctx, uint64_t *d_pos, uint64_t *d_packed, int64_t n,
+                                    const uint64_t *d_ref_packed, uint64_t pos_base, int64_t n_ref, uint64_t *d_u_pos,
+                                    uint64_t *d_u_packed, uint32_t *d_u_freq, uint8_t *d_u_isref, uint64_t *d_n_unique)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n >= 0 && n < ((int64_t)1 << 31), "gb2_tally_haplotypes: row count must be below 2^31 per call");
+    GB2_REQUIRE(ctx, d_n_unique != nullptr, "gb2_tally_haplotypes: null counter");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB2_CUDA(ctx, cudaMemsetAsync(d_n_unique, 0, sizeof(uint64_t), ctx->stream));
+    if (n == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_pos && d_packed && d_u_pos && d_u_packed && d_u_freq && d_u_isref, "gb2_tally_haplotypes: null buffer");
+    const int ni = (int)n;
+    size_t cub_sort = 0, cub_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const unsigned long long *)nullptr, (unsigned long long *)nullptr, ni, 0, 64, ctx->stream);
+    cub::DeviceScan::InclusiveSum(nullptr, cub_scan, (const uint32_t *)nullptr, (unsigned long long *)nullptr, ni, ctx->stream);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t cub_bytes = std::max(cub_sort, cub_scan);
+    const size_t need = align(cub_bytes) + 3 * align((size_t)n * 8) + align((size_t)n * 4);
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    unsigned long long *a = (unsigned long long *)base; base += align((size_t)n * 8);
+    unsigned long long *b = (unsigned long long *)base; base += align((size_t)n * 8);
+    unsigned long long *scan = (unsigned long long *)base; base += align((size_t)n * 8);
+    uint32_t *flags = (uint32_t *)base;
+    unsigned long long *pos = (unsigned long long *)d_pos, *pk = (unsigned long long *)d_packed;
+    // LSD: stable sort by k-mer, then by position  =>  ordered by (position, k-mer)
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_sort, pk, a, pos, b, ni, 0, 64, ctx->stream));
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_sort, b, pos, a, pk, ni, 0, 64, ctx->stream));
+    ctx->launches += 2;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)gb2_div_up(n, threads);
+    gb2_tally_heads_kernel<<<blocks, threads, 0, ctx->stream>>>(pos, pk, n, flags);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceScan::InclusiveSum(d_tmp, cub_scan, flags, scan, ni, ctx->stream));
+    ctx->launches += 1;
+    gb2_tally_emit_kernel<<<blocks, threads, 0, ctx->stream>>>(pos, pk, n, flags, scan, (const unsigned long long *)d_ref_packed,
+                                                              pos_base, n_ref, (unsigned long long *)d_u_pos,
+                                                              (unsigned long long *)d_u_packed, a, d_u_isref,
+                                                              (unsigned long long *)d_n_unique);
+    GB2_LAUNCH_CHECK(ctx);
+    gb2_tally_freq_kernel<<<blocks, threads, 0, ctx->stream>>>(a, (const unsigned long long *)d_n_unique, n, d_u_freq);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}

@@ -1,0 +1,286 @@
+"""Thin Python objects over the C ABI (include/grafimo_b200.h).
+
+torch is used for what it is good at here -- device memory, streams and torch.distributed -- and
+nothing else: every computation is a call into libgrafimo_b200.so with raw pointers.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GrafimoB200Error, Hit, MotifInfo, check
+
+_HIT_BYTES = ctypes.sizeof(Hit)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One per (process, GPU): owns a CUDA stream and the library context bound to it."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available() or self.lib.gb2_device_count() == 0:
+            raise GrafimoB200Error(2, "grafimo_b200.Context", "no CUDA device: grafimo_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        h = ctypes.c_void_p()
+        check(self.lib.gb2_ctx_create(self.device.index, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(h)),
+              "gb2_ctx_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gb2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------------------
+    def enter(self):
+        """Order this context's stream after the caller's current stream."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
+    def leave(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def sync(self):
+        check(self.lib.gb2_ctx_sync(self.h), "gb2_ctx_sync", self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.gb2_ctx_launch_count(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.lib.gb2_ctx_sm_count(self.h))
+
+    def empty(self, n, dtype):
+        with torch.cuda.stream(self.stream):
+            return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def zeros(self, n, dtype):
+        with torch.cuda.stream(self.stream):
+            return torch.zeros(int(n), dtype=dtype, device=self.device)
+
+    # -- K1 -----------------------------------------------------------------------------------
+    def encode(self, ascii_rows, width=None):
+        """uint8 device tensor [n, stride] (ASCII k-mers) -> (packed int64[n] (uint64 bits), nmask int32[ceil(n/32)],
+        counts int64[2] = rows masked, rows with a non-ACGTN symbol)."""
+        assert ascii_rows.is_cuda and ascii_rows.dtype == torch.uint8 and ascii_rows.dim() == 2
+        assert ascii_rows.stride(1) == 1
+        n, stride = ascii_rows.shape[0], ascii_rows.stride(0) if ascii_rows.shape[0] > 1 else ascii_rows.shape[1]
+        w = ascii_rows.shape[1] if width is None else int(width)
+        self.enter()
+        ascii_rows.record_stream(self.stream)
+        packed = self.empty(n + (n & 1), torch.int64)[:n]
+        nmask = self.zeros((n + 31) // 32, torch.int32)
+        counts = self.zeros(2, torch.int64)
+        check(self.lib.gb2_encode_kmers(self.h, _ptr(ascii_rows), n, w, stride, _ptr(packed), _ptr(nmask), _ptr(counts)),
+              "gb2_encode_kmers", self.h)
+        self.leave()
+        return packed, nmask, counts
+
+    # -- K3 -----------------------------------------------------------------------------------
+    def pval_dp_batched(self, score_matrices, backgrounds):
+        """list of int[4,w] (rows A,C,G,T) + list of [A,C,G,T] backgrounds -> list of float64[1000*w+1]."""
+        m = len(score_matrices)
+        if m == 0:
+            return []
+        widths = np.array([np.asarray(s).shape[1] for s in score_matrices], dtype=np.int32)
+        sm = np.concatenate([np.ascontiguousarray(s, dtype=np.int64).reshape(-1) for s in score_matrices])
+        bgs = np.ascontiguousarray(np.asarray(backgrounds, dtype=np.float64).reshape(m, 4))
+        lens = _lib.RANGE * widths.astype(np.int64) + 1
+        out = np.empty(int(lens.sum()), dtype=np.float64)
+        check(self.lib.gb2_pval_dp_batched(self.h, m, _np_ptr(widths), _np_ptr(sm), _np_ptr(bgs), _np_ptr(out)),
+              "gb2_pval_dp_batched", self.h)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        return [out[offs[i]:offs[i + 1]].copy() for i in range(m)]
+
+    def motif(self, score_matrix, pval_mat, min_val, scale, offset):
+        return DeviceMotif(self, score_matrix, pval_mat, min_val, scale, offset)
+
+    # -- haplotype tally -------------------------------------------------------------------------
+    def tally_haplotypes(self, pos, packed, ref_packed=None, pos_base=0):
+        """Per-haplotype windows (pos int64[n], packed int64[n], device; sorted in place) -> deduplicated rows:
+        (pos, packed, freq, isref) device tensors trimmed to the number of distinct rows."""
+        n = pos.shape[0]
+        self.enter()
+        u_pos = self.empty(n, torch.int64)
+        u_packed = self.empty(n, torch.int64)
+        u_freq = self.empty(n, torch.int32)
+        u_isref = self.empty(n, torch.uint8)
+        n_unique = self.zeros(1, torch.int64)
+        n_ref = 0 if ref_packed is None else ref_packed.shape[0]
+        check(self.lib.gb2_tally_haplotypes(self.h, _ptr(pos), _ptr(packed), n, _ptr(ref_packed), pos_base, n_ref,
+                                            _ptr(u_pos), _ptr(u_packed), _ptr(u_freq), _ptr(u_isref), _ptr(n_unique)),
+              "gb2_tally_haplotypes", self.h)
+        self.sync()
+        k = int(n_unique.item())
+        self.leave()
+        return u_pos[:k], u_packed[:k], u_freq[:k], u_isref[:k]
+
+
+class DeviceMotif:
+    """Device-resident motif: chunk LUTs + the score -> p-value table (K4)."""
+
+    def __init__(self, ctx, score_matrix, pval_mat, min_val, scale, offset):
+        self.ctx = ctx
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int64)
+        if sm.ndim != 2 or sm.shape[0] != 4:
+            raise ValueError("score_matrix must be int[4, w] with rows A,C,G,T")
+        w = sm.shape[1]
+        pm = np.ascontiguousarray(pval_mat, dtype=np.float64)
+        if pm.shape != (_lib.RANGE * w + 1,):
+            raise ValueError(f"pval_mat must have {_lib.RANGE * w + 1} entries for width {w}")
+        h = ctypes.c_void_p()
+        check(ctx.lib.gb2_motif_create(ctx.h, _np_ptr(sm), w, _np_ptr(pm), int(min_val), int(scale), float(offset),
+                                       ctypes.byref(h)), "gb2_motif_create", ctx.h)
+        self.h = h
+        info = MotifInfo()
+        check(ctx.lib.gb2_motif_get_info(h, ctypes.byref(info)), "gb2_motif_get_info")
+        self.info = info
+        self.width, self.lo, self.hi, self.span = info.width, info.lo, info.hi, info.span
+        self._ptable = None
+
+    @property
+    def ptable(self):
+        """float64[span]: p-value of integer score lo+k (bit-exact to score_sequences.py:390-391)."""
+        if self._ptable is None:
+            out = np.empty(self.span, dtype=np.float64)
+            check(self.ctx.lib.gb2_motif_get_ptable(self.ctx.h, self.h, _np_ptr(out)), "gb2_motif_get_ptable", self.ctx.h)
+            self._ptable = out
+        return self._ptable
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gb2_motif_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scan:
+    """State of one scan of one motif on one GPU: histogram, hit buffer, counters.
+
+    score() may be called for any number of batches; histogram() exposes the per-score counts as an
+    int64 tensor so that multi-GPU runs can all-reduce it (the only cross-GPU traffic); finalize()
+    turns the hits into the numeric columns of the report."""
+
+    def __init__(self, ctx, motif, strands=2, threshold=1e-4, want_q=True, hit_capacity=1 << 20, dense=False):
+        self.ctx, self.motif = ctx, motif
+        self.strands, self.threshold, self.want_q = int(strands), float(threshold), bool(want_q)
+        self.capacity = int(hit_capacity)
+        self.hist = ctx.zeros(motif.span + 1, torch.int64) if want_q else None
+        self.hits = ctx.empty(max(self.capacity, 1) * _HIT_BYTES, torch.uint8)
+        self.counters = ctx.zeros(4, torch.int64)  # [0] hits found, [1] kept, [2] total N
+        self.rows_scored = 0
+        self.dense = dense
+
+    def reset(self):
+        with torch.cuda.stream(self.ctx.stream):
+            if self.hist is not None:
+                self.hist.zero_()
+            self.counters.zero_()
+        self.rows_scored = 0
+
+    def score(self, packed, nmask=None, row_base=0, dense_out=None):
+        n = packed.shape[0]
+        lib, ctx = self.ctx.lib, self.ctx
+        ctx.enter()
+        check(lib.gb2_score(ctx.h, self.motif.h, _ptr(packed), _ptr(nmask), n, int(row_base), self.strands, self.threshold,
+                            _ptr(self.hist), _ptr(self.hits), self.capacity, _ptr(self.counters), _ptr(dense_out)),
+              "gb2_score", ctx.h)
+        self.rows_scored += n
+
+    def histogram(self):
+        return self.hist
+
+    def qvalues(self):
+        """K5 on the (possibly all-reduced) histogram -> (qtab float64[span+1], rank int32[span+1]) device tensors."""
+        ctx = self.ctx
+        ctx.enter()
+        nb = self.motif.span + 1
+        self.qtab = ctx.empty(nb, torch.float64) if self.want_q else None
+        self.rank = ctx.empty(nb, torch.int32)
+        check(ctx.lib.gb2_qvalues_from_hist(ctx.h, self.motif.h, _ptr(self.hist), _ptr(self.qtab), _ptr(self.rank),
+                                            ctypes.c_void_p(self.counters.data_ptr() + 16)), "gb2_qvalues_from_hist", ctx.h)
+        return self.qtab, self.rank
+
+    def n_hits(self):
+        self.ctx.sync()
+        return int(self.counters[0].item())
+
+    def finalize(self, q_filter=False):
+        """K6 -> dict of numpy columns sorted by (p ascending, row, strand)."""
+        ctx = self.ctx
+        if not hasattr(self, "rank"):
+            self.qvalues()
+        n = self.n_hits()
+        if n > self.capacity:
+            raise GrafimoB200Error(_lib.GB2_ERR_CAPACITY, "Scan.finalize", f"{n} hits exceed the capacity {self.capacity}")
+        cap = max(n, 1)
+        o_row = ctx.empty(cap, torch.int64)
+        o_strand = ctx.empty(cap, torch.uint8)
+        o_iscore = ctx.empty(cap, torch.int32)
+        o_score = ctx.empty(cap, torch.float64)
+        o_p = ctx.empty(cap, torch.float64)
+        o_q = ctx.empty(cap, torch.float64) if self.want_q else None
+        check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, _ptr(self.qtab) if self.want_q else None,
+                                        _ptr(self.rank), int(bool(q_filter)), self.threshold, _ptr(o_row), _ptr(o_strand),
+                                        _ptr(o_iscore), _ptr(o_score), _ptr(o_p), _ptr(o_q),
+                                        ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits", ctx.h)
+        ctx.sync()
+        with torch.cuda.stream(ctx.stream):
+            kept = int(self.counters[1].item())
+            out = {
+                "row": o_row[:kept].cpu().numpy(), "strand": o_strand[:kept].cpu().numpy(),
+                "int_score": o_iscore[:kept].cpu().numpy(), "score": o_score[:kept].cpu().numpy(),
+                "p-value": o_p[:kept].cpu().numpy(),
+            }
+            if self.want_q:
+                out["q-value"] = o_q[:kept].cpu().numpy()
+            out["total"] = int(self.counters[2].item()) if self.want_q else None
+        return out
+
+
+def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):
+    """gb2_scan_host: numpy/pinned-torch uint8 [n, w] host k-mers -> dict of numpy columns (+ stats)."""
+    if isinstance(ascii_rows, torch.Tensor):
+        assert not ascii_rows.is_cuda
+        base, n, stride = ascii_rows.data_ptr(), ascii_rows.shape[0], ascii_rows.stride(0)
+        w = ascii_rows.shape[1]
+    else:
+        a = np.ascontiguousarray(ascii_rows, dtype=np.uint8)
+        base, n, stride, w = a.ctypes.data, a.shape[0], a.strides[0], a.shape[1]
+    cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n * strands, 1 << 26)))
+    row = np.empty(cap, np.uint64); strand = np.empty(cap, np.uint8); isc = np.empty(cap, np.int32)
+    score = np.empty(cap, np.float64); p = np.empty(cap, np.float64); q = np.empty(cap, np.float64) if want_q else None
+    nh = ctypes.c_uint64(0)
+    stats = np.zeros(4, np.uint64)
+    rc = ctx.lib.gb2_scan_host(ctx.h, motif.h, ctypes.c_void_p(base), n, w, stride, int(strands), float(threshold),
+                               int(bool(q_filter)), int(bool(want_q)), cap, _np_ptr(row), _np_ptr(strand), _np_ptr(isc),
+                               _np_ptr(score), _np_ptr(p), _np_ptr(q) if want_q else None, ctypes.byref(nh), _np_ptr(stats))
+    check(rc, "gb2_scan_host", ctx.h)
+    k = int(nh.value)
+    out = {"row": row[:k], "strand": strand[:k], "int_score": isc[:k], "score": score[:k], "p-value": p[:k]}
+    if want_q:
+        out["q-value"] = q[:k]
+    out["stats"] = dict(windows=int(stats[0]), n_rows=int(stats[1]), bad_rows=int(stats[2]), hits=int(stats[3]))
+    return out

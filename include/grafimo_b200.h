@@ -1,0 +1,196 @@
+/*
+ * grafimo_b200.h -- C ABI of the B200-native GRAFIMO motif-scanning hot path.
+ *
+ * The reference (pinellolab/GRAFIMO, pure Python) has no FFI; the seams this library sits behind
+ * are two Python call sites (paths relative to the reference tree):
+ *
+ *   B1  grafimo.score_sequences.compute_results      src/grafimo/score_sequences.py:44-211
+ *   B2  motif_processing.comp_pval_mat               src/grafimo/motif_processing.pyx:608-632
+ *   B3  grafimo.score_sequences.compute_qvalues      src/grafimo/score_sequences.py:401-428
+ *
+ * Every entry point below names the reference lines it replaces.  The ctypes binding a GRAFIMO
+ * maintainer would add is shown in INTEGRATION.md; grafimo_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary; every function returns an int status
+ *     (GB2_OK == 0); gb2_error_string() / gb2_ctx_last_error() give the text;
+ *   - pointers named d_* are DEVICE pointers (cudaMalloc / torch allocations, 16-byte aligned),
+ *     pointers named h_* are HOST pointers; there are no torch types in any signature;
+ *   - calls are stream-ordered on the context's stream; a context belongs to one host thread
+ *     and one device.  Outputs written to d_* buffers are valid after gb2_ctx_sync() (or after
+ *     any later work on the same stream); h_* outputs are valid on return;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GB2_ERR_CUDA.
+ *
+ * Data layout
+ *   packed k-mer  uint64: base i of the k-mer in bits [2i, 2i+1], A=0 C=1 G=2 T=3, bits >= 2w
+ *                 are zero, w <= 32.
+ *   N mask        uint32[ceil(n/32)]: bit (r & 31) of word (r >> 5) is set when row r holds a
+ *                 symbol other than ACGTacgt (the reference scores such rows as `min_val`,
+ *                 p-value 1: score_sequences.py:376-378).
+ *   histogram     uint64[span + 1], span = hi - lo + 1 with lo/hi the smallest/largest reachable
+ *                 integer score; bin k counts scored windows with integer score lo + k, bin
+ *                 `span` counts N-rows (score = min_val, p = 1).
+ */
+#ifndef GRAFIMO_B200_H
+#define GRAFIMO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB2_ABI_VERSION 1
+#define GB2_MAX_WIDTH 32
+#define GB2_RANGE 1000 /* src/grafimo/utils.py:26 */
+
+enum {
+    GB2_OK = 0,
+    GB2_ERR_ARG = 1,      /* bad argument (null pointer, width out of range, misaligned buffer) */
+    GB2_ERR_CUDA = 2,     /* CUDA runtime failure (including "no device") */
+    GB2_ERR_NOMEM = 3,    /* host or device allocation failed */
+    GB2_ERR_CAPACITY = 4, /* more hits than the caller's buffer holds (count still returned) */
+    GB2_ERR_MOTIF = 5,    /* motif not usable: not scaled, empty p-value matrix, index out of range */
+    GB2_ERR_STATE = 6
+};
+
+typedef struct gb2_ctx gb2_ctx;     /* one per (host thread, device): stream + scratch */
+typedef struct gb2_motif gb2_motif; /* device-resident motif: chunk LUTs, p-value table, cut-offs */
+
+/* One hit (a scored window that passed the p-value test). 16 bytes. */
+typedef struct gb2_hit {
+    uint64_t row;    /* global row index = row_base + index within the scored batch */
+    int32_t score;   /* absolute integer score (sum of scaled matrix entries) */
+    uint32_t strand; /* 0 = the k-mer as given ('+' for forward k-mers), 1 = its reverse complement */
+} gb2_hit;
+
+/* Facts about an uploaded motif. */
+typedef struct gb2_motif_info {
+    int32_t width;
+    int32_t n_chunks;      /* 4-base LUT chunks = ceil(width / 4) */
+    int32_t lut_replicas;  /* shared-memory replication factor chosen for the scoring kernel */
+    int32_t monotone;      /* 1 when the p-value table is non-increasing in the score */
+    int64_t lo, hi;        /* smallest / largest reachable integer score */
+    int64_t span;          /* hi - lo + 1 */
+    int64_t min_val;       /* matrix minimum entry (score given to N rows) */
+    int64_t scale;
+    double offset;
+    double total;          /* sequential sum of pval_mat (denominator of every p-value) */
+    int64_t smem_bytes;    /* dynamic shared memory of the scoring kernel for this motif */
+} gb2_motif_info;
+
+int gb2_abi_version(void);
+const char *gb2_error_string(int code);
+
+/* ---- context --------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t to run on (e.g. torch's current stream) or NULL to create one. */
+int gb2_ctx_create(int device, void *stream, gb2_ctx **out);
+int gb2_ctx_destroy(gb2_ctx *ctx);
+int gb2_ctx_set_stream(gb2_ctx *ctx, void *stream);
+int gb2_ctx_sync(gb2_ctx *ctx);
+const char *gb2_ctx_last_error(const gb2_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t gb2_ctx_launch_count(const gb2_ctx *ctx);
+int gb2_device_count(void);
+int gb2_ctx_sm_count(const gb2_ctx *ctx);
+
+/* ---- K1: k-mer encoder ------------------------------------------------------------------ */
+/* Replaces the per-row string handling of score_seqs (score_sequences.py:279,286,375-386):
+ * n ASCII k-mers of w bytes (row stride `stride` >= w bytes) -> packed uint64 + N mask.
+ * d_counts[0] += rows flagged in the mask, d_counts[1] += rows holding a symbol that is neither
+ * ACGTacgt nor 'N' (undefined in the reference; scored like N here). d_counts may be NULL. */
+int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int64_t stride,
+                     uint64_t *d_packed, uint32_t *d_nmask, uint64_t *d_counts);
+
+/* ---- K3: batched score-distribution DP --------------------------------------------------- */
+/* Replaces comp_pval_mat (motif_processing.pyx:552-603) for n_motifs motifs at once.
+ * h_widths[m] = w_m; h_score_mats = concatenated int64[4][w_m] (rows A,C,G,T); h_bgs = [A,C,G,T]
+ * per motif; h_out = concatenated float64[1000*w_m+1].  Bit-exact to the reference for any
+ * background (accumulation order A,C,G,T; product and sum rounded separately). Host pointers. */
+int gb2_pval_dp_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *h_score_mats,
+                        const double *h_bgs, double *h_out);
+
+/* ---- motif upload (+ K4: score -> p-value table) ------------------------------------------ */
+/* Takes what Motif carries (motif.py:18): score_matrix int64[4][w] (rows A,C,G,T), pval_matrix
+ * float64[1000*w+1], min_val, scale, offset.  Builds the 4-base chunk LUTs and, on the device, the
+ * table p[s] = seqsum(pval_mat[s:]) / seqsum(pval_mat) for every reachable s in the reference's
+ * summation order (score_sequences.py:390-391).  Host pointers. */
+int gb2_motif_create(gb2_ctx *ctx, const int64_t *h_score_matrix, int w, const double *h_pval_mat,
+                     int64_t min_val, int64_t scale, double offset, gb2_motif **out);
+int gb2_motif_destroy(gb2_motif *motif);
+int gb2_motif_get_info(const gb2_motif *motif, gb2_motif_info *info);
+/* copies the p-value table (span doubles, score lo..hi) to the host */
+int gb2_motif_get_ptable(gb2_ctx *ctx, const gb2_motif *motif, double *h_ptable);
+/* device pointer of the same table (span doubles), owned by the motif */
+const double *gb2_motif_ptable_device(const gb2_motif *motif);
+
+/* ---- K2: scoring ---------------------------------------------------------------------------- */
+/* Replaces compute_score_seq (score_sequences.py:331-396) and the p-value test of
+ * ResultTmp.to_df (resultsTmp.py:303-307) for a batch of packed k-mers.
+ *   strands      1: score each k-mer as given; 2: also its reverse complement (what `vg find -E`
+ *                emits as the '-' row) from the same 8-byte read.
+ *   p_threshold  a window is a hit when p < p_threshold (strict). N rows never hit. With
+ *                p_threshold > 1 every window with p <= 1 is a hit (used by tests).
+ *   d_hist       uint64[span+1] or NULL (no q-values wanted): += per-score counts.
+ *   d_hits / hit_capacity / d_hit_count: hit records appended at *d_hit_count (device counter,
+ *                += hits found even when capacity is exceeded; excess records are dropped).
+ *   d_dense      uint32[n] or NULL: per k-mer ((rc - lo) << 16 | (fwd - lo)); 0xFFFFFFFF for N rows.
+ * d_packed must be 16-byte aligned.  row_base is added to the row index in hit records. */
+int gb2_score(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_packed, const uint32_t *d_nmask,
+              int64_t n, uint64_t row_base, int strands, double p_threshold, uint64_t *d_hist,
+              gb2_hit *d_hits, uint64_t hit_capacity, uint64_t *d_hit_count, uint32_t *d_dense);
+
+/* ---- K5: Benjamini-Hochberg from the score histogram ----------------------------------------- */
+/* Replaces compute_qvalues (score_sequences.py:401-428; statsmodels fdr_bh) given the (globally
+ * all-reduced) histogram: sorts bins by p ascending, C = cumulative count, q = reverse running
+ * minimum of p / (C / float(N)), clipped at 1.
+ *   d_qtab   double[span+1]  q-value per histogram bin
+ *   d_rank   uint32[span+1]  position of the bin in p-ascending order (sort key for K6)
+ *   d_total  uint64[1]       N = number of scored windows */
+int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_hist, double *d_qtab,
+                          uint32_t *d_rank, uint64_t *d_total);
+
+/* ---- K6: finalize hits -------------------------------------------------------------------------- */
+/* Replaces the filter + sort of ResultTmp.to_df (resultsTmp.py:303-313) and the log-odds / p / q
+ * columns (score_sequences.py:393; resultsTmp.py:277-279): optional q < q_threshold filter
+ * (--qvalueT), CUB radix sort by (p ascending, row ascending, strand) -- a deterministic order; the
+ * reference's tie order is undefined -- and the numeric columns.  d_qtab/d_rank may be NULL when no
+ * q-values were computed (then the sort uses the score and d_q is not written).
+ * All outputs have room for n_hits entries; *d_n_out receives the number kept. */
+int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *motif, const gb2_hit *d_hits, uint64_t n_hits,
+                      const double *d_qtab, const uint32_t *d_rank, int q_filter, double q_threshold,
+                      uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p,
+                      double *d_q, uint64_t *d_n_out);
+
+/* ---- haplotype tally ---------------------------------------------------------------------------- */
+/* Per-haplotype windows -> vg-like deduplicated rows: sorts (position, packed k-mer) pairs and
+ * run-length encodes them (segmented reduction).  Gives what `vg find -E -H gbwt` reports in the
+ * frequency and ref columns consumed at score_sequences.py:292-293.
+ *   d_pos[n], d_packed[n]      per-haplotype windows (any order); both arrays are sorted in place
+ *   d_ref_packed               reference window per position (indexed by pos - pos_base) or NULL
+ *   outputs (capacity n): d_u_pos, d_u_packed, d_u_freq (haplotype count), d_u_isref (1 when equal
+ *   to the reference window); *d_n_unique = number of distinct rows. */
+int gb2_tally_haplotypes(gb2_ctx *ctx, uint64_t *d_pos, uint64_t *d_packed, int64_t n,
+                         const uint64_t *d_ref_packed, uint64_t pos_base, int64_t n_ref,
+                         uint64_t *d_u_pos, uint64_t *d_u_packed, uint32_t *d_u_freq, uint8_t *d_u_isref,
+                         uint64_t *d_n_unique);
+
+/* ---- host-buffer convenience: the whole path in one call ------------------------------------------ */
+/* compute_results' numeric core (score_sequences.py:273-321 numeric part, :194-198, resultsTmp.py:
+ * 303-313) from HOST memory: h_ascii holds n k-mers of w bytes (stride bytes apart; pinned memory
+ * gives full PCIe speed).  Copies in chunks overlapped with compute, encodes, scores, builds the
+ * histogram, BH, finalizes, and copies the hit table back.
+ *   strands 1|2, p_threshold, q_filter (0/1: threshold applies to q), want_q (0 = --no-qvalue).
+ *   Outputs (host, capacity hit_capacity): h_row, h_strand, h_iscore, h_score, h_p, h_q (h_q may be
+ *   NULL when want_q == 0); *h_n_hits = rows kept; h_stats[4] = {windows scored, N rows, bad rows,
+ *   hits before the q filter}.  Returns GB2_ERR_CAPACITY when hit_capacity was too small. */
+int gb2_scan_host(gb2_ctx *ctx, const gb2_motif *motif, const uint8_t *h_ascii, int64_t n, int w,
+                  int64_t stride, int strands, double p_threshold, int q_filter, int want_q,
+                  uint64_t hit_capacity, uint64_t *h_row, uint8_t *h_strand, int32_t *h_iscore,
+                  double *h_score, double *h_p, double *h_q, uint64_t *h_n_hits, uint64_t *h_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAFIMO_B200_H */
