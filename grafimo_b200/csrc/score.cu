@@ -46,18 +46,43 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p)
     return r;
 }
 
-template <int NCHUNK, int R>
-__device__ __forceinline__ uint32_t score_word(uint32_t w0, uint32_t w1, const uint32_t *my)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    // my = lut_s + (lane & (R-1)); entry (c, b) at my[(c*256 + b) * R]
-    uint32_t acc = 0;
-#pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-        const uint32_t word = (c < 4) ? w0 : w1;
-        const uint32_t b = (word >> (8 * (c & 3))) & 0xFFu;
-        acc += my[(c * 256 + b) * R];
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+__device__ __forceinline__ void red_shared_inc(uint32_t addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+// Both strands of one packed k-mer (w0 = bases 0..15, w1 = bases 16..31): one byte extract (PRMT), one
+// address add (LEA/IMAD) and one conflict-free LDS per 4-base chunk.  lut32 = shared-window address of
+// the replicated table + 4 * (lane & (R-1)); entry (c, b) sits at lut32 + (c*256 + b) * R * 4.
+template <int C, int NCHUNK, int R>
+struct ChunkSum {
+    static __device__ __forceinline__ uint32_t run(uint32_t w0, uint32_t w1, uint32_t lut32)
+    {
+        const uint32_t word = (C < 4) ? w0 : w1;
+        const uint32_t b = __byte_perm(word, 0u, 0x4440u + (uint32_t)(C & 3));  // PRMT: byte C of the k-mer
+        // table offset of chunk C rides in the LDS immediate; the entry offset is one IMAD/LEA
+        return lds_u32<C * 256 * R * 4>(lut32 + b * (uint32_t)(R * 4)) + ChunkSum<C + 1, NCHUNK, R>::run(w0, w1, lut32);
     }
-    return acc;
+};
+template <int NCHUNK, int R>
+struct ChunkSum<NCHUNK, NCHUNK, R> {
+    static __device__ __forceinline__ uint32_t run(uint32_t, uint32_t, uint32_t) { return 0u; }
+};
+
+template <int NCHUNK, int R>
+__device__ __forceinline__ uint32_t score_word(uint32_t w0, uint32_t w1, uint32_t lut32)
+{
+    return ChunkSum<0, NCHUNK, R>::run(w0, w1, lut32);
 }
 
 // Appends the hits of one (k-mer, strand) slot across the warp: one ballot, one global atomic.
@@ -66,9 +91,10 @@ __device__ __forceinline__ void append_hits(const ScoreParams &p, bool pred, uin
 {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
     if (m == 0) return;
+    const int leader = __ffs(m) - 1;
     unsigned long long base = 0;
-    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(p.hit_count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if ((int)lane == leader) base = atomicAdd(p.hit_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (pred) {
         const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
         if (slot < p.hit_capacity) {
@@ -90,6 +116,20 @@ __device__ __forceinline__ bool bin_hits(const ScoreParams &p, uint32_t bin)
     return (p.bitmap[bin >> 5] >> (bin & 31)) & 1u;
 }
 
+// Rare path, entered by the whole warp: exact per-bin test + warp-aggregated append for one pair.
+__device__ __forceinline__ void emit_pair_hits(const ScoreParams &p, uint32_t a0, uint32_t a1, int64_t j, bool ok, bool two,
+                                               unsigned lane)
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t a = h ? a1 : a0;
+        const uint64_t row = (uint64_t)(2 * j + h);
+        const uint32_t bf = a & 0xFFFFu, br = a >> 16;
+        append_hits(p, ok && bin_hits(p, bf), row, bf, 0u, lane);
+        if (two) append_hits(p, ok && bin_hits(p, br), row, br, 1u, lane);
+    }
+}
+
 template <int NCHUNK, int R, int U>
 __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 {
@@ -99,105 +139,131 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool do_hist = p.hist != nullptr;
 
-    for (int i = tid; i < NCHUNK * 256 * R; i += blockDim.x) lut_s[i] = p.lut[i / R];
+    for (int i = tid; i < NCHUNK * 256 * R; i += 1024) lut_s[i] = p.lut[i / R];
     if (do_hist)
-        for (uint32_t i = tid; i <= p.span; i += blockDim.x) hist_s[i] = 0u;
+        for (uint32_t i = tid; i <= p.span; i += 1024) hist_s[i] = 0u;
     __syncthreads();
 
-    const uint32_t *my = lut_s + (lane & (R - 1));
+    const uint32_t lut32 = smem_u32(lut_s) + 4u * (lane & (R - 1));
+    const uint32_t hist32 = smem_u32(hist_s);
     const uint4 *src = reinterpret_cast<const uint4 *>(p.packed);
     const int64_t npairs = p.n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const uint32_t nsent = (p.span << 16) | p.span;  // both fields -> bin `span`
     const uint32_t cut_hi = p.cut << 16;
     const bool two = p.two_strands != 0;
+    const bool has_n = p.nmask != nullptr;
 
-    // every lane of a warp runs the same trip count (ballots below need the full warp)
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
-    const int64_t warp_first = first - lane;
-    for (int64_t base = warp_first; base < npairs; base += stride * U) {
+    // ---- full tiles: 1024*U pairs, no bounds checks; thread t owns pairs t, t+1024, ... of the tile,
+    //      so every warp-wide load covers 512 contiguous bytes and U loads are in flight per thread
+    constexpr int TILE = 1024 * U;
+    const int64_t nfull = npairs / TILE;
+    for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
+        const int64_t j0 = tile * TILE + tid;
+        const uint4 *s = src + j0;
         uint4 v[U];
-        bool ok[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t j = base + lane + (int64_t)u * stride;
-            ok[u] = j < npairs;
-            v[u] = ok[u] ? ld_stream_u4(src + j) : make_uint4(0, 0, 0, 0);
-        }
+        for (int u = 0; u < U; ++u) v[u] = ld_stream_u4(s + u * 1024);
         uint32_t acc[2 * U];
-        bool any = false;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t j = base + lane + (int64_t)u * stride;
-            uint32_t a0 = score_word<NCHUNK, R>(v[u].x, v[u].y, my);
-            uint32_t a1 = score_word<NCHUNK, R>(v[u].z, v[u].w, my);
-            if (p.nmask != nullptr && ok[u]) {
-                const int64_t row = 2 * j;
-                const uint32_t nb = (__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 3u;
-                if (nb & 1u) a0 = nsent;
-                if (nb & 2u) a1 = nsent;
-            }
-            acc[2 * u] = a0;
-            acc[2 * u + 1] = a1;
-            if (ok[u]) {
-                if (do_hist) {
-                    atomicAdd(&hist_s[a0 & 0xFFFFu], 1u);
-                    atomicAdd(&hist_s[a1 & 0xFFFFu], 1u);
-                    if (two) {
-                        atomicAdd(&hist_s[a0 >> 16], 1u);
-                        atomicAdd(&hist_s[a1 >> 16], 1u);
-                    }
-                }
-                if (p.dense != nullptr) {
-                    uint2 d;
-                    d.x = (a0 == nsent) ? 0xFFFFFFFFu : a0;
-                    d.y = (a1 == nsent) ? 0xFFFFFFFFu : a1;
-                    reinterpret_cast<uint2 *>(p.dense)[j] = d;
-                }
-                any |= ((a0 & 0xFFFFu) >= p.cut) | ((a1 & 0xFFFFu) >= p.cut);
-                if (two) any |= (a0 >= cut_hi) | (a1 >= cut_hi);
-            }
+            acc[2 * u] = score_word<NCHUNK, R>(v[u].x, v[u].y, lut32);
+            acc[2 * u + 1] = score_word<NCHUNK, R>(v[u].z, v[u].w, lut32);
         }
-        if (p.hits != nullptr && __any_sync(0xFFFFFFFFu, any)) {
+        if (has_n) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int64_t j = base + lane + (int64_t)u * stride;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t a = acc[2 * u + h];
-                    const uint64_t row = (uint64_t)(2 * j + h);
-                    const uint32_t bf = a & 0xFFFFu, br = a >> 16;
-                    append_hits(p, ok[u] && bin_hits(p, bf), row, bf, 0u, lane);
-                    if (two) append_hits(p, ok[u] && bin_hits(p, br), row, br, 1u, lane);
-                }
+                const int64_t j = j0 + u * 1024;
+                const uint32_t nb = (__ldg(p.nmask + (j >> 4)) >> ((j & 15) * 2)) & 3u;
+                if (nb & 1u) acc[2 * u] = nsent;
+                if (nb & 2u) acc[2 * u + 1] = nsent;
             }
+        }
+        if (do_hist) {
+#pragma unroll
+            for (int k = 0; k < 2 * U; ++k) {
+                red_shared_inc(hist32 + 4u * __byte_perm(acc[k], 0u, 0x4410u));
+                if (two) red_shared_inc(hist32 + 4u * (acc[k] >> 16));
+            }
+        }
+        if (p.dense != nullptr) {
+            uint2 *d = reinterpret_cast<uint2 *>(p.dense) + j0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                uint2 o;
+                o.x = (acc[2 * u] == nsent) ? 0xFFFFFFFFu : acc[2 * u];
+                o.y = (acc[2 * u + 1] == nsent) ? 0xFFFFFFFFu : acc[2 * u + 1];
+                d[u * 1024] = o;
+            }
+        }
+        // cheap screen: per-field maximum over the 2U k-mers (packed 16-bit max), one compare per strand
+        uint32_t mx = acc[0];
+#pragma unroll
+        for (int k = 1; k + 1 < 2 * U; k += 2) mx = __vimax3_u16x2(mx, acc[k], acc[k + 1]);
+        mx = __vimax3_u16x2(mx, acc[2 * U - 1], acc[2 * U - 1]);
+        const bool any = ((mx & 0xFFFFu) >= p.cut) | (two & (mx >= cut_hi));
+        if (p.hits != nullptr && __any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) emit_pair_hits(p, acc[2 * u], acc[2 * u + 1], j0 + u * 1024, true, two, lane);
         }
     }
 
-    // odd tail: the last k-mer has no pair partner; warp 0 of block 0 handles it
-    if ((p.n & 1) && blockIdx.x == 0 && tid < 32) {
-        const int64_t row = p.n - 1;
-        const bool mine = lane == 0;
-        uint32_t a = 0;
-        if (mine) {
-            const uint64_t x = p.packed[row];
-            a = score_word<NCHUNK, R>((uint32_t)x, (uint32_t)(x >> 32), my);
-            if (p.nmask != nullptr && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) a = nsent;
-            if (do_hist) {
-                atomicAdd(&hist_s[a & 0xFFFFu], 1u);
-                if (two) atomicAdd(&hist_s[a >> 16], 1u);
+    // ---- remainder (< TILE pairs): one CTA, guarded
+    if ((int64_t)blockIdx.x == nfull % gridDim.x) {
+        for (int64_t jb = nfull * TILE; jb < npairs; jb += 1024) {
+            const int64_t j = jb + tid;
+            const bool ok = j < npairs;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (ok) v = ld_stream_u4(src + j);
+            uint32_t a0 = score_word<NCHUNK, R>(v.x, v.y, lut32);
+            uint32_t a1 = score_word<NCHUNK, R>(v.z, v.w, lut32);
+            if (has_n && ok) {
+                const uint32_t nb = (__ldg(p.nmask + (j >> 4)) >> ((j & 15) * 2)) & 3u;
+                if (nb & 1u) a0 = nsent;
+                if (nb & 2u) a1 = nsent;
             }
-            if (p.dense != nullptr) p.dense[row] = (a == nsent) ? 0xFFFFFFFFu : a;
+            if (ok) {
+                if (do_hist) {
+                    red_shared_inc(hist32 + 4u * (a0 & 0xFFFFu));
+                    red_shared_inc(hist32 + 4u * (a1 & 0xFFFFu));
+                    if (two) {
+                        red_shared_inc(hist32 + 4u * (a0 >> 16));
+                        red_shared_inc(hist32 + 4u * (a1 >> 16));
+                    }
+                }
+                if (p.dense != nullptr) {
+                    uint2 o;
+                    o.x = (a0 == nsent) ? 0xFFFFFFFFu : a0;
+                    o.y = (a1 == nsent) ? 0xFFFFFFFFu : a1;
+                    reinterpret_cast<uint2 *>(p.dense)[j] = o;
+                }
+            }
+            if (p.hits != nullptr) emit_pair_hits(p, a0, a1, j, ok, two, lane);
         }
-        if (p.hits != nullptr) {
-            append_hits(p, mine && bin_hits(p, a & 0xFFFFu), (uint64_t)row, a & 0xFFFFu, 0u, lane);
-            if (two) append_hits(p, mine && bin_hits(p, a >> 16), (uint64_t)row, a >> 16, 1u, lane);
+        // odd tail: the last k-mer has no pair partner; warp 0 handles it
+        if ((p.n & 1) && tid < 32) {
+            const int64_t row = p.n - 1;
+            const bool mine = lane == 0;
+            uint32_t a = 0;
+            if (mine) {
+                const uint64_t x = p.packed[row];
+                a = score_word<NCHUNK, R>((uint32_t)x, (uint32_t)(x >> 32), lut32);
+                if (has_n && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) a = nsent;
+                if (do_hist) {
+                    red_shared_inc(hist32 + 4u * (a & 0xFFFFu));
+                    if (two) red_shared_inc(hist32 + 4u * (a >> 16));
+                }
+                if (p.dense != nullptr) p.dense[row] = (a == nsent) ? 0xFFFFFFFFu : a;
+            }
+            if (p.hits != nullptr) {
+                append_hits(p, mine && bin_hits(p, a & 0xFFFFu), (uint64_t)row, a & 0xFFFFu, 0u, lane);
+                if (two) append_hits(p, mine && bin_hits(p, a >> 16), (uint64_t)row, a >> 16, 1u, lane);
+            }
         }
     }
 
     if (do_hist) {
         __syncthreads();
-        for (uint32_t i = tid; i <= p.span; i += blockDim.x) {
+        for (uint32_t i = tid; i <= p.span; i += 1024) {
             const uint32_t c = hist_s[i];
             if (c) atomicAdd(p.hist + i, (unsigned long long)c);
         }
@@ -208,7 +274,7 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 template <int NCHUNK, int R>
 static int launch_score(gb2_ctx *ctx, const ScoreParams &p, size_t smem, int grid)
 {
-    auto kern = gb2_score_kernel<NCHUNK, R, 2>;
+    auto kern = gb2_score_kernel<NCHUNK, R, 4>;
     GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 1024, smem, ctx->stream>>>(p);
     GB2_LAUNCH_CHECK(ctx);
@@ -279,7 +345,7 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     }
 
     const int64_t npairs = n >> 1;
-    int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(npairs, 1024)));
+    int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(npairs, 4096)));
     const size_t smem = (size_t)m->smem_bytes;
     switch (m->n_chunks) {
     case 1: return dispatch_r<1>(ctx, m->replicas, p, smem, grid);

@@ -203,7 +203,7 @@ def test_scan_host_matches_device_path(ctx):
     assert sorted(rows.tolist()) == np.nonzero(pv < 1.0)[0].tolist()
     assert np.array_equal(out["p-value"], pv[rows]) and np.array_equal(out["q-value"], q[rows])
     assert np.array_equal(out["score"], lo[rows])
-    assert out["stats"]["windows"] == len(r["seq"]) and out["stats"]["n_rows"] == 12
+    assert out["stats"]["windows"] == len(r["seq"]) and out["stats"]["n_rows"] == 24
 
 
 def test_hit_capacity_is_reported(ctx):
