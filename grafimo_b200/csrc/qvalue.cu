@@ -11,6 +11,7 @@
 #include <math_constants.h>
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 
 #include "internal.cuh"
 
@@ -135,6 +136,77 @@ extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uin
     gb2_bh_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(k_out, v_out, (const unsigned long long *)d_hist, nb, d_qtab, d_rank,
                                                      (unsigned long long *)d_total);
     GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// B3: stand-alone Benjamini-Hochberg of an arbitrary p-value list (row-wise form of the same formula)
+// ---------------------------------------------------------------------------------------------
+__global__ void gb2_bh_iota_kernel(uint32_t *idx, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = i;
+}
+
+__global__ void gb2_bh_raw_kernel(const double *__restrict__ sorted_p, uint32_t n, double *__restrict__ raw)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) raw[i] = __ddiv_rn(sorted_p[i], __ddiv_rn((double)(i + 1u), (double)n));  // p / (k / float(n))
+}
+
+__global__ void gb2_bh_scatter_kernel(const double *__restrict__ cummin, const uint32_t *__restrict__ order, uint32_t n,
+                                      double *__restrict__ q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[order[i]] = cummin[i] > 1.0 ? 1.0 : cummin[i];
+}
+
+extern "C" int gb2_bh_pvalues(gb2_ctx *ctx, const double *h_p, int64_t n, double *h_q)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n >= 0 && n < ((int64_t)1 << 31), "gb2_bh_pvalues: row count must be below 2^31");
+    if (n == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, h_p && h_q, "gb2_bh_pvalues: null buffer");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int ni = (int)n;
+    size_t cub_sort = 0, cub_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (const double *)nullptr, (double *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, ni, 0, 64, ctx->stream);
+    {
+        thrust::reverse_iterator<const double *> rin((const double *)nullptr);
+        thrust::reverse_iterator<double *> rout((double *)nullptr);
+        cub::DeviceScan::InclusiveScan(nullptr, cub_scan, rin, rout, cub::Min(), ni, ctx->stream);
+    }
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t cub_bytes = std::max(cub_sort, cub_scan);
+    const size_t need = align(cub_bytes) + 3 * align((size_t)n * 8) + 2 * align((size_t)n * 4);
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    double *a = (double *)base; base += align((size_t)n * 8);
+    double *b = (double *)base; base += align((size_t)n * 8);
+    double *c = (double *)base; base += align((size_t)n * 8);
+    uint32_t *i_in = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *i_out = (uint32_t *)base;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)gb2_div_up(n, threads);
+    GB2_CUDA(ctx, cudaMemcpyAsync(a, h_p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    gb2_bh_iota_kernel<<<blocks, threads, 0, ctx->stream>>>(i_in, (uint32_t)n);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_sort, a, b, i_in, i_out, ni, 0, 64, ctx->stream));
+    gb2_bh_raw_kernel<<<blocks, threads, 0, ctx->stream>>>(b, (uint32_t)n, a);
+    GB2_LAUNCH_CHECK(ctx);
+    {
+        thrust::reverse_iterator<const double *> rin((const double *)a + n);
+        thrust::reverse_iterator<double *> rout(c + n);
+        GB2_CUDA(ctx, cub::DeviceScan::InclusiveScan(d_tmp, cub_scan, rin, rout, cub::Min(), ni, ctx->stream));
+    }
+    ctx->launches += 2;
+    gb2_bh_scatter_kernel<<<blocks, threads, 0, ctx->stream>>>(c, i_out, (uint32_t)n, b);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cudaMemcpyAsync(h_q, b, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GB2_OK;
 }
 

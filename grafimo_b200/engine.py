@@ -284,3 +284,11 @@ def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False,
         out["q-value"] = q[:k]
     out["stats"] = dict(windows=int(stats[0]), n_rows=int(stats[1]), bad_rows=int(stats[2]), hits=int(stats[3]))
     return out
+
+
+def bh_from_pvalues(ctx, pvalues):
+    """gb2_bh_pvalues: float64[n] p-values -> float64[n] Benjamini-Hochberg q-values (input order)."""
+    p = np.ascontiguousarray(pvalues, dtype=np.float64)
+    q = np.empty_like(p)
+    check(ctx.lib.gb2_bh_pvalues(ctx.h, _np_ptr(p), p.shape[0], _np_ptr(q)), "gb2_bh_pvalues", ctx.h)
+    return q

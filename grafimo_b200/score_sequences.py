@@ -1,0 +1,199 @@
+"""B1 seam: `compute_results` -- scoring of the k-mers extracted from the variation graph.
+
+Same signature, flags, side effects, error behaviour and returned table as the reference's
+`grafimo.score_sequences.compute_results` (src/grafimo/score_sequences.py:44-211), with the per-row Python /
+numba loop (`score_seqs` :216-326, `compute_score_seq` :331-396), the statsmodels BH step (:401-428) and the
+filter + sort of `ResultTmp.to_df` (src/grafimo/resultsTmp.py:241-314) replaced by ONE call into the CUDA
+library (`gb2_scan_host`: encode -> score -> histogram -> BH -> finalize).  The host keeps what is text:
+reading the `vg find` TSVs, the string columns and the DataFrame.
+
+There is no CPU fallback: without the CUDA library / a GPU this module raises.
+"""
+import glob
+import os
+import time
+from typing import List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import engine
+from .motif import Motif
+from .utils import exception_handler
+
+COLUMNS = ["motif_id", "motif_alt_id", "sequence_name", "start", "stop", "strand", "score", "p-value", "q-value",
+           "matched_sequence", "haplotype_frequency", "reference"]
+
+_ctx = None
+
+
+def _context():
+    global _ctx
+    if _ctx is None:
+        _ctx = engine.Context()
+    return _ctx
+
+
+class KmerTable:
+    """Columns of the `vg find -x XG -H GBWT -K w -E -p REGION` output (7 whitespace-separated fields:
+    region, k-mer, chr:start(+|-), chr:stop(+|-), haplotype count, ref|non.ref, node path), parsed the way
+    score_seqs does (src/grafimo/score_sequences.py:279-293)."""
+
+    def __init__(self, seqname, seq, start, stop, strand, freq, ref):
+        self.seqname, self.seq, self.start, self.stop = seqname, seq, start, stop
+        self.strand, self.freq, self.ref = strand, freq, ref
+
+    def __len__(self):
+        return len(self.seq)
+
+    @staticmethod
+    def read(files: List[str], noreverse: bool) -> "KmerTable":
+        frames = []
+        for fn in files:
+            if os.stat(fn).st_size == 0:
+                continue
+            df = pd.read_csv(fn, sep=r"\s+", header=None, usecols=[0, 1, 2, 3, 4, 5], dtype=str, engine="c",
+                             na_filter=False, quoting=3)
+            frames.append(df)
+        if not frames:
+            empty = np.array([], dtype=object)
+            return KmerTable(empty, empty, np.array([], np.int64), np.array([], np.int64), empty, np.array([], np.int64), empty)
+        df = pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
+        pos2 = df[2].to_numpy(dtype=object)
+        pos3 = df[3].to_numpy(dtype=object)
+        strand = np.array([s[-1] for s in pos2], dtype=object)  # strand = data[2][-1]
+        start = np.array([int(s.split(":")[1][:-1]) for s in pos2], dtype=np.int64)
+        stop = np.array([int(s.split(":")[1][:-1]) for s in pos3], dtype=np.int64)
+        t = KmerTable(df[0].to_numpy(dtype=object), df[1].to_numpy(dtype=object), start, stop, strand,
+                      df[4].to_numpy(dtype=object).astype(np.int64), df[5].to_numpy(dtype=object))
+        if noreverse:  # '-' rows are dropped BEFORE scoring and counting (score_sequences.py:281-282)
+            keep = strand != "-"
+            t = KmerTable(t.seqname[keep], t.seq[keep], t.start[keep], t.stop[keep], t.strand[keep], t.freq[keep], t.ref[keep])
+        return t
+
+    def ascii_matrix(self, width: int, debug: bool):
+        joined = "".join(self.seq.tolist()).encode("ascii")
+        if len(joined) != len(self.seq) * width:
+            exception_handler(ValueError, f"Every k-mer must have exactly {width} symbols (the motif width).\n", debug)
+        import torch
+        buf = torch.empty((len(self.seq), width), dtype=torch.uint8, pin_memory=True)
+        buf.numpy()[...] = np.frombuffer(joined, dtype=np.uint8).reshape(len(self.seq), width)
+        return buf
+
+
+def print_scoring_msg(motif: Motif, noreverse: bool, debug: bool) -> None:
+    if not isinstance(motif, Motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    if not isinstance(noreverse, bool):
+        exception_handler(TypeError, f"Expected bool, got {type(noreverse).__name__}.\n", debug)
+    msg = "Scoring hits for motif {}."
+    print(msg.format("+" + motif.motif_id))
+    if not noreverse:
+        print(msg.format("-" + motif.motif_id), end="\n\n")
+
+
+def device_motif(motif: Motif, ctx=None):
+    """Uploads a Motif (cached on the object): chunk LUTs + the p-value table (K4)."""
+    ctx = ctx or _context()
+    cached = getattr(motif, "_gb2_device", None)
+    if cached is not None and cached.ctx is ctx and cached.h:
+        return cached
+    dm = ctx.motif(motif.score_matrix_acgt(), motif.pval_matrix, motif.min_val, motif.scale, float(motif.offset))
+    motif._gb2_device = dm
+    return dm
+
+
+def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
+                    testmode: Optional[bool] = False) -> pd.DataFrame:
+    """Scores every k-mer row under `<sequence_loc>/width_<w>/*.tsv` and returns the report table
+    (columns and semantics of src/grafimo/resultsTmp.py:269-313).
+
+    args_obj needs the attributes the reference reads (score_sequences.py:93-99): cores (ignored: the GPU
+    does the work), threshold, noqvalue, qvalueT, noreverse, recomb, verbose.
+    Rows are ordered by p-value ascending; ties -- whose order the reference leaves undefined -- by
+    (start, stop, strand, matched_sequence)."""
+    if not isinstance(motif, Motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    if not isinstance(sequence_loc, str):
+        exception_handler(TypeError, f"Expected str, got {type(sequence_loc).__name__}.\n", debug)
+    if not os.path.isdir(sequence_loc):
+        exception_handler(FileNotFoundError, f"Unable to locate {sequence_loc}.\n", debug)
+    if not testmode:
+        needed = ("threshold", "noqvalue", "qvalueT", "noreverse", "recomb", "verbose")
+        if args_obj is None or not all(hasattr(args_obj, a) for a in needed):
+            exception_handler(TypeError, f"Expected Findmotif, got {type(args_obj).__name__}.\n", debug)
+        threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+        no_reverse, recomb, verbose = args_obj.noreverse, args_obj.recomb, args_obj.verbose
+    else:  # the reference's pytest mode (score_sequences.py:100-107)
+        threshold, recomb, no_qvalue, qval_t, no_reverse, verbose = float(1), True, False, False, False, False
+    assert threshold > 0 and threshold <= 1
+    if qval_t:
+        assert not no_qvalue
+    print_scoring_msg(motif, no_reverse, debug)
+    if not motif.is_scaled:
+        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    width = motif.width
+    files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
+    t0 = time.time()
+    table = KmerTable.read(files, no_reverse)
+    n = len(table)
+    if n == 0:  # score_sequences.py:189-192
+        errmsg = "No result retrieved. Unable to proceed.\n"
+        errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
+        exception_handler(ValueError, errmsg, debug)
+    ctx = _context()
+    dm = device_motif(motif, ctx)
+    ascii_rows = table.ascii_matrix(width, debug)
+    # every row is scored as given: `vg find -E` already emits the reverse-strand rows
+    out = engine.scan_host(ctx, dm, ascii_rows, strands=1, threshold=float(threshold), q_filter=bool(qval_t),
+                           want_q=not no_qvalue, hit_capacity=n)
+    if verbose:
+        print("Sequences scored in %.2fs" % (time.time() - t0))
+    if not no_qvalue:
+        print("\nComputing q-values...\n")
+    print(f"Scanned sequences:\t{n}")
+    print(f"Scanned nucleotides:\t{n * width}")
+    t1 = time.time()
+    rows = out["row"].astype(np.int64)
+    freq = table.freq[rows]
+    keep = np.ones(len(rows), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
+    rows = rows[keep]
+    start, stop = table.start[rows], table.stop[rows]
+    ref = table.ref[rows].copy()
+    ref[(ref == "ref") & (np.abs(stop - start) != width)] = "non.ref"  # score_sequences.py:305-307
+    cols = {
+        "motif_id": [motif.motif_id] * len(rows),
+        "motif_alt_id": [motif.motif_name] * len(rows),
+        "sequence_name": table.seqname[rows],
+        "start": start,
+        "stop": stop,
+        "strand": table.strand[rows],
+        "score": out["score"][keep],
+        "p-value": out["p-value"][keep],
+    }
+    if not no_qvalue:
+        cols["q-value"] = out["q-value"][keep]
+    cols["matched_sequence"] = table.seq[rows]
+    cols["haplotype_frequency"] = table.freq[rows]
+    cols["reference"] = ref
+    df = pd.DataFrame(cols)
+    if len(df) > 1:  # deterministic tie order on top of the device's p-ascending order
+        order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
+                            df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
+        df = df.iloc[order].reset_index(drop=True)
+    if verbose:
+        print("\nResults summary built in %.2fs" % (time.time() - t1))
+    return df
+
+
+def compute_qvalues(pvalues: List[float], debug: bool) -> List[float]:
+    """B3 seam (src/grafimo/score_sequences.py:401-428): Benjamini-Hochberg q-values of a list of p-values,
+    same order in and out.  Inside compute_results the q-values come from the score histogram (K5); this
+    stand-alone form bins the distinct p-values and runs the same kernel."""
+    if not isinstance(pvalues, list):
+        exception_handler(TypeError, f"Expected list, got {type(pvalues).__name__}.\n", debug)
+    print("\nComputing q-values...\n")
+    p = np.asarray(pvalues, dtype=np.float64)
+    q = engine.bh_from_pvalues(_context(), p)
+    assert len(q) == len(pvalues)
+    return list(q)

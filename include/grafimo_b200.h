@@ -151,6 +151,11 @@ int gb2_score(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_packed, co
 int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_hist, double *d_qtab,
                           uint32_t *d_rank, uint64_t *d_total);
 
+/* Stand-alone form of the same step for an arbitrary list of p-values (B3 seam: compute_qvalues takes a
+ * list and returns a list, score_sequences.py:401-428): CUB radix sort, raw = p / (k / float(n)), reverse
+ * running minimum, clip at 1, scattered back to input order.  Host pointers. */
+int gb2_bh_pvalues(gb2_ctx *ctx, const double *h_p, int64_t n, double *h_q);
+
 /* ---- K6: finalize hits -------------------------------------------------------------------------- */
 /* Replaces the filter + sort of ResultTmp.to_df (resultsTmp.py:303-313) and the log-odds / p / q
  * columns (score_sequences.py:393; resultsTmp.py:277-279): optional q < q_threshold filter

@@ -1,0 +1,150 @@
+"""GPU tests of the drop-in seams (B1 compute_results, B2 comp_pval_mat / build_motif_*, B3 compute_qvalues)
+against the tables the unmodified reference produced (tests/golden/cases) and its own golden file."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _write(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def _build(tag, tmp_path):
+    from grafimo_b200 import motif_ops as mo
+    g = gu.load_motif(tag)
+    fx = gu.fixtures()
+    fmt = g["fmt"]
+    key = g["source"] if g["source"].endswith("_" + fmt) else g["source"] + "_meme"
+    path = _write(tmp_path, f"motif_{tag}.{fmt}", fx[key])
+    bg = "unfrm_dst" if g["bgfile"] == "unif" else _write(tmp_path, "bg_nt", fx["bg_nt"])
+    if fmt == "meme":
+        m = mo.build_motif_meme(path, bg, g["pseudo"], g["no_reverse"], 1, False, True)[0]
+    else:
+        fn = {"jaspar": mo.build_motif_jaspar, "transfac": mo.build_motif_transfac, "pfm": mo.build_motif_pfm}[fmt]
+        m = fn(path, bg, g["pseudo"], g["no_reverse"], False, True)
+    return m, g
+
+
+@pytest.mark.parametrize("tag", gu.motif_tags())
+def test_build_motif_end_to_end(tag, tmp_path):
+    m, g = _build(tag, tmp_path)
+    assert np.array_equal(m.score_matrix, g["score_matrix"])
+    assert np.array_equal(m.pval_matrix, g["pval_mat"])  # K3, bit-exact
+    assert m.is_scaled and m.scale == g["scale"] and m.offset == g["offset"]
+
+
+def test_comp_pval_mat_seam(tmp_path):
+    from grafimo_b200.motif_processing import comp_pval_mat
+    from grafimo_b200.grafimo_errors import MotifProcessingError
+    from grafimo_b200 import motif_ops as mo
+    m, g = _build("ctcf_meme__bgnt", tmp_path)
+    assert np.array_equal(comp_pval_mat(m, True), g["pval_mat"])
+    fx = gu.fixtures()
+    raw = mo._read_meme(_write(tmp_path, "u.meme", fx["ctcf_meme"]), "unfrm_dst", 0.1, False, False, True)[0]
+    raw.set_motif_score_matrix(np.ones((4, 19)))
+    with pytest.raises(MotifProcessingError):
+        comp_pval_mat(raw, True)  # not scaled yet (motif_processing.pyx:574-576)
+
+
+class _Args:
+    def __init__(self, o):
+        self.cores, self.threshold, self.noqvalue, self.qvalueT = 1, float(o["threshold"]), o["noqvalue"], o["qvalueT"]
+        self.noreverse, self.recomb, self.verbose = o["noreverse"], o["recomb"], False
+
+
+@pytest.mark.parametrize("tag", gu.scoring_tags())
+def test_compute_results_equals_reference_table(tag, tmp_path, capsys):
+    from grafimo_b200.score_sequences import compute_results
+    c = gu.load_scoring(tag)
+    m, g = _build(c["motif_tag"], tmp_path)
+    d = tmp_path / "seqs" / f"width_{m.width}"
+    d.mkdir(parents=True)
+    for k, lines in enumerate(c["files"]):
+        (d / f"region_{k}.tsv").write_text("\n".join(lines) + "\n")
+    testmode = tag == "fixture_testmode"
+    cwd = os.getcwd()
+    df = compute_results(m, str(tmp_path / "seqs") + "/", True, None if testmode else _Args(c["options"]), testmode=testmode)
+    assert os.getcwd() == cwd
+    assert list(df.columns) == c["columns"]
+    got = {col: df[col].to_numpy() for col in df.columns}
+    gu.assert_tables_equal(got, c["table"], c["columns"])
+    assert df["p-value"].is_monotonic_increasing
+    assert df["start"].dtype == np.int64 and df["haplotype_frequency"].dtype == np.int64 and df["score"].dtype == np.float64
+    out = capsys.readouterr().out
+    n = sum(1 for f in c["files"] for ln in f if not (c["options"]["noreverse"] and ln.split()[2][-1] == "-"))
+    assert f"Scanned sequences:\t{n}" in out and f"Scanned nucleotides:\t{n * m.width}" in out
+    assert f"Scoring hits for motif +{m.motif_id}." in out
+
+
+def test_compute_results_reference_own_golden(tmp_path):
+    """The reference's test_scoring: CTCF on width_19/scoring_test_input.tsv == expected_results/scoring_results.tsv."""
+    from grafimo_b200.score_sequences import compute_results
+    fx = gu.fixtures()
+    m, _ = _build("ctcf_meme__unif", tmp_path)
+    d = tmp_path / "input" / "width_19"
+    d.mkdir(parents=True)
+    (d / "scoring_test_input.tsv").write_text(fx["scoring_input_tsv"])
+    results = compute_results(m, str(tmp_path / "input") + "/", True, None, testmode=True)
+    results.to_csv(tmp_path / "scoring_test.tsv", sep="\t")
+    key = ["p-value", "start", "stop"]
+    got = pd.read_csv(tmp_path / "scoring_test.tsv", sep="\t", index_col=0).sort_values(key).reset_index(drop=True)
+    (tmp_path / "expected.tsv").write_text(fx["scoring_results_tsv"])
+    exp = pd.read_csv(tmp_path / "expected.tsv", sep="\t", index_col=0).sort_values(key).reset_index(drop=True)
+    assert got.equals(exp)  # the reference's own assertion (tests/grafimo_run_test.py:127-137)
+
+
+def test_compute_results_errors(tmp_path):
+    from grafimo_b200.score_sequences import compute_results
+    m, _ = _build("ctcf_meme__unif", tmp_path)
+    with pytest.raises(FileNotFoundError):
+        compute_results(m, str(tmp_path / "nope"), True, None, testmode=True)
+    (tmp_path / "empty" / "width_19").mkdir(parents=True)
+    with pytest.raises(ValueError):  # zero rows (score_sequences.py:189-192)
+        compute_results(m, str(tmp_path / "empty"), True, None, testmode=True)
+    with pytest.raises(TypeError):
+        compute_results("not a motif", str(tmp_path), True, None, testmode=True)
+    with pytest.raises(SystemExit) as e:  # debug=False: message + exit code 1 (utils.py:63-78)
+        compute_results(m, str(tmp_path / "nope"), False, None, testmode=True)
+    assert e.value.code == 1
+    d = tmp_path / "bad" / "width_19"
+    d.mkdir(parents=True)
+    (d / "r.tsv").write_text("1:1-30\tACGT\t1:1+\t1:5+\t1\tref\t1+,\n")
+    with pytest.raises(ValueError):
+        compute_results(m, str(tmp_path / "bad"), True, None, testmode=True)
+
+
+def test_compute_qvalues_seam():
+    from grafimo_b200.score_sequences import compute_qvalues
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    p = np.round(rng.random(20000), 4)
+    p[::11] = 1.0
+    q = compute_qvalues(p.tolist(), True)
+    assert isinstance(q, list) and np.array_equal(np.array(q), orc.bh(p))
+
+
+def test_cli_findmotif_writes_reports(tmp_path):
+    from grafimo_b200.__main__ import main
+    fx = gu.fixtures()
+    meme = _write(tmp_path, "MA0139.1.meme", fx["ctcf_meme"])
+    d = tmp_path / "kmers" / "width_19"
+    d.mkdir(parents=True)
+    (d / "a.tsv").write_text(fx["scoring_input_tsv"])
+    out = tmp_path / "out"
+    rc = main(["findmotif", "-m", meme, "--kmers-dir", str(tmp_path / "kmers"), "-t", "0.05", "--recomb", "-o", str(out),
+               "--debug"])
+    assert rc == 0
+    tsv = pd.read_csv(out / "grafimo_out.tsv", sep="\t", index_col=0)
+    c = gu.load_scoring("fixture_t05_norecomb")
+    assert len(tsv) >= len(c["table"]["start"]) and (tsv["p-value"] < 0.05).all()
+    gff = (out / "grafimo_out.gff").read_text().split("\n")
+    assert gff[0] == "##gff-version 3" and len(gff) == len(tsv) + 2
+    assert (out / "grafimo_out.html").exists()

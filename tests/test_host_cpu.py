@@ -1,0 +1,170 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every declared symbol, the motif
+parsers / PWM maths reproduce the reference's goldens bit for bit, the TSV row parser and the report
+writers keep the reference's layout, and the product fails loudly without a GPU."""
+import io
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import golden_util as gu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module")
+def built():
+    from grafimo_b200 import build
+    return build.build()
+
+
+def test_abi_library_exports_every_declared_symbol(built):
+    import ctypes
+    from grafimo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "grafimo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gb2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 22
+    lib = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().gb2_abi_version() == 1
+    assert _lib.load().gb2_error_string(2).decode().startswith("CUDA")
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(built):
+    from grafimo_b200._lib import GrafimoB200Error
+    from grafimo_b200.engine import Context
+    with pytest.raises(GrafimoB200Error):
+        Context()
+    import ctypes
+    from grafimo_b200 import _lib
+    h = ctypes.c_void_p()
+    assert _lib.load().gb2_ctx_create(0, None, ctypes.byref(h)) == 2  # GB2_ERR_CUDA
+
+
+def _write(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+@pytest.mark.parametrize("tag", gu.motif_tags())
+def test_motif_host_maths_bit_exact(tag, tmp_path):
+    """parse -> background -> normalise -> pseudocount -> log-odds -> integer scaling (everything before the DP)."""
+    from grafimo_b200 import motif_ops as mo
+    g = gu.load_motif(tag)
+    fx = gu.fixtures()
+    src, fmt = g["source"], g["fmt"]
+    ext = {"meme": "meme", "jaspar": "jaspar", "transfac": "transfac", "pfm": "pfm"}[fmt]
+    key = src if src.endswith("_" + fmt) else src + "_meme"
+    path = _write(tmp_path, f"motif.{ext}", fx[key])
+    bg = "unfrm_dst" if g["bgfile"] == "unif" else _write(tmp_path, "bg_nt", fx["bg_nt"])
+    reader = {"meme": mo._read_meme, "jaspar": mo._read_jaspar, "transfac": mo._read_transfac, "pfm": mo._read_pfm}[fmt]
+    m = reader(path, bg, g["pseudo"], g["no_reverse"], False, True)
+    m = m[0] if isinstance(m, list) else m
+    assert m.motif_id == g["motif_id"] and m.motif_name == g["motif_name"] and m.width == g["width"]
+    assert list(m.bg.keys()) == g["bg_key_order"]
+    assert np.array_equal(m.bg_acgt(), g["bg_acgt"])
+    assert np.array_equal(m.count_matrix, g["count_matrix"])
+    mo._scale_motif(m, True)
+    assert np.array_equal(m.score_matrix, g["score_matrix"])
+    assert (m.min_val, m.max_val, m.scale) == (g["min_val"], g["max_val"], g["scale"])
+    assert isinstance(m.offset, np.double) and m.offset == g["offset"]
+    assert np.array_equal(m.score_matrix_acgt(), g["score_matrix"])
+
+
+def test_reference_integer_matrix_goldens(tmp_path):
+    """The reference's own expected matrices (tests/test_data/expected_results/motif_processing_test_*.txt)."""
+    from grafimo_b200 import motif_ops as mo
+    fx = gu.fixtures()
+    exp_meme = np.loadtxt(io.StringIO(fx["expected_matrix_meme"])).astype(int)
+    exp_jaspar = np.loadtxt(io.StringIO(fx["expected_matrix_jaspar"])).astype(int)
+    m = mo._read_meme(_write(tmp_path, "a.meme", fx["ctcf_meme"]), "unfrm_dst", 0.1, False, False, True)[0]
+    assert (mo._scale_motif(m, True).score_matrix == exp_meme).all()
+    for fmt, reader in (("jaspar", mo._read_jaspar), ("transfac", mo._read_transfac), ("pfm", mo._read_pfm)):
+        m = reader(_write(tmp_path, f"a.{fmt}", fx[f"ctcf_{fmt}"]), "unfrm_dst", 0.1, False, False, True)
+        assert (mo._scale_motif(m, True).score_matrix == exp_jaspar).all(), fmt
+    assert (exp_meme != exp_jaspar).sum() == 1  # 52 vs 53 in one cell
+
+
+def test_format_sniffers(tmp_path):
+    from grafimo_b200 import utils
+    fx = gu.fixtures()
+    paths = {fmt: _write(tmp_path, f"MA0139.1.{fmt}", fx[f"ctcf_{fmt}"]) for fmt in ("meme", "jaspar", "transfac", "pfm")}
+    assert utils.is_meme(paths["meme"]) and not utils.is_jaspar(paths["meme"])
+    assert utils.is_jaspar(paths["jaspar"]) and not utils.is_meme(paths["jaspar"])
+    assert utils.is_transfac(paths["transfac"]) and not utils.is_meme(paths["transfac"])
+    assert utils.is_pfm(paths["pfm"]) and not utils.is_transfac(paths["pfm"])
+
+
+def test_kmer_table_parser_matches_reference_field_rules(tmp_path):
+    from grafimo_b200.score_sequences import KmerTable
+    from oracle import oracle as orc
+    c = gu.load_scoring("fixture_plus_N_2files")
+    files = []
+    for k, lines in enumerate(c["files"]):
+        files.append(_write(tmp_path, f"r{k}.tsv", "\n".join(lines) + "\n"))
+    for norev in (False, True):
+        t = KmerTable.read(files, norev)
+        r = orc.parse_rows([ln for f in c["files"] for ln in f], norev)
+        assert list(t.seq) == r["seq"] and list(t.seqname) == r["seqname"] and list(t.strand) == r["strand"]
+        assert np.array_equal(t.start, r["start"]) and np.array_equal(t.stop, r["stop"]) and np.array_equal(t.freq, r["freq"])
+        assert list(t.ref) == r["ref"]
+    # the reference's own k-mer fixture (expected_seqs.tsv: no GBWT -> freq 0, single-digit node ids)
+    fx = gu.fixtures()
+    t = KmerTable.read([_write(tmp_path, "x.tsv", fx["expected_seqs_tsv"])], False)
+    assert len(t) == 32 and set(t.strand) == {"+", "-"} and set(t.freq.tolist()) == {0}
+
+
+@pytest.mark.parametrize("tag", ["fixture_testmode", "fixture_noq", "synth_w8"])
+def test_writers_keep_the_reference_layout(tag, tmp_path):
+    from grafimo_b200.res_writer import writeGFF3
+    c = gu.load_scoring(tag)
+    df = pd.DataFrame({col: c["table"][col] for col in c["columns"]}).head(25)
+    noq = c["options"]["noqvalue"]
+    prefix = str(tmp_path / "out")
+    writeGFF3(prefix, df, noq, True)
+    assert open(prefix + ".gff").read() == c["gff3_head25"]
+    buf = io.StringIO()
+    df.to_csv(buf, sep="\t", encoding="utf-8")
+    assert buf.getvalue() == c["tsv_head25"]
+
+
+def test_gff3_known_row():
+    """Verbatim reference output for golden row 0."""
+    from grafimo_b200.res_writer import gff3_lines
+    df = pd.DataFrame({
+        "motif_id": ["MA0139.1"], "motif_alt_id": ["CTCF"], "sequence_name": ["22:19723256-19723526"],
+        "start": [19723401], "stop": [19723382], "strand": ["-"], "score": [1.2096774193548185],
+        "p-value": [0.0013399618583207484], "q-value": [0.49884025391656905], "matched_sequence": ["CTATCGCCGGAGGCCGCAG"],
+        "haplotype_frequency": [5096], "reference": ["ref"]})
+    assert list(gff3_lines(df, False)) == [
+        "22\tgrafimo\tnucleotide_motif\t19723382\t19723401\t1.2\t-\t.\tName=MA0139.1_22:19723256-19723526-:ref;"
+        "Alias=CTCF;ID=MA0139.1=-=CTCF=-=22:19723256-19723526;pvalue==1.3399618583207484e-03;"
+        "qvalue=4.9884025391656905e-01;sequence==CTATCGCCGGAGGCCGCAG=;\n"]
+
+
+def test_findmotif_container_and_cli_parser():
+    from grafimo_b200.__main__ import get_parser
+    from grafimo_b200.workflow import Findmotif
+    a = get_parser().parse_args(["findmotif", "-m", "x.meme", "--kmers-dir", "d", "-t", "0.01", "--recomb", "-r"])
+    wf = Findmotif(motif=a.motif, kmers_dir=a.kmers_dir, threshold=a.threshold, recomb=a.recomb, no_reverse=a.no_reverse)
+    assert (wf.threshold, wf.recomb, wf.noreverse, wf.noqvalue, wf.qvalueT, wf.bgfile, wf.pseudo) == \
+        (0.01, True, True, False, False, "unfrm_dst", 0.1)
+    with pytest.raises(ValueError):
+        Findmotif(qval_t=True, no_qvalue=True)
+    with pytest.raises(TypeError):
+        Findmotif(threshold=1)
