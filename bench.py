@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native GRAFIMO motif-scanning path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): scored windows / second, both strands, beside the HBM roofline and the reference's
+CPU path.  Workload at N=1 (BASELINE.json configs[1]): CTCF MA0139.1 on a synthetic 1 Mb region with 2,504
+haplotype paths -- every 19-bp window of every haplotype as a packed uint64, 2.50e9 k-mers = 20.0 GB resident
+in HBM (inputs >> 126 MB L2, so no L2 flush is needed between steps).  For N>1 every rank holds its own region
+of the same size (weak scaling, as a whole-genome scan shards by chromosome) and the only cross-GPU traffic is
+the all-reduce of the score histogram that makes the q-values global.
+
+A step = one pass of the hot path over the resident batch: K2 (score both strands + histogram + hit
+compaction) -> [all-reduce] -> K5 (Benjamini-Hochberg from the histogram) -> K6 (filter/sort/annotate hits).
+`value` is device-timed (CUDA events on the launching stream, max over ranks).  `e2e` is the same work through
+the host-buffer C-ABI call gb2_scan_host (ASCII k-mers in pinned host memory -> hit table in host memory;
+host<->device copies inside the timed region).  `cpu_baseline` / `--impl reference` time the CPU oracle
+(oracle/, a C restatement of the reference's algorithm incl. its per-row p-value sums) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REGION_LEN = 1_000_000
+N_HAP = 2504
+THRESHOLD = 1e-4
+SEED = 20240
+METRIC = "scored_windows_per_sec_both_strands"
+UNIT = "windows/s"
+
+
+def load_fixture_motif_text():
+    with open(os.path.join(ROOT, "tests", "golden", "fixtures.json")) as fh:
+        return json.load(fh)["ctcf_meme"]
+
+
+def golden_motif_arrays():
+    """CTCF arrays produced by the reference (no GPU needed) -- used by the reference arm only."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cases", "motif_ctcf_meme__unif.npz"))
+    return dict(score_matrix=z["score_matrix"], pval_mat=z["pval_mat"], min_val=int(z["min_val"]), scale=int(z["scale"]),
+                offset=float(z["offset"]), width=int(z["width"]))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().split("\n") if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip() == "Active":
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_median": float(np.median(power)), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample_rows(n_kmers, seed):
+    """ASCII rows of the same synthetic workload (forward k-mers + their reverse-complement rows, which is what
+    `vg find -E` hands the reference), generated on the CPU."""
+    import torch
+    from grafimo_b200 import synth
+    per = 20000 - 19 + 1
+    n_hap = max(1, (n_kmers + per - 1) // per)
+    packed, _ = synth.haplotype_windows(20000, n_hap, 19, seed, device="cpu")
+    fwd = synth.windows_to_ascii(packed[:n_kmers], 19).numpy()
+    return np.ascontiguousarray(np.concatenate([fwd, synth.revcomp_ascii(fwd)]))
+
+
+def time_oracle(rows, m, threads):
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    orc.score_rows(rows, m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"], nthreads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    orc.build()
+    m = golden_motif_arrays()
+    threads = os.cpu_count() or 1
+    calib = cpu_sample_rows(20000, SEED)
+    t = time_oracle(calib, m, threads)
+    rate = calib.shape[0] / t
+    rows_per_step = int(max(20000, min(rate * 4.0, 4_000_000)))  # ~4 s of CPU work per step
+    rows = cpu_sample_rows(rows_per_step // 2, SEED + 1)
+    for _ in range(max(args.warmup, 0)):
+        time_oracle(rows[: max(2000, rows.shape[0] // 20)], m, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_oracle(rows, m, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = rows.shape[0] / dt
+    sample = (f"{rows.shape[0]} rows/step ({rows.shape[0] // 2} forward 19-mers of the synthetic haplotype workload + their "
+              f"reverse-complement rows), oracle C port of compute_score_seq incl. its two per-row pval_mat sums, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "i64+f64", "data": "synthetic",
+        "config": {"workload": "CTCF MA0139.1, synthetic 1 Mb region x 2504 haplotype paths, both strands, t=1e-4 "
+                               "(bounded sample per step; the Python reference cannot travel to the GPU box, so this is "
+                               "the oracle port of its algorithm)", "rows_per_step": int(rows.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def build_ctcf(tmpdir):
+    """CTCF through the product path: MEME parser -> log-odds -> scaling (host) -> K3 DP (GPU)."""
+    from grafimo_b200.motif_ops import build_motif_meme
+    path = os.path.join(tmpdir, "MA0139.1.meme")
+    with open(path, "w") as fh:
+        fh.write(load_fixture_motif_text())
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return build_motif_meme(path, "unfrm_dst", 0.1, False, 1, False, True)[0]
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 8 << 30
+
+
+def run_ours(args):
+    import torch
+    from grafimo_b200 import dist as gdist
+    from grafimo_b200 import engine, synth
+    from grafimo_b200.score_sequences import device_motif
+
+    if args.gpus > 1 and "RANK" not in os.environ:  # plain `python bench.py --gpus N`: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        if args.region_len != REGION_LEN:
+            cmd += ["--region-len", str(args.region_len)]
+        if args.haplotypes != N_HAP:
+            cmd += ["--haplotypes", str(args.haplotypes)]
+        return subprocess.call(cmd)
+
+    info = gdist.init_from_env("nccl")
+    rank, world, local = info["rank"], info["world"], info["local"]
+    torch.cuda.set_device(local)
+    ctx = engine.Context(local)
+    tmpdir = tempfile.mkdtemp(prefix="gb2_bench_")
+    motif = build_ctcf(tmpdir)
+    dm = device_motif(motif, ctx)
+    w = motif.width
+    L, H = args.region_len, args.haplotypes
+    per = L - w + 1
+    n = per * H
+    with torch.cuda.stream(ctx.stream):
+        windows, model = synth.haplotype_windows(L, H, w, SEED + rank, device=ctx.device, hap_batch=32)
+    ctx.sync()
+    scan = engine.Scan(ctx, dm, strands=2, threshold=THRESHOLD, want_q=True, hit_capacity=1 << 23)
+    ev_pairs = []
+
+    def step(timed):
+        scan.reset()
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ctx.stream)
+        scan.score(windows)
+        if timed:
+            b.record(ctx.stream)
+            ev_pairs.append((a, b))
+        if world > 1:
+            with torch.cuda.stream(ctx.stream):
+                gdist.allreduce_histogram(scan.histogram())
+        scan.qvalues()
+        return scan.finalize_device()
+
+    for _ in range(max(args.warmup, 3)):
+        kept = step(False)
+    ctx.sync()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local)
+    launches0 = ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record(ctx.stream)
+    for _ in range(args.steps):
+        kept = step(True)
+    t1.record(ctx.stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    ms_total = t0.elapsed_time(t1)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        torch.distributed.barrier()
+    ms_total = gdist.allreduce_max(ms_total, device=ctx.device)
+    ms_step = ms_total / args.steps
+    total_windows = 2 * n * world
+    value = total_windows / (ms_step * 1e-3)
+    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
+    n_hits = scan.n_hits()
+    algo_bytes = 8.0 * n + 16.0 * n_hits
+    peak, peak_src = peaks()
+    achieved = algo_bytes / (k2_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as fh:
+            tj = json.load(fh)
+            if int(tj.get("n_kmers", -1)) == n:
+                traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "gb2_score_kernel<5,32,4>", "kernel_ms": k2_ms,
+                "kernel_share_of_step": k2_ms / ms_step, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32 (u16x2 packed score adds); f64 p/q-values", "data": "synthetic",
+        "config": {"workload": f"CTCF MA0139.1 (w=19, uniform bg) on a synthetic {L} bp region x {H} haplotype paths per GPU "
+                               f"(1000G-like SNP/indel density), both strands, p<{THRESHOLD:g}, q-values on",
+                   "kmers_per_gpu": n, "bytes_resident_per_gpu": 8 * n, "l2_policy": "inputs larger than L2 (no flush needed)",
+                   "parallelism": f"rows sharded by region over {world} GPU(s); one all-reduce of the score histogram",
+                   "hits_per_gpu": n_hits, "kept_after_finalize": kept},
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+    }
+
+    # ---- e2e: ASCII k-mers in pinned host memory through gb2_scan_host (rank-local; max over ranks) ----------
+    e2e_rows = n
+    budget = int(mem_available_bytes() * 0.30 / world)
+    if e2e_rows * w > budget:
+        e2e_rows = max(1 << 20, budget // w)
+    if args.e2e_rows:
+        e2e_rows = min(n, args.e2e_rows)
+    host = torch.empty((e2e_rows, w), dtype=torch.uint8, pin_memory=True)
+    chunk = 1 << 24
+    with torch.cuda.stream(ctx.stream):
+        for lo in range(0, e2e_rows, chunk):
+            hi = min(lo + chunk, e2e_rows)
+            host[lo:hi].copy_(synth.windows_to_ascii(windows[lo:hi], w), non_blocking=True)
+    ctx.sync()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    out = engine.scan_host(ctx, dm, host, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23)  # warm-up
+    if world > 1:
+        torch.distributed.barrier()
+    ts = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = engine.scan_host(ctx, dm, host, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23)
+    dt = (time.perf_counter() - ts) / e2e_steps
+    dt = gdist.allreduce_max(dt, device=ctx.device)
+    d2h = int(len(out["row"]) * (8 + 1 + 4 + 8 + 8 + 8) + 5 * 8 + 8)
+    line["e2e"] = {"value": 2.0 * e2e_rows * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(e2e_rows * w),
+                   "d2h_bytes_per_step": d2h, "rows_per_step_per_gpu": int(e2e_rows), "steps": e2e_steps,
+                   "ms_per_step": dt * 1e3, "api": "gb2_scan_host (ASCII k-mers, pinned host memory)",
+                   "hits": int(len(out["row"]))}
+    del host
+
+    # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload ---------------
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build()
+        m = dict(score_matrix=motif.score_matrix_acgt(), pval_mat=motif.pval_matrix, min_val=motif.min_val,
+                 scale=motif.scale, offset=float(motif.offset))
+        threads = os.cpu_count() or 1
+        with torch.cuda.stream(ctx.stream):
+            fwd = synth.windows_to_ascii(windows[: 1 << 23], w).cpu().numpy()
+        calib = np.ascontiguousarray(np.concatenate([fwd[:10000], synth.revcomp_ascii(fwd[:10000])]))
+        rate = calib.shape[0] / time_oracle(calib, m, threads)
+        k = int(max(10000, min(fwd.shape[0], rate * 12.0 / 2)))  # ~12 s of CPU work
+        rows = np.ascontiguousarray(np.concatenate([fwd[:k], synth.revcomp_ascii(fwd[:k])]))
+        t = time_oracle(rows, m, threads)
+        line["cpu_baseline"] = {
+            "value": rows.shape[0] / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rows.shape[0]} rows = first {k} forward 19-mers of the workload + their reverse-complement rows; "
+                      f"oracle C port of the reference's per-row scoring (incl. two pval_mat sums per row), {threads} threads, {t:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--region-len", type=int, default=REGION_LEN)
+    ap.add_argument("--haplotypes", type=int, default=N_HAP)
+    ap.add_argument("--e2e-rows", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

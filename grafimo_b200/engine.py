@@ -227,8 +227,8 @@ class Scan:
         self.ctx.sync()
         return int(self.counters[0].item())
 
-    def finalize(self, q_filter=False):
-        """K6 -> dict of numpy columns sorted by (p ascending, row, strand)."""
+    def finalize_device(self, q_filter=False):
+        """K6 with the columns left on the device (self.out: dict of device tensors); returns the rows kept."""
         ctx = self.ctx
         if not hasattr(self, "rank"):
             self.qvalues()
@@ -236,19 +236,28 @@ class Scan:
         if n > self.capacity:
             raise GrafimoB200Error(_lib.GB2_ERR_CAPACITY, "Scan.finalize", f"{n} hits exceed the capacity {self.capacity}")
         cap = max(n, 1)
-        o_row = ctx.empty(cap, torch.int64)
-        o_strand = ctx.empty(cap, torch.uint8)
-        o_iscore = ctx.empty(cap, torch.int32)
-        o_score = ctx.empty(cap, torch.float64)
-        o_p = ctx.empty(cap, torch.float64)
-        o_q = ctx.empty(cap, torch.float64) if self.want_q else None
+        if getattr(self, "_out_cap", 0) < cap:
+            self._o = dict(row=ctx.empty(cap, torch.int64), strand=ctx.empty(cap, torch.uint8),
+                           iscore=ctx.empty(cap, torch.int32), score=ctx.empty(cap, torch.float64),
+                           p=ctx.empty(cap, torch.float64), q=ctx.empty(cap, torch.float64) if self.want_q else None)
+            self._out_cap = cap
+        o = self._o
         check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, _ptr(self.qtab) if self.want_q else None,
-                                        _ptr(self.rank), int(bool(q_filter)), self.threshold, _ptr(o_row), _ptr(o_strand),
-                                        _ptr(o_iscore), _ptr(o_score), _ptr(o_p), _ptr(o_q),
+                                        _ptr(self.rank), int(bool(q_filter)), self.threshold, _ptr(o["row"]), _ptr(o["strand"]),
+                                        _ptr(o["iscore"]), _ptr(o["score"]), _ptr(o["p"]), _ptr(o["q"]),
                                         ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits", ctx.h)
         ctx.sync()
         with torch.cuda.stream(ctx.stream):
             kept = int(self.counters[1].item())
+        self.out = o
+        return kept
+
+    def finalize(self, q_filter=False):
+        """K6 -> dict of numpy columns sorted by (p ascending, row, strand)."""
+        ctx = self.ctx
+        kept = self.finalize_device(q_filter)
+        o_row, o_strand, o_iscore, o_score, o_p, o_q = (self.out[k] for k in ("row", "strand", "iscore", "score", "p", "q"))
+        with torch.cuda.stream(ctx.stream):
             out = {
                 "row": o_row[:kept].cpu().numpy(), "strand": o_strand[:kept].cpu().numpy(),
                 "int_score": o_iscore[:kept].cpu().numpy(), "score": o_score[:kept].cpu().numpy(),

@@ -1,0 +1,100 @@
+"""Seeded synthetic inputs of the shapes named in BASELINE.json / SURVEY.md 8(d).
+
+`haplotype_windows` builds the throughput form of config C2: a random reference region, 1000-Genomes-like
+variant sites (density 1/40 bp, 90 % SNPs / 10 % indels of 1-5 bp, allele frequency ~ 1/x on [1/H, 0.5]), H
+haplotypes that carry each variant with probability af, and every motif-width window of every haplotype as a
+2-bit packed uint64 (the layout of include/grafimo_b200.h).  Works on CPU tensors (tests, reference arm) and on
+CUDA tensors (bench) with the same code.  These are generators of test/bench inputs, not part of the scanning path.
+"""
+import numpy as np
+import torch
+
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def variant_model(region_len, n_hap, seed, density=1.0 / 40.0, indel_frac=0.1, device="cpu"):
+    """Reference codes + variant sites.  Returns a dict of tensors on `device`."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    pad = 64
+    ref = torch.randint(0, 4, (region_len + pad,), generator=g, dtype=torch.int64)
+    n_var = max(1, int(region_len * density))
+    site = torch.randperm(region_len - 1, generator=g)[:n_var].sort().values + 1
+    is_indel = torch.rand(n_var, generator=g) < indel_frac
+    length = torch.randint(1, 6, (n_var,), generator=g)
+    sign = torch.where(torch.rand(n_var, generator=g) < 0.5, -1, 1)
+    lo, hi = 1.0 / n_hap, 0.5
+    af = lo * (hi / lo) ** torch.rand(n_var, generator=g, dtype=torch.float64)  # density ~ 1/x
+    alt = (ref[site] + torch.randint(1, 4, (n_var,), generator=g)) % 4
+    m = dict(ref=ref, site=site, is_indel=is_indel, shift=(length * sign) * is_indel, af=af.float(), alt=alt,
+             region_len=region_len, pad=pad, seed=int(seed), n_hap=n_hap)
+    return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in m.items()}
+
+
+def haplotype_codes(model, hap_lo, hap_hi):
+    """int64 [hap_hi-hap_lo, region_len] base codes of the haplotypes (deterministic per haplotype index)."""
+    dev = model["ref"].device
+    L, nh = model["region_len"], hap_hi - hap_lo
+    n_var = model["site"].shape[0]
+    g = torch.Generator(device=dev)
+    g.manual_seed(model["seed"] * 1000003 + hap_lo)
+    carry = torch.rand((nh, n_var), generator=g, device=dev) < model["af"][None, :]
+    # indels shift the reference coordinate of everything downstream
+    delta = torch.zeros((nh, L), dtype=torch.int32, device=dev)
+    delta[:, model["site"]] = (carry * model["shift"][None, :]).to(torch.int32)
+    idx = torch.arange(L, device=dev)[None, :] + torch.cumsum(delta, dim=1)
+    idx.clamp_(0, L + model["pad"] - 1)
+    hap = model["ref"][idx]
+    # SNP alleles, placed in reference coordinates and carried through the same index map
+    snp = torch.full((nh, L + model["pad"]), -1, dtype=torch.int64, device=dev)
+    snp_sites = model["site"][~model["is_indel"]]
+    snp[:, snp_sites] = torch.where(carry[:, ~model["is_indel"]], model["alt"][~model["is_indel"]][None, :], -1)
+    alt = torch.gather(snp, 1, idx)
+    return torch.where(alt >= 0, alt, hap)
+
+
+def pack_windows(codes, w):
+    """int64 [H, L] codes -> int64 [H, L-w+1] packed windows (base i in bits 2i, 2i+1)."""
+    n = codes.shape[1] - w + 1
+    out = torch.zeros((codes.shape[0], n), dtype=torch.int64, device=codes.device)
+    for j in range(w):
+        out |= codes[:, j:j + n] << (2 * j)
+    return out
+
+
+def haplotype_windows(region_len, n_hap, w, seed, device="cpu", hap_batch=32, out=None):
+    """Packed windows of every haplotype, flattened haplotype-major: int64 [n_hap * (region_len - w + 1)]."""
+    model = variant_model(region_len, n_hap, seed, device=device)
+    per = region_len - w + 1
+    if out is None:
+        out = torch.empty(n_hap * per, dtype=torch.int64, device=device)
+    for lo in range(0, n_hap, hap_batch):
+        hi = min(lo + hap_batch, n_hap)
+        out[lo * per:hi * per] = pack_windows(haplotype_codes(model, lo, hi), w).reshape(-1)
+    return out, model
+
+
+def windows_to_ascii(packed, w, out=None):
+    """int64 [n] packed windows -> uint8 [n, w] ASCII k-mers (on the tensor's device)."""
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=packed.device)
+    sh = 2 * torch.arange(w, device=packed.device, dtype=torch.int64)
+    codes = (packed[:, None] >> sh[None, :]) & 3
+    a = lut[codes]
+    if out is not None:
+        out.copy_(a)
+        return out
+    return a
+
+
+def revcomp_ascii(a):
+    """uint8 [n, w] ASCII -> reverse complement (numpy)."""
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[:] = ord("N")
+    for x, y in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[x] = y
+    return np.ascontiguousarray(comp[a][:, ::-1])
+
+
+def reference_windows(model, w):
+    """Packed windows of the unmodified reference (for the ref / non.ref flag of the tally)."""
+    return pack_windows(model["ref"][None, :model["region_len"]], w).reshape(-1)
