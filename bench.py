@@ -237,12 +237,16 @@ def run_ours(args):
     launches0 = ctx.launches
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if os.environ.get("GB2_PROFILE_RANGE"):  # ncu --profile-from-start off: capture the timed region only
+        torch.cuda.profiler.start()
     t0.record(ctx.stream)
     for _ in range(args.steps):
         kept = step(True)
     t1.record(ctx.stream)
     ctx.sync()
     torch.cuda.synchronize()
+    if os.environ.get("GB2_PROFILE_RANGE"):
+        torch.cuda.profiler.stop()
     ms_total = t0.elapsed_time(t1)
     launches = ctx.launches - launches0
     clocks = sampler.stop()

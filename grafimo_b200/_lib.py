@@ -65,7 +65,7 @@ SIGNATURES = {
     "gb2_score": (_int, [_vp, _vp, _vp, _vp, _i64, _u64, _int, _dbl, _vp, _vp, _u64, _vp, _vp]),
     "gb2_qvalues_from_hist": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_bh_pvalues": (_int, [_vp, _vp, _i64, _vp]),
-    "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_tally_haplotypes": (_int, [_vp, _vp, _vp, _i64, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),

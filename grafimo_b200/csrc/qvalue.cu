@@ -129,10 +129,16 @@ extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uin
     double *k_out = (double *)base; base += align(nb * sizeof(double));
     uint32_t *v_in = (uint32_t *)base; base += align(nb * sizeof(uint32_t));
     uint32_t *v_out = (uint32_t *)base;
-    gb2_bh_keys_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(m->d_ptab, span, k_in, v_in);
-    GB2_LAUNCH_CHECK(ctx);
-    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, (int)nb, 0, 64, ctx->stream));
-    ctx->launches += 1;
+    if (m->monotone) {
+        // p is non-increasing in the score: descending score IS ascending p (N bin, p = 1, last) -- no sort needed
+        gb2_bh_keys_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(m->d_ptab, span, k_out, v_out);
+        GB2_LAUNCH_CHECK(ctx);
+    } else {
+        gb2_bh_keys_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(m->d_ptab, span, k_in, v_in);
+        GB2_LAUNCH_CHECK(ctx);
+        GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, (int)nb, 0, 64, ctx->stream));
+        ctx->launches += 1;
+    }
     gb2_bh_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(k_out, v_out, (const unsigned long long *)d_hist, nb, d_qtab, d_rank,
                                                      (unsigned long long *)d_total);
     GB2_LAUNCH_CHECK(ctx);
@@ -213,9 +219,10 @@ extern "C" int gb2_bh_pvalues(gb2_ctx *ctx, const double *h_p, int64_t n, double
 // ---------------------------------------------------------------------------------------------
 // K6
 // ---------------------------------------------------------------------------------------------
-__global__ void gb2_hit_keys_kernel(const gb2_hit *__restrict__ hits, uint64_t n, int32_t lo,
-                                    const double *__restrict__ qtab, const uint32_t *__restrict__ rank, int q_filter,
-                                    double q_thr, unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx,
+__global__ void gb2_hit_keys_kernel(const gb2_hit *__restrict__ hits, uint64_t n, int32_t lo, uint32_t span,
+                                    const double *__restrict__ ptab, const double *__restrict__ qtab,
+                                    const uint32_t *__restrict__ rank, double p_thr, int q_filter, double q_thr,
+                                    int row_bits, unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx,
                                     unsigned long long *__restrict__ n_kept)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,9 +230,11 @@ __global__ void gb2_hit_keys_kernel(const gb2_hit *__restrict__ hits, uint64_t n
     if (i < n) {
         const gb2_hit h = hits[i];
         const uint32_t bin = (uint32_t)(h.score - lo);
-        keep = !q_filter || qtab[bin] < q_thr;  // strict, resultsTmp.py:305
+        const double p = bin < span ? ptab[bin] : 1.0;  // bin == span: N row (score = min_val, p = 1)
+        keep = p < p_thr && (!q_filter || qtab[bin] < q_thr);  // strict, resultsTmp.py:305-307
         // (p rank, row, strand): p ascending, then a deterministic order among equal p
-        unsigned long long key = ((unsigned long long)rank[bin] << 48) | ((h.row & 0x7FFFFFFFFFFFull) << 1) | (h.strand & 1u);
+        const unsigned long long row = h.row & ((1ull << row_bits) - 1ull);
+        unsigned long long key = ((unsigned long long)rank[bin] << (row_bits + 1)) | (row << 1) | (h.strand & 1u);
         keys[i] = keep ? key : ~0ull;
         idx[i] = (uint32_t)i;
     }
@@ -234,8 +243,8 @@ __global__ void gb2_hit_keys_kernel(const gb2_hit *__restrict__ hits, uint64_t n
 }
 
 __global__ void gb2_hit_gather_kernel(const gb2_hit *__restrict__ hits, const uint32_t *__restrict__ order,
-                                      const unsigned long long *__restrict__ n_kept, int32_t lo, int w, double scale,
-                                      double offset, const double *__restrict__ ptab, const double *__restrict__ qtab,
+                                      const unsigned long long *__restrict__ n_kept, int32_t lo, uint32_t span, int w,
+                                      double scale, double offset, const double *__restrict__ ptab, const double *__restrict__ qtab,
                                       uint64_t *__restrict__ o_row, uint8_t *__restrict__ o_strand,
                                       int32_t *__restrict__ o_iscore, double *__restrict__ o_score,
                                       double *__restrict__ o_p, double *__restrict__ o_q)
@@ -249,14 +258,14 @@ __global__ void gb2_hit_gather_kernel(const gb2_hit *__restrict__ hits, const ui
     o_iscore[i] = h.score;
     // logodds = (score / scale) + (width * offset)            score_sequences.py:393
     o_score[i] = __dadd_rn(__ddiv_rn((double)h.score, scale), __dmul_rn((double)w, offset));
-    o_p[i] = ptab[bin];
+    o_p[i] = bin < span ? ptab[bin] : 1.0;
     if (o_q != nullptr && qtab != nullptr) o_q[i] = qtab[bin];
 }
 
 extern "C" int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *m, const gb2_hit *d_hits, uint64_t n_hits,
-                                 const double *d_qtab, const uint32_t *d_rank, int q_filter, double q_threshold,
-                                 uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p,
-                                 double *d_q, uint64_t *d_n_out)
+                                 uint64_t row_limit, const double *d_qtab, const uint32_t *d_rank, double p_threshold,
+                                 int q_filter, double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore,
+                                 double *d_score, double *d_p, double *d_q, uint64_t *d_n_out)
 {
     if (!ctx || !m) return GB2_ERR_ARG;
     GB2_REQUIRE(ctx, d_n_out != nullptr && d_rank != nullptr, "gb2_finalize_hits: null counter or rank table");
@@ -267,6 +276,14 @@ extern "C" int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *m, const gb2_hit
     if (n_hits == 0) return GB2_OK;
     GB2_REQUIRE(ctx, d_hits && d_row && d_strand && d_iscore && d_score && d_p, "gb2_finalize_hits: null buffer");
     const int n = (int)n_hits;
+    // sort key = [p rank | row | strand], using only the bits that can be set (fewer radix passes)
+    int rank_bits = 1, row_bits = 47;
+    while ((1ll << rank_bits) < m->span + 1) ++rank_bits;
+    if (row_limit > 0) {
+        row_bits = 1;
+        while (row_bits < 47 && (1ull << row_bits) < row_limit) ++row_bits;
+    }
+    const int end_bit = rank_bits + row_bits + 1;  // <= 16 + 47 + 1
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 64, ctx->stream);
@@ -282,14 +299,18 @@ extern "C" int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *m, const gb2_hit
     uint32_t *v_out = (uint32_t *)base;
     const int threads = 256;
     const unsigned blocks = (unsigned)gb2_div_up(n, threads);
-    gb2_hit_keys_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, n_hits, (int32_t)m->lo, d_qtab, d_rank, q_filter,
-                                                            q_threshold, k_in, v_in, (unsigned long long *)d_n_out);
+    gb2_hit_keys_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, n_hits, (int32_t)m->lo, (uint32_t)m->span, m->d_ptab,
+                                                            d_qtab, d_rank, p_threshold, q_filter, q_threshold, row_bits,
+                                                            k_in, v_in, (unsigned long long *)d_n_out);
     GB2_LAUNCH_CHECK(ctx);
-    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, n, 0, 64, ctx->stream));
+    // dropped hits carry the all-ones key: they sort last for any end_bit because kept keys are < 2^end_bit
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, n, 0,
+                                                  end_bit < 64 ? end_bit + 1 : 64, ctx->stream));
     ctx->launches += 1;
     gb2_hit_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, v_out, (const unsigned long long *)d_n_out,
-                                                              (int32_t)m->lo, m->w, (double)m->scale, m->offset, m->d_ptab,
-                                                              d_qtab, d_row, d_strand, d_iscore, d_score, d_p, d_q);
+                                                              (int32_t)m->lo, (uint32_t)m->span, m->w, (double)m->scale,
+                                                              m->offset, m->d_ptab, d_qtab, d_row, d_strand, d_iscore, d_score,
+                                                              d_p, d_q);
     GB2_LAUNCH_CHECK(ctx);
     return GB2_OK;
 }

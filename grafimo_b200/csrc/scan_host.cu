@@ -119,7 +119,8 @@ extern "C" int gb2_scan_host(gb2_ctx *ctx, const gb2_motif *m, const uint8_t *h_
             rc = GB2_ERR_CAPACITY;
             goto done;
         }
-        rc = gb2_finalize_hits(ctx, m, d_hits, n_hits, want_q ? d_qtab : nullptr, d_rank, q_filter, p_threshold, o_row,
+        rc = gb2_finalize_hits(ctx, m, d_hits, n_hits, (uint64_t)n, want_q ? d_qtab : nullptr, d_rank, p_threshold, q_filter,
+                               p_threshold, o_row,
                                o_strand, o_iscore, o_score, o_p, want_q ? o_q : nullptr, d_cnt + 3);
         if (rc != GB2_OK) goto done;
         SH_CUDA(cudaMemcpyAsync(ctx->h_mail + 8, d_cnt + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     return v;
 }
 
+// compiles to ATOMS.POPC.INC (same cost as ATOMS.ADD on B200: tools/ubench_atoms.cu, and merges same-address lanes)
 __device__ __forceinline__ void red_shared_inc(uint32_t addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");

@@ -191,6 +191,7 @@ class Scan:
         self.hits = ctx.empty(max(self.capacity, 1) * _HIT_BYTES, torch.uint8)
         self.counters = ctx.zeros(4, torch.int64)  # [0] hits found, [1] kept, [2] total N
         self.rows_scored = 0
+        self.row_limit = 0
         self.dense = dense
 
     def reset(self):
@@ -199,6 +200,7 @@ class Scan:
                 self.hist.zero_()
             self.counters.zero_()
         self.rows_scored = 0
+        self.row_limit = 0
 
     def score(self, packed, nmask=None, row_base=0, dense_out=None):
         n = packed.shape[0]
@@ -208,6 +210,7 @@ class Scan:
                             _ptr(self.hist), _ptr(self.hits), self.capacity, _ptr(self.counters), _ptr(dense_out)),
               "gb2_score", ctx.h)
         self.rows_scored += n
+        self.row_limit = max(self.row_limit, int(row_base) + n)
 
     def histogram(self):
         return self.hist
@@ -242,8 +245,9 @@ class Scan:
                            p=ctx.empty(cap, torch.float64), q=ctx.empty(cap, torch.float64) if self.want_q else None)
             self._out_cap = cap
         o = self._o
-        check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, _ptr(self.qtab) if self.want_q else None,
-                                        _ptr(self.rank), int(bool(q_filter)), self.threshold, _ptr(o["row"]), _ptr(o["strand"]),
+        check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, int(self.row_limit),
+                                        _ptr(self.qtab) if self.want_q else None, _ptr(self.rank), self.threshold,
+                                        int(bool(q_filter)), self.threshold, _ptr(o["row"]), _ptr(o["strand"]),
                                         _ptr(o["iscore"]), _ptr(o["score"]), _ptr(o["p"]), _ptr(o["q"]),
                                         ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits", ctx.h)
         ctx.sync()

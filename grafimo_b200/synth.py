@@ -31,8 +31,9 @@ def variant_model(region_len, n_hap, seed, density=1.0 / 40.0, indel_frac=0.1, d
     return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in m.items()}
 
 
-def haplotype_codes(model, hap_lo, hap_hi):
-    """int64 [hap_hi-hap_lo, region_len] base codes of the haplotypes (deterministic per haplotype index)."""
+def haplotype_codes(model, hap_lo, hap_hi, return_index=False):
+    """int64 [hap_hi-hap_lo, region_len] base codes of the haplotypes (deterministic per haplotype index).
+    With return_index also the reference coordinate of every haplotype base (indels shift it)."""
     dev = model["ref"].device
     L, nh = model["region_len"], hap_hi - hap_lo
     n_var = model["site"].shape[0]
@@ -50,7 +51,8 @@ def haplotype_codes(model, hap_lo, hap_hi):
     snp_sites = model["site"][~model["is_indel"]]
     snp[:, snp_sites] = torch.where(carry[:, ~model["is_indel"]], model["alt"][~model["is_indel"]][None, :], -1)
     alt = torch.gather(snp, 1, idx)
-    return torch.where(alt >= 0, alt, hap)
+    codes = torch.where(alt >= 0, alt, hap)
+    return (codes, idx) if return_index else codes
 
 
 def pack_windows(codes, w):
@@ -98,3 +100,21 @@ def revcomp_ascii(a):
 def reference_windows(model, w):
     """Packed windows of the unmodified reference (for the ref / non.ref flag of the tally)."""
     return pack_windows(model["ref"][None, :model["region_len"]], w).reshape(-1)
+
+
+def synthetic_meme_collection(n_motifs=800, seed=20242, wmin=6, wmax=30, alpha=0.5):
+    """A JASPAR-CORE-sized MEME file (text) with seeded random motifs: widths in [wmin, wmax] with mode ~11,
+    Dirichlet(alpha) columns, nsites 100-5000 (JASPAR itself is not available offline)."""
+    rng = np.random.default_rng(seed)
+    widths = np.clip(np.round(rng.gamma(shape=6.0, scale=2.0, size=n_motifs)).astype(int) + 1, wmin, wmax)
+    lines = ["MEME version 4", "", "ALPHABET= ACGT", "", "strands: + -", "", "Background letter frequencies",
+             "A 0.25 C 0.25 G 0.25 T 0.25", ""]
+    for k, w in enumerate(widths):
+        nsites = int(rng.integers(100, 5001))
+        lines.append(f"MOTIF SYN{k:04d}.1 SYN{k:04d}")
+        lines.append(f"letter-probability matrix: alength= 4 w= {w} nsites= {nsites} E= 0")
+        for row in rng.dirichlet([alpha] * 4, size=int(w)):
+            lines.append(" " + "  ".join(f"{v:.6f}" for v in row))
+        lines.append("URL none")
+        lines.append("")
+    return "\n".join(lines), widths

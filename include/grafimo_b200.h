@@ -162,11 +162,14 @@ int gb2_bh_pvalues(gb2_ctx *ctx, const double *h_p, int64_t n, double *h_q);
  * (--qvalueT), CUB radix sort by (p ascending, row ascending, strand) -- a deterministic order; the
  * reference's tie order is undefined -- and the numeric columns.  d_qtab/d_rank may be NULL when no
  * q-values were computed (then the sort uses the score and d_q is not written).
+ *   row_limit     exclusive upper bound of the row indices in d_hits (0 = unknown): fewer radix passes.
+ *   p_threshold   hits with p >= p_threshold are dropped (hit records produced by gb2_score already satisfy it;
+ *                 records expanded from dense scores do not).
  * All outputs have room for n_hits entries; *d_n_out receives the number kept. */
-int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *motif, const gb2_hit *d_hits, uint64_t n_hits,
-                      const double *d_qtab, const uint32_t *d_rank, int q_filter, double q_threshold,
-                      uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p,
-                      double *d_q, uint64_t *d_n_out);
+int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *motif, const gb2_hit *d_hits, uint64_t n_hits, uint64_t row_limit,
+                      const double *d_qtab, const uint32_t *d_rank, double p_threshold, int q_filter,
+                      double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score,
+                      double *d_p, double *d_q, uint64_t *d_n_out);
 
 /* ---- haplotype tally ---------------------------------------------------------------------------- */
 /* Per-haplotype windows -> vg-like deduplicated rows: sorts (position, packed k-mer) pairs and
