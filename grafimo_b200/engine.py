@@ -93,6 +93,32 @@ class Context:
         self.leave()
         return packed, nmask, counts
 
+    # -- K1b: k-mer TSV on the device ------------------------------------------------------------
+    def parse_kmer_tsv(self, text, width, skip_minus=False):
+        """uint8 host tensor (pinned for speed) or device tensor with the bytes of `vg find -K w -E` TSV files ->
+        DeviceRows (packed k-mers, N mask and the numeric side arrays on the device)."""
+        assert text.dtype == torch.uint8 and text.dim() == 1
+        n_bytes = text.shape[0]
+        self.enter()
+        with torch.cuda.stream(self.stream):
+            d_text = text if text.is_cuda else text.to(self.device, non_blocking=True)
+        # one line needs at least 12 bytes ("a c a:1+ a:2+ 1 ref" is 19): bound the offset array by that
+        cap = n_bytes // 12 + 2
+        line_off = self.empty(cap, torch.int64)
+        n_rows_d = self.zeros(1, torch.int64)
+        check(self.lib.gb2_tsv_index_lines(self.h, _ptr(d_text), n_bytes, int(bool(skip_minus)), _ptr(line_off), _ptr(n_rows_d)),
+              "gb2_tsv_index_lines", self.h)
+        self.sync()
+        n = int(n_rows_d.item())
+        rows = DeviceRows(self, d_text, line_off[:n], n, width)
+        if n:
+            check(self.lib.gb2_tsv_parse_rows(self.h, _ptr(d_text), n_bytes, _ptr(rows.line_off), n, int(width), _ptr(rows.packed),
+                                              _ptr(rows.nmask), _ptr(rows.start), _ptr(rows.stop), _ptr(rows.strand),
+                                              _ptr(rows.freq), _ptr(rows.ref), _ptr(rows.name_len), _ptr(rows.seq_off),
+                                              _ptr(rows.counts)), "gb2_tsv_parse_rows", self.h)
+        self.leave()
+        return rows
+
     # -- K3 -----------------------------------------------------------------------------------
     def pval_dp_batched(self, score_matrices, backgrounds):
         """list of int[4,w] (rows A,C,G,T) + list of [A,C,G,T] backgrounds -> list of float64[1000*w+1]."""
@@ -131,6 +157,36 @@ class Context:
         k = int(n_unique.item())
         self.leave()
         return u_pos[:k], u_packed[:k], u_freq[:k], u_isref[:k]
+
+
+class DeviceRows:
+    """Device-resident rows of a k-mer TSV: what score_seqs keeps per line (score_sequences.py:285-293), as arrays."""
+
+    def __init__(self, ctx, d_text, line_off, n, width):
+        self.ctx, self.d_text, self.line_off, self.n, self.width = ctx, d_text, line_off, n, width
+        m = max(n, 1)
+        self.packed = ctx.empty(m + (m & 1), torch.int64)[:m]
+        self.nmask = ctx.zeros((m + 31) // 32, torch.int32)
+        self.start = ctx.empty(m, torch.int64)
+        self.stop = ctx.empty(m, torch.int64)
+        self.strand = ctx.empty(m, torch.uint8)
+        self.freq = ctx.empty(m, torch.int64)
+        self.ref = ctx.empty(m, torch.uint8)
+        self.name_len = ctx.empty(m, torch.int32)
+        self.seq_off = ctx.empty(m, torch.int32)
+        self.counts = ctx.zeros(4, torch.int64)  # masked rows, bad-symbol rows, malformed lines
+
+    def stats(self):
+        self.ctx.sync()
+        c = self.counts.cpu().numpy()
+        return dict(n_rows=int(c[0]), bad_rows=int(c[1]), malformed=int(c[2]))
+
+    def gather(self, rows):
+        """Side arrays of the selected rows (device int64 indices) as numpy arrays."""
+        with torch.cuda.stream(self.ctx.stream):
+            out = {k: getattr(self, k)[rows].cpu().numpy() for k in
+                   ("start", "stop", "strand", "freq", "ref", "name_len", "seq_off", "line_off")}
+        return out
 
 
 class DeviceMotif:

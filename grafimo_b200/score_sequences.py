@@ -3,9 +3,10 @@
 Same signature, flags, side effects, error behaviour and returned table as the reference's
 `grafimo.score_sequences.compute_results` (src/grafimo/score_sequences.py:44-211), with the per-row Python /
 numba loop (`score_seqs` :216-326, `compute_score_seq` :331-396), the statsmodels BH step (:401-428) and the
-filter + sort of `ResultTmp.to_df` (src/grafimo/resultsTmp.py:241-314) replaced by ONE call into the CUDA
-library (`gb2_scan_host`: encode -> score -> histogram -> BH -> finalize).  The host keeps what is text:
-reading the `vg find` TSVs, the string columns and the DataFrame.
+filter + sort of `ResultTmp.to_df` (src/grafimo/resultsTmp.py:241-314) replaced by calls into the CUDA
+library: the TSV bytes are indexed and parsed on the device (K1b), scored (K2), the q-values come from the score
+histogram (K5) and the hits are filtered and sorted there (K6).  The host keeps what is text: reading the files,
+the two string columns of the reported rows and the DataFrame.
 
 There is no CPU fallback: without the CUDA library / a GPU this module raises.
 """
@@ -103,6 +104,69 @@ def device_motif(motif: Motif, ctx=None):
     return dm
 
 
+_CHUNK_BYTES = 1 << 30  # TSV text is parsed on the device in chunks of at most 1 GiB (cut at line boundaries)
+
+
+def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
+    """Yields (pinned) uint8 tensors holding whole lines of the concatenated files; every file is
+    newline-terminated, chunks are cut at line boundaries."""
+    import torch
+    pin = torch.cuda.is_available()
+    left = sum(os.stat(f).st_size + 1 for f in files)
+
+    def new_buf(carry_len):
+        t = torch.empty(max(2, min(chunk_bytes, left + carry_len + 1)), dtype=torch.uint8, pin_memory=pin)
+        return t, t.numpy()
+
+    buf, view = new_buf(0)
+    fill = 0
+    for fn in files:
+        with open(fn, "rb") as fh:
+            while True:
+                room = view.shape[0] - fill - 1  # one spare byte for a file-terminating newline
+                if room <= 0:  # buffer full: emit the whole lines, carry the partial one
+                    lo = max(0, fill - (1 << 20))
+                    cut = bytes(memoryview(view)[lo:fill]).rfind(b"\n")
+                    if cut < 0:
+                        raise ValueError(f"{fn}: a line longer than the chunk size / 1 MiB")
+                    cut += lo + 1
+                    carry = view[cut:fill].copy()
+                    yield buf[:cut]
+                    buf, view = new_buf(len(carry))
+                    view[:len(carry)] = carry
+                    fill = len(carry)
+                    continue
+                got = fh.readinto(memoryview(view)[fill:fill + room])
+                if not got:
+                    break
+                fill += got
+                left -= got
+        if fill > 0 and view[fill - 1] != 10:
+            view[fill] = 10
+            fill += 1
+        left -= 1
+    if fill > 0:
+        yield buf[:fill]
+
+
+def _fixed_strings(text: np.ndarray, offs: np.ndarray, length: int) -> np.ndarray:
+    if len(offs) == 0:
+        return np.array([], dtype=object)
+    idx = offs[:, None] + np.arange(length, dtype=np.int64)[None, :]
+    return np.char.decode(np.ascontiguousarray(text[idx]).view(f"S{length}").ravel(), "ascii").astype(object)
+
+
+def _var_strings(text: np.ndarray, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
+    if len(offs) == 0:
+        return np.array([], dtype=object)
+    mx = int(lens.max())
+    col = np.arange(mx, dtype=np.int64)[None, :]
+    idx = np.minimum(offs[:, None] + col, text.shape[0] - 1)
+    chars = text[idx]
+    chars[col >= lens[:, None]] = 0
+    return np.char.decode(np.ascontiguousarray(chars).view(f"S{mx}").ravel(), "ascii").astype(object)
+
+
 def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
                     testmode: Optional[bool] = False) -> pd.DataFrame:
     """Scores every k-mer row under `<sequence_loc>/width_<w>/*.tsv` and returns the report table
@@ -110,6 +174,9 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
 
     args_obj needs the attributes the reference reads (score_sequences.py:93-99): cores (ignored: the GPU
     does the work), threshold, noqvalue, qvalueT, noreverse, recomb, verbose.
+    The TSV bytes go to the GPU as they are: lines are indexed and parsed there (K1b), k-mers packed, scored (K2),
+    q-values derived from the score histogram (K5) and the hits filtered and sorted (K6); only the reported rows
+    come back, and only their two string fields are sliced from the host copy of the text.
     Rows are ordered by p-value ascending; ties -- whose order the reference leaves undefined -- by
     (start, stop, strand, matched_sequence)."""
     if not isinstance(motif, Motif):
@@ -134,19 +201,31 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
     width = motif.width
     files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
+    files = [f for f in files if os.stat(f).st_size > 0]
     t0 = time.time()
-    table = KmerTable.read(files, no_reverse)
-    n = len(table)
+    ctx = _context()
+    dm = device_motif(motif, ctx)
+    chunks = []  # (host text, DeviceRows, first global row)
+    n = 0
+    for text in _text_chunks(files, _CHUNK_BYTES) if files else ():
+        rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
+        rows.d_text = None  # the device copy of the text is only needed while parsing
+        chunks.append((text.numpy(), rows, n))
+        n += rows.n
     if n == 0:  # score_sequences.py:189-192
         errmsg = "No result retrieved. Unable to proceed.\n"
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
         exception_handler(ValueError, errmsg, debug)
-    ctx = _context()
-    dm = device_motif(motif, ctx)
-    ascii_rows = table.ascii_matrix(width, debug)
+    bad = sum(c[1].stats()["malformed"] for c in chunks)
+    if bad:
+        exception_handler(ValueError, f"{bad} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
+                          "symbols are required).\n", debug)
     # every row is scored as given: `vg find -E` already emits the reverse-strand rows
-    out = engine.scan_host(ctx, dm, ascii_rows, strands=1, threshold=float(threshold), q_filter=bool(qval_t),
-                           want_q=not no_qvalue, hit_capacity=n)
+    scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=n)
+    for _, rows, base in chunks:
+        if rows.n:
+            scan.score(rows.packed, rows.nmask, row_base=base)
+    kept = scan.finalize_device(q_filter=bool(qval_t))
     if verbose:
         print("Sequences scored in %.2fs" % (time.time() - t0))
     if not no_qvalue:
@@ -154,28 +233,61 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     print(f"Scanned sequences:\t{n}")
     print(f"Scanned nucleotides:\t{n * width}")
     t1 = time.time()
-    rows = out["row"].astype(np.int64)
-    freq = table.freq[rows]
-    keep = np.ones(len(rows), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
-    rows = rows[keep]
-    start, stop = table.start[rows], table.stop[rows]
-    ref = table.ref[rows].copy()
+    import torch
+    with torch.cuda.stream(ctx.stream):
+        sel = scan.out["row"][:kept]
+        score = scan.out["score"][:kept].cpu().numpy()
+        pval = scan.out["p"][:kept].cpu().numpy()
+        qval = scan.out["q"][:kept].cpu().numpy() if not no_qvalue else None
+        sel_h = sel.cpu().numpy()
+    bases = np.array([c[2] for c in chunks] + [n], dtype=np.int64)
+    which = np.searchsorted(bases, sel_h, side="right") - 1
+    seqname = np.empty(kept, dtype=object); seq = np.empty(kept, dtype=object); strand = np.empty(kept, dtype=object)
+    start = np.empty(kept, dtype=np.int64); stop = np.empty(kept, dtype=np.int64); freq = np.empty(kept, dtype=np.int64)
+    ref = np.empty(kept, dtype=object)
+    for k, (text, rows, base) in enumerate(chunks):
+        m = np.nonzero(which == k)[0]
+        if len(m) == 0:
+            continue
+        with torch.cuda.stream(ctx.stream):
+            g = rows.gather(torch.from_numpy(sel_h[m] - base).to(ctx.device))
+        off = g["line_off"].astype(np.int64)
+        # leading blanks of a line belong to no field: the name starts at the first non-blank byte
+        lead = np.zeros(len(m), dtype=np.int64)
+        if len(off):
+            first = text[off]
+            while True:
+                blank = (first == 32) | (first == 9)
+                if not blank.any():
+                    break
+                lead[blank] += 1
+                first = text[np.minimum(off + lead, text.shape[0] - 1)]
+        seqname[m] = _var_strings(text, off + lead, g["name_len"].astype(np.int64))
+        seq[m] = _fixed_strings(text, off + g["seq_off"].astype(np.int64), width)
+        strand[m] = np.char.decode(g["strand"].view("S1"), "ascii").astype(object)
+        start[m], stop[m], freq[m] = g["start"], g["stop"], g["freq"]
+        r = np.where(g["ref"] == 1, "ref", "non.ref").astype(object)
+        other = np.nonzero(g["ref"] == 2)[0]
+        for i in other:  # a sixth field that is neither "ref" nor "non.ref" is passed through verbatim
+            r[i] = bytes(text[off[i]:off[i] + 4096]).split(b"\n", 1)[0].split()[5].decode("ascii")
+        ref[m] = r
+    keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     ref[(ref == "ref") & (np.abs(stop - start) != width)] = "non.ref"  # score_sequences.py:305-307
     cols = {
-        "motif_id": [motif.motif_id] * len(rows),
-        "motif_alt_id": [motif.motif_name] * len(rows),
-        "sequence_name": table.seqname[rows],
-        "start": start,
-        "stop": stop,
-        "strand": table.strand[rows],
-        "score": out["score"][keep],
-        "p-value": out["p-value"][keep],
+        "motif_id": [motif.motif_id] * int(keep.sum()),
+        "motif_alt_id": [motif.motif_name] * int(keep.sum()),
+        "sequence_name": seqname[keep],
+        "start": start[keep],
+        "stop": stop[keep],
+        "strand": strand[keep],
+        "score": score[keep],
+        "p-value": pval[keep],
     }
     if not no_qvalue:
-        cols["q-value"] = out["q-value"][keep]
-    cols["matched_sequence"] = table.seq[rows]
-    cols["haplotype_frequency"] = table.freq[rows]
-    cols["reference"] = ref
+        cols["q-value"] = qval[keep]
+    cols["matched_sequence"] = seq[keep]
+    cols["haplotype_frequency"] = freq[keep]
+    cols["reference"] = ref[keep]
     df = pd.DataFrame(cols)
     if len(df) > 1:  # deterministic tie order on top of the device's p-ascending order
         order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),

@@ -103,6 +103,24 @@ int gb2_ctx_sm_count(const gb2_ctx *ctx);
 int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int64_t stride,
                      uint64_t *d_packed, uint32_t *d_nmask, uint64_t *d_counts);
 
+/* ---- K1b: device-side reader of the `vg find -K w -E` k-mer TSV ---------------------------------------- */
+/* Replaces the per-line parsing of score_seqs (score_sequences.py:273-293).  d_text holds the bytes of one or more
+ * TSV files (each line: region, k-mer, chr:start(+|-), chr:stop(+|-), haplotype count, ref|non.ref, node path;
+ * any run of blanks/tabs separates fields).
+ * gb2_tsv_index_lines: byte offset of every non-blank line -> d_line_off (capacity: one per line), *d_n_rows.
+ *   skip_minus != 0 drops rows whose third field ends in '-' (what --no-reverse does BEFORE scoring and counting,
+ *   score_sequences.py:281-282).  n_bytes < 2^31 per call.
+ * gb2_tsv_parse_rows: per line -> packed k-mer + N mask (fused K1), start, stop, strand character, haplotype
+ *   count, ref code (1 = "ref", 0 = "non.ref", 2 = other), length of the region name and offset of the k-mer
+ *   within the line (so the host can slice the two strings of reported rows from its copy of the text).
+ *   d_counts[0] += rows masked (N or bad symbol), [1] += rows with a symbol outside ACGTacgtN, [2] += malformed
+ *   lines (fewer than six fields, k-mer not exactly w symbols, non-numeric position or count). */
+int gb2_tsv_index_lines(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, int skip_minus, uint64_t *d_line_off,
+                        uint64_t *d_n_rows);
+int gb2_tsv_parse_rows(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off, int64_t n_rows,
+                       int w, uint64_t *d_packed, uint32_t *d_nmask, int64_t *d_start, int64_t *d_stop, uint8_t *d_strand,
+                       int64_t *d_freq, uint8_t *d_ref, uint32_t *d_name_len, uint32_t *d_seq_off, uint64_t *d_counts);
+
 /* ---- K3: batched score-distribution DP --------------------------------------------------- */
 /* Replaces comp_pval_mat (motif_processing.pyx:552-603) for n_motifs motifs at once.
  * h_widths[m] = w_m; h_score_mats = concatenated int64[4][w_m] (rows A,C,G,T); h_bgs = [A,C,G,T]

@@ -148,3 +148,20 @@ def test_cli_findmotif_writes_reports(tmp_path):
     gff = (out / "grafimo_out.gff").read_text().split("\n")
     assert gff[0] == "##gff-version 3" and len(gff) == len(tsv) + 2
     assert (out / "grafimo_out.html").exists()
+
+
+def test_compute_results_multi_chunk_text(tmp_path, monkeypatch):
+    """The TSV text is parsed in chunks; force tiny chunks and expect the same table."""
+    from grafimo_b200 import score_sequences as ss
+    c = gu.load_scoring("fixture_plus_N_2files")
+    m, g = _build(c["motif_tag"], tmp_path)
+    d = tmp_path / "seqs" / "width_19"
+    d.mkdir(parents=True)
+    for k, lines in enumerate(c["files"]):
+        (d / f"region_{k}.tsv").write_text("\n".join(lines) + ("\n" if k else ""))
+    monkeypatch.setattr(ss, "_CHUNK_BYTES", 8192)
+    chunks = list(ss._text_chunks(sorted(str(p) for p in d.iterdir()), 8192))
+    assert len(chunks) > 5
+    df = ss.compute_results(m, str(tmp_path / "seqs"), True, _Args(c["options"]))
+    got = {col: df[col].to_numpy() for col in df.columns}
+    gu.assert_tables_equal(got, c["table"], c["columns"])

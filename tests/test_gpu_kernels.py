@@ -278,3 +278,48 @@ def test_large_batch_properties(ctx):
     ctx.sync()
     dn = dense[torch.from_numpy(idx).cuda()].cpu().numpy().view(np.uint32)
     assert np.array_equal((dn & 0xFFFF).astype(np.int64) + dm.lo, isf)
+
+
+def test_k1b_device_tsv_reader(ctx):
+    """gb2_tsv_index_lines / gb2_tsv_parse_rows against the reference's field rules (oracle.parse_rows)."""
+    orc = _orc()
+    c = gu.load_scoring("fixture_plus_N_2files")
+    lines = [ln for f in c["files"] for ln in f]
+    # the same rows with awkward but legal whitespace: blanks instead of tabs, CRLF, leading blanks, empty lines
+    odd = []
+    for i, ln in enumerate(lines):
+        f = ln.split("\t")
+        if i % 5 == 1:
+            ln = "  ".join(f)
+        elif i % 5 == 2:
+            ln = "\t" + ln + "\r"
+        elif i % 5 == 3:
+            ln = ln + "\n"  # followed by an empty line
+        odd.append(ln)
+    text = ("\n".join(odd) + "\n").encode()
+    for skip in (False, True):
+        rows = ctx.parse_kmer_tsv(torch.frombuffer(bytearray(text), dtype=torch.uint8), 19, skip_minus=skip)
+        r = orc.parse_rows(lines, skip)
+        assert rows.n == len(r["seq"])
+        st = rows.stats()
+        assert st["malformed"] == 0
+        a = orc.kmers_to_matrix(r["seq"], 19)
+        packed, nmask, counts = ctx.encode(torch.from_numpy(a).cuda())
+        ctx.sync()
+        assert torch.equal(rows.packed, packed) and torch.equal(rows.nmask, nmask)
+        assert st["n_rows"] == int(counts[0]) and st["bad_rows"] == int(counts[1])
+        assert np.array_equal(rows.start.cpu().numpy(), r["start"]) and np.array_equal(rows.stop.cpu().numpy(), r["stop"])
+        assert np.array_equal(rows.freq.cpu().numpy(), r["freq"])
+        assert [chr(x) for x in rows.strand.cpu().tolist()] == r["strand"]
+        assert [("ref" if x == 1 else "non.ref") for x in rows.ref.cpu().tolist()] == r["ref"]
+        off, nl, so = rows.line_off.cpu().numpy(), rows.name_len.cpu().numpy(), rows.seq_off.cpu().numpy()
+        for k in range(0, rows.n, 37):
+            line = text[off[k]:].split(b"\n", 1)[0]
+            assert line.split()[0].decode() == r["seqname"][k] and len(r["seqname"][k]) == nl[k]
+            assert text[off[k] + so[k]:off[k] + so[k] + 19].decode() == r["seq"][k]
+    # malformed lines are counted, not silently scored
+    bad = b"1:1-9\tACGT\t1:1+\t1:5+\t3\tref\t1+,\n1:1-9\tACGTACGTACGTACGTACG\t1:1+\t1:20+\tx\tref\t1+,\n1:1-9\tACGTACGTACGTACGTACG\t1:1+\n"
+    rows = ctx.parse_kmer_tsv(torch.frombuffer(bytearray(bad), dtype=torch.uint8), 19)
+    assert rows.n == 3 and rows.stats()["malformed"] == 3
+    empty = ctx.parse_kmer_tsv(torch.frombuffer(bytearray(b"\n\n  \n"), dtype=torch.uint8), 19)
+    assert empty.n == 0

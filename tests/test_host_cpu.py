@@ -168,3 +168,20 @@ def test_findmotif_container_and_cli_parser():
         Findmotif(qval_t=True, no_qvalue=True)
     with pytest.raises(TypeError):
         Findmotif(threshold=1)
+
+
+def test_text_chunks_cut_at_line_boundaries(tmp_path):
+    from grafimo_b200.score_sequences import _text_chunks
+    rng = np.random.default_rng(0)
+    files, want = [], b""
+    for k in range(4):
+        lines = [("x" * int(rng.integers(1, 90))).encode() for _ in range(int(rng.integers(1, 60)))]
+        body = b"\n".join(lines) + (b"\n" if k % 2 else b"")  # every other file lacks the final newline
+        p = tmp_path / f"f{k}.tsv"
+        p.write_bytes(body)
+        files.append(str(p))
+        want += body if body.endswith(b"\n") else body + b"\n"
+    for chunk_bytes in (128, 1000, 1 << 20):
+        chunks = [bytes(c.numpy()) for c in _text_chunks(files, chunk_bytes)]
+        assert all(c.endswith(b"\n") and len(c) <= chunk_bytes for c in chunks)
+        assert b"".join(chunks) == want
