@@ -216,15 +216,16 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         errmsg = "No result retrieved. Unable to proceed.\n"
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
         exception_handler(ValueError, errmsg, debug)
-    bad = sum(c[1].stats()["malformed"] for c in chunks)
+    stats = [c[1].stats() for c in chunks]
+    bad = sum(st["malformed"] for st in stats)
     if bad:
         exception_handler(ValueError, f"{bad} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
                           "symbols are required).\n", debug)
     # every row is scored as given: `vg find -E` already emits the reverse-strand rows
     scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=n)
-    for _, rows, base in chunks:
-        if rows.n:
-            scan.score(rows.packed, rows.nmask, row_base=base)
+    for (_, rows, base), st in zip(chunks, stats):
+        if rows.n:  # the N mask is only read by the kernel when some row of the chunk needs it
+            scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=base)
     kept = scan.finalize_device(q_filter=bool(qval_t))
     if verbose:
         print("Sequences scored in %.2fs" % (time.time() - t0))
