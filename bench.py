@@ -129,7 +129,9 @@ def run_reference_arm(args):
     calib = cpu_sample_rows(20000, SEED)
     t = time_oracle(calib, m, threads)
     rate = calib.shape[0] / t
-    rows_per_step = int(max(20000, min(rate * 4.0, 4_000_000)))  # ~4 s of CPU work per step
+    # bounded sample: the whole --steps K run should take about two minutes whatever K is
+    per_step_s = min(8.0, max(0.25, 120.0 / max(1, args.steps)))
+    rows_per_step = int(max(20000, min(rate * per_step_s, 8_000_000)))
     rows = cpu_sample_rows(rows_per_step // 2, SEED + 1)
     for _ in range(max(args.warmup, 0)):
         time_oracle(rows[: max(2000, rows.shape[0] // 20)], m, threads)
