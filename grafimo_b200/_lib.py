@@ -56,7 +56,7 @@ SIGNATURES = {
     "gb2_device_count": (_int, []),
     "gb2_ctx_sm_count": (_int, [_vp]),
     "gb2_encode_kmers": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
-    "gb2_tsv_index_lines": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "gb2_tsv_index_lines": (_int, [_vp, _vp, _i64, _int, _vp, _u64, _vp]),
     "gb2_tsv_parse_rows": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_pval_dp_batched": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "gb2_motif_create": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _dbl, ctypes.POINTER(_vp)]),

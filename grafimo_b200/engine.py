@@ -102,14 +102,18 @@ class Context:
         self.enter()
         with torch.cuda.stream(self.stream):
             d_text = text if text.is_cuda else text.to(self.device, non_blocking=True)
-        # one line needs at least 12 bytes ("a c a:1+ a:2+ 1 ref" is 19): bound the offset array by that
+        # a well-formed line is at least 20 bytes ("a c a:1+ a:2+ 1 ref"); size the offset array for 12 and grow if needed
         cap = n_bytes // 12 + 2
-        line_off = self.empty(cap, torch.int64)
         n_rows_d = self.zeros(1, torch.int64)
-        check(self.lib.gb2_tsv_index_lines(self.h, _ptr(d_text), n_bytes, int(bool(skip_minus)), _ptr(line_off), _ptr(n_rows_d)),
-              "gb2_tsv_index_lines", self.h)
-        self.sync()
-        n = int(n_rows_d.item())
+        while True:
+            line_off = self.empty(cap, torch.int64)
+            check(self.lib.gb2_tsv_index_lines(self.h, _ptr(d_text), n_bytes, int(bool(skip_minus)), _ptr(line_off), cap,
+                                               _ptr(n_rows_d)), "gb2_tsv_index_lines", self.h)
+            self.sync()
+            n = int(n_rows_d.item())
+            if n <= cap:
+                break
+            cap = n
         rows = DeviceRows(self, d_text, line_off[:n], n, width)
         if n:
             check(self.lib.gb2_tsv_parse_rows(self.h, _ptr(d_text), n_bytes, _ptr(rows.line_off), n, int(width), _ptr(rows.packed),

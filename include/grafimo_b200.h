@@ -107,7 +107,8 @@ int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int
 /* Replaces the per-line parsing of score_seqs (score_sequences.py:273-293).  d_text holds the bytes of one or more
  * TSV files (each line: region, k-mer, chr:start(+|-), chr:stop(+|-), haplotype count, ref|non.ref, node path;
  * any run of blanks/tabs separates fields).
- * gb2_tsv_index_lines: byte offset of every non-blank line -> d_line_off (capacity: one per line), *d_n_rows.
+ * gb2_tsv_index_lines: byte offset of every non-blank line -> d_line_off[capacity]; *d_n_rows = number of lines found
+ *   (offsets beyond `capacity` are not written: call again with a larger buffer when *d_n_rows > capacity).
  *   skip_minus != 0 drops rows whose third field ends in '-' (what --no-reverse does BEFORE scoring and counting,
  *   score_sequences.py:281-282).  n_bytes < 2^31 per call.
  * gb2_tsv_parse_rows: per line -> packed k-mer + N mask (fused K1), start, stop, strand character, haplotype
@@ -116,7 +117,7 @@ int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int
  *   d_counts[0] += rows masked (N or bad symbol), [1] += rows with a symbol outside ACGTacgtN, [2] += malformed
  *   lines (fewer than six fields, k-mer not exactly w symbols, non-numeric position or count). */
 int gb2_tsv_index_lines(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, int skip_minus, uint64_t *d_line_off,
-                        uint64_t *d_n_rows);
+                        uint64_t capacity, uint64_t *d_n_rows);
 int gb2_tsv_parse_rows(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off, int64_t n_rows,
                        int w, uint64_t *d_packed, uint32_t *d_nmask, int64_t *d_start, int64_t *d_stop, uint8_t *d_strand,
                        int64_t *d_freq, uint8_t *d_ref, uint32_t *d_name_len, uint32_t *d_seq_off, uint64_t *d_counts);

@@ -184,4 +184,7 @@ def test_text_chunks_cut_at_line_boundaries(tmp_path):
     for chunk_bytes in (128, 1000, 1 << 20):
         chunks = [bytes(c.numpy()) for c in _text_chunks(files, chunk_bytes)]
         assert all(c.endswith(b"\n") and len(c) <= chunk_bytes for c in chunks)
-        assert b"".join(chunks) == want
+        # blank lines may be added between files (the device line index skips them); the lines themselves are intact
+        assert [ln for ln in b"".join(chunks).split(b"\n") if ln] == [ln for ln in want.split(b"\n") if ln]
+        for c in chunks[:-1]:
+            assert c.endswith(b"\n")
