@@ -239,16 +239,30 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     width = motif.width
     files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
     files = [f for f in files if os.stat(f).st_size > 0]
+    # several GPUs (one process per GPU under torchrun): every rank takes every world-th file, like the reference
+    # splits its files over `--cores` processes (score_sequences.py:120-147)
+    import torch
+    import torch.distributed as tdist
+    from . import dist as gdist
+    world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+    rank = tdist.get_rank() if world > 1 else 0
+    files = files[rank::world]
     t0 = time.time()
     ctx = _context()
     dm = device_motif(motif, ctx)
-    chunks = []  # (host text, DeviceRows, first global row)
-    n = 0
+    chunks = []  # (host text, DeviceRows, first local row)
+    n_local = 0
     for text in _text_chunks(files, _CHUNK_BYTES) if files else ():
         rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
         rows.d_text = None  # the device copy of the text is only needed while parsing
-        chunks.append((text.numpy(), rows, n))
-        n += rows.n
+        chunks.append((text.numpy(), rows, n_local))
+        n_local += rows.n
+    if world > 1:
+        counts = [None] * world
+        tdist.all_gather_object(counts, n_local)
+        rank_base, n = sum(counts[:rank]), sum(counts)
+    else:
+        rank_base, n = 0, n_local
     if n == 0:  # score_sequences.py:189-192
         errmsg = "No result retrieved. Unable to proceed.\n"
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
@@ -258,27 +272,37 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     if bad:
         exception_handler(ValueError, f"{bad} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
                           "symbols are required).\n", debug)
-    # every row is scored as given: `vg find -E` already emits the reverse-strand rows
-    scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=n)
-    for (_, rows, base), st in zip(chunks, stats):
-        if rows.n:  # the N mask is only read by the kernel when some row of the chunk needs it
-            scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=base)
+    # every row is scored as given: `vg find -E` already emits the reverse-strand rows.  The hit buffer starts
+    # small for selective thresholds and the (cheap) scoring pass is repeated in the rare case it overflows.
+    cap = n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8))
+    while True:
+        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        for (_, rows, base), st in zip(chunks, stats):
+            if rows.n:  # the N mask is only read by the kernel when some row of the chunk needs it
+                scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=rank_base + base)
+        found = scan.n_hits()
+        if found <= cap:
+            break
+        cap = found
+    if world > 1 and not no_qvalue:  # the one exchange step: global score histogram -> global q-values
+        with torch.cuda.stream(ctx.stream):
+            gdist.allreduce_histogram(scan.histogram())
     kept = scan.finalize_device(q_filter=bool(qval_t))
-    if verbose:
-        print("Sequences scored in %.2fs" % (time.time() - t0))
-    if not no_qvalue:
-        print("\nComputing q-values...\n")
-    print(f"Scanned sequences:\t{n}")
-    print(f"Scanned nucleotides:\t{n * width}")
+    if rank == 0:
+        if verbose:
+            print("Sequences scored in %.2fs" % (time.time() - t0))
+        if not no_qvalue:
+            print("\nComputing q-values...\n")
+        print(f"Scanned sequences:\t{n}")
+        print(f"Scanned nucleotides:\t{n * width}")
     t1 = time.time()
-    import torch
     with torch.cuda.stream(ctx.stream):
-        sel = scan.out["row"][:kept]
+        sel = scan.out["row"][:kept] - rank_base
         score = scan.out["score"][:kept].cpu().numpy()
         pval = scan.out["p"][:kept].cpu().numpy()
         qval = scan.out["q"][:kept].cpu().numpy() if not no_qvalue else None
         sel_h = sel.cpu().numpy()
-    bases = np.array([c[2] for c in chunks] + [n], dtype=np.int64)
+    bases = np.array([c[2] for c in chunks] + [n_local], dtype=np.int64)
     which = np.searchsorted(bases, sel_h, side="right") - 1
     seqname = np.empty(kept, dtype=object); seq = np.empty(kept, dtype=object); strand = np.empty(kept, dtype=object)
     start = np.empty(kept, dtype=np.int64); stop = np.empty(kept, dtype=np.int64); freq = np.empty(kept, dtype=np.int64)
@@ -327,11 +351,15 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     cols["haplotype_frequency"] = freq[keep]
     cols["reference"] = ref[keep]
     df = pd.DataFrame(cols)
+    if world > 1:  # every rank returns the whole table
+        parts = [None] * world
+        tdist.all_gather_object(parts, df)
+        df = pd.concat(parts, ignore_index=True)
     if len(df) > 1:  # deterministic tie order on top of the device's p-ascending order
         order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
                             df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
         df = df.iloc[order].reset_index(drop=True)
-    if verbose:
+    if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df
 

@@ -165,3 +165,17 @@ def test_compute_results_multi_chunk_text(tmp_path, monkeypatch):
     df = ss.compute_results(m, str(tmp_path / "seqs"), True, _Args(c["options"]))
     got = {col: df[col].to_numpy() for col in df.columns}
     gu.assert_tables_equal(got, c["table"], c["columns"])
+
+
+def test_compute_results_over_two_gpus(tmp_path):
+    """Needs two visible GPUs: torchrun with 2 ranks, files split over the ranks, global q-values via NCCL."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_compute_results_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", worker, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
