@@ -55,13 +55,47 @@ __global__ void __launch_bounds__(ENC_ROWS) gb2_encode_kernel(const uint8_t *__r
     uint64_t x = 0;
     uint32_t flag = 0;  // bit0: masked (N or bad), bit1: bad symbol
     if (tid < rows) {
-        const uint8_t *s = stage + head + (int64_t)tid * stride;
-        for (int i = 0; i < w; ++i) {
-            const uint32_t code = base_code(s[i]);
-            x |= (uint64_t)(code & 3u) << (2 * i);
-            flag |= (code >= 4u ? 1u : 0u) | (code == 5u ? 2u : 0u);
+        // Four symbols at a time, SIMD within a 32-bit register: 2-bit codes from bits 1-2 of each byte
+        // (A,C,G,T -> 0,1,3,2 -> 0,1,2,3), one multiply gathers the four codes into a byte, and the expected
+        // letter is rebuilt from the code and compared with the upper-cased input to catch anything else.
+        const uint32_t addr = (uint32_t)head + (uint32_t)tid * (uint32_t)stride;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (addr >> 2);
+        const uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
+        const int nwords = (w + 3) >> 2;
+        uint32_t lo = 0, hi = 0, bad = 0;
+        uint32_t cur = sw[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nwords) {
+                const uint32_t nxt = sw[j + 1];
+                uint32_t v = __byte_perm(cur, nxt, sel);  // bytes 4j .. 4j+3 of the row
+                cur = nxt;
+                const int rem = w - 4 * j;                // symbols left, >= 1
+                if (rem < 4) {
+                    const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - rem));
+                    v = (v & keep) | (0x41414141u & ~keep);  // pad with 'A' (code 0)
+                }
+                const uint32_t u = v & 0xDFDFDFDFu;
+                const uint32_t t = (v >> 1) & 0x03030303u;
+                const uint32_t c = t ^ ((t >> 1) & 0x01010101u);
+                const uint32_t ge2 = (c >> 1) & 0x01010101u;
+                const uint32_t eq3 = ge2 & c;
+                const uint32_t letters = 0x41414141u + 2u * c + 2u * ge2 + 11u * eq3;  // A C G T = 41 43 47 54
+                bad |= u ^ letters;
+                const uint32_t four = (c * 0x01041040u) >> 24;  // codes of the 4 symbols in 8 bits
+                if (j < 4) lo |= four << (8 * j);
+                else hi |= four << (8 * (j - 4));
+            }
         }
-        if (flag) x = 0;
+        x = ((uint64_t)hi << 32) | lo;
+        if (bad) {  // rare: find out whether it is an N or a symbol the reference does not define
+            const uint8_t *sb = stage + addr;
+            for (int i = 0; i < w; ++i) {
+                const uint32_t code = base_code(sb[i]);
+                flag |= (code >= 4u ? 1u : 0u) | (code == 5u ? 2u : 0u);
+            }
+            if (flag) x = 0;
+        }
         packed[row0 + tid] = x;
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, flag & 1u);

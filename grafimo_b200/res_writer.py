@@ -16,30 +16,33 @@ from .motif import Motif
 from .utils import DEFAULT_OUTDIR, PHASE, SOURCE, TP, dftolist, exception_handler
 
 
+def _format_unique(values, fmt):
+    """Formats a float column through its distinct values: p, q and score take one value per score bin, so a
+    report of millions of rows has only a few thousand distinct numbers to format."""
+    arr = np.asarray(values, dtype=np.float64)
+    uniq, inv = np.unique(arr, return_inverse=True)
+    return np.array([fmt(u) for u in uniq.tolist()], dtype=object)[inv]
+
+
 def gff3_lines(data: pd.DataFrame, no_qvalue: bool, debug: bool = False):
-    """Yields the GFF3 body lines (src/grafimo/res_writer.py:262-298)."""
+    """The GFF3 body lines (src/grafimo/res_writer.py:262-298), built column-wise."""
     cols = dftolist(data, no_qvalue, debug)
     if not no_qvalue and len(cols) != 12:
         exception_handler(ValueError, "Q-values columns seems to be missing.\n", debug)
     motif_ids, motif_names, seqnames, starts, stops, strands, scores, pvalues, seqs, _freqs, refs = cols[:11]
-    qvalues = cols[11] if not no_qvalue else None
+    score_s = _format_unique(scores, lambda v: str(round(v, 1)))
+    p_s = _format_unique(pvalues, lambda v: str(np.format_float_scientific(v, exp_digits=2)))
+    q_s = _format_unique(cols[11], lambda v: str(np.format_float_scientific(v, exp_digits=2))) if not no_qvalue else None
+    out = []
     for i in range(len(seqnames)):
-        seqname = seqnames[i]
-        chrom = seqname.split(":")[0]
-        strand = strands[i]
+        seqname, strand = seqnames[i], strands[i]
         # '-' rows carry start > stop; GFF3 wants forward coordinates
         first, second = (stops[i], starts[i]) if strand == "-" else (starts[i], stops[i])
-        attrs = [
-            "".join(["Name=", motif_ids[i], "_", seqname, strand, ":", refs[i]]),
-            "=".join(["Alias", motif_names[i]]),
-            "=".join(["ID", motif_ids[i], "-", motif_names[i], "-", seqname]),
-            "=".join(["pvalue=", str(np.format_float_scientific(pvalues[i], exp_digits=2))]),
-        ]
-        if not no_qvalue:
-            attrs.append("=".join(["qvalue", str(np.format_float_scientific(qvalues[i], exp_digits=2))]))
-        attrs.append("=".join(["sequence=", seqs[i], ";\n"]))
-        yield "\t".join([chrom, SOURCE, TP, str(first), str(second), str(round(scores[i], 1)), strand, PHASE,
-                         ";".join(attrs)])
+        qpart = f"qvalue={q_s[i]};" if q_s is not None else ""
+        out.append(f"{seqname.split(':')[0]}\t{SOURCE}\t{TP}\t{first}\t{second}\t{score_s[i]}\t{strand}\t{PHASE}\t"
+                   f"Name={motif_ids[i]}_{seqname}{strand}:{refs[i]};Alias={motif_names[i]};"
+                   f"ID={motif_ids[i]}=-={motif_names[i]}=-={seqname};pvalue=={p_s[i]};{qpart}sequence=={seqs[i]}=;\n")
+    return out
 
 
 def writeGFF3(prefix: str, data: pd.DataFrame, no_qvalue: bool, debug: bool) -> None:

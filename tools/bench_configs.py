@@ -16,6 +16,22 @@ tmp = tempfile.mkdtemp(prefix="gb2_cfg_")
 def ev():
     return torch.cuda.Event(enable_timing=True)
 
+ONLY = os.environ.get("GB2_ONLY", "")
+g = torch.Generator(device="cuda"); g.manual_seed(3)
+if ONLY == "k1":
+    print("K1 encoder")
+    for w in (8, 19, 30):
+        n1 = 1 << 27
+        a = synth.windows_to_ascii(torch.randint(0, 1 << (2 * w), (1 << 20,), dtype=torch.int64, device="cuda"), w).repeat(n1 >> 20, 1)
+        for rep in range(3):
+            e0, e1 = ev(), ev()
+            e0.record(ctx.stream)
+            packed, nmask, counts = ctx.encode(a)
+            e1.record(ctx.stream); ctx.sync()
+        ms = e0.elapsed_time(e1)
+        print(f"    w={w}: {n1 / ms / 1e6:.1f} G k-mers/s, {(n1 * (w + 8)) / ms / 1e6:.0f} GB/s (read {w} + write 8 B per k-mer)")
+        del a, packed
+    sys.exit(0)
 # ---------------------------------------------------------------- C3
 text, widths = synth.synthetic_meme_collection(800, 20242)
 path = os.path.join(tmp, "jaspar_like.meme"); open(path, "w").write(text)
