@@ -278,12 +278,13 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "i32 (u16x2 packed score adds); f64 p/q-values", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"CTCF MA0139.1 (w=19, uniform bg) on a synthetic {L} bp region x {H} haplotype paths per GPU "
                                f"(1000G-like SNP/indel density), both strands, p<{THRESHOLD:g}, q-values on",
                    "kmers_per_gpu": n, "bytes_resident_per_gpu": 8 * n, "l2_policy": "inputs larger than L2 (no flush needed)",
                    "parallelism": f"rows sharded by region over {world} GPU(s); one all-reduce of the score histogram",
-                   "hits_per_gpu": n_hits, "kept_after_finalize": kept},
+                   "hits_per_gpu": n_hits, "kept_after_finalize": kept,
+                   "arithmetic": "integer scores as packed u16x2 adds in u32 (both strands per add); p/q-values f64"},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
     }
 
