@@ -69,6 +69,11 @@ SIGNATURES = {
     "gb2_bh_pvalues": (_int, [_vp, _vp, _i64, _vp]),
     "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_tally_haplotypes": (_int, [_vp, _vp, _vp, _i64, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_graph_create": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32,
+                                _i64, _vp, ctypes.POINTER(_vp)]),
+    "gb2_graph_destroy": (_int, [_vp]),
+    "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _int, ctypes.POINTER(_u64)]),
+    "gb2_graph_extract": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),
 }

@@ -1,0 +1,427 @@
+// graph.cu -- K7: k-mer extraction from a variation graph, on the device.
+//
+// Replaces the external program the reference shells out to for every BED region,
+//     vg find -p REGION -x XG -H GBWT -K w -E > width_w/REGION.tsv      (src/grafimo/extract_regions.py:180,225,326)
+// and with it the text round trip into score_seqs (src/grafimo/score_sequences.py:273-293): the walks of every
+// region are enumerated here straight into the packed k-mers + side arrays the scoring kernel (K2) consumes.
+// First "next" row of SURVEY.md 8(f).  The graph arrays are built on the host by grafimo_b200/vgraph.py.
+//
+//   gb2_graph_prepare  pass 1: one thread per candidate first base (all regions in one launch) walks the graph
+//                      depth-first and counts its w-base walks that lie inside the region; exclusive scan -> row
+//                      offsets and the total (returned to the host so that it can size the outputs);
+//   gb2_graph_extract  pass 2: the same traversal writes the rows at those offsets: packed k-mer, N flag, start,
+//                      stop, haplotype frequency, ref flag, region index (optionally the node walk).
+//
+// Haplotype frequency of a walk = popcount(AND of the haplotype bit sets of its edges) -- in a DAG a haplotype
+// contains the node sequence n1..nk exactly when it takes every edge n_i -> n_i+1 -- which is what
+// `vg find -H` asks the GBWT; walks that no haplotype follows are emitted with frequency 0, like vg does.
+// Rows come out in (region, first base, depth-first over ascending target node) order: deterministic.
+#include <cub/cub.cuh>
+
+#include <new>
+
+#include "internal.cuh"
+
+#define GB2_NO_CONS 0xFFFFFFFFu
+#define WALK_THREADS 128
+#define WALK_LIMIT (1u << 24)  // walks from one first base; beyond this the region is reported as too dense
+
+struct GraphView {
+    int64_t n_nodes;
+    const uint32_t *node_off;   // [n_nodes+1] first base of the node in seq
+    const uint8_t *seq;         // base codes 0..3, 4 = anything else
+    const int64_t *node_a0;     // reference coordinate of base 0 (before clamping)
+    const int64_t *node_clamp;  // coordinates are clamped to this (end of the allele's reference span)
+    const uint8_t *node_flags;  // bit 0: on the reference path
+    const uint32_t *node_cons;  // haplotype-set row of the node or GB2_NO_CONS (every haplotype)
+    const uint32_t *edge_off;   // [n_nodes+1] CSR
+    const uint32_t *edge_to;
+    const uint32_t *edge_cons;  // haplotype-set row of the edge or GB2_NO_CONS
+    const uint32_t *cons_bits;  // [n_cons][words]
+    int32_t n_hap, words;
+};
+
+struct QueryView {
+    int32_t n_regions, w;
+    const int64_t *rs, *re;          // region [start, stop) on the reference path
+    const int64_t *node_lo;          // candidate first nodes [node_lo, node_hi)
+    const int64_t *node_hi;
+    const unsigned long long *tprefix;  // [n_regions+1] threads before region r
+};
+
+struct RowsOut {
+    uint64_t *packed;
+    uint32_t *nmask;
+    int64_t *start, *stop;
+    int32_t *freq;
+    uint8_t *isref;
+    uint32_t *region;
+    uint32_t *walk;      // [capacity][GB2_MAX_WIDTH] node indices, or nullptr
+    uint8_t *walk_len;   // nodes in the walk
+    uint8_t *walk_off;   // offset of the first base in the first node
+    unsigned long long capacity;
+    unsigned long long *counts;  // [0] += rows with a non-ACGT base
+};
+
+struct gb2_graph {
+    int device = 0;
+    GraphView v{};
+    void *blocks[16] = {nullptr};
+    int n_blocks = 0;
+    // prepared query
+    bool q_valid = false;
+    QueryView q{};
+    int64_t q_threads = 0;
+    unsigned long long q_total = 0;
+    void *q_mem = nullptr;             // region arrays
+    uint32_t *d_counts = nullptr;      // per thread
+    unsigned long long *d_offsets = nullptr;
+    int64_t q_cap_threads = 0;
+    uint32_t *d_flag = nullptr;        // [0] != 0: a first base exceeded WALK_LIMIT
+};
+
+template <typename T>
+__device__ __forceinline__ int64_t upper_bound_dev(const T *a, int64_t lo, int64_t hi, T x)
+{  // first index in [lo, hi) with a[i] > x
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Haplotypes that follow the walk: AND of the listed bit-set rows, population count.
+__device__ __forceinline__ int32_t walk_frequency(const GraphView &g, const uint32_t *cons, int n_cons)
+{
+    if (g.n_hap == 0) return 0;
+    if (n_cons == 0) return g.n_hap;
+    int32_t total = 0;
+    const int nq = g.words >> 2;
+    for (int q = 0; q < nq; ++q) {
+        uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)cons[0] * g.words) + q);
+        for (int c = 1; c < n_cons; ++c) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)cons[c] * g.words) + q);
+            acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
+        }
+        total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
+    }
+    return total;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const GraphView g, const QueryView q, int64_t n_threads,
+                                                                      uint32_t *__restrict__ counts,
+                                                                      const unsigned long long *__restrict__ offsets,
+                                                                      const RowsOut out, uint32_t *__restrict__ flag)
+{
+    const int64_t t = (int64_t)blockIdx.x * WALK_THREADS + threadIdx.x;
+    if (t >= n_threads) return;
+    const int r = (int)upper_bound_dev<unsigned long long>(q.tprefix, 0, (int64_t)q.n_regions + 1, (unsigned long long)t) - 1;
+    const int64_t nlo = q.node_lo[r], nhi = q.node_hi[r];
+    const uint32_t gbase = g.node_off[nlo] + (uint32_t)((unsigned long long)t - q.tprefix[r]);
+    const int64_t node0 = upper_bound_dev<uint32_t>(g.node_off, nlo, nhi + 1, gbase) - 1;
+    const int off0 = (int)(gbase - g.node_off[node0]);
+    const int64_t rs = q.rs[r], re = q.re[r];
+    const int w = q.w;
+    const int64_t start = min(g.node_a0[node0] + off0, g.node_clamp[node0]);
+    uint32_t n_found = 0;
+    if (start >= rs && start < re) {
+        // depth-first traversal; every node on the stack contributes at least one base, so depth < w <= 32
+        uint32_t st_node[GB2_MAX_WIDTH], st_edge[GB2_MAX_WIDTH], st_cons[GB2_MAX_WIDTH];
+        uint8_t st_have[GB2_MAX_WIDTH];  // bases collected before the node at this depth
+        unsigned long long packed = 0;
+        uint32_t nbits = 0;              // bit i: base i of the k-mer is not ACGT
+        uint32_t nonref = 0;             // bit d: node at depth d is off the reference path
+        int depth = 0, have = 0;
+        st_node[0] = (uint32_t)node0;
+        st_have[0] = 0;
+        st_cons[0] = g.node_cons[node0];
+        bool entering = true;
+        const unsigned long long row0 = WRITE ? offsets[t] : 0ull;
+        while (true) {
+            bool pop = false;
+            if (entering) {
+                const uint32_t n = st_node[depth];
+                const int o = depth == 0 ? off0 : 0;
+                const uint32_t b0 = g.node_off[n];
+                const int len = (int)(g.node_off[n + 1] - b0);
+                const int take = min(len - o, w - have);
+                if (WRITE) {
+                    for (int k = 0; k < take; ++k) {
+                        const uint32_t c = g.seq[b0 + o + k];
+                        if (c < 4u) packed |= (unsigned long long)c << (2 * (have + k));
+                        else nbits |= 1u << (have + k);
+                    }
+                }
+                if (g.node_flags[n] & 1u) nonref &= ~(1u << depth); else nonref |= 1u << depth;
+                have += take;
+                if (have < w) {  // node used up: go on through its edges
+                    st_edge[depth] = g.edge_off[n];
+                    entering = false;
+                    continue;
+                }
+                // a complete walk ending at base o + take - 1 of node n
+                const int64_t stop = min(g.node_a0[n] + (o + take), g.node_clamp[n]);
+                if (stop <= re) {
+                    if (WRITE) {
+                        const unsigned long long row = row0 + n_found;
+                        if (row < out.capacity) {
+                            uint32_t cons[GB2_MAX_WIDTH];
+                            int nc = 0;
+                            if (depth == 0) {
+                                if (st_cons[0] != GB2_NO_CONS) cons[nc++] = st_cons[0];
+                            } else {
+                                for (int d = 1; d <= depth; ++d)
+                                    if (st_cons[d] != GB2_NO_CONS) cons[nc++] = st_cons[d];
+                            }
+                            out.packed[row] = packed;
+                            out.start[row] = start;
+                            out.stop[row] = stop;
+                            out.freq[row] = walk_frequency(g, cons, nc);
+                            out.isref[row] = (nonref & ((2u << depth) - 1u)) == 0 ? 1 : 0;
+                            out.region[row] = (uint32_t)r;
+                            if (nbits) {
+                                atomicOr(out.nmask + (row >> 5), 1u << (row & 31));
+                                atomicAdd(out.counts, 1ull);
+                            }
+                            if (out.walk != nullptr) {
+                                for (int d = 0; d <= depth; ++d) out.walk[row * GB2_MAX_WIDTH + d] = st_node[d];
+                                out.walk_len[row] = (uint8_t)(depth + 1);
+                                out.walk_off[row] = (uint8_t)off0;
+                            }
+                        }
+                    }
+                    if (++n_found >= WALK_LIMIT) {
+                        atomicExch(flag, 1u);
+                        break;
+                    }
+                }
+                pop = true;
+            } else {  // next edge of the node at `depth` (its bases are already in the k-mer)
+                const uint32_t n = st_node[depth];
+                const uint32_t e = st_edge[depth];
+                if (e < g.edge_off[n + 1]) {
+                    st_edge[depth] = e + 1;
+                    ++depth;
+                    st_node[depth] = g.edge_to[e];
+                    st_cons[depth] = g.edge_cons[e];
+                    st_have[depth] = (uint8_t)have;
+                    entering = true;
+                } else {
+                    pop = true;
+                }
+            }
+            if (pop) {
+                if (depth == 0) break;
+                have = st_have[depth];  // the bases of the node being left go away
+                --depth;
+                entering = false;
+                if (WRITE) {
+                    packed &= (1ull << (2 * have)) - 1ull;  // have < w <= 32 here
+                    nbits &= (1u << have) - 1u;
+                }
+            }
+        }
+    }
+    if (!WRITE) counts[t] = n_found;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(gb2_ctx *ctx, gb2_graph *g, const T *h, size_t n, const T **d_out)
+{
+    void *d = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    GB2_CUDA(ctx, cudaMalloc(&d, bytes + 16));
+    g->blocks[g->n_blocks++] = d;
+    if (n) GB2_CUDA(ctx, cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = (const T *)d;
+    return GB2_OK;
+}
+
+extern "C" int gb2_graph_destroy(gb2_graph *g)
+{
+    if (!g) return GB2_OK;
+    cudaSetDevice(g->device);
+    for (int i = 0; i < g->n_blocks; ++i)
+        if (g->blocks[i]) cudaFree(g->blocks[i]);
+    if (g->q_mem) cudaFree(g->q_mem);
+    if (g->d_counts) cudaFree(g->d_counts);
+    if (g->d_offsets) cudaFree(g->d_offsets);
+    if (g->d_flag) cudaFree(g->d_flag);
+    delete g;
+    return GB2_OK;
+}
+
+extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, const uint8_t *h_seq,
+                                const int64_t *h_node_a0, const int64_t *h_node_clamp, const uint8_t *h_node_flags,
+                                const uint32_t *h_node_cons, int64_t n_edges, const uint32_t *h_edge_off,
+                                const uint32_t *h_edge_to, const uint32_t *h_edge_cons, int32_t n_hap, int32_t words,
+                                int64_t n_cons, const uint32_t *h_cons_bits, gb2_graph **out)
+{
+    if (!ctx || !out) return GB2_ERR_ARG;
+    *out = nullptr;
+    GB2_REQUIRE(ctx, n_nodes >= 1 && n_nodes < ((int64_t)1 << 31), "gb2_graph_create: node count out of range");
+    GB2_REQUIRE(ctx, h_node_off && h_seq && h_node_a0 && h_node_clamp && h_node_flags && h_node_cons && h_edge_off,
+                "gb2_graph_create: null array");
+    GB2_REQUIRE(ctx, n_edges >= 0 && (n_edges == 0 || (h_edge_to && h_edge_cons)), "gb2_graph_create: null edge array");
+    GB2_REQUIRE(ctx, n_hap >= 0 && words >= 4 && (words & 3) == 0 && (int64_t)words * 32 >= n_hap,
+                "gb2_graph_create: haplotype bit sets need a multiple of 4 words covering %d haplotypes", n_hap);
+    GB2_REQUIRE(ctx, n_cons >= 0 && (n_cons == 0 || h_cons_bits), "gb2_graph_create: null haplotype sets");
+    GB2_REQUIRE(ctx, h_edge_off[n_nodes] == (uint32_t)n_edges, "gb2_graph_create: edge offsets do not end at n_edges");
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        GB2_REQUIRE(ctx, h_node_off[i + 1] > h_node_off[i], "gb2_graph_create: node %lld is empty", (long long)i);
+        GB2_REQUIRE(ctx, h_edge_off[i + 1] >= h_edge_off[i], "gb2_graph_create: edge offsets not monotone");
+        GB2_REQUIRE(ctx, h_node_cons[i] == GB2_NO_CONS || (int64_t)h_node_cons[i] < n_cons, "gb2_graph_create: bad node set index");
+    }
+    for (int64_t e = 0; e < n_edges; ++e) {
+        GB2_REQUIRE(ctx, (int64_t)h_edge_to[e] < n_nodes, "gb2_graph_create: edge target out of range");
+        GB2_REQUIRE(ctx, h_edge_cons[e] == GB2_NO_CONS || (int64_t)h_edge_cons[e] < n_cons, "gb2_graph_create: bad edge set index");
+    }
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    gb2_graph *g = new (std::nothrow) gb2_graph();
+    if (!g) return GB2_ERR_NOMEM;
+    g->device = ctx->device;
+    const size_t n_bases = h_node_off[n_nodes];
+    int rc = GB2_OK;
+    do {
+        if ((rc = upload(ctx, g, h_node_off, (size_t)n_nodes + 1, &g->v.node_off)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_seq, n_bases, &g->v.seq)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_node_a0, (size_t)n_nodes, &g->v.node_a0)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_node_clamp, (size_t)n_nodes, &g->v.node_clamp)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_node_flags, (size_t)n_nodes, &g->v.node_flags)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_node_cons, (size_t)n_nodes, &g->v.node_cons)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_edge_off, (size_t)n_nodes + 1, &g->v.edge_off)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_edge_to, (size_t)n_edges, &g->v.edge_to)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_edge_cons, (size_t)n_edges, &g->v.edge_cons)) != GB2_OK) break;
+        if ((rc = upload(ctx, g, h_cons_bits, (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
+        if (cudaMalloc((void **)&g->d_flag, sizeof(uint32_t)) != cudaSuccess) { rc = GB2_ERR_NOMEM; break; }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // host arrays may go away
+    } while (0);
+    if (rc != GB2_OK) {
+        if (!ctx->err[0]) GB2_SET_ERR(ctx, "gb2_graph_create: upload failed");
+        gb2_graph_destroy(g);
+        return rc;
+    }
+    g->v.n_nodes = n_nodes;
+    g->v.n_hap = n_hap;
+    g->v.words = words;
+    *out = g;
+    return GB2_OK;
+}
+
+struct U32ToU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t x) const { return (unsigned long long)x; }
+};
+
+extern "C" int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *g, int32_t n_regions, const int64_t *h_start,
+                                 const int64_t *h_stop, const int64_t *h_node_lo, const int64_t *h_node_hi, int w,
+                                 uint64_t *h_n_rows)
+{
+    if (!ctx || !g || !h_n_rows) return GB2_ERR_ARG;
+    *h_n_rows = 0;
+    g->q_valid = false;
+    GB2_REQUIRE(ctx, g->device == ctx->device, "gb2_graph_prepare: graph lives on device %d, context on %d", g->device, ctx->device);
+    GB2_REQUIRE(ctx, w >= 1 && w <= GB2_MAX_WIDTH, "gb2_graph_prepare: width %d outside [1,%d]", w, GB2_MAX_WIDTH);
+    GB2_REQUIRE(ctx, n_regions >= 0 && (n_regions == 0 || (h_start && h_stop && h_node_lo && h_node_hi)), "gb2_graph_prepare: null region array");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    // threads per region = bases of its candidate first nodes (host copy of node_off is not kept: read the two ends)
+    std::vector<unsigned long long> tprefix((size_t)n_regions + 1, 0ull);
+    std::vector<uint32_t> ends((size_t)n_regions * 2);
+    for (int r = 0; r < n_regions; ++r) {
+        GB2_REQUIRE(ctx, h_node_lo[r] >= 0 && h_node_lo[r] <= h_node_hi[r] && h_node_hi[r] <= g->v.n_nodes,
+                    "gb2_graph_prepare: node range of region %d out of bounds", r);
+        GB2_REQUIRE(ctx, h_start[r] <= h_stop[r], "gb2_graph_prepare: region %d has start > stop", r);
+    }
+    for (int r = 0; r < n_regions; ++r) {
+        GB2_CUDA(ctx, cudaMemcpyAsync(&ends[2 * (size_t)r], g->v.node_off + h_node_lo[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GB2_CUDA(ctx, cudaMemcpyAsync(&ends[2 * (size_t)r + 1], g->v.node_off + h_node_hi[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < n_regions; ++r) tprefix[(size_t)r + 1] = tprefix[(size_t)r] + (ends[2 * (size_t)r + 1] - ends[2 * (size_t)r]);
+    const int64_t T = (int64_t)tprefix[(size_t)n_regions];
+    g->q_threads = T;
+    g->q_total = 0;
+    g->q.n_regions = n_regions;
+    g->q.w = w;
+    if (T == 0) {
+        g->q_valid = true;
+        return GB2_OK;
+    }
+    // region arrays on the device
+    if (g->q_mem) { GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(g->q_mem); g->q_mem = nullptr; }
+    const size_t nr = (size_t)n_regions;
+    GB2_CUDA(ctx, cudaMalloc(&g->q_mem, (4 * nr + nr + 1) * 8 + 64));
+    int64_t *base = (int64_t *)g->q_mem;
+    GB2_CUDA(ctx, cudaMemcpyAsync(base, h_start, nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(base + nr, h_stop, nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(base + 2 * nr, h_node_lo, nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(base + 3 * nr, h_node_hi, nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(base + 4 * nr, tprefix.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    g->q.rs = base; g->q.re = base + nr; g->q.node_lo = base + 2 * nr; g->q.node_hi = base + 3 * nr;
+    g->q.tprefix = (const unsigned long long *)(base + 4 * nr);
+    if (T > g->q_cap_threads) {
+        GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (g->d_counts) cudaFree(g->d_counts);
+        if (g->d_offsets) cudaFree(g->d_offsets);
+        g->d_counts = nullptr; g->d_offsets = nullptr; g->q_cap_threads = 0;
+        GB2_CUDA(ctx, cudaMalloc((void **)&g->d_counts, (size_t)(T + 1) * sizeof(uint32_t)));
+        GB2_CUDA(ctx, cudaMalloc((void **)&g->d_offsets, (size_t)(T + 1) * sizeof(unsigned long long)));
+        g->q_cap_threads = T;
+    }
+    GB2_CUDA(ctx, cudaMemsetAsync(g->d_flag, 0, sizeof(uint32_t), ctx->stream));
+    GB2_CUDA(ctx, cudaMemsetAsync(g->d_counts + T, 0, sizeof(uint32_t), ctx->stream));
+    const int64_t grid = gb2_div_up(T, WALK_THREADS);
+    GB2_REQUIRE(ctx, grid < ((int64_t)1 << 31), "gb2_graph_prepare: too many candidate bases (%lld)", (long long)T);
+    RowsOut none{};
+    gb2_graph_walk_kernel<false><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, g->d_counts, nullptr, none, g->d_flag);
+    GB2_LAUNCH_CHECK(ctx);
+    // exclusive scan over T+1 counts (the extra zero makes offsets[T] the total)
+    size_t cub_bytes = 0;
+    cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t *> it(g->d_counts, U32ToU64());
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, g->d_offsets, (int64_t)(T + 1), ctx->stream);
+    int rc = gb2_scratch_reserve(ctx, cub_bytes);
+    if (rc != GB2_OK) return rc;
+    GB2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scratch, cub_bytes, it, g->d_offsets, (int64_t)(T + 1), ctx->stream));
+    ctx->launches += 2;
+    GB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, g->d_offsets + T, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 1, g->d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((uint32_t)ctx->h_mail[1] != 0) {
+        GB2_SET_ERR(ctx, "gb2_graph_prepare: more than %u walks start at one base (variants too dense for width %d)", WALK_LIMIT, w);
+        return GB2_ERR_CAPACITY;
+    }
+    g->q_total = ctx->h_mail[0];
+    g->q_valid = true;
+    *h_n_rows = g->q_total;
+    return GB2_OK;
+}
+
+extern "C" int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *g, uint64_t capacity, uint64_t *d_packed, uint32_t *d_nmask,
+                                 int64_t *d_start, int64_t *d_stop, int32_t *d_freq, uint8_t *d_isref, uint32_t *d_region,
+                                 uint32_t *d_walk, uint8_t *d_walk_len, uint8_t *d_walk_off, uint64_t *d_counts)
+{
+    if (!ctx || !g) return GB2_ERR_ARG;
+    if (!g->q_valid) {
+        GB2_SET_ERR(ctx, "gb2_graph_extract: call gb2_graph_prepare first");
+        return GB2_ERR_STATE;
+    }
+    if (g->q_total > capacity) {
+        GB2_SET_ERR(ctx, "gb2_graph_extract: %llu rows, capacity %llu", (unsigned long long)g->q_total, (unsigned long long)capacity);
+        return GB2_ERR_CAPACITY;
+    }
+    if (g->q_total == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_packed && d_nmask && d_start && d_stop && d_freq && d_isref && d_region && d_counts, "gb2_graph_extract: null output");
+    GB2_REQUIRE(ctx, d_walk == nullptr || (d_walk_len && d_walk_off), "gb2_graph_extract: walk output needs its length/offset arrays");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    RowsOut o;
+    o.packed = d_packed; o.nmask = d_nmask; o.start = d_start; o.stop = d_stop; o.freq = d_freq; o.isref = d_isref;
+    o.region = d_region; o.walk = d_walk; o.walk_len = d_walk_len; o.walk_off = d_walk_off;
+    o.capacity = capacity; o.counts = (unsigned long long *)d_counts;
+    GB2_CUDA(ctx, cudaMemsetAsync(d_nmask, 0, (size_t)gb2_div_up((int64_t)g->q_total, 32) * sizeof(uint32_t), ctx->stream));
+    const int64_t T = g->q_threads;
+    const int64_t grid = gb2_div_up(T, WALK_THREADS);
+    gb2_graph_walk_kernel<true><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, nullptr, g->d_offsets, o, g->d_flag);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}

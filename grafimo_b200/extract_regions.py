@@ -1,0 +1,235 @@
+"""K-mer extraction from the variation graph, on the GPU.
+
+The reference's `scan_graph` (src/grafimo/extract_regions.py:55-237) runs, for every BED region and motif width,
+the external command `vg find -p REGION -x XG -H GBWT -K w -E > width_w/REGION.tsv` in an `mp.Pool`
+(:128,180,225,275,326) and hands the directory of TSVs to `compute_results`.  Here the graph lives on the device
+(`DeviceGraph`, built from the same inputs `grafimo buildvg` takes: reference FASTA + phased VCF, see vgraph.py) and
+all regions of a chromosome are enumerated in two kernel launches (`gb2_graph_prepare` / `gb2_graph_extract`,
+csrc/graph.cu) into `GraphRows` -- packed k-mers and side arrays that `score_sequences.compute_results_rows` scores
+without any text in between.  `GraphRows.to_vg_tsv` / `scan_graph` still write vg's 7-column text for callers (and
+parity tests) that want the reference's file interface.
+
+No CPU fallback: DeviceGraph needs the CUDA library and a GPU.
+"""
+import ctypes
+import gzip
+import os
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import check
+from .utils import exception_handler
+from .vgraph import VariationGraph
+
+MAX_WIDTH = 32
+
+
+def get_regions_bed(bedfile: str, debug: bool) -> Tuple[Dict[str, List], int]:
+    """BED reader with the reference's behaviour (src/grafimo/extract_regions.py:371-433): only lines that start
+    with "chr" are data, the first three fields are kept as strings, regions are grouped by chromosome in file
+    order."""
+    if not isinstance(bedfile, str):
+        exception_handler(TypeError, f"Expected str, got {type(bedfile).__name__}.\n", debug)
+    if not os.path.isfile(bedfile):
+        exception_handler(FileNotFoundError, f"Unable to locate {bedfile}.\n", debug)
+    if os.stat(bedfile).st_size == 0:
+        exception_handler(IOError, f"{bedfile} is empty.\n", debug)
+    regions, n = {}, 0
+    op = gzip.open if bedfile.split(".")[-1] == "gz" else open
+    with op(bedfile, "rt") as fh:
+        for line in fh:
+            if line.startswith("chr"):
+                chrom, start, stop = line.strip().split()[:3]
+                regions.setdefault(chrom, []).append((start, stop))
+                n += 1
+    return regions, n
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class DeviceGraph:
+    """A VariationGraph resident in HBM (gb2_graph_create)."""
+
+    def __init__(self, ctx, graph: VariationGraph):
+        self.ctx, self.graph = ctx, graph
+        g = graph
+        h = ctypes.c_void_p()
+        arrays = dict(node_off=np.ascontiguousarray(g.node_off, np.uint32), seq=np.ascontiguousarray(g.seq, np.uint8),
+                      a0=np.ascontiguousarray(g.node_a0, np.int64), clamp=np.ascontiguousarray(g.node_clamp, np.int64),
+                      flags=np.ascontiguousarray(g.node_flags, np.uint8), ncons=np.ascontiguousarray(g.node_cons, np.uint32),
+                      eoff=np.ascontiguousarray(g.edge_off, np.uint32), eto=np.ascontiguousarray(g.edge_to, np.uint32),
+                      econs=np.ascontiguousarray(g.edge_cons, np.uint32), bits=np.ascontiguousarray(g.cons_bits, np.uint32))
+        check(ctx.lib.gb2_graph_create(ctx.h, g.n_nodes, _np_ptr(arrays["node_off"]), _np_ptr(arrays["seq"]),
+                                       _np_ptr(arrays["a0"]), _np_ptr(arrays["clamp"]), _np_ptr(arrays["flags"]),
+                                       _np_ptr(arrays["ncons"]), g.n_edges, _np_ptr(arrays["eoff"]), _np_ptr(arrays["eto"]),
+                                       _np_ptr(arrays["econs"]), g.n_hap, g.words, g.n_cons, _np_ptr(arrays["bits"]),
+                                       ctypes.byref(h)), "gb2_graph_create", ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gb2_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, regions, width, want_walks=False):
+        """regions: [(start, stop)] 0-based half-open on the reference path (what `-p chr:start-stop` names).
+        -> GraphRows with every walk of `width` bases reported inside its region, forward strand."""
+        ctx, g = self.ctx, self.graph
+        width = int(width)
+        if not 1 <= width <= MAX_WIDTH:
+            raise ValueError(f"motif width {width} outside [1, {MAX_WIDTH}]")
+        rs = np.array([int(r[0]) for r in regions], dtype=np.int64)
+        re = np.array([int(r[1]) for r in regions], dtype=np.int64)
+        lohi = np.array([g.region_nodes(a, b) for a, b in zip(rs, re)], dtype=np.int64).reshape(len(rs), 2)
+        nlo, nhi = np.ascontiguousarray(lohi[:, 0]), np.ascontiguousarray(lohi[:, 1])
+        n_rows = ctypes.c_uint64(0)
+        ctx.enter()
+        check(ctx.lib.gb2_graph_prepare(ctx.h, self.h, len(rs), _np_ptr(rs), _np_ptr(re), _np_ptr(nlo), _np_ptr(nhi), width,
+                                        ctypes.byref(n_rows)), "gb2_graph_prepare", ctx.h)
+        n = int(n_rows.value)
+        rows = GraphRows(ctx, g.chrom, [(int(a), int(b)) for a, b in zip(rs, re)], width, n, want_walks, g.n_hap)
+        rows.graph = g
+        if n:
+            check(ctx.lib.gb2_graph_extract(ctx.h, self.h, n, _ptr(rows.packed), _ptr(rows.nmask), _ptr(rows.start),
+                                            _ptr(rows.stop), _ptr(rows.freq), _ptr(rows.isref), _ptr(rows.region),
+                                            _ptr(rows.walk), _ptr(rows.walk_len), _ptr(rows.walk_off), _ptr(rows.counts)),
+                  "gb2_graph_extract", ctx.h)
+        ctx.leave()
+        return rows
+
+
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = {65: 84, 67: 71, 71: 67, 84: 65, 78: 78}
+
+
+def decode_kmers(packed: np.ndarray, width: int) -> np.ndarray:
+    """uint64/int64 [n] packed k-mers -> uint8 [n, width] ASCII."""
+    p = packed.astype(np.uint64)
+    sh = (2 * np.arange(width, dtype=np.uint64))[None, :]
+    return _ASCII[((p[:, None] >> sh) & np.uint64(3)).astype(np.intp)]
+
+
+class GraphRows:
+    """Device-resident rows of an extraction: what one `vg find -K w -E -H` call per region would have printed
+    (forward strand), as arrays.  Row order: (region, first base, depth-first)."""
+
+    def __init__(self, ctx, chrom, regions, width, n, want_walks, n_hap):
+        self.ctx, self.chrom, self.regions, self.width, self.n, self.n_hap = ctx, chrom, regions, width, n, n_hap
+        m = max(n, 1)
+        self.packed = ctx.empty(m + (m & 1), torch.int64)[:m]
+        self.nmask = ctx.zeros((m + 31) // 32, torch.int32)
+        self.start = ctx.empty(m, torch.int64)
+        self.stop = ctx.empty(m, torch.int64)
+        self.freq = ctx.empty(m, torch.int32)
+        self.isref = ctx.empty(m, torch.uint8)
+        self.region = ctx.empty(m, torch.int32)
+        self.counts = ctx.zeros(2, torch.int64)
+        self.walk = ctx.empty(m * MAX_WIDTH, torch.int32) if want_walks else None
+        self.walk_len = ctx.empty(m, torch.uint8) if want_walks else None
+        self.walk_off = ctx.empty(m, torch.uint8) if want_walks else None
+
+    def region_name(self, r):
+        a, b = self.regions[r]
+        return f"{self.chrom}:{a}-{b}"
+
+    def n_masked(self):
+        self.ctx.sync()
+        return int(self.counts[0].item())
+
+    def host(self):
+        """All columns as numpy arrays (tests, TSV writer)."""
+        n = self.n
+        with torch.cuda.stream(self.ctx.stream):
+            out = dict(packed=self.packed[:n].cpu().numpy(), start=self.start[:n].cpu().numpy(), stop=self.stop[:n].cpu().numpy(),
+                       freq=self.freq[:n].cpu().numpy(), isref=self.isref[:n].cpu().numpy(), region=self.region[:n].cpu().numpy(),
+                       nmask=self.nmask.cpu().numpy())
+            if self.walk is not None:
+                out["walk"] = self.walk.cpu().numpy().reshape(-1, MAX_WIDTH)[:n]
+                out["walk_len"] = self.walk_len[:n].cpu().numpy()
+                out["walk_off"] = self.walk_off[:n].cpu().numpy()
+        self.ctx.sync()
+        return out
+
+    def to_vg_tsv(self, both_strands=True):
+        """-> {region index: [lines]} in vg's 7-column layout (pinned by the reference's expected_seqs.tsv).  Rows
+        holding a non-ACGT base print 'N' there.  The node path column needs want_walks=True (else it is empty)."""
+        h = self.host()
+        n, w = self.n, self.width
+        asc = decode_kmers(h["packed"], w) if n else np.zeros((0, w), np.uint8)
+        if n and h["nmask"].any():
+            # the packed form has no room for N: the (rare) masked rows are spelled again from their walks
+            bad = np.nonzero((h["nmask"].view(np.uint32)[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1)[0]
+            for i in bad:
+                asc[i] = self._ascii_of_walk(h, i)
+        comp = np.zeros(256, np.uint8)
+        for k, v in _COMP.items():
+            comp[k] = v
+        out = {r: [] for r in range(len(self.regions))}
+        for i in range(n):
+            r = int(h["region"][i])
+            seq = asc[i].tobytes().decode("ascii")
+            flag = "ref" if h["isref"][i] else "non.ref"
+            if "walk" in h:
+                nodes = h["walk"][i, :h["walk_len"][i]].astype(np.int64) + 1
+                fw = "".join(f"{x}+," for x in nodes)
+                rv = "".join(f"{x}-," for x in nodes[::-1])
+            else:
+                fw = rv = ""
+            c, name = self.chrom, self.region_name(r)
+            out[r].append(f"{name}\t{seq}\t{c}:{h['start'][i]}+\t{c}:{h['stop'][i]}+\t{h['freq'][i]}\t{flag}\t{fw}")
+            if both_strands:
+                rc = comp[asc[i]][::-1].tobytes().decode("ascii")
+                out[r].append(f"{name}\t{rc}\t{c}:{h['stop'][i]}-\t{c}:{h['start'][i]}-\t{h['freq'][i]}\t{flag}\t{rv}")
+        return out
+
+    def _ascii_of_walk(self, h, i):
+        if "walk" not in h:
+            raise ValueError("rows with non-ACGT bases can only be printed when the walks were kept (want_walks=True)")
+        g = self.graph
+        seq, need = [], self.width
+        off = int(h["walk_off"][i])
+        codes = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        for d, nd in enumerate(h["walk"][i, :h["walk_len"][i]]):
+            b0, b1 = int(g.node_off[nd]), int(g.node_off[nd + 1])
+            o = off if d == 0 else 0
+            take = min(b1 - b0 - o, need)
+            seq.append(codes[g.seq[b0 + o:b0 + o + take]])
+            need -= take
+        return np.concatenate(seq)
+
+
+def scan_graph(graphs: Dict[str, DeviceGraph], bedfile: str, widths, outdir: str, debug: bool = False, chroms_prefix: str = "") -> str:
+    """File-interface twin of the reference's scan_graph (src/grafimo/extract_regions.py:55-237): writes
+    `<outdir>/width_<w>/<chrom>_<start>-<stop>.tsv` for every BED region and width, in vg's layout, and returns
+    outdir -- the `sequence_loc` compute_results takes.  `graphs` maps the BED chromosome name without its "chr"
+    prefix (what the reference puts in the region name, :150-170) to a DeviceGraph."""
+    regions, _ = get_regions_bed(bedfile, debug)
+    for w in widths:
+        d = os.path.join(outdir, f"width_{int(w)}")
+        os.makedirs(d, exist_ok=True)
+        for chrom, spans in regions.items():
+            key = chrom[3:] if chrom.startswith("chr") else chrom
+            name = chroms_prefix + key
+            dg = graphs.get(name) or graphs.get(key) or graphs.get(chrom)
+            if dg is None:
+                exception_handler(KeyError, f"No variation graph for chromosome {chrom}.\n", debug)
+            rows = dg.extract([(int(a), int(b)) for a, b in spans], int(w), want_walks=True)
+            for r, lines in rows.to_vg_tsv().items():
+                a, b = rows.regions[r]
+                with open(os.path.join(d, f"{rows.chrom}_{a}-{b}.tsv"), "w") as fh:
+                    fh.write("".join(line + "\n" for line in lines))
+    return outdir

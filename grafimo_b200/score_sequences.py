@@ -364,6 +364,123 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     return df
 
 
+def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmode: Optional[bool] = False) -> pd.DataFrame:
+    """compute_results for k-mers that are already on the device: `rows` is a GraphRows (or a list of them, one per
+    chromosome) from extract_regions.DeviceGraph.extract -- the forward walks of every region, with start/stop,
+    haplotype frequency and ref flag as side arrays.  Returns the table compute_results would return for the TSVs
+    `vg find -K w -E` writes for the same regions (GraphRows.to_vg_tsv): both strands are scored from the one
+    packed k-mer (the '-' row of a walk is its reverse complement with start and stop swapped), every
+    row of both strands counts in the q-values, and the same flags apply (score_sequences.py:93-107)."""
+    if not isinstance(motif, Motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    if not testmode:
+        needed = ("threshold", "noqvalue", "qvalueT", "noreverse", "recomb", "verbose")
+        if args_obj is None or not all(hasattr(args_obj, a) for a in needed):
+            exception_handler(TypeError, f"Expected Findmotif, got {type(args_obj).__name__}.\n", debug)
+        threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+        no_reverse, recomb, verbose = args_obj.noreverse, args_obj.recomb, args_obj.verbose
+    else:
+        threshold, recomb, no_qvalue, qval_t, no_reverse, verbose = float(1), True, False, False, False, False
+    assert threshold > 0 and threshold <= 1
+    if qval_t:
+        assert not no_qvalue
+    print_scoring_msg(motif, no_reverse, debug)
+    if not motif.is_scaled:
+        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    import torch
+    batches = [r for r in (rows if isinstance(rows, (list, tuple)) else [rows])]
+    width = motif.width
+    for b in batches:
+        if b.width != width:
+            exception_handler(ValueError, f"k-mers of width {b.width} given to a motif of width {width}.\n", debug)
+    strands = 1 if no_reverse else 2
+    n_kmers = sum(b.n for b in batches)
+    n = n_kmers * strands
+    if n == 0:  # score_sequences.py:189-192
+        errmsg = "No result retrieved. Unable to proceed.\n"
+        errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
+        exception_handler(ValueError, errmsg, debug)
+    t0 = time.time()
+    ctx = batches[0].ctx
+    dm = device_motif(motif, ctx)
+    bases = np.concatenate([[0], np.cumsum([b.n for b in batches])]).astype(np.int64)
+    cap = n if threshold >= 0.25 else min(n, max(1 << 20, n // 8))
+    while True:
+        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        for b, base in zip(batches, bases[:-1]):
+            if b.n:
+                scan.score(b.packed, b.nmask if b.n_masked() else None, row_base=int(base))
+        found = scan.n_hits()
+        if found <= cap:
+            break
+        cap = found
+    kept = scan.finalize_device(q_filter=bool(qval_t))
+    if verbose:
+        print("Sequences scored in %.2fs" % (time.time() - t0))
+    if not no_qvalue:
+        print("\nComputing q-values...\n")
+    print(f"Scanned sequences:\t{n}")
+    print(f"Scanned nucleotides:\t{n * width}")
+    t1 = time.time()
+    with torch.cuda.stream(ctx.stream):
+        sel = scan.out["row"][:kept]
+        minus = scan.out["strand"][:kept].cpu().numpy().astype(bool)
+        score = scan.out["score"][:kept].cpu().numpy()
+        pval = scan.out["p"][:kept].cpu().numpy()
+        qval = scan.out["q"][:kept].cpu().numpy() if not no_qvalue else None
+        sel_h = sel.cpu().numpy().astype(np.int64)
+    which = np.searchsorted(bases, sel_h, side="right") - 1
+    seqname = np.empty(kept, dtype=object); seq = np.empty(kept, dtype=object)
+    start = np.empty(kept, dtype=np.int64); stop = np.empty(kept, dtype=np.int64); freq = np.empty(kept, dtype=np.int64)
+    isref = np.empty(kept, dtype=bool)
+    from .extract_regions import decode_kmers
+    comp = np.zeros(256, np.uint8)
+    comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
+    for k, b in enumerate(batches):
+        m = np.nonzero(which == k)[0]
+        if len(m) == 0:
+            continue
+        with torch.cuda.stream(ctx.stream):
+            idx = torch.from_numpy(sel_h[m] - bases[k]).to(ctx.device)
+            g = {c: getattr(b, c)[idx].cpu().numpy() for c in ("packed", "start", "stop", "freq", "isref", "region")}
+        asc = decode_kmers(g["packed"], width)
+        rc = comp[asc][:, ::-1]
+        asc = np.where(minus[m][:, None], rc, asc)
+        seq[m] = np.char.decode(np.ascontiguousarray(asc).view(f"S{width}").ravel(), "ascii").astype(object)
+        names = np.array([b.region_name(r) for r in range(len(b.regions))], dtype=object)
+        seqname[m] = names[g["region"]]
+        # the '-' row of a walk starts where the walk stops (SURVEY.md F1)
+        start[m] = np.where(minus[m], g["stop"], g["start"])
+        stop[m] = np.where(minus[m], g["start"], g["stop"])
+        freq[m] = g["freq"]
+        isref[m] = g["isref"].astype(bool)
+    ref = np.where(isref & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
+    keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
+    cols = {
+        "motif_id": [motif.motif_id] * int(keep.sum()),
+        "motif_alt_id": [motif.motif_name] * int(keep.sum()),
+        "sequence_name": seqname[keep],
+        "start": start[keep],
+        "stop": stop[keep],
+        "strand": np.where(minus, "-", "+").astype(object)[keep],
+        "score": score[keep],
+        "p-value": pval[keep],
+    }
+    if not no_qvalue:
+        cols["q-value"] = qval[keep]
+    cols["matched_sequence"] = seq[keep]
+    cols["haplotype_frequency"] = freq[keep]
+    cols["reference"] = ref[keep]
+    df = pd.DataFrame(cols)
+    if len(df) > 1:
+        order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
+                            df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
+        df = df.iloc[order].reset_index(drop=True)
+    if verbose:
+        print("\nResults summary built in %.2fs" % (time.time() - t1))
+    return df
+
+
 def compute_qvalues(pvalues: List[float], debug: bool) -> List[float]:
     """B3 seam (src/grafimo/score_sequences.py:401-428): Benjamini-Hochberg q-values of a list of p-values,
     same order in and out.  Inside compute_results the q-values come from the score histogram (K5); this

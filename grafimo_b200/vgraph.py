@@ -1,0 +1,340 @@
+"""Variation graph of one chromosome, laid out for the GPU k-mer extractor (csrc/graph.cu).
+
+This is the first "next" row of SURVEY.md 8(f): the reference obtains its k-mers by running the external `vg`
+program once per BED region (`vg find -p REGION -x XG -H GBWT -K w -E > width_w/REGION.tsv`,
+src/grafimo/extract_regions.py:180,225,326) on a graph built by `vg construct -r REF -v VCF -C -a` and
+`vg index -G gbwt -x xg` (src/grafimo/constructVG.py:332,394-396), and then parses the text again
+(src/grafimo/score_sequences.py:273-293).  Here the same inputs -- reference sequence, phased variants -- become
+flat arrays that live in HBM, and the walks of every region are enumerated there straight into packed k-mers
+(DeviceGraph.extract), so no text is written or parsed between the graph and the scoring kernel.
+
+Graph model (what `vg construct` builds, restated; pinned on the reference's own vg fixture, see
+oracle/graph_oracle.py):
+  * the reference is cut at every allele boundary; one node per reference segment and per non-empty alternative
+    allele, nodes longer than `max_node_len` (vg's default 32) are chained; a deletion is an edge;
+  * at a breakpoint everything that ends there is joined to everything that starts there; an insertion sits between
+    the two sides;
+  * node ids: at a breakpoint the alternative alleles first (input order), then the reference segment;
+  * haplotypes (two per VCF sample, what `vg index -G` threads into the GBWT) follow their alleles; a variant that
+    begins inside an allele the haplotype already took is ignored for that haplotype.
+Per walk the extractor reports what `vg find -K -E -H` prints: sequence, start/stop on the reference path,
+the number of haplotypes that contain the walk's node sequence (0 for walks no haplotype follows -- the rows
+`--recomb` is about), and whether every node lies on the reference path.
+
+Haplotype support is stored as bit sets: one row per node (haplotypes through the node) and one per edge
+(haplotypes that take the edge).  In a DAG a haplotype contains the node sequence n1..nk exactly when it takes
+every edge (n_i -> n_i+1), so the frequency of a walk is popcount(AND of its edge rows) -- or of the node row for
+a walk inside one node.  Rows equal to "every haplotype" are not stored (sentinel NO_CONS).
+"""
+import gzip
+
+import numpy as np
+
+NO_CONS = 0xFFFFFFFF
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _i
+    _CODE[_c + 32] = _i  # lower case
+
+
+def read_fasta(path):
+    """-> {name: str}.  Plain or gzipped FASTA."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    seqs, name, parts = {}, None, []
+    with op(path, "rt") as fh:
+        for line in fh:
+            if line.startswith(">"):
+                if name is not None:
+                    seqs[name] = "".join(parts)
+                name, parts = line[1:].split()[0], []
+            else:
+                parts.append(line.strip())
+    if name is not None:
+        seqs[name] = "".join(parts)
+    return seqs
+
+
+def reduce_allele(pos0, ref, alt):
+    """VCF REF/ALT -> (pos0, ref, alt) without the shared prefix (first) and suffix."""
+    ref, alt = ref.upper(), alt.upper()
+    k = 0
+    n = min(len(ref), len(alt))
+    while k < n and ref[k] == alt[k]:
+        k += 1
+    ref, alt, pos0 = ref[k:], alt[k:], pos0 + k
+    k = 0
+    n = min(len(ref), len(alt))
+    while k < n and ref[len(ref) - 1 - k] == alt[len(alt) - 1 - k]:
+        k += 1
+    if k:
+        ref, alt = ref[:len(ref) - k], alt[:len(alt) - k]
+    return pos0, ref, alt
+
+
+def read_vcf(path, chrom=None):
+    """Phased VCF (plain or .gz) -> (variants [(pos0, ref, alt)], gt uint8 [n_variants, n_haplotypes], samples).
+    One entry per ALT allele; symbolic / '*' alleles are skipped; a missing call counts as reference; '/' is read
+    like '|'.  Haplotype 2i, 2i+1 = the two alleles of sample i (one column for haploid calls)."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    variants, rows, samples, ploidy = [], [], [], None
+    with op(path, "rt") as fh:
+        for line in fh:
+            if line.startswith("##") or not line.strip():
+                continue
+            f = line.rstrip("\n").split("\t")
+            if line.startswith("#"):
+                samples = f[9:]
+                continue
+            if chrom is not None and f[0] != chrom:
+                continue
+            calls = []
+            for s in f[9:]:
+                g = s.split(":", 1)[0].replace("/", "|").split("|")
+                if ploidy is None:
+                    ploidy = len(g)
+                g = (g + ["0"] * ploidy)[:ploidy]
+                calls.extend(int(x) if x.isdigit() else 0 for x in g)
+            calls = np.asarray(calls, dtype=np.int32)
+            for k, alt in enumerate(f[4].split(","), start=1):
+                if alt in (".", "*") or alt.startswith("<") or "[" in alt or "]" in alt:
+                    continue
+                s, r, a = reduce_allele(int(f[1]) - 1, f[3], alt)
+                if r == a:
+                    continue
+                variants.append((s, r, a))
+                rows.append((calls == k).astype(np.uint8))
+    n_hap = len(samples) * (ploidy or 2)
+    gt = np.stack(rows) if rows else np.zeros((0, n_hap), dtype=np.uint8)
+    return variants, gt, samples
+
+
+def pack_bits(gt, words):
+    """uint8/bool [n, n_hap] -> uint32 [n, words] (haplotype h = bit h & 31 of word h >> 5)."""
+    gt = np.ascontiguousarray(gt, dtype=np.uint8)
+    n, h = gt.shape
+    out = np.zeros((n, words * 4), dtype=np.uint8)
+    if h:
+        b = np.packbits(gt, axis=1, bitorder="little")
+        out[:, :b.shape[1]] = b
+    return out.view(np.uint32)
+
+
+class VariationGraph:
+    """Flat arrays of one chromosome's graph (host side).  Node index = vg node id - 1."""
+
+    def __init__(self):
+        self.chrom = ""
+        self.length = 0
+        self.n_hap = 0
+        self.words = 0          # uint32 words per haplotype bit set (multiple of 4)
+        self.max_node_len = 32
+
+    # ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def build(chrom, ref, variants, gt=None, max_node_len=32):
+        """ref: str/bytes; variants: [(pos0, ref_allele, alt_allele)] (reduced); gt: uint8 [n_variants, n_hap] or
+        None (no haplotype index: every frequency is reported as 0, as `vg find` does without -H)."""
+        g = VariationGraph()
+        g.chrom, g.max_node_len = str(chrom), int(max_node_len)
+        refb = ref.encode("ascii") if isinstance(ref, str) else bytes(ref)
+        L = len(refb)
+        g.length = L
+        ref_codes = _CODE[np.frombuffer(refb, dtype=np.uint8)]
+        nv = len(variants)
+        vs = np.array([v[0] for v in variants], dtype=np.int64).reshape(nv)
+        vr = np.array([len(v[1]) for v in variants], dtype=np.int64).reshape(nv)
+        va = np.array([len(v[2]) for v in variants], dtype=np.int64).reshape(nv)
+        if nv and (vs.min() < 0 or (vs + vr).max() > L):
+            raise ValueError("variant outside the reference sequence")
+        order = np.argsort(vs, kind="stable")  # by start, input order within a start
+        refu = refb.upper()
+        for i in order:
+            s, r, a = variants[i]
+            if refu[s:s + len(r)] != r.upper().encode("ascii"):
+                raise ValueError(f"REF allele of variant at {s} does not match the reference sequence")
+            if r.upper() == a.upper():
+                raise ValueError(f"variant at {s} has identical alleles")
+        alt_codes = [_CODE[np.frombuffer(variants[i][2].encode("ascii"), dtype=np.uint8)] for i in range(nv)]
+        alt_off = np.concatenate([[0], np.cumsum(va)]).astype(np.int64)
+        all_codes = np.concatenate([ref_codes] + alt_codes) if nv else ref_codes
+
+        bps = np.unique(np.concatenate([[0, L], vs, vs + vr])).astype(np.int64)
+        nb = len(bps) - 1
+        # ---- items in node-id order: per breakpoint the non-empty alternative alleles, then the reference segment
+        alt_v = order[va[order] > 0]
+        it_bp = np.concatenate([np.searchsorted(bps, vs[alt_v]), np.arange(nb)])
+        it_isref = np.concatenate([np.zeros(len(alt_v), np.int64), np.ones(nb, np.int64)])
+        it_var = np.concatenate([alt_v, np.full(nb, -1)])
+        it_rank = np.concatenate([np.arange(len(alt_v)), np.arange(nb)])
+        o = np.lexsort((it_rank, it_isref, it_bp))
+        it_bp, it_isref, it_var = it_bp[o], it_isref[o], it_var[o]
+        n_items = len(o)
+        isref = it_isref == 1
+        safe_var = np.where(isref, 0, it_var)
+        it_len = np.where(isref, bps[np.minimum(it_bp + 1, nb)] - bps[it_bp], va[safe_var])
+        it_a0 = np.where(isref, bps[it_bp], vs[safe_var])
+        it_clamp = np.where(isref, -1, vs[safe_var] + vr[safe_var])
+        it_src = np.where(isref, bps[it_bp], L + alt_off[safe_var])
+        M = g.max_node_len
+        it_chunks = (it_len + M - 1) // M
+        it_first = np.concatenate([[0], np.cumsum(it_chunks)]).astype(np.int64)
+        n_nodes = int(it_first[-1])
+        nd_item = np.repeat(np.arange(n_items), it_chunks)
+        nd_k = np.arange(n_nodes) - it_first[nd_item]
+        nd_len = np.minimum(M, it_len[nd_item] - nd_k * M)
+        nd_a0 = it_a0[nd_item] + nd_k * M
+        nd_isref = isref[nd_item]
+        nd_clamp = np.where(nd_isref, nd_a0 + nd_len, it_clamp[nd_item])
+        node_off = np.concatenate([[0], np.cumsum(nd_len)]).astype(np.int64)
+        total = int(node_off[-1])
+        if total >= 2 ** 32 or n_nodes >= 2 ** 31:
+            raise ValueError("graph too large for 32-bit base offsets")
+        src0 = it_src[nd_item] + nd_k * M
+        gather = np.repeat(src0 - node_off[:-1], nd_len) + np.arange(total)
+        g.seq = np.ascontiguousarray(all_codes[gather], dtype=np.uint8)
+        g.node_off = node_off.astype(np.uint32)
+        g.node_a0 = nd_a0.astype(np.int64)
+        g.node_clamp = nd_clamp.astype(np.int64)
+        g.node_flags = nd_isref.astype(np.uint8)
+        g.node_key = np.where(nd_isref, nd_a0, it_a0[nd_item]).astype(np.int64)  # non-decreasing in the node index
+        g.n_nodes = n_nodes
+        g.max_ref_allele = int(vr.max()) if nv else 0
+
+        # first / last node of every item; items by (breakpoint, kind)
+        first_node = it_first[:-1]
+        last_node = it_first[1:] - 1
+        ref_item_of_bp = np.nonzero(isref)[0]  # one per breakpoint 0..nb-1, ascending
+        item_of_var = np.full(nv, -1, dtype=np.int64)
+        item_of_var[it_var[~isref]] = np.nonzero(~isref)[0]
+
+        # ---- haplotype bit sets
+        n_hap = 0 if gt is None else int(np.asarray(gt).shape[1])
+        g.n_hap = n_hap
+        W = max(4, ((n_hap + 31) // 32 + 3) // 4 * 4)
+        g.words = W
+        have_h = gt is not None and n_hap > 0
+        if have_h:
+            if np.asarray(gt).shape[0] != nv:
+                raise ValueError("gt must have one row per variant")
+            G = pack_bits(gt, W)
+            full = pack_bits(np.ones((1, n_hap), np.uint8), W)[0]
+        zero = np.zeros(W, dtype=np.uint32)
+        cons_rows = []
+
+        def cons_id(bits):
+            if not have_h or np.array_equal(bits, full):
+                return NO_CONS
+            cons_rows.append(bits)
+            return len(cons_rows) - 1
+
+        node_cons = np.full(n_nodes, NO_CONS, dtype=np.uint32)
+        e_src, e_dst, e_cons = [], [], []
+        # chain-internal edges: everything on a node continues to the next node of its item
+        inner = np.nonzero(nd_k > 0)[0]
+        chain_src, chain_dst = inner - 1, inner
+
+        # variants by breakpoint index
+        v_bp = np.searchsorted(bps, vs[order])
+        v_lo = np.searchsorted(v_bp, np.arange(nb + 1), side="left")
+        arrive = [None] * (nb + 1)       # bit set of haplotypes arriving at breakpoint i
+        sources = [[] for _ in range(nb + 1)]  # [(last node, bit set)] that end at breakpoint i
+        if have_h:
+            arrive[0] = full.copy()
+        item_set = [None] * n_items
+        for i in range(nb):
+            here = order[v_lo[i]:v_lo[i + 1]]
+            A = arrive[i] if have_h and arrive[i] is not None else zero
+            src = sources[i]
+            # insertions: between what ends here and what starts here
+            ins = [v for v in here if vr[v] == 0]
+            if ins:
+                left = A.copy() if have_h else zero
+                nsrc = []
+                for v in ins:
+                    it = item_of_var[v]
+                    took = (left & G[v]) if have_h else zero
+                    if have_h:
+                        left = left & ~took
+                    item_set[it] = took
+                    for u, S in src:
+                        e_src.append(u); e_dst.append(first_node[it]); e_cons.append(cons_id(S & took) if have_h else NO_CONS)
+                    nsrc.append((last_node[it], took))
+                src = [(u, (S & left) if have_h else zero) for u, S in src] + nsrc
+            # replacements and deletions that start here, then the reference segment
+            left = A.copy() if have_h else zero
+            for v in here:
+                if vr[v] == 0:
+                    continue
+                took = (left & G[v]) if have_h else zero
+                if have_h:
+                    left = left & ~took
+                j = int(np.searchsorted(bps, vs[v] + vr[v]))
+                if have_h:
+                    arrive[j] = took.copy() if arrive[j] is None else (arrive[j] | took)
+                if va[v] > 0:
+                    it = item_of_var[v]
+                    item_set[it] = took
+                    for u, S in src:
+                        e_src.append(u); e_dst.append(first_node[it]); e_cons.append(cons_id(S & took) if have_h else NO_CONS)
+                    sources[j].append((last_node[it], took))
+                else:  # deletion: whatever ended here now ends at its far side
+                    sources[j].extend((u, (S & took) if have_h else zero) for u, S in src)
+            it = ref_item_of_bp[i]
+            item_set[it] = left
+            for u, S in src:
+                e_src.append(u); e_dst.append(first_node[it]); e_cons.append(cons_id(S & left) if have_h else NO_CONS)
+            sources[i + 1].append((last_node[it], left))
+            if have_h:
+                arrive[i + 1] = left.copy() if arrive[i + 1] is None else (arrive[i + 1] | left)
+            arrive[i] = None
+            sources[i] = None
+        if have_h:
+            it_cons = np.array([cons_id(s if s is not None else zero) for s in item_set], dtype=np.uint32)
+            node_cons = it_cons[nd_item]
+        g.node_cons = node_cons.astype(np.uint32)
+        # structural edges may repeat (two deletions with the same ends): merge, OR-ing their haplotype sets
+        es = np.concatenate([np.asarray(e_src, dtype=np.int64), chain_src])
+        ed = np.concatenate([np.asarray(e_dst, dtype=np.int64), chain_dst])
+        ec = np.concatenate([np.asarray(e_cons, dtype=np.uint32), node_cons[chain_src].astype(np.uint32)])
+        o = np.lexsort((ed, es))
+        es, ed, ec = es[o], ed[o], ec[o]
+        if len(es) > 1:
+            dup = np.nonzero((es[1:] == es[:-1]) & (ed[1:] == ed[:-1]))[0] + 1
+            if len(dup):
+                for k in dup:  # rare
+                    a, b = int(ec[k - 1]), int(ec[k])
+                    if a == NO_CONS or b == NO_CONS:
+                        ec[k] = NO_CONS
+                    else:
+                        cons_rows.append(cons_rows[a] | cons_rows[b])
+                        ec[k] = cons_id(cons_rows.pop())
+                keep = np.ones(len(es), dtype=bool)
+                keep[dup - 1] = False
+                es, ed, ec = es[keep], ed[keep], ec[keep]
+        g.edge_off = np.searchsorted(es, np.arange(n_nodes + 1), side="left").astype(np.uint32)
+        g.edge_to = ed.astype(np.uint32)
+        g.edge_cons = ec.astype(np.uint32)
+        g.n_edges = len(ed)
+        g.cons_bits = (np.stack(cons_rows) if cons_rows else np.zeros((1, W), dtype=np.uint32)).astype(np.uint32)
+        g.n_cons = len(cons_rows)
+        return g
+
+    @staticmethod
+    def from_files(fasta, vcf, chrom, max_node_len=32, use_haplotypes=True):
+        seqs = read_fasta(fasta)
+        if chrom not in seqs:
+            raise KeyError(f"{chrom} is not a sequence of {fasta}")
+        variants, gt, _ = read_vcf(vcf, chrom)
+        return VariationGraph.build(chrom, seqs[chrom], variants, gt if use_haplotypes else None, max_node_len)
+
+    # ---------------------------------------------------------------------------------------------------
+    def region_nodes(self, start, stop):
+        """Node index range [lo, hi) that can hold the first base of a walk reported inside [start, stop)."""
+        span = max(self.max_node_len, self.max_ref_allele)
+        lo = int(np.searchsorted(self.node_key, start - span, side="left"))
+        hi = int(np.searchsorted(self.node_key, stop, side="left"))
+        return lo, max(lo, hi)
+
+    def to_device(self, ctx):
+        from .extract_regions import DeviceGraph
+        return DeviceGraph(ctx, self)

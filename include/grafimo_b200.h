@@ -57,6 +57,7 @@ enum {
 
 typedef struct gb2_ctx gb2_ctx;     /* one per (host thread, device): stream + scratch */
 typedef struct gb2_motif gb2_motif; /* device-resident motif: chunk LUTs, p-value table, cut-offs */
+typedef struct gb2_graph gb2_graph; /* device-resident variation graph of one chromosome (K7) */
 
 /* One hit (a scored window that passed the p-value test). 16 bytes. */
 typedef struct gb2_hit {
@@ -216,6 +217,45 @@ int gb2_scan_host(gb2_ctx *ctx, const gb2_motif *motif, const uint8_t *h_ascii, 
                   int64_t stride, int strands, double p_threshold, int q_filter, int want_q,
                   uint64_t hit_capacity, uint64_t *h_row, uint8_t *h_strand, int32_t *h_iscore,
                   double *h_score, double *h_p, double *h_q, uint64_t *h_n_hits, uint64_t *h_stats);
+
+/* ---- K7: k-mer extraction from a variation graph ---------------------------------- */
+/* Replaces the external `vg find -p REGION -x XG -H GBWT -K w -E` call the reference issues per BED region
+ * (src/grafimo/extract_regions.py:180,225,326) and the text parse that follows it (score_sequences.py:273-293).
+ * The graph is what `vg construct -r REF -v VCF` + `vg index -G` hold (constructVG.py:332,394-396), as flat host arrays
+ * (built by grafimo_b200/vgraph.py):
+ *   h_node_off[n_nodes+1]  first base of node i in h_seq (nodes are non-empty; node index = vg node id - 1)
+ *   h_seq                  base codes 0..3 = A,C,G,T, 4 = anything else
+ *   h_node_a0 / h_node_clamp   a walk that STARTS at base j of node i is reported at min(a0 + j, clamp), one that ENDS
+ *                          there at min(a0 + j + 1, clamp) (reference-path coordinates, 0-based, end exclusive)
+ *   h_node_flags           bit 0: node lies on the reference path
+ *   h_edge_off[n_nodes+1], h_edge_to[n_edges]   out-edges, CSR, targets ascending
+ *   h_node_cons / h_edge_cons   row of h_cons_bits with the haplotypes through the node / along the edge, or
+ *                          0xFFFFFFFF = every haplotype
+ *   h_cons_bits[n_cons][words]  haplotype bit sets (bit h & 31 of word h >> 5), words a multiple of 4
+ *   n_hap == 0             no haplotype index: every frequency is reported as 0 (vg find without -H)
+ * Host pointers; the arrays are copied. */
+int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, const uint8_t *h_seq,
+                     const int64_t *h_node_a0, const int64_t *h_node_clamp, const uint8_t *h_node_flags,
+                     const uint32_t *h_node_cons, int64_t n_edges, const uint32_t *h_edge_off, const uint32_t *h_edge_to,
+                     const uint32_t *h_edge_cons, int32_t n_hap, int32_t words, int64_t n_cons,
+                     const uint32_t *h_cons_bits, gb2_graph **out);
+int gb2_graph_destroy(gb2_graph *graph);
+/* Pass 1 for n_regions regions [h_start[r], h_stop[r]) at once: counts the w-base walks whose reported start and stop
+ * lie inside the region (first bases are looked for in nodes [h_node_lo[r], h_node_hi[r])) and keeps the row offsets
+ * in the graph object.  *h_n_rows = rows gb2_graph_extract will write.  Synchronises the stream.
+ * GB2_ERR_CAPACITY: more than 2^24 walks start at one base (variants too dense for this width). */
+int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *graph, int32_t n_regions, const int64_t *h_start, const int64_t *h_stop,
+                      const int64_t *h_node_lo, const int64_t *h_node_hi, int w, uint64_t *h_n_rows);
+/* Pass 2 of the prepared query (stream-ordered): rows in (region, first base, depth-first) order, forward strand only
+ * (the '-' row vg prints for a walk is its reverse complement with start/stop swapped: score with strands = 2).
+ *   d_packed uint64[cap] (16-byte aligned), d_nmask uint32[ceil(cap/32)], d_start/d_stop int64[cap], d_freq int32[cap]
+ *   (haplotypes containing the walk's node sequence), d_isref uint8[cap] (1 = every node on the reference path; the
+ *   reference rewrites it when |stop-start| != w, score_sequences.py:305-307), d_region uint32[cap] (index into the
+ *   region arrays), optional d_walk uint32[cap][32] + d_walk_len + d_walk_off (node indices of the walk, offset of the
+ *   first base) for writing vg's node-path column; d_counts[0] += rows holding a non-ACGT base. */
+int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *graph, uint64_t capacity, uint64_t *d_packed, uint32_t *d_nmask,
+                      int64_t *d_start, int64_t *d_stop, int32_t *d_freq, uint8_t *d_isref, uint32_t *d_region,
+                      uint32_t *d_walk, uint8_t *d_walk_len, uint8_t *d_walk_off, uint64_t *d_counts);
 
 #ifdef __cplusplus
 }

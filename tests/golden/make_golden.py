@@ -24,6 +24,7 @@ the GPU box, where /root/reference does not exist; tests/ reads only the bundles
 import argparse
 import glob
 import io
+import gzip
 import json
 import os
 import shutil
@@ -248,6 +249,9 @@ def main():
         expected_seqs_tsv=read_text(os.path.join(exp, "expected_seqs.tsv")),
         expected_matrix_meme=read_text(os.path.join(exp, "motif_processing_test_meme.txt")),
         expected_matrix_jaspar=read_text(os.path.join(exp, "motif_processing_test_jaspar.txt")),
+        # inputs of the reference's vg tests (tests/grafimo_run_test.py:15-63): the graph expected_seqs.tsv came from
+        test_fa=read_text(os.path.join(inp, "test.fa")),
+        test_vcf=gzip.open(os.path.join(inp, "test.vcf.gz"), "rt").read(),
     )
     rng = np.random.default_rng(20242)
     synth = {}

@@ -1,0 +1,147 @@
+"""GPU tests of K7 (csrc/graph.cu): k-mer extraction from the variation graph against oracle/graph_oracle.py and the
+reference's vg fixture, and the text-free path graph -> K7 -> K2/K5/K6 against the TSV path on the same rows."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import graph_util as gr
+from oracle import graph_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from grafimo_b200.engine import Context
+    return Context(0)
+
+
+def _rows_as_tuples(rows, width):
+    from grafimo_b200.extract_regions import decode_kmers
+    h = rows.host()
+    asc = decode_kmers(h["packed"], width)
+    n = rows.n
+    bad = (h["nmask"].view(np.uint32)[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1 if n else np.zeros(0)
+    out = []
+    for i in range(n):
+        seq = asc[i].tobytes().decode()
+        nodes = tuple(int(x) + 1 for x in h["walk"][i, :h["walk_len"][i]])
+        out.append((int(h["region"][i]), int(h["start"][i]), int(h["stop"][i]), seq, int(h["freq"][i]), bool(h["isref"][i]),
+                    nodes, bool(bad[i])))
+    return out
+
+
+def test_extract_equals_reference_vg_fixture(ctx):
+    """test.fa + test.vcf.gz, region x:0-20, K=19 -> the 32 lines of expected_seqs.tsv, node paths included."""
+    from grafimo_b200.vgraph import VariationGraph
+    fx = gu.fixtures()
+    ref = "".join(fx["test_fa"].split("\n")[1:])
+    variants, _ = go.parse_vcf_text(fx["test_vcf"], "x")
+    dg = VariationGraph.build("x", ref, variants, None).to_device(ctx)
+    rows = dg.extract([(0, 20)], 19, want_walks=True)
+    lines = rows.to_vg_tsv()[0]
+    exp = [ln for ln in fx["expected_seqs_tsv"].split("\n") if ln]
+    assert sorted(lines) == sorted(exp)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_extract_equals_oracle_random_graphs(ctx, seed):
+    from grafimo_b200.vgraph import VariationGraph
+    ref, vs, gt = gr.random_case(200 + seed, length=600, n_var=60, n_hap=70 if seed % 2 else 12,
+                                 n_frac=0.01 if seed % 3 == 0 else 0.0)
+    m = 8 if seed % 2 else 32
+    dg = VariationGraph.build("c", ref, vs, gt, max_node_len=m).to_device(ctx)
+    regions = [(0, 600), (37, 301), (100, 250), (590, 600), (250, 250)]
+    for w in (5, 19, 32):
+        rows = dg.extract(regions, w, want_walks=True)
+        got = _rows_as_tuples(rows, w)
+        exp = []
+        for r, region in enumerate(regions):
+            for (start, stop, seq, freq, isref, nodes) in gr.oracle_rows(ref, vs, gt, region, w, max_node=m):
+                exp.append((r, start, stop, seq.replace("N", "A"), freq, isref, nodes, "N" in seq))
+        assert sorted(got) == sorted(exp)
+        assert [g[0] for g in got] == sorted(g[0] for g in got)  # rows are grouped by region, in order
+        assert rows.n_masked() == sum(e[7] for e in exp)
+        # the text form spells the N rows from their walks
+        if w == 19:
+            text = sorted(ln for lines in rows.to_vg_tsv().values() for ln in lines)
+            og = go.build_graph(ref, vs, max_node=m)
+            want = sorted(ln for region in regions if region[0] < region[1] for ln in
+                          go.vg_tsv_lines(go.extract_rows(og, gt.tolist(), region, w), "c", region))
+            assert text == want
+
+
+def test_extract_without_haplotypes_and_errors(ctx):
+    from grafimo_b200._lib import GrafimoB200Error
+    from grafimo_b200.vgraph import VariationGraph
+    ref, vs, gt = gr.random_case(7, length=300, n_var=20)
+    dg = VariationGraph.build("c", ref, vs, None).to_device(ctx)
+    rows = dg.extract([(0, 300)], 11)
+    assert rows.n > 0 and int(rows.freq[:rows.n].max().item()) == 0
+    empty = dg.extract([], 11)
+    assert empty.n == 0
+    with pytest.raises(ValueError):
+        dg.extract([(0, 10)], 33)
+    with pytest.raises(GrafimoB200Error):
+        dg.extract([(10, 0)], 11)
+
+
+def _motif(tmp_path):
+    from grafimo_b200 import motif_ops as mo
+    p = tmp_path / "ctcf.meme"
+    p.write_text(gu.fixtures()["ctcf_meme"])
+    return mo.build_motif_meme(str(p), "unfrm_dst", 0.1, False, 1, False, True)[0]
+
+
+class _Args:
+    def __init__(self, threshold=1.0, noqvalue=False, qvalueT=False, noreverse=False, recomb=True):
+        self.cores, self.threshold, self.noqvalue, self.qvalueT = 1, float(threshold), noqvalue, qvalueT
+        self.noreverse, self.recomb, self.verbose = noreverse, recomb, False
+
+
+@pytest.mark.parametrize("opts", [dict(threshold=1.0), dict(threshold=0.05, recomb=False), dict(threshold=0.2, noreverse=True),
+                                  dict(threshold=0.5, qvalueT=True), dict(threshold=0.01, noqvalue=True)])
+def test_graph_to_table_equals_tsv_path_and_oracle(ctx, tmp_path, opts, capsys):
+    """graph -> K7 -> K2/K5/K6 (no text) == compute_results on the vg-format TSVs of the same regions == the oracle's
+    scoring of those TSV rows (score, p, q bit-exact)."""
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.vgraph import VariationGraph
+    from oracle import oracle as orc
+    ss._ctx = ctx
+    motif = _motif(tmp_path)
+    ref, vs, gt = gr.random_case(321, length=3000, n_var=150, n_hap=40, n_frac=0.002)
+    dg = VariationGraph.build("7", ref, vs, gt).to_device(ctx)
+    regions = [(0, 1200), (1100, 3000)]
+    rows = dg.extract(regions, 19, want_walks=True)
+    args = _Args(**opts)
+    df = ss.compute_results_rows(motif, rows, True, args)
+    d = tmp_path / "seqs" / "width_19"
+    d.mkdir(parents=True)
+    lines_all = []
+    for r, lines in rows.to_vg_tsv().items():
+        (d / f"r{r}.tsv").write_text("\n".join(lines) + "\n")
+        lines_all += lines
+    df2 = ss.compute_results(motif, str(tmp_path / "seqs"), True, args)
+    assert list(df.columns) == list(df2.columns)
+    gu.assert_tables_equal({c: df[c].to_numpy() for c in df.columns}, {c: df2[c].to_numpy() for c in df2.columns}, list(df.columns))
+    out = capsys.readouterr().out
+    n = rows.n * (1 if args.noreverse else 2)
+    assert out.count(f"Scanned sequences:\t{n}") == 2
+    # the oracle on the TSV rows
+    f = [ln.split("\t") for ln in lines_all if not (args.noreverse and ln.split("\t")[2][-1] == "-")]
+    a = orc.kmers_to_matrix([x[1] for x in f], 19)
+    _, lo, p = orc.score_rows(a, motif.score_matrix_acgt(), motif.pval_matrix, motif.min_val, motif.scale, float(motif.offset))
+    q = orc.bh(p)
+    start = np.array([int(x[2].split(":")[1][:-1]) for x in f]); stop = np.array([int(x[3].split(":")[1][:-1]) for x in f])
+    freq = np.array([int(x[4]) for x in f])
+    keep = (q < args.threshold) if args.qvalueT else (p < args.threshold)
+    if not args.recomb:
+        keep &= freq > 0
+    exp = {"start": start[keep], "stop": stop[keep], "strand": np.array([x[2][-1] for x in f], dtype=object)[keep],
+           "score": lo[keep], "p-value": p[keep], "q-value": q[keep],
+           "matched_sequence": np.array([x[1] for x in f], dtype=object)[keep], "haplotype_frequency": freq[keep],
+           "reference": np.array(["ref" if (x[5] == "ref" and abs(int(b) - int(a_)) == 19) else "non.ref"
+                                  for x, a_, b in zip(f, start, stop)], dtype=object)[keep]}
+    cols = [c for c in df.columns if c in exp and not (c == "q-value" and args.noqvalue)]
+    gu.assert_tables_equal({c: df[c].to_numpy() for c in df.columns}, exp, cols)
+    assert len(df) > 0

