@@ -68,6 +68,7 @@ struct gb2_graph {
     GraphView v{};
     void *blocks[16] = {nullptr};
     int n_blocks = 0;
+    std::vector<uint32_t> h_node_off;  // host copy: threads per region without a device round trip
     // prepared query
     bool q_valid = false;
     QueryView q{};
@@ -303,6 +304,7 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
         gb2_graph_destroy(g);
         return rc;
     }
+    g->h_node_off.assign(h_node_off, h_node_off + n_nodes + 1);
     g->v.n_nodes = n_nodes;
     g->v.n_hap = n_hap;
     g->v.words = words;
@@ -325,20 +327,14 @@ extern "C" int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *g, int32_t n_regions, 
     GB2_REQUIRE(ctx, w >= 1 && w <= GB2_MAX_WIDTH, "gb2_graph_prepare: width %d outside [1,%d]", w, GB2_MAX_WIDTH);
     GB2_REQUIRE(ctx, n_regions >= 0 && (n_regions == 0 || (h_start && h_stop && h_node_lo && h_node_hi)), "gb2_graph_prepare: null region array");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    // threads per region = bases of its candidate first nodes (host copy of node_off is not kept: read the two ends)
+    // threads per region = bases of its candidate first nodes
     std::vector<unsigned long long> tprefix((size_t)n_regions + 1, 0ull);
-    std::vector<uint32_t> ends((size_t)n_regions * 2);
     for (int r = 0; r < n_regions; ++r) {
         GB2_REQUIRE(ctx, h_node_lo[r] >= 0 && h_node_lo[r] <= h_node_hi[r] && h_node_hi[r] <= g->v.n_nodes,
                     "gb2_graph_prepare: node range of region %d out of bounds", r);
         GB2_REQUIRE(ctx, h_start[r] <= h_stop[r], "gb2_graph_prepare: region %d has start > stop", r);
+        tprefix[(size_t)r + 1] = tprefix[(size_t)r] + (g->h_node_off[(size_t)h_node_hi[r]] - g->h_node_off[(size_t)h_node_lo[r]]);
     }
-    for (int r = 0; r < n_regions; ++r) {
-        GB2_CUDA(ctx, cudaMemcpyAsync(&ends[2 * (size_t)r], g->v.node_off + h_node_lo[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
-        GB2_CUDA(ctx, cudaMemcpyAsync(&ends[2 * (size_t)r + 1], g->v.node_off + h_node_hi[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int r = 0; r < n_regions; ++r) tprefix[(size_t)r + 1] = tprefix[(size_t)r] + (ends[2 * (size_t)r + 1] - ends[2 * (size_t)r]);
     const int64_t T = (int64_t)tprefix[(size_t)n_regions];
     g->q_threads = T;
     g->q_total = 0;

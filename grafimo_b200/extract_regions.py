@@ -94,8 +94,7 @@ class DeviceGraph:
             raise ValueError(f"motif width {width} outside [1, {MAX_WIDTH}]")
         rs = np.array([int(r[0]) for r in regions], dtype=np.int64)
         re = np.array([int(r[1]) for r in regions], dtype=np.int64)
-        lohi = np.array([g.region_nodes(a, b) for a, b in zip(rs, re)], dtype=np.int64).reshape(len(rs), 2)
-        nlo, nhi = np.ascontiguousarray(lohi[:, 0]), np.ascontiguousarray(lohi[:, 1])
+        nlo, nhi = g.region_nodes(rs, re)
         n_rows = ctypes.c_uint64(0)
         ctx.enter()
         check(ctx.lib.gb2_graph_prepare(ctx.h, self.h, len(rs), _np_ptr(rs), _np_ptr(re), _np_ptr(nlo), _np_ptr(nhi), width,

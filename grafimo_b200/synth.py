@@ -118,3 +118,38 @@ def synthetic_meme_collection(n_motifs=800, seed=20242, wmin=6, wmax=30, alpha=0
         lines.append("URL none")
         lines.append("")
     return "\n".join(lines), widths
+
+
+def variant_set(region_len, n_hap, seed, density=1.0 / 40.0, indel_frac=0.1, max_indel=5):
+    """Seeded phased variant set of the C2 shape for the graph path (vgraph.VariationGraph.build): a random reference,
+    variant sites at `density`, `indel_frac` of them insertions/deletions of 1..max_indel bp, allele frequency ~ 1/x
+    on [1/n_hap, 0.5], every haplotype carrying each variant with probability af.
+    -> (reference str, [(pos0, ref_allele, alt_allele)], uint8 [n_variants, n_hap])."""
+    rng = np.random.default_rng(int(seed))
+    codes = rng.integers(0, 4, size=region_len, dtype=np.uint8)
+    ref = _ASCII[codes].tobytes().decode("ascii")
+    n_var = max(1, int(region_len * density))
+    pos = np.sort(rng.choice(np.arange(1, region_len - max_indel - 1), size=n_var, replace=False))
+    kind = rng.random(n_var)
+    length = rng.integers(1, max_indel + 1, size=n_var)
+    alt_shift = rng.integers(1, 4, size=n_var)
+    ins = rng.integers(0, 4, size=(n_var, max_indel), dtype=np.uint8)
+    variants, last_end = [], 0
+    keep = np.zeros(n_var, dtype=bool)
+    for i in range(n_var):
+        p = int(pos[i])
+        if p < last_end:  # keep the set free of overlapping alleles
+            continue
+        if kind[i] >= indel_frac:
+            r, a = ref[p], "ACGT"[(codes[p] + alt_shift[i]) % 4]
+        elif kind[i] < indel_frac / 2:
+            r, a = "", _ASCII[ins[i, :length[i]]].tobytes().decode("ascii")
+        else:
+            r, a = ref[p:p + int(length[i])], ""
+        variants.append((p, r, a))
+        keep[i] = True
+        last_end = p + max(len(r), 1)
+    lo, hi = 1.0 / n_hap, 0.5
+    af = lo * (hi / lo) ** rng.random(len(variants))
+    gt = (rng.random((len(variants), n_hap), dtype=np.float32) < af[:, None].astype(np.float32)).astype(np.uint8)
+    return ref, variants, gt

@@ -221,11 +221,17 @@ class VariationGraph:
         zero = np.zeros(W, dtype=np.uint32)
         cons_rows = []
 
+        cons_index = {}  # identical sets share a row (an allele's node and the edges into it, ...)
+
         def cons_id(bits):
             if not have_h or np.array_equal(bits, full):
                 return NO_CONS
-            cons_rows.append(bits)
-            return len(cons_rows) - 1
+            key = bits.tobytes()
+            k = cons_index.get(key)
+            if k is None:
+                k = cons_index[key] = len(cons_rows)
+                cons_rows.append(bits)
+            return k
 
         node_cons = np.full(n_nodes, NO_CONS, dtype=np.uint32)
         e_src, e_dst, e_cons = [], [], []
@@ -306,8 +312,7 @@ class VariationGraph:
                     if a == NO_CONS or b == NO_CONS:
                         ec[k] = NO_CONS
                     else:
-                        cons_rows.append(cons_rows[a] | cons_rows[b])
-                        ec[k] = cons_id(cons_rows.pop())
+                        ec[k] = cons_id(cons_rows[a] | cons_rows[b])
                 keep = np.ones(len(es), dtype=bool)
                 keep[dup - 1] = False
                 es, ed, ec = es[keep], ed[keep], ec[keep]
@@ -329,11 +334,15 @@ class VariationGraph:
 
     # ---------------------------------------------------------------------------------------------------
     def region_nodes(self, start, stop):
-        """Node index range [lo, hi) that can hold the first base of a walk reported inside [start, stop)."""
+        """Node index range [lo, hi) that can hold the first base of a walk reported inside [start, stop); scalars
+        or arrays."""
         span = max(self.max_node_len, self.max_ref_allele)
-        lo = int(np.searchsorted(self.node_key, start - span, side="left"))
-        hi = int(np.searchsorted(self.node_key, stop, side="left"))
-        return lo, max(lo, hi)
+        start, stop = np.asarray(start, dtype=np.int64), np.asarray(stop, dtype=np.int64)
+        lo = np.searchsorted(self.node_key, start - span, side="left").astype(np.int64)
+        hi = np.maximum(lo, np.searchsorted(self.node_key, stop, side="left").astype(np.int64))
+        if lo.ndim == 0:
+            return int(lo), int(hi)
+        return np.ascontiguousarray(lo), np.ascontiguousarray(hi)
 
     def to_device(self, ctx):
         from .extract_regions import DeviceGraph

@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""K7 benchmark: k-mer extraction from a synthetic variation graph (C2 parity form: 1 Mb region, 2,504 haplotypes,
+1000G-like SNP/indel density) and the text-free path graph -> K7 -> K2/K5/K6 -> report table.
+
+    python tools/bench_graph.py [--region-len 1000000] [--haplotypes 2504] [--width 19] [--reps 5]
+
+Prints one JSON line.  Timings are wall clock around stream-synchronised calls (gb2_graph_prepare synchronises itself).
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--region-len", type=int, default=1_000_000)
+    ap.add_argument("--haplotypes", type=int, default=2504)
+    ap.add_argument("--width", type=int, default=19)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--regions", type=int, default=1, help="split the region into this many BED-like regions")
+    ap.add_argument("--indel-frac", type=float, default=0.1)
+    ap.add_argument("--density", type=float, default=1.0 / 40.0)
+    a = ap.parse_args()
+    import torch
+    from grafimo_b200 import engine, synth
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.motif_ops import build_motif_meme
+    from grafimo_b200.vgraph import VariationGraph
+
+    ctx = engine.Context(0)
+    ss._ctx = ctx
+    t = time.perf_counter()
+    ref, variants, gt = synth.variant_set(a.region_len, a.haplotypes, 20240, density=a.density, indel_frac=a.indel_frac)
+    t_gen = time.perf_counter() - t
+    t = time.perf_counter()
+    g = VariationGraph.build("1", ref, variants, gt)
+    t_build = time.perf_counter() - t
+    t = time.perf_counter()
+    dg = g.to_device(ctx)
+    ctx.sync()
+    t_upload = time.perf_counter() - t
+    L = a.region_len
+    step = (L + a.regions - 1) // a.regions
+    regions = [(lo, min(L, lo + step + a.width - 1)) for lo in range(0, L, step)]
+    rows = dg.extract(regions, a.width)  # warm-up
+    ctx.sync()
+    tp, te = [], []
+    lib = ctx.lib
+    for _ in range(a.reps):
+        t0 = time.perf_counter()
+        rows = dg.extract(regions, a.width)
+        ctx.sync()
+        te.append(time.perf_counter() - t0)
+    n = rows.n
+    # invariant: the frequencies of the walks that share a first base add up to the haplotypes through that base
+    rw = dg.extract(regions[:1], a.width, want_walks=True)
+    with torch.cuda.stream(ctx.stream):
+        first = rw.walk.view(-1, 32)[:rw.n, 0].to(torch.int64) * 64 + rw.walk_off[:rw.n].to(torch.int64)
+        uniq, inv = torch.unique_consecutive(first, return_inverse=True)
+        sums = torch.zeros(uniq.shape[0], dtype=torch.int64, device=ctx.device).index_add_(0, inv, rw.freq[:rw.n].to(torch.int64))
+        node = (uniq // 64).cpu().numpy()
+        sums = sums.cpu().numpy()
+    ctx.sync()
+    through = np.array([a.haplotypes if c == 0xFFFFFFFF else int(np.unpackbits(g.cons_bits[c].view(np.uint8)).sum())
+                        for c in g.node_cons[node]])
+    # walks that run off the end of the chromosome do not exist: skip first bases in the last w positions
+    inner = g.node_a0[node] < regions[0][1] - 64
+    invariant_ok = bool(np.array_equal(sums[inner], through[inner]))
+
+    tmp = tempfile.mkdtemp(prefix="gb2_graph_")
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
+    mp = os.path.join(tmp, "ctcf.meme")
+    open(mp, "w").write(fx["ctcf_meme"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        motif = build_motif_meme(mp, "unfrm_dst", 0.1, False, 1, False, True)[0]
+
+    class Args:
+        cores, threshold, noqvalue, qvalueT, noreverse, recomb, verbose = 1, 1e-4, False, False, False, False, False
+    tt = []
+    for _ in range(max(2, a.reps // 2 + 1)):
+        t0 = time.perf_counter()
+        r2 = dg.extract(regions, a.width)
+        with contextlib.redirect_stdout(io.StringIO()):
+            df = ss.compute_results_rows(motif, r2, True, Args) if a.width == 19 else None
+        tt.append(time.perf_counter() - t0)
+    out = {
+        "workload": f"synthetic {L} bp region, {a.haplotypes} haplotypes, {len(variants)} variants "
+                    f"({a.indel_frac:.0%} indels), width {a.width}, {len(regions)} region(s)",
+        "graph": {"nodes": g.n_nodes, "edges": g.n_edges, "haplotype_set_rows": g.n_cons,
+                  "haplotype_set_mb": g.cons_bits.nbytes / 1e6, "gen_s": t_gen, "build_host_s": t_build, "upload_s": t_upload},
+        "kmer_rows": n, "rows_with_freq0": int((rows.freq[:n] == 0).sum().item()),
+        "extract_ms_best": min(te) * 1e3, "extract_ms_median": float(np.median(te)) * 1e3,
+        "rows_per_s": n / min(te), "scored_windows_equiv_per_s": 2 * n / min(te),
+        "freq_sum_invariant_ok": invariant_ok,
+        "graph_to_table_s_best": min(tt), "hits": None if df is None else int(len(df)),
+        "launches_total": ctx.launches,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
