@@ -4,14 +4,16 @@ Keeps the findmotif flags that drive the path in the reference (src/grafimo/__ma
 -k/--bgfile, -p/--pseudo, -t/--threshold, -q/--no-qvalue, -r/--no-reverse, -f/--text-only, --recomb, --qvalueT,
 -o/--out, -j/--cores, --verbose, --debug.  The variation-graph arguments (-g/-d/-b, `vg` subprocesses) are
 replaced by --kmers-dir: the directory `scan_graph` would have produced (`width_<w>/*.tsv` from
-`vg find -K w -E`), because this implementation drops in after k-mer extraction.
+`vg find -K w -E`), because this implementation drops in after k-mer extraction -- or by -l/-v/-b (the inputs of
+`grafimo buildvg` plus the BED file): then the graph is built here and its k-mers are extracted and scored on the GPU
+without `vg` and without any text in between.
 """
 import argparse
 import sys
 
 from .motif_ops import get_motif_pwm
 from .res_writer import print_results, write_results
-from .score_sequences import compute_results
+from .score_sequences import compute_results, compute_results_rows
 from .utils import DEFAULT_OUTDIR, UNIF
 from .workflow import Findmotif
 
@@ -21,7 +23,13 @@ def get_parser():
     sub = p.add_subparsers(dest="workflow")
     f = sub.add_parser("findmotif", help="scan pre-extracted variation-graph k-mers for motif occurrences")
     f.add_argument("-m", "--motif", nargs="+", required=True, metavar="MOTIF-FILE")
-    f.add_argument("--kmers-dir", required=True, metavar="DIR", help="directory holding width_<w>/*.tsv k-mer files")
+    f.add_argument("--kmers-dir", default="", metavar="DIR", help="directory holding width_<w>/*.tsv k-mer files")
+    f.add_argument("-l", "--linear-genome", default="", metavar="REFERENCE-FASTA", dest="linear_genome",
+                   help="reference genome: with -v and -b the variation graph is built and scanned on the GPU")
+    f.add_argument("-v", "--vcf", default="", metavar="VCF", help="phased variants (VCF or VCF.gz)")
+    f.add_argument("-b", "--bedfile", default="", metavar="BEDFILE", help="regions to scan (UCSC BED)")
+    f.add_argument("--chroms-prefix-find", default="", dest="chroms_prefix", metavar="PREFIX",
+                   help="prefix of the sequence names in the FASTA/VCF (e.g. chr)")
     f.add_argument("-k", "--bgfile", default=UNIF)
     f.add_argument("-p", "--pseudo", type=float, default=0.1)
     f.add_argument("-t", "--threshold", type=float, default=1e-4)
@@ -42,12 +50,42 @@ def findmotif(wf: Findmotif, debug: bool) -> None:
     motifs = []
     for mf in wf.motif:
         motifs += get_motif_pwm(mf, wf, wf.cores, debug)
+    graphs = load_graphs(wf, debug) if wf.has_graph_inputs() else None
     for motif in motifs:
-        res = compute_results(motif, wf.kmers_dir, debug, wf)
+        if graphs is not None:  # scan_graph + compute_results without the text in between
+            rows = [dg.extract(spans, motif.width) for dg, spans in graphs]
+            res = compute_results_rows(motif, rows, debug, wf)
+        else:
+            res = compute_results(motif, wf.kmers_dir, debug, wf)
         if wf.text_only:
             print_results(res, debug)
         else:
             write_results(res, motif, len(motifs), wf, debug)
+
+
+def load_graphs(wf: Findmotif, debug: bool):
+    """One device-resident graph per BED chromosome (what `grafimo buildvg` + scan_graph set up with vg,
+    src/grafimo/grafimo.py:32-78, extract_regions.py:55-237).  Regions are named like the reference names them:
+    `<chromosome without prefix>:<start>-<stop>` (extract_regions.py:164-170)."""
+    from . import score_sequences as ss
+    from .extract_regions import get_regions_bed
+    from .utils import exception_handler
+    from .vgraph import VariationGraph, read_fasta, read_vcf
+    regions, n = get_regions_bed(wf.bedfile, debug)
+    if n == 0:
+        exception_handler(ValueError, f"No region found in {wf.bedfile}.\n", debug)
+    seqs = read_fasta(wf.linear_genome)
+    ctx = ss._context()
+    out = []
+    for chrom, spans in regions.items():
+        key = chrom[3:] if chrom.startswith("chr") else chrom
+        name = wf.chroms_prefix + key
+        if name not in seqs:
+            exception_handler(KeyError, f"{name} is not a sequence of {wf.linear_genome}. Consider --chroms-prefix-find.\n", debug)
+        variants, gt, _ = read_vcf(wf.vcf, name) if wf.vcf else ([], None, [])
+        g = VariationGraph.build(key, seqs[name], variants, gt if wf.vcf else None)
+        out.append((g.to_device(ctx), [(int(a), int(b)) for a, b in spans]))
+    return out
 
 
 def main(argv=None):
@@ -58,7 +96,10 @@ def main(argv=None):
     wf = Findmotif(motif=args.motif, kmers_dir=args.kmers_dir, bgfile=args.bgfile, pseudo=args.pseudo,
                    threshold=args.threshold, out=args.out, cores=args.cores, recomb=args.recomb,
                    no_qvalue=args.no_qvalue, no_reverse=args.no_reverse, text_only=args.text_only, qval_t=args.qval_t,
-                   verbose=args.verbose)
+                   verbose=args.verbose, linear_genome=args.linear_genome, vcf=args.vcf, bedfile=args.bedfile,
+                   chroms_prefix=args.chroms_prefix)
+    if not wf.kmers_dir and not wf.has_graph_inputs():
+        get_parser().error("give --kmers-dir, or -l/--linear-genome with -b/--bedfile (and -v/--vcf)")
     findmotif(wf, args.debug)
     return 0
 

@@ -10,7 +10,8 @@
 //                      depth-first and counts its w-base walks that lie inside the region; exclusive scan -> row
 //                      offsets and the total (returned to the host so that it can size the outputs);
 //   gb2_graph_extract  pass 2: the same traversal writes the rows at those offsets: packed k-mer, N flag, start,
-//                      stop, haplotype frequency, ref flag, region index (optionally the node walk).
+//                      stop, ref flag, region index (optionally the node walk) and the walk's haplotype-set ids;
+//                      pass 3: eight lanes per row AND those sets and count the haplotypes (coalesced 16-byte loads).
 //
 // Haplotype frequency of a walk = popcount(AND of the haplotype bit sets of its edges) -- in a DAG a haplotype
 // contains the node sequence n1..nk exactly when it takes every edge n_i -> n_i+1 -- which is what
@@ -25,11 +26,16 @@
 #define GB2_NO_CONS 0xFFFFFFFFu
 #define WALK_THREADS 128
 #define WALK_LIMIT (1u << 24)  // walks from one first base; beyond this the region is reported as too dense
+#define FREQ_MAX_CONS 8        // walks with more haplotype sets than this are counted by their own thread (rare)
+#define FREQ_GROUP 8           // lanes that share one row in the frequency pass
 
 struct GraphView {
     int64_t n_nodes;
     const uint32_t *node_off;   // [n_nodes+1] first base of the node in seq
+    const uint32_t *blk_node;   // [ceil(n_bases/32)] node holding base 32*i: base -> node without a binary search
     const uint8_t *seq;         // base codes 0..3, 4 = anything else
+    const uint2 *node_bits;     // per node: its bases 2-bit packed (x = bases 0..15, y = 16..31), or nullptr when a node
+    const uint32_t *node_nbits; //           is longer than 32 bases; node_nbits: bit j = base j is not ACGT
     const int64_t *node_a0;     // reference coordinate of base 0 (before clamping)
     const int64_t *node_clamp;  // coordinates are clamped to this (end of the allele's reference span)
     const uint8_t *node_flags;  // bit 0: on the reference path
@@ -61,6 +67,8 @@ struct RowsOut {
     uint8_t *walk_off;   // offset of the first base in the first node
     unsigned long long capacity;
     unsigned long long *counts;  // [0] += rows with a non-ACGT base
+    uint32_t *cons8;     // scratch [capacity][FREQ_MAX_CONS]: haplotype-set rows of the walk, for the frequency pass
+    uint8_t *ncons;      // scratch [capacity]: how many (0 = frequency already final)
 };
 
 struct gb2_graph {
@@ -78,6 +86,9 @@ struct gb2_graph {
     uint32_t *d_counts = nullptr;      // per thread
     unsigned long long *d_offsets = nullptr;
     int64_t q_cap_threads = 0;
+    uint32_t *d_cons8 = nullptr;       // frequency-pass scratch, per row
+    uint8_t *d_ncons = nullptr;
+    unsigned long long q_cap_rows = 0;
     uint32_t *d_flag = nullptr;        // [0] != 0: a first base exceeded WALK_LIMIT
 };
 
@@ -118,9 +129,10 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
     const int64_t t = (int64_t)blockIdx.x * WALK_THREADS + threadIdx.x;
     if (t >= n_threads) return;
     const int r = (int)upper_bound_dev<unsigned long long>(q.tprefix, 0, (int64_t)q.n_regions + 1, (unsigned long long)t) - 1;
-    const int64_t nlo = q.node_lo[r], nhi = q.node_hi[r];
+    const int64_t nlo = q.node_lo[r];
     const uint32_t gbase = g.node_off[nlo] + (uint32_t)((unsigned long long)t - q.tprefix[r]);
-    const int64_t node0 = upper_bound_dev<uint32_t>(g.node_off, nlo, nhi + 1, gbase) - 1;
+    int64_t node0 = g.blk_node[gbase >> 5];  // node of the 32-base block's first base, then a short scan forward
+    while (g.node_off[node0 + 1] <= gbase) ++node0;
     const int off0 = (int)(gbase - g.node_off[node0]);
     const int64_t rs = q.rs[r], re = q.re[r];
     const int w = q.w;
@@ -148,10 +160,21 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                 const int len = (int)(g.node_off[n + 1] - b0);
                 const int take = min(len - o, w - have);
                 if (WRITE) {
-                    for (int k = 0; k < take; ++k) {
-                        const uint32_t c = g.seq[b0 + o + k];
-                        if (c < 4u) packed |= (unsigned long long)c << (2 * (have + k));
-                        else nbits |= 1u << (have + k);
+                    if (g.node_bits != nullptr) {  // one 8-byte load: the node's bases, shifted into place
+                        const uint2 nb = __ldg(g.node_bits + n);
+                        unsigned long long bits = ((unsigned long long)nb.y << 32) | nb.x;
+                        bits >>= 2 * o;
+                        if (take < 32) bits &= (1ull << (2 * take)) - 1ull;
+                        packed |= bits << (2 * have);
+                        uint32_t bad = __ldg(g.node_nbits + n) >> o;
+                        if (take < 32) bad &= (1u << take) - 1u;
+                        nbits |= bad << have;
+                    } else {
+                        for (int k = 0; k < take; ++k) {
+                            const uint32_t c = g.seq[b0 + o + k];
+                            if (c < 4u) packed |= (unsigned long long)c << (2 * (have + k));
+                            else nbits |= 1u << (have + k);
+                        }
                     }
                 }
                 if (g.node_flags[n] & 1u) nonref &= ~(1u << depth); else nonref |= 1u << depth;
@@ -178,7 +201,13 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                             out.packed[row] = packed;
                             out.start[row] = start;
                             out.stop[row] = stop;
-                            out.freq[row] = walk_frequency(g, cons, nc);
+                            if (nc == 0 || nc > FREQ_MAX_CONS || g.n_hap == 0) {
+                                out.freq[row] = walk_frequency(g, cons, nc);
+                                out.ncons[row] = 0;
+                            } else {  // counted by gb2_graph_freq_kernel, FREQ_GROUP lanes per row, coalesced
+                                for (int c = 0; c < nc; ++c) out.cons8[row * FREQ_MAX_CONS + c] = cons[c];
+                                out.ncons[row] = (uint8_t)nc;
+                            }
                             out.isref[row] = (nonref & ((2u << depth) - 1u)) == 0 ? 1 : 0;
                             out.region[row] = (uint32_t)r;
                             if (nbits) {
@@ -227,6 +256,41 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
     if (!WRITE) counts[t] = n_found;
 }
 
+// Frequency pass: FREQ_GROUP lanes per row AND the row's haplotype sets 16 bytes at a time (neighbouring lanes read
+// neighbouring 16-byte pieces of the same set) and add up the population counts.
+__global__ void __launch_bounds__(256) gb2_graph_freq_kernel(const GraphView g, unsigned long long n_rows,
+                                                             const uint32_t *__restrict__ cons8,
+                                                             const uint8_t *__restrict__ ncons, int32_t *__restrict__ freq)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    const unsigned long long row = t / FREQ_GROUP;
+    const int sub = (int)(t % FREQ_GROUP);
+    int nc = 0;
+    if (row < n_rows) nc = ncons[row];
+    int32_t total = 0;
+    if (nc) {
+        uint32_t ids[FREQ_MAX_CONS];
+#pragma unroll
+        for (int c = 0; c < FREQ_MAX_CONS; ++c) ids[c] = c < nc ? cons8[row * FREQ_MAX_CONS + c] : 0u;
+        const int nq = g.words >> 2;
+        for (int q = sub; q < nq; q += FREQ_GROUP) {
+            uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[0] * g.words) + q);
+#pragma unroll
+            for (int c = 1; c < FREQ_MAX_CONS; ++c) {
+                if (c < nc) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[c] * g.words) + q);
+                    acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
+                }
+            }
+            total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
+        }
+    }
+    // the FREQ_GROUP lanes of a row are neighbours inside one warp
+#pragma unroll
+    for (int d = FREQ_GROUP / 2; d >= 1; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
+    if (nc && sub == 0) freq[row] = total;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 static int upload(gb2_ctx *ctx, gb2_graph *g, const T *h, size_t n, const T **d_out)
@@ -250,6 +314,8 @@ extern "C" int gb2_graph_destroy(gb2_graph *g)
     if (g->d_counts) cudaFree(g->d_counts);
     if (g->d_offsets) cudaFree(g->d_offsets);
     if (g->d_flag) cudaFree(g->d_flag);
+    if (g->d_cons8) cudaFree(g->d_cons8);
+    if (g->d_ncons) cudaFree(g->d_ncons);
     delete g;
     return GB2_OK;
 }
@@ -288,6 +354,38 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
     do {
         if ((rc = upload(ctx, g, h_node_off, (size_t)n_nodes + 1, &g->v.node_off)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_seq, n_bases, &g->v.seq)) != GB2_OK) break;
+        {   // nodes of at most 32 bases (vg's default): their bases as one 64-bit word each
+            bool fits = true;
+            for (int64_t i = 0; i < n_nodes && fits; ++i) fits = h_node_off[i + 1] - h_node_off[i] <= 32u;
+            if (fits) {
+                std::vector<uint2> nb((size_t)n_nodes);
+                std::vector<uint32_t> bad((size_t)n_nodes);
+                for (int64_t i = 0; i < n_nodes; ++i) {
+                    unsigned long long bits = 0;
+                    uint32_t m = 0;
+                    const uint32_t len = h_node_off[i + 1] - h_node_off[i];
+                    for (uint32_t j = 0; j < len; ++j) {
+                        const uint8_t c = h_seq[h_node_off[i] + j];
+                        if (c < 4) bits |= (unsigned long long)c << (2 * j); else m |= 1u << j;
+                    }
+                    nb[(size_t)i] = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
+                    bad[(size_t)i] = m;
+                }
+                if ((rc = upload(ctx, g, nb.data(), (size_t)n_nodes, &g->v.node_bits)) != GB2_OK) break;
+                if ((rc = upload(ctx, g, bad.data(), (size_t)n_nodes, &g->v.node_nbits)) != GB2_OK) break;
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // nb, bad go out of scope
+            }
+        }
+        {
+            std::vector<uint32_t> blk((n_bases + 31) / 32);
+            int64_t nd = 0;
+            for (size_t b = 0; b < blk.size(); ++b) {
+                while (h_node_off[nd + 1] <= b * 32) ++nd;
+                blk[b] = (uint32_t)nd;
+            }
+            if ((rc = upload(ctx, g, blk.data(), blk.size(), &g->v.blk_node)) != GB2_OK) break;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }
+        }
         if ((rc = upload(ctx, g, h_node_a0, (size_t)n_nodes, &g->v.node_a0)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_node_clamp, (size_t)n_nodes, &g->v.node_clamp)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_node_flags, (size_t)n_nodes, &g->v.node_flags)) != GB2_OK) break;
@@ -414,10 +512,27 @@ extern "C" int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *g, uint64_t capacity, 
     o.packed = d_packed; o.nmask = d_nmask; o.start = d_start; o.stop = d_stop; o.freq = d_freq; o.isref = d_isref;
     o.region = d_region; o.walk = d_walk; o.walk_len = d_walk_len; o.walk_off = d_walk_off;
     o.capacity = capacity; o.counts = (unsigned long long *)d_counts;
+    if (g->q_total > g->q_cap_rows) {
+        GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (g->d_cons8) cudaFree(g->d_cons8);
+        if (g->d_ncons) cudaFree(g->d_ncons);
+        g->d_cons8 = nullptr; g->d_ncons = nullptr; g->q_cap_rows = 0;
+        GB2_CUDA(ctx, cudaMalloc((void **)&g->d_cons8, (size_t)g->q_total * FREQ_MAX_CONS * sizeof(uint32_t)));
+        GB2_CUDA(ctx, cudaMalloc((void **)&g->d_ncons, (size_t)g->q_total));
+        g->q_cap_rows = g->q_total;
+    }
+    o.cons8 = g->d_cons8;
+    o.ncons = g->d_ncons;
     GB2_CUDA(ctx, cudaMemsetAsync(d_nmask, 0, (size_t)gb2_div_up((int64_t)g->q_total, 32) * sizeof(uint32_t), ctx->stream));
     const int64_t T = g->q_threads;
     const int64_t grid = gb2_div_up(T, WALK_THREADS);
     gb2_graph_walk_kernel<true><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, nullptr, g->d_offsets, o, g->d_flag);
     GB2_LAUNCH_CHECK(ctx);
+    if (g->v.n_hap > 0) {
+        const int64_t fgrid = gb2_div_up((int64_t)g->q_total * FREQ_GROUP, 256);
+        GB2_REQUIRE(ctx, fgrid < ((int64_t)1 << 31), "gb2_graph_extract: too many rows for one launch (%llu)", (unsigned long long)g->q_total);
+        gb2_graph_freq_kernel<<<(unsigned)fgrid, 256, 0, ctx->stream>>>(g->v, g->q_total, g->d_cons8, g->d_ncons, d_freq);
+        GB2_LAUNCH_CHECK(ctx);
+    }
     return GB2_OK;
 }
