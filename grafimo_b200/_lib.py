@@ -28,6 +28,11 @@ class Hit(ctypes.Structure):
     _fields_ = [("row", ctypes.c_uint64), ("score", ctypes.c_int32), ("strand", ctypes.c_uint32)]
 
 
+class GraphInfo(ctypes.Structure):
+    _fields_ = [("n_nodes", ctypes.c_int64), ("n_edges", ctypes.c_int64), ("n_bases", ctypes.c_int64),
+                ("n_sets", ctypes.c_int64), ("n_hap", ctypes.c_int32), ("words", ctypes.c_int32)]
+
+
 class MotifInfo(ctypes.Structure):
     _fields_ = [
         ("width", ctypes.c_int32), ("n_chunks", ctypes.c_int32), ("lut_replicas", ctypes.c_int32),
@@ -72,7 +77,10 @@ SIGNATURES = {
     "gb2_graph_create": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32,
                                 _i64, _vp, ctypes.POINTER(_vp)]),
     "gb2_graph_destroy": (_int, [_vp]),
-    "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _int, ctypes.POINTER(_u64)]),
+    "gb2_graph_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_int32,
+                               ctypes.POINTER(_vp)]),
+    "gb2_graph_get_info": (_int, [_vp, _vp]),
+    "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _int, ctypes.POINTER(_u64)]),
     "gb2_graph_extract": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),

@@ -19,6 +19,7 @@
 // Rows come out in (region, first base, depth-first over ascending target node) order: deterministic.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <new>
 
 #include "internal.cuh"
@@ -77,6 +78,10 @@ struct gb2_graph {
     void *blocks[16] = {nullptr};
     int n_blocks = 0;
     std::vector<uint32_t> h_node_off;  // host copy: threads per region without a device round trip
+    // region -> candidate first nodes: two non-decreasing envelopes of the coordinates a node can report as a start
+    std::vector<int64_t> h_low_key;    // [i] = min over nodes >= i of their smallest start coordinate
+    std::vector<int64_t> h_high_key;   // [i] = max over nodes <= i of their largest start coordinate
+    int64_t n_edges = 0, n_bases = 0, n_cons = 0;
     // prepared query
     bool q_valid = false;
     QueryView q{};
@@ -403,6 +408,20 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
         return rc;
     }
     g->h_node_off.assign(h_node_off, h_node_off + n_nodes + 1);
+    g->h_low_key.resize((size_t)n_nodes);
+    g->h_high_key.resize((size_t)n_nodes);
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        const int64_t len = (int64_t)h_node_off[i + 1] - h_node_off[i];
+        const int64_t hi = std::min(h_node_a0[i] + len - 1, h_node_clamp[i]);
+        g->h_high_key[(size_t)i] = i ? std::max(g->h_high_key[(size_t)i - 1], hi) : hi;
+    }
+    for (int64_t i = n_nodes - 1; i >= 0; --i) {
+        const int64_t lo = std::min(h_node_a0[i], h_node_clamp[i]);
+        g->h_low_key[(size_t)i] = i + 1 < n_nodes ? std::min(g->h_low_key[(size_t)i + 1], lo) : lo;
+    }
+    g->n_edges = n_edges;
+    g->n_bases = (int64_t)n_bases;
+    g->n_cons = n_cons;
     g->v.n_nodes = n_nodes;
     g->v.n_hap = n_hap;
     g->v.words = words;
@@ -414,25 +433,37 @@ struct U32ToU64 {
     __host__ __device__ unsigned long long operator()(uint32_t x) const { return (unsigned long long)x; }
 };
 
+extern "C" int gb2_graph_get_info(const gb2_graph *g, gb2_graph_info *info)
+{
+    if (!g || !info) return GB2_ERR_ARG;
+    info->n_nodes = g->v.n_nodes; info->n_edges = g->n_edges; info->n_bases = g->n_bases; info->n_sets = g->n_cons;
+    info->n_hap = g->v.n_hap; info->words = g->v.words;
+    return GB2_OK;
+}
+
 extern "C" int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *g, int32_t n_regions, const int64_t *h_start,
-                                 const int64_t *h_stop, const int64_t *h_node_lo, const int64_t *h_node_hi, int w,
-                                 uint64_t *h_n_rows)
+                                 const int64_t *h_stop, int w, uint64_t *h_n_rows)
 {
     if (!ctx || !g || !h_n_rows) return GB2_ERR_ARG;
     *h_n_rows = 0;
     g->q_valid = false;
     GB2_REQUIRE(ctx, g->device == ctx->device, "gb2_graph_prepare: graph lives on device %d, context on %d", g->device, ctx->device);
     GB2_REQUIRE(ctx, w >= 1 && w <= GB2_MAX_WIDTH, "gb2_graph_prepare: width %d outside [1,%d]", w, GB2_MAX_WIDTH);
-    GB2_REQUIRE(ctx, n_regions >= 0 && (n_regions == 0 || (h_start && h_stop && h_node_lo && h_node_hi)), "gb2_graph_prepare: null region array");
+    GB2_REQUIRE(ctx, n_regions >= 0 && (n_regions == 0 || (h_start && h_stop)), "gb2_graph_prepare: null region array");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    // threads per region = bases of its candidate first nodes
+    // candidate first nodes of a region [rs, re): those that can report a start in it.  Nodes up to the last one whose
+    // running-maximum start is < rs are out, and so are the nodes from the first one whose running-minimum start is >= re.
+    std::vector<int64_t> node_lo((size_t)n_regions), node_hi((size_t)n_regions);
     std::vector<unsigned long long> tprefix((size_t)n_regions + 1, 0ull);
     for (int r = 0; r < n_regions; ++r) {
-        GB2_REQUIRE(ctx, h_node_lo[r] >= 0 && h_node_lo[r] <= h_node_hi[r] && h_node_hi[r] <= g->v.n_nodes,
-                    "gb2_graph_prepare: node range of region %d out of bounds", r);
         GB2_REQUIRE(ctx, h_start[r] <= h_stop[r], "gb2_graph_prepare: region %d has start > stop", r);
-        tprefix[(size_t)r + 1] = tprefix[(size_t)r] + (g->h_node_off[(size_t)h_node_hi[r]] - g->h_node_off[(size_t)h_node_lo[r]]);
+        const int64_t lo = std::lower_bound(g->h_high_key.begin(), g->h_high_key.end(), h_start[r]) - g->h_high_key.begin();
+        const int64_t hi = std::lower_bound(g->h_low_key.begin(), g->h_low_key.end(), h_stop[r]) - g->h_low_key.begin();
+        node_lo[(size_t)r] = lo;
+        node_hi[(size_t)r] = std::max(lo, hi);
+        tprefix[(size_t)r + 1] = tprefix[(size_t)r] + (g->h_node_off[(size_t)node_hi[(size_t)r]] - g->h_node_off[(size_t)lo]);
     }
+    const int64_t *h_node_lo = node_lo.data(), *h_node_hi = node_hi.data();
     const int64_t T = (int64_t)tprefix[(size_t)n_regions];
     g->q_threads = T;
     g->q_total = 0;

@@ -1,0 +1,298 @@
+// graph_build.cu -- host-side construction of the variation graph K7 walks (gb2_graph_build).
+//
+// Replaces, for the graph path, what the reference delegates to external programs: `vg construct -r REF -v VCF` and
+// `vg index -G gbwt -x xg` (src/grafimo/constructVG.py:332,394-396).  Input is the reference sequence plus reduced,
+// position-sorted alleles and the phased genotypes as bit sets; output is the flat graph of csrc/graph.cu, created
+// directly on the device.  Same model as grafimo_b200/vgraph.py (which stays as the readable second implementation the
+// tests compare this one with) and oracle/graph_oracle.py:
+//   * the reference is cut at every allele boundary; per breakpoint the non-empty alternative alleles (input order),
+//     then the reference segment; items longer than max_node_len are chained; a deletion is an edge;
+//   * everything that ends at a breakpoint is joined to everything that starts there, an insertion sits in between;
+//   * a haplotype follows its alleles; one that is inside an allele it took never arrives at the breakpoints under it;
+//   * one bit set per node (haplotypes through it) and per edge (haplotypes along it); identical sets share a row and
+//     "every haplotype" is not stored.
+// One pass over the breakpoints, bit-set work proportional to (variants x words): ~10 ms per Mb at 2,504 haplotypes.
+#include <algorithm>
+#include <map>
+#include <unordered_map>
+
+#include "internal.cuh"
+
+#define GB2_NO_CONS 0xFFFFFFFFu
+
+namespace {
+
+typedef std::vector<uint32_t> Bits;
+
+struct SetTable {
+    int words = 0;
+    bool on = false;
+    Bits full;
+    std::vector<uint32_t> flat;  // rows back to back
+    std::unordered_multimap<uint64_t, uint32_t> index;
+
+    static uint64_t hash(const uint32_t *p, int n)
+    {
+        uint64_t h = 1469598103934665603ull;
+        for (int i = 0; i < n; ++i) {
+            h ^= p[i];
+            h *= 1099511628211ull;
+            h ^= h >> 29;
+        }
+        return h;
+    }
+    uint32_t id(const uint32_t *p)
+    {
+        if (!on) return GB2_NO_CONS;
+        if (memcmp(p, full.data(), (size_t)words * 4) == 0) return GB2_NO_CONS;
+        const uint64_t h = hash(p, words);
+        auto range = index.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it)
+            if (memcmp(p, flat.data() + (size_t)it->second * words, (size_t)words * 4) == 0) return it->second;
+        const uint32_t k = (uint32_t)(flat.size() / (size_t)words);
+        flat.insert(flat.end(), p, p + words);
+        index.emplace(h, k);
+        return k;
+    }
+    const uint32_t *row(uint32_t k) const { return flat.data() + (size_t)k * words; }
+};
+
+struct Source {
+    uint32_t node;
+    Bits set;  // haplotypes whose last node is `node` when they reach the breakpoint (empty vector when sets are off)
+};
+
+struct Edge {
+    uint32_t src, dst, cons;
+};
+
+inline uint8_t code_of(uint8_t c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+
+inline void and_into(Bits &dst, const Bits &a, const uint32_t *b)
+{
+    for (size_t i = 0; i < dst.size(); ++i) dst[i] = a[i] & b[i];
+}
+
+}  // namespace
+
+extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, const uint8_t *h_seq,
+                                const int64_t *h_node_a0, const int64_t *h_node_clamp, const uint8_t *h_node_flags,
+                                const uint32_t *h_node_cons, int64_t n_edges, const uint32_t *h_edge_off,
+                                const uint32_t *h_edge_to, const uint32_t *h_edge_cons, int32_t n_hap, int32_t words,
+                                int64_t n_cons, const uint32_t *h_cons_bits, gb2_graph **out);
+
+extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants,
+                               const int64_t *h_var_pos, const int32_t *h_var_ref_len, const int64_t *h_alt_off,
+                               const uint8_t *h_alt, int32_t n_hap, int32_t words, const uint32_t *h_gt_bits,
+                               int32_t max_node_len, gb2_graph **out)
+{
+    if (!ctx || !out) return GB2_ERR_ARG;
+    *out = nullptr;
+    GB2_REQUIRE(ctx, h_ref && ref_len >= 1, "gb2_graph_build: empty reference");
+    GB2_REQUIRE(ctx, n_variants >= 0 && (n_variants == 0 || (h_var_pos && h_var_ref_len && h_alt_off && h_alt)),
+                "gb2_graph_build: null variant array");
+    GB2_REQUIRE(ctx, max_node_len >= 1, "gb2_graph_build: max_node_len must be positive");
+    GB2_REQUIRE(ctx, n_hap >= 0 && words >= 4 && (words & 3) == 0 && (int64_t)words * 32 >= n_hap,
+                "gb2_graph_build: haplotype bit sets need a multiple of 4 words covering %d haplotypes", n_hap);
+    const int64_t L = ref_len, nv = n_variants;
+    for (int64_t v = 0; v < nv; ++v) {
+        const int64_t s = h_var_pos[v], r = h_var_ref_len[v], a = h_alt_off[v + 1] - h_alt_off[v];
+        GB2_REQUIRE(ctx, s >= 0 && r >= 0 && a >= 0 && s + r <= L, "gb2_graph_build: variant %lld outside the reference", (long long)v);
+        GB2_REQUIRE(ctx, r > 0 || a > 0, "gb2_graph_build: variant %lld has two empty alleles", (long long)v);
+        GB2_REQUIRE(ctx, v == 0 || h_var_pos[v - 1] <= s, "gb2_graph_build: variants must be sorted by position");
+    }
+    SetTable sets;
+    sets.words = words;
+    sets.on = h_gt_bits != nullptr && n_hap > 0;
+    if (sets.on) {
+        sets.full.assign((size_t)words, 0u);
+        for (int h = 0; h < n_hap; ++h) sets.full[(size_t)(h >> 5)] |= 1u << (h & 31);
+    }
+    const Bits none;  // stands for "no set" when sets are off
+
+    // breakpoints
+    std::vector<int64_t> bps;
+    bps.reserve((size_t)(2 * nv + 2));
+    bps.push_back(0);
+    bps.push_back(L);
+    for (int64_t v = 0; v < nv; ++v) {
+        bps.push_back(h_var_pos[v]);
+        bps.push_back(h_var_pos[v] + h_var_ref_len[v]);
+    }
+    std::sort(bps.begin(), bps.end());
+    bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+    const int64_t nb = (int64_t)bps.size() - 1;
+    auto bp_index = [&](int64_t pos) { return (int64_t)(std::lower_bound(bps.begin(), bps.end(), pos) - bps.begin()); };
+
+    std::vector<uint32_t> node_off(1, 0u), node_cons;
+    std::vector<uint8_t> seq, flags;
+    std::vector<int64_t> a0, clamp;
+    std::vector<Edge> edges;
+    seq.reserve((size_t)L + (size_t)(nv ? h_alt_off[nv] : 0));
+
+    // appends the chain of nodes of one item -> (first, last) node index; the haplotype set of the item is filled in by
+    // set_item_cons once it is known (node ids must follow input order, the sets are computed insertions first)
+    struct Item { uint32_t first, last; size_t edge_lo, edge_hi; };
+    auto add_chain = [&](const uint8_t *bases, int64_t len, int64_t start, int64_t clamp_at, bool isref) {
+        Item it{0, 0, edges.size(), edges.size()};
+        for (int64_t c0 = 0; c0 < len; c0 += max_node_len) {
+            const int64_t n = std::min<int64_t>(max_node_len, len - c0);
+            const uint32_t id = (uint32_t)a0.size();
+            for (int64_t k = 0; k < n; ++k) seq.push_back(code_of(bases[c0 + k]));
+            node_off.push_back((uint32_t)seq.size());
+            a0.push_back(start + c0);
+            clamp.push_back(isref ? start + c0 + n : clamp_at);
+            flags.push_back(isref ? 1 : 0);
+            node_cons.push_back(GB2_NO_CONS);
+            if (c0 == 0) it.first = id; else edges.push_back(Edge{id - 1, id, GB2_NO_CONS});
+            it.last = id;
+        }
+        it.edge_hi = edges.size();
+        return it;
+    };
+    auto set_item_cons = [&](const Item &it, uint32_t cons) {
+        for (uint32_t n = it.first; n <= it.last; ++n) node_cons[n] = cons;
+        for (size_t e = it.edge_lo; e < it.edge_hi; ++e) edges[e].cons = cons;
+    };
+
+    std::map<int64_t, Bits> arrive;                    // breakpoint index -> haplotypes arriving there
+    std::map<int64_t, std::vector<Source>> sources;    // breakpoint index -> what ends there
+    if (sets.on) arrive[0] = sets.full;
+    Bits A, left, took, tmp;
+    if (sets.on) { A.resize((size_t)words); left.resize((size_t)words); took.resize((size_t)words); tmp.resize((size_t)words); }
+    int64_t v_next = 0;
+    const size_t total_guard = (size_t)1 << 32;
+
+    for (int64_t i = 0; i < nb; ++i) {
+        const int64_t b = bps[(size_t)i];
+        const int64_t v_lo = v_next;
+        while (v_next < nv && h_var_pos[v_next] == b) ++v_next;
+        const int64_t v_hi = v_next;
+        if (sets.on) {
+            auto it = arrive.find(i);
+            if (it != arrive.end()) { A = it->second; arrive.erase(it); } else std::fill(A.begin(), A.end(), 0u);
+        }
+        std::vector<Source> src;
+        {
+            auto it = sources.find(i);
+            if (it != sources.end()) { src.swap(it->second); sources.erase(it); }
+        }
+        auto edge_from_sources = [&](uint32_t target, const Bits &sel) {
+            for (const Source &s : src) {
+                uint32_t c = GB2_NO_CONS;
+                if (sets.on) { and_into(tmp, s.set, sel.data()); c = sets.id(tmp.data()); }
+                edges.push_back(Edge{s.node, target, c});
+            }
+        };
+        // ---- nodes of this breakpoint, in id order: alternative alleles (input order), then the reference segment
+        std::vector<Item> alt_item((size_t)(v_hi - v_lo));
+        bool any_ins = false;
+        for (int64_t v = v_lo; v < v_hi; ++v) {
+            const int64_t alen = h_alt_off[v + 1] - h_alt_off[v];
+            any_ins |= h_var_ref_len[v] == 0;
+            if (alen > 0) alt_item[(size_t)(v - v_lo)] = add_chain(h_alt + h_alt_off[v], alen, b, b + h_var_ref_len[v], false);
+        }
+        const Item ref_item = add_chain(h_ref + b, bps[(size_t)i + 1] - b, b, 0, true);
+        // ---- insertions sit between what ends here and what starts here
+        if (any_ins) {
+            if (sets.on) left = A;
+            std::vector<Source> added;
+            for (int64_t v = v_lo; v < v_hi; ++v) {
+                if (h_var_ref_len[v] != 0) continue;
+                if (sets.on) {
+                    and_into(took, left, h_gt_bits + (size_t)v * words);
+                    for (int k = 0; k < words; ++k) left[(size_t)k] &= ~took[(size_t)k];
+                }
+                const Item &it = alt_item[(size_t)(v - v_lo)];
+                set_item_cons(it, sets.on ? sets.id(took.data()) : GB2_NO_CONS);
+                edge_from_sources(it.first, took);
+                added.push_back(Source{it.last, sets.on ? took : none});
+            }
+            if (sets.on)
+                for (Source &s : src)
+                    for (int k = 0; k < words; ++k) s.set[(size_t)k] &= left[(size_t)k];
+            for (Source &s : added) src.push_back(std::move(s));
+        }
+        // ---- replacements and deletions that start here (first carried one wins), then the reference segment
+        if (sets.on) left = A;
+        for (int64_t v = v_lo; v < v_hi; ++v) {
+            const int64_t r = h_var_ref_len[v];
+            if (r == 0) continue;
+            if (sets.on) {
+                and_into(took, left, h_gt_bits + (size_t)v * words);
+                for (int k = 0; k < words; ++k) left[(size_t)k] &= ~took[(size_t)k];
+            }
+            const int64_t j = bp_index(b + r);
+            if (sets.on) {
+                auto it = arrive.find(j);
+                if (it == arrive.end()) arrive[j] = took;
+                else for (int k = 0; k < words; ++k) it->second[(size_t)k] |= took[(size_t)k];
+            }
+            if (h_alt_off[v + 1] - h_alt_off[v] > 0) {
+                const Item &it = alt_item[(size_t)(v - v_lo)];
+                set_item_cons(it, sets.on ? sets.id(took.data()) : GB2_NO_CONS);
+                edge_from_sources(it.first, took);
+                sources[j].push_back(Source{it.last, sets.on ? took : none});
+            } else {  // deletion: whatever ended here now ends at its far side
+                std::vector<Source> &dst = sources[j];
+                for (const Source &s : src) {
+                    Source t{s.node, none};
+                    if (sets.on) { t.set.resize((size_t)words); and_into(t.set, s.set, took.data()); }
+                    dst.push_back(std::move(t));
+                }
+            }
+        }
+        set_item_cons(ref_item, sets.on ? sets.id(left.data()) : GB2_NO_CONS);
+        edge_from_sources(ref_item.first, left);
+        sources[i + 1].push_back(Source{ref_item.last, sets.on ? left : none});
+        if (sets.on) {
+            auto it = arrive.find(i + 1);
+            if (it == arrive.end()) arrive[i + 1] = left;
+            else for (int k = 0; k < words; ++k) it->second[(size_t)k] |= left[(size_t)k];
+        }
+        if (seq.size() >= total_guard || a0.size() >= ((size_t)1 << 31)) {
+            GB2_SET_ERR(ctx, "gb2_graph_build: graph too large for 32-bit base offsets");
+            return GB2_ERR_ARG;
+        }
+    }
+
+    // ---- CSR: by (source, target); repeated structural edges (two deletions with the same ends) are merged
+    const int64_t n_nodes = (int64_t)a0.size();
+    std::sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.src != y.src ? x.src < y.src : x.dst < y.dst; });
+    std::vector<uint32_t> edge_off((size_t)n_nodes + 1, 0u), edge_to, edge_cons;
+    edge_to.reserve(edges.size());
+    edge_cons.reserve(edges.size());
+    for (size_t e = 0; e < edges.size(); ++e) {
+        if (!edge_to.empty() && e > 0 && edges[e].src == edges[e - 1].src && edges[e].dst == edges[e - 1].dst) {
+            uint32_t &c = edge_cons.back();
+            if (c != GB2_NO_CONS && edges[e].cons != GB2_NO_CONS) {
+                Bits u(sets.row(c), sets.row(c) + words);
+                const uint32_t *o = sets.row(edges[e].cons);
+                for (int k = 0; k < words; ++k) u[(size_t)k] |= o[k];
+                c = sets.id(u.data());
+            } else {
+                c = GB2_NO_CONS;
+            }
+            continue;
+        }
+        edge_to.push_back(edges[e].dst);
+        edge_cons.push_back(edges[e].cons);
+        edge_off[(size_t)edges[e].src + 1]++;
+    }
+    for (int64_t n = 0; n < n_nodes; ++n) edge_off[(size_t)n + 1] += edge_off[(size_t)n];
+    std::vector<Edge>().swap(edges);
+    const int64_t n_cons = sets.on ? (int64_t)(sets.flat.size() / (size_t)words) : 0;
+    static const uint32_t dummy[4] = {0, 0, 0, 0};
+    return gb2_graph_create(ctx, n_nodes, node_off.data(), seq.data(), a0.data(), clamp.data(), flags.data(), node_cons.data(),
+                            (int64_t)edge_to.size(), edge_off.data(), edge_to.data(), edge_cons.data(), sets.on ? n_hap : 0, words,
+                            n_cons, n_cons ? sets.flat.data() : dummy, out);
+}

@@ -19,7 +19,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 import torch
 
-from ._lib import check
+from ._lib import GraphInfo, check
 from .utils import exception_handler
 from .vgraph import VariationGraph
 
@@ -56,23 +56,83 @@ def _np_ptr(a):
 
 
 class DeviceGraph:
-    """A VariationGraph resident in HBM (gb2_graph_create)."""
+    """A variation graph resident in HBM: from host arrays (gb2_graph_create, `DeviceGraph(ctx, VariationGraph)`) or
+    built by the library from reference + alleles + genotype bit sets (gb2_graph_build, `DeviceGraph.build`)."""
 
-    def __init__(self, ctx, graph: VariationGraph):
+    def __init__(self, ctx, graph: VariationGraph = None, handle=None, chrom=None):
         self.ctx, self.graph = ctx, graph
-        g = graph
+        if handle is not None:
+            self.h, self.chrom = handle, str(chrom)
+        else:
+            g = graph
+            self.chrom = g.chrom
+            h = ctypes.c_void_p()
+            arrays = dict(node_off=np.ascontiguousarray(g.node_off, np.uint32), seq=np.ascontiguousarray(g.seq, np.uint8),
+                          a0=np.ascontiguousarray(g.node_a0, np.int64), clamp=np.ascontiguousarray(g.node_clamp, np.int64),
+                          flags=np.ascontiguousarray(g.node_flags, np.uint8), ncons=np.ascontiguousarray(g.node_cons, np.uint32),
+                          eoff=np.ascontiguousarray(g.edge_off, np.uint32), eto=np.ascontiguousarray(g.edge_to, np.uint32),
+                          econs=np.ascontiguousarray(g.edge_cons, np.uint32), bits=np.ascontiguousarray(g.cons_bits, np.uint32))
+            check(ctx.lib.gb2_graph_create(ctx.h, g.n_nodes, _np_ptr(arrays["node_off"]), _np_ptr(arrays["seq"]),
+                                           _np_ptr(arrays["a0"]), _np_ptr(arrays["clamp"]), _np_ptr(arrays["flags"]),
+                                           _np_ptr(arrays["ncons"]), g.n_edges, _np_ptr(arrays["eoff"]), _np_ptr(arrays["eto"]),
+                                           _np_ptr(arrays["econs"]), g.n_hap, g.words, g.n_cons, _np_ptr(arrays["bits"]),
+                                           ctypes.byref(h)), "gb2_graph_create", ctx.h)
+            self.h = h
+        info = GraphInfo()
+        check(ctx.lib.gb2_graph_get_info(self.h, ctypes.byref(info)), "gb2_graph_get_info")
+        self.info = info
+        self.n_hap = int(info.n_hap)
+
+    @staticmethod
+    def build(ctx, chrom, ref, variants, gt=None, gt_bits=None, max_node_len=32):
+        """Native builder (gb2_graph_build).  ref: str/bytes/uint8 array; variants: [(pos0, ref_allele, alt_allele)]
+        (reduced) or a dict of arrays {pos int64, ref_len int32, alt_off int64[n+1], alt uint8}; genotypes as
+        gt uint8 [n_variants, n_hap] or gt_bits uint32 [n_variants, words] + n_hap (tuple) -- None: no haplotype index.
+        Variants are put in position order (stable) like vgraph.VariationGraph.build does."""
+        from .vgraph import pack_bits
+        if isinstance(ref, str):
+            ref = ref.encode("ascii")
+        refa = np.frombuffer(ref, dtype=np.uint8) if isinstance(ref, (bytes, bytearray)) else np.ascontiguousarray(ref, np.uint8)
+        if isinstance(variants, dict):
+            pos = np.ascontiguousarray(variants["pos"], np.int64)
+            rlen = np.ascontiguousarray(variants["ref_len"], np.int32)
+            alt_off = np.ascontiguousarray(variants["alt_off"], np.int64)
+            alt = np.ascontiguousarray(variants["alt"], np.uint8)
+            if len(pos) > 1 and (np.diff(pos) < 0).any():
+                raise ValueError("variant arrays must be sorted by position")
+            order = None
+        else:
+            nv = len(variants)
+            pos = np.array([v[0] for v in variants], dtype=np.int64).reshape(nv)
+            order = np.argsort(pos, kind="stable")
+            up = refa.tobytes().upper()
+            for s_, r_, a_ in variants:
+                if up[s_:s_ + len(r_)] != r_.upper().encode("ascii"):
+                    raise ValueError(f"REF allele of variant at {s_} does not match the reference sequence")
+            pos = np.ascontiguousarray(pos[order])
+            rlen = np.array([len(variants[i][1]) for i in order], dtype=np.int32).reshape(nv)
+            alts = [variants[i][2].encode("ascii") for i in order]
+            alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alts])]).astype(np.int64)
+            alt = np.frombuffer(b"".join(alts), dtype=np.uint8) if alts else np.zeros(0, np.uint8)
+        nv = len(pos)
+        n_hap, bits = 0, None
+        if gt_bits is not None:
+            bits, n_hap = gt_bits
+            bits = np.ascontiguousarray(bits, np.uint32)
+        elif gt is not None:
+            gt = np.asarray(gt)
+            n_hap = int(gt.shape[1])
+            words = max(4, ((n_hap + 31) // 32 + 3) // 4 * 4)
+            bits = pack_bits(gt if order is None else gt[order], words)
+        words = bits.shape[1] if bits is not None else 4
+        if bits is not None and bits.shape[0] != nv:
+            raise ValueError("one genotype row per variant is required")
         h = ctypes.c_void_p()
-        arrays = dict(node_off=np.ascontiguousarray(g.node_off, np.uint32), seq=np.ascontiguousarray(g.seq, np.uint8),
-                      a0=np.ascontiguousarray(g.node_a0, np.int64), clamp=np.ascontiguousarray(g.node_clamp, np.int64),
-                      flags=np.ascontiguousarray(g.node_flags, np.uint8), ncons=np.ascontiguousarray(g.node_cons, np.uint32),
-                      eoff=np.ascontiguousarray(g.edge_off, np.uint32), eto=np.ascontiguousarray(g.edge_to, np.uint32),
-                      econs=np.ascontiguousarray(g.edge_cons, np.uint32), bits=np.ascontiguousarray(g.cons_bits, np.uint32))
-        check(ctx.lib.gb2_graph_create(ctx.h, g.n_nodes, _np_ptr(arrays["node_off"]), _np_ptr(arrays["seq"]),
-                                       _np_ptr(arrays["a0"]), _np_ptr(arrays["clamp"]), _np_ptr(arrays["flags"]),
-                                       _np_ptr(arrays["ncons"]), g.n_edges, _np_ptr(arrays["eoff"]), _np_ptr(arrays["eto"]),
-                                       _np_ptr(arrays["econs"]), g.n_hap, g.words, g.n_cons, _np_ptr(arrays["bits"]),
-                                       ctypes.byref(h)), "gb2_graph_create", ctx.h)
-        self.h = h
+        alt_p = alt if len(alt) else np.zeros(1, np.uint8)
+        check(ctx.lib.gb2_graph_build(ctx.h, _np_ptr(refa), len(refa), nv, _np_ptr(pos), _np_ptr(rlen), _np_ptr(alt_off),
+                                      _np_ptr(alt_p), n_hap, words, _np_ptr(bits) if bits is not None else None,
+                                      int(max_node_len), ctypes.byref(h)), "gb2_graph_build", ctx.h)
+        return DeviceGraph(ctx, None, handle=h, chrom=chrom)
 
     def close(self):
         if getattr(self, "h", None):
@@ -94,13 +154,12 @@ class DeviceGraph:
             raise ValueError(f"motif width {width} outside [1, {MAX_WIDTH}]")
         rs = np.array([int(r[0]) for r in regions], dtype=np.int64)
         re = np.array([int(r[1]) for r in regions], dtype=np.int64)
-        nlo, nhi = g.region_nodes(rs, re)
         n_rows = ctypes.c_uint64(0)
         ctx.enter()
-        check(ctx.lib.gb2_graph_prepare(ctx.h, self.h, len(rs), _np_ptr(rs), _np_ptr(re), _np_ptr(nlo), _np_ptr(nhi), width,
-                                        ctypes.byref(n_rows)), "gb2_graph_prepare", ctx.h)
+        check(ctx.lib.gb2_graph_prepare(ctx.h, self.h, len(rs), _np_ptr(rs), _np_ptr(re), width, ctypes.byref(n_rows)),
+              "gb2_graph_prepare", ctx.h)
         n = int(n_rows.value)
-        rows = GraphRows(ctx, g.chrom, [(int(a), int(b)) for a, b in zip(rs, re)], width, n, want_walks, g.n_hap)
+        rows = GraphRows(ctx, self.chrom, [(int(a), int(b)) for a, b in zip(rs, re)], width, n, want_walks, self.n_hap)
         rows.graph = g
         if n:
             check(ctx.lib.gb2_graph_extract(ctx.h, self.h, n, _ptr(rows.packed), _ptr(rows.nmask), _ptr(rows.start),
@@ -196,8 +255,9 @@ class GraphRows:
         return out
 
     def _ascii_of_walk(self, h, i):
-        if "walk" not in h:
-            raise ValueError("rows with non-ACGT bases can only be printed when the walks were kept (want_walks=True)")
+        if "walk" not in h or self.graph is None:
+            raise ValueError("rows with non-ACGT bases can only be printed when the walks were kept (want_walks=True) "
+                             "and the graph came from host arrays (vgraph.VariationGraph)")
         g = self.graph
         seq, need = [], self.width
         off = int(h["walk_off"][i])

@@ -239,13 +239,27 @@ int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, 
                      const uint32_t *h_node_cons, int64_t n_edges, const uint32_t *h_edge_off, const uint32_t *h_edge_to,
                      const uint32_t *h_edge_cons, int32_t n_hap, int32_t words, int64_t n_cons,
                      const uint32_t *h_cons_bits, gb2_graph **out);
+/* The same graph built by the library from the inputs of `vg construct` / `vg index -G` (constructVG.py:332,394-396):
+ * reference sequence (ASCII, any case, non-ACGT = N), reduced alleles sorted by position (h_var_pos[v] 0-based start,
+ * h_var_ref_len[v] reference bases replaced, alternative allele = h_alt[h_alt_off[v] .. h_alt_off[v+1]) ASCII; within a
+ * position input order decides node ids and which carried allele wins), phased genotypes as bit sets
+ * h_gt_bits[n_variants][words] (bit h = haplotype h carries the alternative allele; NULL = no haplotype index, every
+ * frequency 0), nodes chained at max_node_len bases (vg's default 32).  Host pointers. */
+int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
+                    const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
+                    int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, gb2_graph **out);
+typedef struct gb2_graph_info {
+    int64_t n_nodes, n_edges, n_bases, n_sets; /* n_sets: stored haplotype-set rows */
+    int32_t n_hap, words;
+} gb2_graph_info;
+int gb2_graph_get_info(const gb2_graph *graph, gb2_graph_info *info);
 int gb2_graph_destroy(gb2_graph *graph);
 /* Pass 1 for n_regions regions [h_start[r], h_stop[r]) at once: counts the w-base walks whose reported start and stop
- * lie inside the region (first bases are looked for in nodes [h_node_lo[r], h_node_hi[r])) and keeps the row offsets
- * in the graph object.  *h_n_rows = rows gb2_graph_extract will write.  Synchronises the stream.
+ * lie inside the region and keeps the row offsets in the graph object.  *h_n_rows = rows gb2_graph_extract will
+ * write.  Synchronises the stream.
  * GB2_ERR_CAPACITY: more than 2^24 walks start at one base (variants too dense for this width). */
 int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *graph, int32_t n_regions, const int64_t *h_start, const int64_t *h_stop,
-                      const int64_t *h_node_lo, const int64_t *h_node_hi, int w, uint64_t *h_n_rows);
+                      int w, uint64_t *h_n_rows);
 /* Pass 2 of the prepared query (stream-ordered): rows in (region, first base, depth-first) order, forward strand only
  * (the '-' row vg prints for a walk is its reverse complement with start/stop swapped: score with strands = 2).
  *   d_packed uint64[cap] (16-byte aligned), d_nmask uint32[ceil(cap/32)], d_start/d_stop int64[cap], d_freq int32[cap]

@@ -44,13 +44,22 @@ def test_extract_equals_reference_vg_fixture(ctx):
     assert sorted(lines) == sorted(exp)
 
 
+@pytest.mark.parametrize("builder", ["numpy", "native"])
 @pytest.mark.parametrize("seed", range(6))
-def test_extract_equals_oracle_random_graphs(ctx, seed):
+def test_extract_equals_oracle_random_graphs(ctx, seed, builder):
+    """Both graph builders -- vgraph.VariationGraph.build (numpy, host arrays -> gb2_graph_create) and the library's
+    gb2_graph_build -- against the oracle: same rows, coordinates, node ids, ref flags, frequencies."""
+    from grafimo_b200.extract_regions import DeviceGraph
     from grafimo_b200.vgraph import VariationGraph
     ref, vs, gt = gr.random_case(200 + seed, length=600, n_var=60, n_hap=70 if seed % 2 else 12,
                                  n_frac=0.01 if seed % 3 == 0 else 0.0)
     m = (8, 32, 64)[seed % 3]  # 64: nodes longer than one packed word take the byte path of the kernel
-    dg = VariationGraph.build("c", ref, vs, gt, max_node_len=m).to_device(ctx)
+    if builder == "numpy":
+        dg = VariationGraph.build("c", ref, vs, gt, max_node_len=m).to_device(ctx)
+    else:
+        dg = DeviceGraph.build(ctx, "c", ref, vs, gt=gt, max_node_len=m)
+        dg.graph = VariationGraph.build("c", ref, vs, gt, max_node_len=m)  # host arrays, only to spell N rows as text
+        assert (dg.info.n_nodes, dg.info.n_edges, dg.info.n_sets) == (dg.graph.n_nodes, dg.graph.n_edges, dg.graph.n_cons)
     regions = [(0, 600), (37, 301), (100, 250), (590, 600), (250, 250)]
     for w in (5, 19, 32):
         rows = dg.extract(regions, w, want_walks=True)
@@ -78,6 +87,12 @@ def test_extract_without_haplotypes_and_errors(ctx):
     dg = VariationGraph.build("c", ref, vs, None).to_device(ctx)
     rows = dg.extract([(0, 300)], 11)
     assert rows.n > 0 and int(rows.freq[:rows.n].max().item()) == 0
+    from grafimo_b200.extract_regions import DeviceGraph
+    dn = DeviceGraph.build(ctx, "c", ref, vs)  # native builder, no genotypes
+    rn = dn.extract([(0, 300)], 11)
+    assert rn.n == rows.n and bool((rn.packed[:rn.n] == rows.packed[:rows.n]).all()) and int(rn.freq[:rn.n].max().item()) == 0
+    with pytest.raises(ValueError):
+        DeviceGraph.build(ctx, "c", ref, [(5, "A" if ref[5] != "A" else "C", "G")])  # REF allele mismatch
     empty = dg.extract([], 11)
     assert empty.n == 0
     with pytest.raises(ValueError):

@@ -67,8 +67,9 @@ def test_indel_graph_sampled_regions_equal_oracle(ctx):
     from grafimo_b200.extract_regions import decode_kmers
     from grafimo_b200.vgraph import VariationGraph
     L, H, w = 300_000, 500, 19
+    from grafimo_b200.extract_regions import DeviceGraph
     ref, variants, gt = synth.variant_set(L, H, 99, indel_frac=0.3, density=1 / 25)
-    dg = VariationGraph.build("1", ref, variants, gt).to_device(ctx)
+    dg = DeviceGraph.build(ctx, "1", ref, variants, gt=gt)  # the library's builder
     rng = np.random.default_rng(5)
     regions = [(int(s), int(s) + 200) for s in rng.integers(1000, L - 1000, size=6)]
     rows = dg.extract(regions, w)
@@ -99,6 +100,17 @@ def test_frequency_sums_per_first_base(ctx):
     dg = g.to_device(ctx)
     rows = dg.extract([(0, L)], w, want_walks=True)
     assert 1_400_000 < rows.n < 1_800_000
+    # the library's builder gives the very same rows (k-mers, coordinates, frequencies, flags, walks)
+    from grafimo_b200.extract_regions import DeviceGraph
+    dn = DeviceGraph.build(ctx, "1", ref, variants, gt=gt)
+    assert (dn.info.n_nodes, dn.info.n_edges, dn.info.n_sets) == (g.n_nodes, g.n_edges, g.n_cons)
+    rn = dn.extract([(0, L)], w, want_walks=True)
+    assert rn.n == rows.n
+    for col in ("packed", "start", "stop", "freq", "isref", "walk_len", "walk_off"):
+        assert bool(torch.equal(getattr(rn, col)[:rn.n], getattr(rows, col)[:rows.n])), col
+    wl = rows.walk_len[:rows.n].to(torch.int64)
+    valid = torch.arange(32, device=ctx.device)[None, :] < wl[:, None]
+    assert bool(torch.equal(rn.walk.view(-1, 32)[:rn.n][valid], rows.walk.view(-1, 32)[:rows.n][valid]))
     with torch.cuda.stream(ctx.stream):
         first = rows.walk.view(-1, 32)[:rows.n, 0].to(torch.int64) * 64 + rows.walk_off[:rows.n].to(torch.int64)
         uniq, inv = torch.unique_consecutive(first, return_inverse=True)
