@@ -370,7 +370,9 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     haplotype frequency and ref flag as side arrays.  Returns the table compute_results would return for the TSVs
     `vg find -K w -E` writes for the same regions (GraphRows.to_vg_tsv): both strands are scored from the one
     packed k-mer (the '-' row of a walk is its reverse complement with start and stop swapped), every
-    row of both strands counts in the q-values, and the same flags apply (score_sequences.py:93-107)."""
+    row of both strands counts in the q-values, and the same flags apply (score_sequences.py:93-107).
+    Under torchrun (one process per GPU, e.g. chromosomes sharded over the ranks) every rank passes its own rows: the
+    score histograms are all-reduced so the q-values are global, and every rank returns the whole table."""
     if not isinstance(motif, Motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not testmode:
@@ -395,16 +397,27 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
             exception_handler(ValueError, f"k-mers of width {b.width} given to a motif of width {width}.\n", debug)
     strands = 1 if no_reverse else 2
     n_kmers = sum(b.n for b in batches)
-    n = n_kmers * strands
+    import torch.distributed as tdist
+    from . import dist as gdist
+    world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+    rank = tdist.get_rank() if world > 1 else 0
+    if world > 1:
+        counts = [None] * world
+        tdist.all_gather_object(counts, n_kmers)
+        rank_base, n_all = sum(counts[:rank]), sum(counts)
+    else:
+        rank_base, n_all = 0, n_kmers
+    n = n_all * strands
     if n == 0:  # score_sequences.py:189-192
         errmsg = "No result retrieved. Unable to proceed.\n"
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
         exception_handler(ValueError, errmsg, debug)
     t0 = time.time()
-    ctx = batches[0].ctx
+    ctx = batches[0].ctx if batches else _context()
     dm = device_motif(motif, ctx)
-    bases = np.concatenate([[0], np.cumsum([b.n for b in batches])]).astype(np.int64)
-    cap = n if threshold >= 0.25 else min(n, max(1 << 20, n // 8))
+    bases = (rank_base + np.concatenate([[0], np.cumsum([b.n for b in batches])])).astype(np.int64)
+    n_local = n_kmers * strands
+    cap = max(1, n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8)))
     while True:
         scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
         for b, base in zip(batches, bases[:-1]):
@@ -414,13 +427,17 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         if found <= cap:
             break
         cap = found
+    if world > 1 and not no_qvalue:  # the one exchange step: global score histogram -> global q-values
+        with torch.cuda.stream(ctx.stream):
+            gdist.allreduce_histogram(scan.histogram())
     kept = scan.finalize_device(q_filter=bool(qval_t))
-    if verbose:
-        print("Sequences scored in %.2fs" % (time.time() - t0))
-    if not no_qvalue:
-        print("\nComputing q-values...\n")
-    print(f"Scanned sequences:\t{n}")
-    print(f"Scanned nucleotides:\t{n * width}")
+    if rank == 0:
+        if verbose:
+            print("Sequences scored in %.2fs" % (time.time() - t0))
+        if not no_qvalue:
+            print("\nComputing q-values...\n")
+        print(f"Scanned sequences:\t{n}")
+        print(f"Scanned nucleotides:\t{n * width}")
     t1 = time.time()
     with torch.cuda.stream(ctx.stream):
         sel = scan.out["row"][:kept]
@@ -472,11 +489,15 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     cols["haplotype_frequency"] = freq[keep]
     cols["reference"] = ref[keep]
     df = pd.DataFrame(cols)
+    if world > 1:  # every rank returns the whole table
+        parts = [None] * world
+        tdist.all_gather_object(parts, df)
+        df = pd.concat(parts, ignore_index=True)
     if len(df) > 1:
         order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
                             df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
         df = df.iloc[order].reset_index(drop=True)
-    if verbose:
+    if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df
 

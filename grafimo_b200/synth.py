@@ -153,3 +153,44 @@ def variant_set(region_len, n_hap, seed, density=1.0 / 40.0, indel_frac=0.1, max
     af = lo * (hi / lo) ** rng.random(len(variants))
     gt = (rng.random((len(variants), n_hap), dtype=np.float32) < af[:, None].astype(np.float32)).astype(np.uint8)
     return ref, variants, gt
+
+
+def variant_arrays(region_len, n_hap, seed, density=1.0 / 40.0, indel_frac=0.1, max_indel=5, device="cpu"):
+    """Array form of `variant_set` for chromosome-sized inputs (no per-variant Python): the layout gb2_graph_build takes.
+    -> (reference uint8 ASCII numpy, {pos int64, ref_len int32, alt_off int64[n+1], alt uint8 ASCII}, (gt_bits uint32
+    [n, words], n_hap)).  Genotype bits are drawn on `device` (a CUDA device makes 10^6 variants x 5,008 haplotypes a
+    matter of seconds) with allele frequency ~ 1/x on [1/n_hap, 0.5]; alleles never overlap."""
+    rng = np.random.default_rng(int(seed))
+    codes = rng.integers(0, 4, size=region_len, dtype=np.uint8)
+    ref = _ASCII[codes]
+    n_var = max(1, int(region_len * density))
+    pos = np.unique(rng.integers(1, region_len - max_indel - 1, size=n_var))
+    pos = pos[np.concatenate([[True], np.diff(pos) > max_indel + 1])]
+    n = len(pos)
+    kind = rng.random(n)
+    length = rng.integers(1, max_indel + 1, size=n)
+    is_snp, is_ins = kind >= indel_frac, kind < indel_frac / 2
+    is_del = ~is_snp & ~is_ins
+    ref_len = np.where(is_snp, 1, np.where(is_del, length, 0)).astype(np.int32)
+    alt_len = np.where(is_snp, 1, np.where(is_ins, length, 0)).astype(np.int64)
+    alt_off = np.concatenate([[0], np.cumsum(alt_len)]).astype(np.int64)
+    alt_codes = rng.integers(0, 4, size=int(alt_off[-1]), dtype=np.uint8)
+    snp_alt = (codes[pos[is_snp]] + rng.integers(1, 4, size=int(is_snp.sum()), dtype=np.uint8)) % 4
+    alt_codes[alt_off[:-1][is_snp]] = snp_alt
+    alt = _ASCII[alt_codes]
+    lo, hi = 1.0 / n_hap, 0.5
+    af = torch.from_numpy(lo * (hi / lo) ** rng.random(n)).to(device=device, dtype=torch.float32)
+    words = max(4, ((n_hap + 31) // 32 + 3) // 4 * 4)
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) + 12345)
+    weights = (2 ** torch.arange(32, device=device, dtype=torch.int64))[None, None, :]
+    bits = torch.empty((n, words), dtype=torch.int32, device="cpu")
+    chunk = max(1, (1 << 28) // (words * 32))
+    valid = (torch.arange(words * 32, device=device) < n_hap)[None, :]
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        carry = (torch.rand((b - a, words * 32), generator=g, device=device) < af[a:b, None]) & valid
+        packed = (carry.view(b - a, words, 32).to(torch.int64) * weights).sum(dim=2)
+        bits[a:b] = packed.to(torch.int32).cpu()  # low 32 bits
+    variants = {"pos": pos.astype(np.int64), "ref_len": ref_len, "alt_off": alt_off, "alt": alt}
+    return ref, variants, (bits.numpy().view(np.uint32), n_hap)

@@ -195,3 +195,33 @@ def test_cli_findmotif_from_fasta_vcf_bed(ctx, tmp_path):
     gu.assert_tables_equal({c: got[c].to_numpy() for c in got.columns}, {c: exp[c].to_numpy() for c in exp.columns},
                            [c for c in exp.columns if c not in ("motif_id", "motif_alt_id")])
     assert (out / "grafimo_out.gff").exists()
+
+
+def test_graph_path_over_two_gpus(ctx, tmp_path):
+    """Chromosomes sharded over two ranks (torchrun, NCCL all-reduce of the histogram) == one process with both."""
+    import pickle
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import dist_graph_worker as wk
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.extract_regions import DeviceGraph
+    ss._ctx = ctx
+    for r in (0, 1):
+        (tmp_path / f"r{r}").mkdir()
+    motif = wk.build_motif(str(tmp_path / "r0"))
+    rows = []
+    for name, ref, vs, gt in wk.chromosomes():
+        dg = DeviceGraph.build(ctx, name, ref, vs, gt=gt)
+        rows.append(dg.extract([(0, len(ref) // 2), (len(ref) // 2 - 10, len(ref))], motif.width))
+    df = ss.compute_results_rows(motif, rows, True, wk.Args)
+    assert len(df) > 50
+    pickle.dump({c: df[c].to_numpy() for c in df.columns}, open(tmp_path / "expected.pkl", "wb"))
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_graph_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29578", worker, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
