@@ -68,9 +68,9 @@ def load_graphs(wf: Findmotif, debug: bool):
     src/grafimo/grafimo.py:32-78, extract_regions.py:55-237).  Regions are named like the reference names them:
     `<chromosome without prefix>:<start>-<stop>` (extract_regions.py:164-170)."""
     from . import score_sequences as ss
-    from .extract_regions import get_regions_bed
+    from .extract_regions import DeviceGraph, get_regions_bed
     from .utils import exception_handler
-    from .vgraph import VariationGraph, read_fasta, read_vcf
+    from .vgraph import read_fasta
     regions, n = get_regions_bed(wf.bedfile, debug)
     if n == 0:
         exception_handler(ValueError, f"No region found in {wf.bedfile}.\n", debug)
@@ -82,9 +82,8 @@ def load_graphs(wf: Findmotif, debug: bool):
         name = wf.chroms_prefix + key
         if name not in seqs:
             exception_handler(KeyError, f"{name} is not a sequence of {wf.linear_genome}. Consider --chroms-prefix-find.\n", debug)
-        variants, gt, _ = read_vcf(wf.vcf, name) if wf.vcf else ([], None, [])
-        g = VariationGraph.build(key, seqs[name], variants, gt if wf.vcf else None)
-        out.append((g.to_device(ctx), [(int(a), int(b)) for a, b in spans]))
+        dg = DeviceGraph.from_files(ctx, seqs, wf.vcf, name, display_name=key)
+        out.append((dg, [(int(a), int(b)) for a, b in spans]))
     return out
 
 

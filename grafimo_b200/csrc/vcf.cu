@@ -1,0 +1,208 @@
+// vcf.cu -- K9: device-side reader of phased VCF text (the variants + haplotypes the variation graph is built from).
+//
+// The reference hands the VCF to external programs (`vg construct -v VCF`, `vg index -G x.gbwt -v VCF`,
+// src/grafimo/constructVG.py:332,394-396).  For the graph path (csrc/graph.cu, graph_build.cu) the same text is
+// tokenised here: a 1000-Genomes chromosome is ~10^6 lines of ~10 KB (one "a|b" call per sample), far too much for
+// per-line host parsing, and all of it is independent byte work.
+//
+//   gb2_vcf_parse_fields     one thread per line: the eight fixed columns + FORMAT -> kind (header / data / malformed),
+//                            POS, byte ranges of CHROM / REF / ALT, number of ALT alleles, where the samples start;
+//   gb2_vcf_parse_genotypes  one CTA per data line: 2 KB tiles, tab ordinals by a block scan, every call "a|b" / "a/b" /
+//                            "a" parsed where its tab is found, bit (sample * ploidy + j) set in the row of allele a --
+//                            the rows are the haplotype bit sets gb2_graph_build takes (h_gt_bits).
+// Line starts come from gb2_tsv_index_lines (csrc/tsv.cu).
+#include <cub/cub.cuh>
+
+#include "internal.cuh"
+
+#define VCF_MAX_ALT 16       // ALT alleles per line whose genotype rows are built (more: line is counted and skipped)
+#define GT_THREADS 128
+#define GT_BYTES_PER_THREAD 16
+
+__device__ __forceinline__ bool vcf_eol(uint8_t c) { return c == '\n' || c == '\r' || c == 0; }
+
+__global__ void __launch_bounds__(128) gb2_vcf_fields_kernel(const uint8_t *__restrict__ text, int64_t n_bytes,
+                                                             const unsigned long long *__restrict__ line_off, int64_t n_lines,
+                                                             uint8_t *__restrict__ kind, int32_t *__restrict__ chrom_len,
+                                                             long long *__restrict__ pos, int32_t *__restrict__ ref_off,
+                                                             int32_t *__restrict__ ref_len, int32_t *__restrict__ alt_off,
+                                                             int32_t *__restrict__ alt_len, int32_t *__restrict__ n_alts,
+                                                             int32_t *__restrict__ samples_off, int32_t *__restrict__ line_len)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    const int64_t lo = (int64_t)line_off[i];
+    const int64_t hi = (i + 1 < n_lines) ? (int64_t)line_off[i + 1] : n_bytes;  // next line start bounds this one
+    int64_t p = lo;
+    uint8_t k = 1;
+    int32_t clen = 0, roff = 0, rlen = 0, aoff = 0, alen = 0, na = 0, soff = -1;
+    long long v = 0;
+    if (text[lo] == '#') {
+        k = 0;
+    } else {
+        // field f spans [fb, p); fields are TAB separated (VCF 4.x)
+        bool gt_first = false;
+        for (int f = 0;; ++f) {
+            const int64_t fb = p;
+            while (p < hi && text[p] != '\t' && !vcf_eol(text[p])) ++p;
+            const int64_t fl = p - fb;
+            if (f == 0) {
+                clen = (int32_t)fl;
+                if (fl == 0) k = 2;
+            } else if (f == 1) {
+                if (fl == 0 || fl > 18) k = 2;
+                for (int64_t q = fb; q < p; ++q) {
+                    const uint8_t c = text[q];
+                    if (c < '0' || c > '9') { k = 2; break; }
+                    v = v * 10 + (c - '0');
+                }
+            } else if (f == 3) {
+                roff = (int32_t)(fb - lo); rlen = (int32_t)fl;
+                if (fl == 0) k = 2;
+            } else if (f == 4) {
+                aoff = (int32_t)(fb - lo); alen = (int32_t)fl;
+                if (fl == 0) k = 2;
+                else if (!(fl == 1 && text[fb] == '.')) {
+                    na = 1;
+                    for (int64_t q = fb; q < p; ++q) na += text[q] == ',';
+                }
+            } else if (f == 8) {  // FORMAT: the genotype must be its first key (VCF: "GT must be the first field if present")
+                gt_first = fl >= 2 && text[fb] == 'G' && text[fb + 1] == 'T' && (fl == 2 || text[fb + 2] == ':');
+            }
+            const bool tab = p < hi && text[p] == '\t';
+            if (f == 8) {
+                if (tab && gt_first) soff = (int32_t)(p + 1 - lo);
+                break;
+            }
+            if (!tab) {
+                if (f < 7) k = 2;  // fewer than eight columns; exactly eight = a sites-only line
+                break;
+            }
+            ++p;
+        }
+    }
+    int64_t e = p;
+    while (e < hi && !vcf_eol(text[e])) ++e;
+    kind[i] = k;
+    chrom_len[i] = clen;
+    pos[i] = v;
+    ref_off[i] = roff; ref_len[i] = rlen; alt_off[i] = aoff; alt_len[i] = alen;
+    n_alts[i] = k == 1 ? na : 0;
+    samples_off[i] = (k == 1 && soff >= 0) ? soff : -1;
+    line_len[i] = (int32_t)(e - lo);
+}
+
+// One CTA per line.  Bits are accumulated in shared memory ([n_alts][words]) and written out once.
+__global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *__restrict__ text,
+                                                                const unsigned long long *__restrict__ line_off,
+                                                                const int32_t *__restrict__ samples_off,
+                                                                const int32_t *__restrict__ line_len,
+                                                                const int32_t *__restrict__ n_alts,
+                                                                const long long *__restrict__ row_base, int ploidy, int n_hap,
+                                                                int words, uint32_t *__restrict__ bits,
+                                                                unsigned long long *__restrict__ counts)
+{
+    extern __shared__ uint32_t rows_s[];  // [min(n_alts, VCF_MAX_ALT)][words]
+    typedef cub::BlockScan<uint32_t, GT_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int64_t line = blockIdx.x;
+    const long long base = row_base[line];
+    if (base < 0) return;
+    const int na = n_alts[line];
+    if (na <= 0) return;
+    if (na > VCF_MAX_ALT) {
+        if (threadIdx.x == 0) atomicAdd(counts, 1ull);
+        return;
+    }
+    for (int k = threadIdx.x; k < na * words; k += GT_THREADS) rows_s[k] = 0u;
+    __syncthreads();
+    const int64_t lo = (int64_t)line_off[line];
+    const int soff = samples_off[line];
+    if (soff > 0) {
+        const int64_t first = lo + soff - 1;  // the TAB in front of sample 0
+        const int64_t end = lo + line_len[line];
+        uint32_t carry = 0;                   // tabs seen in earlier tiles == index of the next sample
+        unsigned long long bad = 0;
+        for (int64_t tile = first; tile < end; tile += GT_THREADS * GT_BYTES_PER_THREAD) {
+            const int64_t b0 = tile + (int64_t)threadIdx.x * GT_BYTES_PER_THREAD;
+            uint32_t tabs = 0;
+#pragma unroll
+            for (int k = 0; k < GT_BYTES_PER_THREAD; ++k)
+                if (b0 + k < end && text[b0 + k] == '\t') tabs |= 1u << k;
+            uint32_t before, total;
+            Scan(tmp).ExclusiveSum((uint32_t)__popc(tabs), before, total);
+            uint32_t s = carry + before;
+            while (tabs) {
+                const int k = __ffs((int)tabs) - 1;
+                tabs &= tabs - 1;
+                // the call of sample s: alleles separated by '|' or '/', up to the first ':' / TAB / end of line
+                int64_t q = b0 + k + 1;
+                int j = 0, val = -1;
+                while (true) {
+                    const uint8_t c = q < end ? text[q] : (uint8_t)'\n';
+                    if (c >= '0' && c <= '9') {
+                        val = (val < 0 ? 0 : val) * 10 + (c - '0');
+                        if (val > 1 << 20) val = 1 << 20;
+                    } else {
+                        if (val >= 1 && j < ploidy) {
+                            const long long h = (long long)s * ploidy + j;
+                            if (val <= na && h < n_hap) atomicOr(&rows_s[(val - 1) * words + (int)(h >> 5)], 1u << (h & 31));
+                            else ++bad;
+                        }
+                        if (c != '|' && c != '/') break;
+                        ++j;
+                        val = -1;
+                    }
+                    ++q;
+                }
+                ++s;
+            }
+            carry += total;
+            __syncthreads();  // tmp is reused by the next tile's scan
+        }
+        if (bad) atomicAdd(counts + 1, bad);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < na * words; k += GT_THREADS) bits[(size_t)base * words + k] = rows_s[k];
+}
+
+extern "C" int gb2_vcf_parse_fields(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off,
+                                    int64_t n_lines, uint8_t *d_kind, int32_t *d_chrom_len, int64_t *d_pos,
+                                    int32_t *d_ref_off, int32_t *d_ref_len, int32_t *d_alt_off, int32_t *d_alt_len,
+                                    int32_t *d_n_alts, int32_t *d_samples_off, int32_t *d_line_len)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n_lines >= 0 && n_bytes >= 0 && n_bytes < ((int64_t)1 << 31), "gb2_vcf_parse_fields: at most 2^31-1 bytes per call");
+    if (n_lines == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_text && d_line_off && d_kind && d_chrom_len && d_pos && d_ref_off && d_ref_len && d_alt_off && d_alt_len &&
+                    d_n_alts && d_samples_off && d_line_len, "gb2_vcf_parse_fields: null buffer");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    gb2_vcf_fields_kernel<<<(unsigned)gb2_div_up(n_lines, 128), 128, 0, ctx->stream>>>(
+        d_text, n_bytes, (const unsigned long long *)d_line_off, n_lines, d_kind, d_chrom_len, (long long *)d_pos, d_ref_off,
+        d_ref_len, d_alt_off, d_alt_len, d_n_alts, d_samples_off, d_line_len);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+extern "C" int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, const uint64_t *d_line_off, int64_t n_lines,
+                                       const int32_t *d_samples_off, const int32_t *d_line_len, const int32_t *d_n_alts,
+                                       const int64_t *d_row_base, int ploidy, int32_t n_hap, int32_t words,
+                                       uint32_t *d_bits, uint64_t *d_counts)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n_lines >= 0 && n_lines < ((int64_t)1 << 31), "gb2_vcf_parse_genotypes: line count out of range");
+    GB2_REQUIRE(ctx, ploidy >= 1 && ploidy <= 8, "gb2_vcf_parse_genotypes: ploidy %d outside [1,8]", ploidy);
+    GB2_REQUIRE(ctx, n_hap >= 0 && words >= 1 && (int64_t)words * 32 >= n_hap, "gb2_vcf_parse_genotypes: %d words do not hold %d haplotypes", words, n_hap);
+    if (n_lines == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_text && d_line_off && d_samples_off && d_line_len && d_n_alts && d_row_base && d_bits && d_counts,
+                "gb2_vcf_parse_genotypes: null buffer");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)VCF_MAX_ALT * words * sizeof(uint32_t);
+    GB2_REQUIRE(ctx, smem <= (size_t)ctx->max_smem_optin - 4096, "gb2_vcf_parse_genotypes: too many haplotypes for one CTA (%d)", n_hap);
+    GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_vcf_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gb2_vcf_gt_kernel<<<(unsigned)n_lines, GT_THREADS, smem, ctx->stream>>>(
+        d_text, (const unsigned long long *)d_line_off, d_samples_off, d_line_len, d_n_alts, (const long long *)d_row_base, ploidy,
+        n_hap, words, d_bits, (unsigned long long *)d_counts);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}

@@ -93,17 +93,11 @@ class Context:
         self.leave()
         return packed, nmask, counts
 
-    # -- K1b: k-mer TSV on the device ------------------------------------------------------------
-    def parse_kmer_tsv(self, text, width, skip_minus=False):
-        """uint8 host tensor (pinned for speed) or device tensor with the bytes of `vg find -K w -E` TSV files ->
-        DeviceRows (packed k-mers, N mask and the numeric side arrays on the device)."""
-        assert text.dtype == torch.uint8 and text.dim() == 1
-        n_bytes = text.shape[0]
-        self.enter()
-        with torch.cuda.stream(self.stream):
-            d_text = text if text.is_cuda else text.to(self.device, non_blocking=True)
-        # a well-formed line is at least 20 bytes ("a c a:1+ a:2+ 1 ref"); size the offset array for 12 and grow if needed
-        cap = n_bytes // 12 + 2
+    # -- line index shared by the text readers (K1b, K9) -------------------------------------------
+    def index_lines(self, d_text, skip_minus=False, min_line_bytes=12):
+        """Byte offsets of the non-blank lines of a device text buffer -> (line_off int64[n] device tensor, n)."""
+        n_bytes = d_text.shape[0]
+        cap = n_bytes // max(1, int(min_line_bytes)) + 2
         n_rows_d = self.zeros(1, torch.int64)
         while True:
             line_off = self.empty(cap, torch.int64)
@@ -114,7 +108,20 @@ class Context:
             if n <= cap:
                 break
             cap = n
-        rows = DeviceRows(self, d_text, line_off[:n], n, width)
+        return line_off[:n], n
+
+    # -- K1b: k-mer TSV on the device ------------------------------------------------------------
+    def parse_kmer_tsv(self, text, width, skip_minus=False):
+        """uint8 host tensor (pinned for speed) or device tensor with the bytes of `vg find -K w -E` TSV files ->
+        DeviceRows (packed k-mers, N mask and the numeric side arrays on the device)."""
+        assert text.dtype == torch.uint8 and text.dim() == 1
+        n_bytes = text.shape[0]
+        self.enter()
+        with torch.cuda.stream(self.stream):
+            d_text = text if text.is_cuda else text.to(self.device, non_blocking=True)
+        # a well-formed line is at least 20 bytes ("a c a:1+ a:2+ 1 ref"); size the offset array for 12 and grow if needed
+        line_off, n = self.index_lines(d_text, skip_minus, 12)
+        rows = DeviceRows(self, d_text, line_off, n, width)
         if n:
             check(self.lib.gb2_tsv_parse_rows(self.h, _ptr(d_text), n_bytes, _ptr(rows.line_off), n, int(width), _ptr(rows.packed),
                                               _ptr(rows.nmask), _ptr(rows.start), _ptr(rows.stop), _ptr(rows.strand),

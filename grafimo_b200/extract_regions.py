@@ -134,6 +134,23 @@ class DeviceGraph:
                                       int(max_node_len), ctypes.byref(h)), "gb2_graph_build", ctx.h)
         return DeviceGraph(ctx, None, handle=h, chrom=chrom)
 
+    @staticmethod
+    def from_files(ctx, fasta, vcf, chrom, display_name=None, max_node_len=32, use_haplotypes=True):
+        """Reference FASTA + phased VCF (the inputs of `grafimo buildvg`, src/grafimo/__main__.py:198-217) -> graph on
+        the device: the VCF is tokenised on the GPU (K9), the graph is built by the library (gb2_graph_build)."""
+        from .vgraph import read_fasta, read_vcf_device
+        seqs = fasta if isinstance(fasta, dict) else read_fasta(fasta)  # a dict {name: sequence} is taken as is
+        if chrom not in seqs:
+            raise KeyError(f"{chrom} is not a sequence of {fasta}")
+        if vcf:
+            variants, gtb, _ = read_vcf_device(ctx, vcf, chrom)
+        else:
+            variants, gtb = [], None
+        if not use_haplotypes or (gtb is not None and gtb[1] == 0):
+            gtb = None
+        return DeviceGraph.build(ctx, display_name if display_name is not None else chrom, seqs[chrom], variants, gt_bits=gtb,
+                                 max_node_len=max_node_len)
+
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.gb2_graph_destroy(self.h)

@@ -347,3 +347,168 @@ class VariationGraph:
     def to_device(self, ctx):
         from .extract_regions import DeviceGraph
         return DeviceGraph(ctx, self)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K9: the VCF read on the device (csrc/vcf.cu) -- same result as read_vcf, for files of 1000-Genomes size
+# ---------------------------------------------------------------------------------------------------------
+def _vcf_chunks(path, chunk_bytes):
+    """Yields pinned uint8 tensors holding whole lines of a plain or gzipped VCF."""
+    import torch
+    pin = torch.cuda.is_available()
+    op = gzip.open if str(path).endswith(".gz") else open
+    carry = b""
+    with op(path, "rb") as fh:
+        while True:
+            data = fh.read(chunk_bytes - len(carry))
+            if not data:
+                break
+            data = carry + data
+            cut = data.rfind(b"\n") + 1
+            if cut == 0:
+                carry = data
+                if len(carry) >= chunk_bytes:
+                    raise ValueError(f"{path}: a line longer than the chunk size")
+                continue
+            carry = data[cut:]
+            t = torch.empty(cut, dtype=torch.uint8, pin_memory=pin)
+            t.numpy()[:] = np.frombuffer(data, dtype=np.uint8, count=cut)
+            yield t
+    if carry:
+        t = torch.empty(len(carry) + 1, dtype=torch.uint8, pin_memory=pin)
+        t.numpy()[:-1] = np.frombuffer(carry, dtype=np.uint8)
+        t.numpy()[-1] = 10
+        yield t
+
+
+def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
+    """Phased VCF -> ({pos int64, ref_len int32, alt_off int64[n+1], alt uint8}, (gt_bits uint32 [n, words], n_hap),
+    samples): the arrays DeviceGraph.build / gb2_graph_build take, alleles reduced, one entry per ALT allele, in file
+    order (stable-sorted by position).  The text is tokenised on the GPU (gb2_tsv_index_lines, gb2_vcf_parse_fields,
+    gb2_vcf_parse_genotypes); the host only slices the allele strings.  Same conventions as read_vcf."""
+    import ctypes
+
+    import torch
+
+    from ._lib import check
+
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    samples, ploidy = None, None
+    want = None if chrom is None else np.frombuffer(str(chrom).encode("ascii"), dtype=np.uint8)
+    out_pos, out_rlen, out_alt, out_bits = [], [], [], []
+    n_hap = words = 0
+    skipped_many = bad_calls = 0
+    ctx.enter()
+    for text in _vcf_chunks(path, chunk_bytes):
+        host = text.numpy()
+        with torch.cuda.stream(ctx.stream):
+            d_text = text.to(ctx.device, non_blocking=True)
+        line_off, n = ctx.index_lines(d_text, False, 2)
+        if n == 0:
+            continue
+        i32 = lambda: ctx.empty(n, torch.int32)  # noqa: E731
+        kind, clen, pos = ctx.empty(n, torch.uint8), i32(), ctx.empty(n, torch.int64)
+        roff, rlen, aoff, alen, nalt, soff, llen = i32(), i32(), i32(), i32(), i32(), i32(), i32()
+        check(ctx.lib.gb2_vcf_parse_fields(ctx.h, ptr(d_text), d_text.shape[0], ptr(line_off), n, ptr(kind), ptr(clen), ptr(pos),
+                                           ptr(roff), ptr(rlen), ptr(aoff), ptr(alen), ptr(nalt), ptr(soff), ptr(llen)),
+              "gb2_vcf_parse_fields", ctx.h)
+        with torch.cuda.stream(ctx.stream):
+            h = {k: v.cpu().numpy() for k, v in dict(kind=kind, clen=clen, pos=pos, roff=roff, rlen=rlen, aoff=aoff, alen=alen,
+                                                     nalt=nalt, soff=soff, llen=llen, off=line_off).items()}
+        ctx.sync()
+        if (h["kind"] == 2).any():
+            bad = int(np.nonzero(h["kind"] == 2)[0][0])
+            lo = int(h["off"][bad])
+            raise ValueError(f"{path}: malformed VCF line: {bytes(host[lo:lo + 80])!r}")
+        if samples is None:  # the column header precedes the first data line
+            for i in np.nonzero(h["kind"] == 0)[0]:
+                lo = int(h["off"][i])
+                if bytes(host[lo:lo + 6]) == b"#CHROM":
+                    samples = bytes(host[lo:lo + int(h["llen"][i])]).decode("ascii").rstrip("\r").split("\t")[9:]
+        data = h["kind"] == 1
+        if want is not None and data.any():
+            same = data & (h["clen"] == len(want))
+            idx = np.nonzero(same)[0]
+            if len(idx):
+                names = host[h["off"][idx][:, None] + np.arange(len(want))[None, :]]
+                same[idx] = (names == want[None, :]).all(axis=1)
+            data = same
+        sel = np.nonzero(data & (h["nalt"] > 0))[0]
+        if len(sel) == 0:
+            continue
+        if samples is None:
+            samples = []
+        if ploidy is None:
+            with_s = sel[h["soff"][sel] >= 0]
+            ploidy = 2
+            if len(with_s):
+                lo = int(h["off"][with_s[0]] + h["soff"][with_s[0]])
+                call = bytes(host[lo:lo + 64]).split(b"\t")[0].split(b"\n")[0].split(b":")[0]
+                ploidy = call.count(b"|") + call.count(b"/") + 1
+            n_hap = len(samples) * ploidy
+            words = max(4, ((n_hap + 31) // 32 + 3) // 4 * 4)
+        row_base = np.full(n, -1, dtype=np.int64)
+        counts_alt = h["nalt"][sel].astype(np.int64)
+        row_base[sel] = np.concatenate([[0], np.cumsum(counts_alt)[:-1]])
+        n_rows = int(counts_alt.sum())
+        with torch.cuda.stream(ctx.stream):
+            d_bits = torch.zeros((n_rows, words), dtype=torch.int32, device=ctx.device)
+            d_base = torch.from_numpy(row_base).to(ctx.device)
+            d_counts = torch.zeros(2, dtype=torch.int64, device=ctx.device)
+        check(ctx.lib.gb2_vcf_parse_genotypes(ctx.h, ptr(d_text), ptr(line_off), n, ptr(soff), ptr(llen), ptr(nalt), ptr(d_base),
+                                              int(ploidy), n_hap, words, ptr(d_bits), ptr(d_counts)), "gb2_vcf_parse_genotypes", ctx.h)
+        with torch.cuda.stream(ctx.stream):
+            bits = d_bits.cpu().numpy().view(np.uint32)
+            cnt = d_counts.cpu().numpy()
+        ctx.sync()
+        skipped_many += int(cnt[0]); bad_calls += int(cnt[1])
+        # alleles: single-base REF/ALT lines need no trimming and no per-line Python
+        off = h["off"][sel].astype(np.int64)
+        simple = (h["rlen"][sel] == 1) & (h["alen"][sel] == 1)
+        rb = row_base[sel]
+        pos0 = np.zeros(n_rows, dtype=np.int64); rl = np.zeros(n_rows, dtype=np.int32)
+        alts = [None] * n_rows
+        keep = np.zeros(n_rows, dtype=bool)
+        si = np.nonzero(simple)[0]
+        if len(si):
+            r = host[off[si] + h["roff"][sel][si]]
+            a_ = host[off[si] + h["aoff"][sel][si]]
+            ok = ((a_ & 0xDF) >= 65) & ((a_ & 0xDF) <= 90) & ((a_ & 0xDF) != (r & 0xDF))  # a letter other than REF
+            rows_i = rb[si]
+            pos0[rows_i] = h["pos"][sel][si] - 1
+            rl[rows_i] = 1
+            keep[rows_i] = ok
+            up = (a_ & 0xDF)
+            for row, ch in zip(rows_i[ok].tolist(), up[ok].tolist()):
+                alts[row] = bytes([ch])
+        for k in np.nonzero(~simple)[0]:
+            lo = int(off[k])
+            ref_s = bytes(host[lo + int(h["roff"][sel][k]):lo + int(h["roff"][sel][k]) + int(h["rlen"][sel][k])]).decode("ascii")
+            alt_s = bytes(host[lo + int(h["aoff"][sel][k]):lo + int(h["aoff"][sel][k]) + int(h["alen"][sel][k])]).decode("ascii")
+            for j, alt in enumerate(alt_s.split(",")):
+                if alt in (".", "*") or alt.startswith("<") or "[" in alt or "]" in alt:
+                    continue
+                s, r, a_ = reduce_allele(int(h["pos"][sel][k]) - 1, ref_s, alt)
+                if r == a_:
+                    continue
+                row = int(rb[k]) + j
+                pos0[row], rl[row], alts[row], keep[row] = s, len(r), a_.encode("ascii"), True
+        kept = np.nonzero(keep)[0]
+        out_pos.append(pos0[kept]); out_rlen.append(rl[kept]); out_alt.extend(alts[i] for i in kept.tolist())
+        out_bits.append(bits[kept])
+    ctx.leave()
+    if samples is None:
+        samples = []
+    if not out_pos:
+        empty = {"pos": np.zeros(0, np.int64), "ref_len": np.zeros(0, np.int32), "alt_off": np.zeros(1, np.int64), "alt": np.zeros(0, np.uint8)}
+        return empty, (np.zeros((0, max(words, 4)), np.uint32), n_hap), samples
+    pos = np.concatenate(out_pos); rlen = np.concatenate(out_rlen); bits = np.concatenate(out_bits)
+    order = np.argsort(pos, kind="stable")
+    alt_list = [out_alt[i] for i in order.tolist()]
+    alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alt_list])]).astype(np.int64)
+    alt = np.frombuffer(b"".join(alt_list), dtype=np.uint8) if alt_list else np.zeros(0, np.uint8)
+    variants = {"pos": np.ascontiguousarray(pos[order]), "ref_len": np.ascontiguousarray(rlen[order]), "alt_off": alt_off,
+                "alt": alt, "skipped_lines_with_many_alts": skipped_many, "calls_out_of_range": bad_calls}
+    return variants, (np.ascontiguousarray(bits[order]), n_hap), samples

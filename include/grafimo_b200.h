@@ -271,6 +271,28 @@ int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *graph, uint64_t capacity, uint64_
                       int64_t *d_start, int64_t *d_stop, int32_t *d_freq, uint8_t *d_isref, uint32_t *d_region,
                       uint32_t *d_walk, uint8_t *d_walk_len, uint8_t *d_walk_off, uint64_t *d_counts);
 
+/* ---- K9: device-side reader of phased VCF text (the input of the graph path) ---------------------------- */
+/* Replaces, for the graph path, the VCF reading the reference leaves to `vg construct -v` / `vg index -G -v`
+ * (src/grafimo/constructVG.py:332,394-396).  d_text holds whole lines of VCF text; d_line_off the byte offset of every
+ * non-blank line (gb2_tsv_index_lines with skip_minus = 0).
+ * gb2_vcf_parse_fields, per line: d_kind (0 = header/comment line, 1 = data line, 2 = malformed), d_chrom_len (CHROM
+ *   starts at the line start), d_pos (POS as written, 1-based), byte range of REF and of the whole ALT column relative to
+ *   the line start, d_n_alts (comma-separated ALT alleles; 0 for "."), d_samples_off (offset of the first sample column,
+ *   -1 when the line has no samples or FORMAT does not begin with GT), d_line_len (bytes up to the end of line).
+ * gb2_vcf_parse_genotypes, per data line with d_row_base[line] >= 0: rows d_row_base[line] .. +n_alts-1 of d_bits
+ *   (uint32 [rows][words]) receive the haplotype bit set of each ALT allele: bit (sample * ploidy + j) is set when the
+ *   j-th allele of the sample's call ("a|b", "a/b", "a"; "." = reference) is that allele.  d_counts[0] += lines with more
+ *   than 16 ALT alleles (skipped, rows left untouched), d_counts[1] += calls naming an allele that does not exist or a
+ *   haplotype >= n_hap. */
+int gb2_vcf_parse_fields(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off, int64_t n_lines,
+                         uint8_t *d_kind, int32_t *d_chrom_len, int64_t *d_pos, int32_t *d_ref_off, int32_t *d_ref_len,
+                         int32_t *d_alt_off, int32_t *d_alt_len, int32_t *d_n_alts, int32_t *d_samples_off,
+                         int32_t *d_line_len);
+int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, const uint64_t *d_line_off, int64_t n_lines,
+                            const int32_t *d_samples_off, const int32_t *d_line_len, const int32_t *d_n_alts,
+                            const int64_t *d_row_base, int ploidy, int32_t n_hap, int32_t words, uint32_t *d_bits,
+                            uint64_t *d_counts);
+
 #ifdef __cplusplus
 }
 #endif

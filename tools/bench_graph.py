@@ -98,7 +98,21 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             df = ss.compute_results_rows(motif, r2, True, Args) if a.width == 19 else None
         tt.append(time.perf_counter() - t0)
+    # CPU beside it: the oracle (oracle/graph_oracle.py, pure Python: every haplotype spelled out) on a bounded sample
+    from oracle import graph_oracle as go
+    samp = 3000
+    sub = [(p, r, al) for (p, r, al) in variants if p + len(r) < samp - 10]
+    t0 = time.perf_counter()
+    og = go.build_graph(ref[:samp], sub)
+    orows = go.extract_rows(og, gt[:len(sub)].tolist(), (0, samp), a.width)
+    t_or = time.perf_counter() - t0
     out = {
+        "cpu_baseline": {"kind": "port", "what": f"oracle/graph_oracle.py (pure Python, 1 core) on the first {samp} bp x "
+                         f"{a.haplotypes} haplotypes: graph + walks + explicit haplotype counting", "rows": len(orows),
+                         "seconds": t_or, "rows_per_s": len(orows) / t_or,
+                         "context": "the reference runs `vg find` here; the paper's supplementary benchmark gives 1246.6 s (1 thread) "
+                                    "to 212.5 s (16 threads) for GRAFIMO incl. vg on 1 Mbp of regions with 2,548 individuals "
+                                    "(docs/paper_results/time-mem_benchmark, other hardware)"},
         "workload": f"synthetic {L} bp region, {a.haplotypes} haplotypes, {len(variants)} variants "
                     f"({a.indel_frac:.0%} indels), width {a.width}, {len(regions)} region(s)",
         "graph": {"nodes": g.n_nodes, "edges": g.n_edges, "haplotype_set_rows": g.n_cons,
