@@ -83,7 +83,7 @@ SIGNATURES = {
     "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _int, ctypes.POINTER(_u64)]),
     "gb2_graph_extract": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_vcf_parse_fields": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gb2_vcf_parse_genotypes": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
+    "gb2_vcf_parse_genotypes": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),
 }

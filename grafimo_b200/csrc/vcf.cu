@@ -17,7 +17,7 @@
 
 #define VCF_MAX_ALT 16       // ALT alleles per line whose genotype rows are built (more: line is counted and skipped)
 #define GT_THREADS 128
-#define GT_BYTES_PER_THREAD 16
+#define GT_BYTES_PER_THREAD 32
 
 __device__ __forceinline__ bool vcf_eol(uint8_t c) { return c == '\n' || c == '\r' || c == 0; }
 
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(128) gb2_vcf_fields_kernel(const uint8_t *__re
             ++p;
         }
     }
-    int64_t e = p;
-    while (e < hi && !vcf_eol(text[e])) ++e;
+    int64_t e = hi;  // the line ends where the next one starts, minus its line terminator(s) and blank lines
+    while (e > p && (vcf_eol(text[e - 1]) || text[e - 1] == ' ' || text[e - 1] == '\t')) --e;
     kind[i] = k;
     chrom_len[i] = clen;
     pos[i] = v;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) gb2_vcf_fields_kernel(const uint8_t *__re
 }
 
 // One CTA per line.  Bits are accumulated in shared memory ([n_alts][words]) and written out once.
-__global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *__restrict__ text,
+__global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *__restrict__ text, int64_t n_bytes,
                                                                 const unsigned long long *__restrict__ line_off,
                                                                 const int32_t *__restrict__ samples_off,
                                                                 const int32_t *__restrict__ line_len,
@@ -123,12 +123,33 @@ __global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *_
         const int64_t end = lo + line_len[line];
         uint32_t carry = 0;                   // tabs seen in earlier tiles == index of the next sample
         unsigned long long bad = 0;
-        for (int64_t tile = first; tile < end; tile += GT_THREADS * GT_BYTES_PER_THREAD) {
+        // tiles start on a 16-byte boundary so that every thread reads its 32 bytes as two 128-bit loads
+        for (int64_t tile = first & ~(int64_t)15; tile < end; tile += GT_THREADS * GT_BYTES_PER_THREAD) {
             const int64_t b0 = tile + (int64_t)threadIdx.x * GT_BYTES_PER_THREAD;
             uint32_t tabs = 0;
+            if (b0 < end) {
+                if (b0 + GT_BYTES_PER_THREAD <= n_bytes) {
+                    const uint4 *v = reinterpret_cast<const uint4 *>(text + b0);
 #pragma unroll
-            for (int k = 0; k < GT_BYTES_PER_THREAD; ++k)
-                if (b0 + k < end && text[b0 + k] == '\t') tabs |= 1u << k;
+                    for (int h = 0; h < GT_BYTES_PER_THREAD / 16; ++h) {
+                        const uint4 x = __ldg(v + h);
+                        const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // per-byte compare with TAB (0xFF where equal), then the four flags gathered into a nibble
+                            const uint32_t eq = __vcmpeq4(wv[k], 0x09090909u) & 0x01010101u;
+                            const uint32_t m = ((eq * 0x01020408u) >> 24) & 0xFu;
+                            tabs |= m << (16 * h + 4 * k);
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < GT_BYTES_PER_THREAD; ++k)
+                        if (b0 + k < n_bytes && text[b0 + k] == '\t') tabs |= 1u << k;
+                }
+                // only TABs inside [first, end) count
+                if (b0 < first) tabs &= ~((1u << (int)(first - b0)) - 1u);
+                if (b0 + GT_BYTES_PER_THREAD > end) tabs &= (end - b0 >= 32) ? ~0u : ((1u << (int)(end - b0)) - 1u);
+            }
             uint32_t before, total;
             Scan(tmp).ExclusiveSum((uint32_t)__popc(tabs), before, total);
             uint32_t s = carry + before;
@@ -137,6 +158,28 @@ __global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *_
                 tabs &= tabs - 1;
                 // the call of sample s: alleles separated by '|' or '/', up to the first ':' / TAB / end of line
                 int64_t q = b0 + k + 1;
+                // common shape "d|d" + terminator: four independent byte loads, no dependent loop
+                if (q + 4 <= end || (q + 3 == end)) {
+                    const uint8_t c0 = text[q], c1 = text[q + 1], c2 = text[q + 2];
+                    const uint8_t c3 = q + 3 < end ? text[q + 3] : (uint8_t)'\n';
+                    const bool sep = c1 == '|' || c1 == '/';
+                    const bool term = c3 == '\t' || c3 == ':' || vcf_eol(c3);
+                    const bool d0 = c0 >= '0' && c0 <= '9', d2 = c2 >= '0' && c2 <= '9';
+                    if (sep && term && (d0 || c0 == '.') && (d2 || c2 == '.') && ploidy >= 2) {
+                        const int v0 = d0 ? c0 - '0' : 0, v1 = d2 ? c2 - '0' : 0;
+                        const long long h = (long long)s * ploidy;
+                        if (v0 >= 1) {
+                            if (v0 <= na && h < n_hap) atomicOr(&rows_s[(v0 - 1) * words + (int)(h >> 5)], 1u << (h & 31));
+                            else ++bad;
+                        }
+                        if (v1 >= 1) {
+                            if (v1 <= na && h + 1 < n_hap) atomicOr(&rows_s[(v1 - 1) * words + (int)((h + 1) >> 5)], 1u << ((h + 1) & 31));
+                            else ++bad;
+                        }
+                        ++s;
+                        continue;
+                    }
+                }
                 int j = 0, val = -1;
                 while (true) {
                     const uint8_t c = q < end ? text[q] : (uint8_t)'\n';
@@ -184,7 +227,7 @@ extern "C" int gb2_vcf_parse_fields(gb2_ctx *ctx, const uint8_t *d_text, int64_t
     return GB2_OK;
 }
 
-extern "C" int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, const uint64_t *d_line_off, int64_t n_lines,
+extern "C" int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off, int64_t n_lines,
                                        const int32_t *d_samples_off, const int32_t *d_line_len, const int32_t *d_n_alts,
                                        const int64_t *d_row_base, int ploidy, int32_t n_hap, int32_t words,
                                        uint32_t *d_bits, uint64_t *d_counts)
@@ -196,12 +239,13 @@ extern "C" int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, cons
     if (n_lines == 0) return GB2_OK;
     GB2_REQUIRE(ctx, d_text && d_line_off && d_samples_off && d_line_len && d_n_alts && d_row_base && d_bits && d_counts,
                 "gb2_vcf_parse_genotypes: null buffer");
+    GB2_REQUIRE(ctx, ((uintptr_t)d_text & 15u) == 0, "gb2_vcf_parse_genotypes: the text buffer must be 16-byte aligned");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t smem = (size_t)VCF_MAX_ALT * words * sizeof(uint32_t);
     GB2_REQUIRE(ctx, smem <= (size_t)ctx->max_smem_optin - 4096, "gb2_vcf_parse_genotypes: too many haplotypes for one CTA (%d)", n_hap);
     GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_vcf_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gb2_vcf_gt_kernel<<<(unsigned)n_lines, GT_THREADS, smem, ctx->stream>>>(
-        d_text, (const unsigned long long *)d_line_off, d_samples_off, d_line_len, d_n_alts, (const long long *)d_row_base, ploidy,
+        d_text, n_bytes, (const unsigned long long *)d_line_off, d_samples_off, d_line_len, d_n_alts, (const long long *)d_row_base, ploidy,
         n_hap, words, d_bits, (unsigned long long *)d_counts);
     GB2_LAUNCH_CHECK(ctx);
     return GB2_OK;

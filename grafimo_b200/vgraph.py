@@ -353,32 +353,45 @@ class VariationGraph:
 # K9: the VCF read on the device (csrc/vcf.cu) -- same result as read_vcf, for files of 1000-Genomes size
 # ---------------------------------------------------------------------------------------------------------
 def _vcf_chunks(path, chunk_bytes):
-    """Yields pinned uint8 tensors holding whole lines of a plain or gzipped VCF."""
+    """Yields uint8 tensors (views of ONE reusable pinned buffer) holding whole lines of a plain or gzipped VCF; the
+    consumer must be done with a chunk before it asks for the next."""
     import torch
     pin = torch.cuda.is_available()
     op = gzip.open if str(path).endswith(".gz") else open
-    carry = b""
+    size = None
+    if not str(path).endswith(".gz"):
+        import os
+        size = os.stat(path).st_size
+    cap = int(chunk_bytes if size is None else min(chunk_bytes, size + 2))
+    buf = torch.empty(max(cap, 2), dtype=torch.uint8, pin_memory=pin)
+    view = buf.numpy()
+    mv = memoryview(view)
+    fill = 0
     with op(path, "rb") as fh:
         while True:
-            data = fh.read(chunk_bytes - len(carry))
-            if not data:
+            room = view.shape[0] - fill - 1
+            got = fh.readinto(mv[fill:fill + room]) if room > 0 else 0
+            if got:
+                fill += got
+                if fill < view.shape[0] - 1:
+                    continue  # keep filling (gzip returns short reads)
+            if fill == 0:
                 break
-            data = carry + data
-            cut = data.rfind(b"\n") + 1
-            if cut == 0:
-                carry = data
-                if len(carry) >= chunk_bytes:
-                    raise ValueError(f"{path}: a line longer than the chunk size")
-                continue
-            carry = data[cut:]
-            t = torch.empty(cut, dtype=torch.uint8, pin_memory=pin)
-            t.numpy()[:] = np.frombuffer(data, dtype=np.uint8, count=cut)
-            yield t
-    if carry:
-        t = torch.empty(len(carry) + 1, dtype=torch.uint8, pin_memory=pin)
-        t.numpy()[:-1] = np.frombuffer(carry, dtype=np.uint8)
-        t.numpy()[-1] = 10
-        yield t
+            if not got:  # end of file: terminate the last line
+                if view[fill - 1] != 10:
+                    view[fill] = 10
+                    fill += 1
+                yield buf[:fill]
+                break
+            lo = max(0, fill - (64 << 20))
+            cut = bytes(mv[lo:fill]).rfind(b"\n")
+            if cut < 0:
+                raise ValueError(f"{path}: a line longer than the chunk size / 64 MiB")
+            cut += lo + 1
+            yield buf[:cut]
+            rest = fill - cut
+            view[:rest] = view[cut:fill].copy()
+            fill = rest
 
 
 def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
@@ -457,7 +470,7 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
             d_bits = torch.zeros((n_rows, words), dtype=torch.int32, device=ctx.device)
             d_base = torch.from_numpy(row_base).to(ctx.device)
             d_counts = torch.zeros(2, dtype=torch.int64, device=ctx.device)
-        check(ctx.lib.gb2_vcf_parse_genotypes(ctx.h, ptr(d_text), ptr(line_off), n, ptr(soff), ptr(llen), ptr(nalt), ptr(d_base),
+        check(ctx.lib.gb2_vcf_parse_genotypes(ctx.h, ptr(d_text), d_text.shape[0], ptr(line_off), n, ptr(soff), ptr(llen), ptr(nalt), ptr(d_base),
                                               int(ploidy), n_hap, words, ptr(d_bits), ptr(d_counts)), "gb2_vcf_parse_genotypes", ctx.h)
         with torch.cuda.stream(ctx.stream):
             bits = d_bits.cpu().numpy().view(np.uint32)
@@ -480,9 +493,9 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
             pos0[rows_i] = h["pos"][sel][si] - 1
             rl[rows_i] = 1
             keep[rows_i] = ok
-            up = (a_ & 0xDF)
-            for row, ch in zip(rows_i[ok].tolist(), up[ok].tolist()):
-                alts[row] = bytes([ch])
+            letters = [bytes([c]) for c in range(256)]
+            for row, ch in zip(rows_i[ok].tolist(), (a_ & 0xDF)[ok].tolist()):
+                alts[row] = letters[ch]
         for k in np.nonzero(~simple)[0]:
             lo = int(off[k])
             ref_s = bytes(host[lo + int(h["roff"][sel][k]):lo + int(h["roff"][sel][k]) + int(h["rlen"][sel][k])]).decode("ascii")

@@ -288,7 +288,7 @@ int gb2_vcf_parse_fields(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, c
                          uint8_t *d_kind, int32_t *d_chrom_len, int64_t *d_pos, int32_t *d_ref_off, int32_t *d_ref_len,
                          int32_t *d_alt_off, int32_t *d_alt_len, int32_t *d_n_alts, int32_t *d_samples_off,
                          int32_t *d_line_len);
-int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, const uint64_t *d_line_off, int64_t n_lines,
+int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, const uint64_t *d_line_off, int64_t n_lines,
                             const int32_t *d_samples_off, const int32_t *d_line_len, const int32_t *d_n_alts,
                             const int64_t *d_row_base, int ploidy, int32_t n_hap, int32_t words, uint32_t *d_bits,
                             uint64_t *d_counts);
