@@ -12,8 +12,8 @@ import argparse
 import sys
 
 from .motif_ops import get_motif_pwm
-from .res_writer import print_results, write_results
-from .score_sequences import compute_results, compute_results_rows
+from .res_writer import print_results, write_results, write_results_device
+from .score_sequences import compute_results, scan_rows_device
 from .utils import DEFAULT_OUTDIR, UNIF
 from .workflow import Findmotif
 
@@ -52,11 +52,15 @@ def findmotif(wf: Findmotif, debug: bool) -> None:
         motifs += get_motif_pwm(mf, wf, wf.cores, debug)
     graphs = load_graphs(wf, debug) if wf.has_graph_inputs() else None
     for motif in motifs:
-        if graphs is not None:  # scan_graph + compute_results without the text in between
+        if graphs is not None:  # scan_graph + compute_results + writers without text or a DataFrame in between
             rows = [dg.extract(spans, motif.width) for dg, spans in graphs]
-            res = compute_results_rows(motif, rows, debug, wf)
-        else:
-            res = compute_results(motif, wf.kmers_dir, debug, wf)
+            report = scan_rows_device(motif, rows, debug, wf)
+            if wf.text_only:
+                print_results(report.to_df(), debug)
+            else:
+                write_results_device(report, motif, len(motifs), wf, debug)
+            continue
+        res = compute_results(motif, wf.kmers_dir, debug, wf)
         if wf.text_only:
             print_results(res, debug)
         else:

@@ -28,6 +28,16 @@ class Hit(ctypes.Structure):
     _fields_ = [("row", ctypes.c_uint64), ("score", ctypes.c_int32), ("strand", ctypes.c_uint32)]
 
 
+class Report(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_uint64), ("index_base", ctypes.c_uint64), ("width", ctypes.c_int32), ("layout", ctypes.c_int32),
+                ("want_q", ctypes.c_int32), ("reserved", ctypes.c_int32), ("d_kmer", ctypes.c_void_p), ("d_strand", ctypes.c_void_p),
+                ("d_start", ctypes.c_void_p), ("d_stop", ctypes.c_void_p), ("d_freq", ctypes.c_void_p), ("d_ref", ctypes.c_void_p),
+                ("d_bin", ctypes.c_void_p), ("d_name", ctypes.c_void_p), ("d_strings", ctypes.c_void_p),
+                ("d_string_off", ctypes.c_void_p), ("first_score", ctypes.c_int32), ("first_p", ctypes.c_int32),
+                ("first_q", ctypes.c_int32), ("first_name", ctypes.c_int32), ("first_chrom", ctypes.c_int32),
+                ("first_const", ctypes.c_int32)]
+
+
 class GraphInfo(ctypes.Structure):
     _fields_ = [("n_nodes", ctypes.c_int64), ("n_edges", ctypes.c_int64), ("n_bases", ctypes.c_int64),
                 ("n_sets", ctypes.c_int64), ("n_hap", ctypes.c_int32), ("words", ctypes.c_int32)]
@@ -84,6 +94,8 @@ SIGNATURES = {
     "gb2_graph_extract": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_vcf_parse_fields": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_vcf_parse_genotypes": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]),
+    "gb2_report_measure": (_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
+    "gb2_report_write": (_int, [_vp, _vp, _vp, _vp, _u64]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),
 }

@@ -502,6 +502,75 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     return df
 
 
+def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
+    """The scoring of compute_results_rows with the report left on the device: -> res_writer.DeviceReport (hit columns
+    in HBM + per-bin score / p / q values) for write_results_device (K8).  Same flags and semantics; rows are ordered by
+    (p-value, row, strand) -- deterministic; the reference leaves ties unordered.  Single process (one GPU)."""
+    import torch
+    from .res_writer import DeviceReport
+    if not isinstance(motif, Motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+    no_reverse, recomb = args_obj.noreverse, args_obj.recomb
+    print_scoring_msg(motif, no_reverse, debug)
+    if not motif.is_scaled:
+        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    batches = [r for r in (rows if isinstance(rows, (list, tuple)) else [rows])]
+    width = motif.width
+    strands = 1 if no_reverse else 2
+    n_kmers = sum(b.n for b in batches)
+    n = n_kmers * strands
+    if n == 0:
+        exception_handler(ValueError, "No result retrieved. Unable to proceed.\n", debug)
+    ctx = batches[0].ctx
+    dev = ctx.device
+    dm = device_motif(motif, ctx)
+    bases = np.concatenate([[0], np.cumsum([b.n for b in batches])]).astype(np.int64)
+    cap = max(1, n if threshold >= 0.25 else min(n, max(1 << 20, n // 8)))
+    while True:
+        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        for b, base in zip(batches, bases[:-1]):
+            if b.n:
+                scan.score(b.packed, b.nmask if b.n_masked() else None, row_base=int(base))
+        found = scan.n_hits()
+        if found <= cap:
+            break
+        cap = found
+    kept = scan.finalize_device(q_filter=bool(qval_t))
+    if not no_qvalue:
+        print("\nComputing q-values...\n")
+    print(f"Scanned sequences:\t{n}")
+    print(f"Scanned nucleotides:\t{n * width}")
+    with torch.cuda.stream(ctx.stream):
+        row = scan.out["row"][:kept]
+        minus = scan.out["strand"][:kept].to(torch.bool)
+        bin_ = (scan.out["iscore"][:kept] - int(dm.lo)).to(torch.int32)
+        cat = lambda name, dt: torch.cat([getattr(b, name)[:b.n].to(dt) for b in batches]) if len(batches) > 1 else getattr(batches[0], name)[:batches[0].n].to(dt)  # noqa: E731
+        packed, start, stop = cat("packed", torch.int64)[row], cat("start", torch.int64)[row], cat("stop", torch.int64)[row]
+        freq, isref = cat("freq", torch.int64)[row], cat("isref", torch.bool)[row]
+        name_base = np.concatenate([[0], np.cumsum([len(b.regions) for b in batches])])
+        region = torch.cat([b.region[:b.n].to(torch.int32) + int(nb) for b, nb in zip(batches, name_base[:-1])])[row]
+        # '-' hits: reverse complement of the k-mer, start/stop swapped (SURVEY.md F1)
+        comp = ~packed
+        rc = torch.zeros_like(packed)
+        for i in range(width):
+            rc |= ((comp >> (2 * i)) & 3) << (2 * (width - 1 - i))
+        kmer = torch.where(minus, rc, packed)
+        s2 = torch.where(minus, stop, start)
+        e2 = torch.where(minus, start, stop)
+        ref = (isref & ((e2 - s2).abs() == width)).to(torch.uint8)  # score_sequences.py:305-307
+        strand = torch.where(minus, torch.tensor(45, dtype=torch.uint8, device=dev), torch.tensor(43, dtype=torch.uint8, device=dev))
+        keep = torch.ones_like(minus) if recomb else freq > 0  # resultsTmp.py:309-310
+        cols = [c[keep].contiguous() for c in (kmer, strand, s2, e2, freq, ref, bin_, region)]
+        qtab = scan.qtab.cpu().numpy() if not no_qvalue else None
+    ctx.sync()
+    seqnames = [b.region_name(r) for b in batches for r in range(len(b.regions))]
+    span = int(dm.span)
+    score_by_bin = (np.arange(span, dtype=np.int64) + int(dm.lo)) / np.float64(motif.scale) + np.float64(width) * np.float64(motif.offset)
+    return DeviceReport(ctx, motif, width, not no_qvalue, *cols, seqnames, score_by_bin, dm.ptable,
+                        qtab[:span] if qtab is not None else None)
+
+
 def compute_qvalues(pvalues: List[float], debug: bool) -> List[float]:
     """B3 seam (src/grafimo/score_sequences.py:401-428): Benjamini-Hochberg q-values of a list of p-values,
     same order in and out.  Inside compute_results the q-values come from the score histogram (K5); this

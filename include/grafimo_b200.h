@@ -293,6 +293,31 @@ int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes
                             const int64_t *d_row_base, int ploidy, int32_t n_hap, int32_t words, uint32_t *d_bits,
                             uint64_t *d_counts);
 
+/* ---- K8: report files formatted on the device ---------------------------------------- */
+/* Replaces `DataFrame.to_csv(sep="\t")` (src/grafimo/res_writer.py:136) and writeGFF3 (res_writer.py:213-303) for
+ * device-resident hit columns; byte layout per SURVEY.md 8a (a14).  Score / p-value / q-value text comes from per-bin
+ * string tables the host formats once with the reference's own formatters; the kernel writes integers, the k-mer and
+ * the literals.  Strings live back to back in d_strings, string k = d_strings[d_string_off[k] .. d_string_off[k+1]).
+ * Tables (index of their first string): first_score / first_p / first_q (+ d_bin[row]), first_name / first_chrom
+ * (+ d_name[row]; chrom = seqname.split(':')[0]), first_const: motif id, motif name, "ref", "non.ref",
+ * "\tgrafimo\tnucleotide_motif\t", "\t.\tName=", ";Alias=", ";ID=", "=-=", ";pvalue==", ";qvalue=", ";sequence==", "=;\n". */
+typedef struct gb2_report {
+    uint64_t n_rows, index_base;       /* index_base: value of the first row's index column (TSV) */
+    int32_t width, layout, want_q, reserved; /* layout 0 = TSV rows, 1 = GFF3 rows; want_q 0 = no q-value column */
+    const uint64_t *d_kmer;            /* the k-mer as reported (reverse-complemented already for '-' hits) */
+    const uint8_t *d_strand;           /* '+' or '-' */
+    const int64_t *d_start, *d_stop, *d_freq;
+    const uint8_t *d_ref;              /* 1 = "ref", 0 = "non.ref" (after the |stop-start| != w rewrite) */
+    const int32_t *d_bin, *d_name;
+    const uint8_t *d_strings;
+    const uint32_t *d_string_off;
+    int32_t first_score, first_p, first_q, first_name, first_chrom, first_const;
+} gb2_report;
+/* Pass 1: byte length of every row -> exclusive offsets in d_row_off[n_rows + 1]; *h_total_bytes = size of the body
+ * (header lines are the caller's).  Synchronises.  Pass 2 writes the rows at those offsets into d_out. */
+int gb2_report_measure(gb2_ctx *ctx, const gb2_report *report, uint64_t *d_row_off, uint64_t *h_total_bytes);
+int gb2_report_write(gb2_ctx *ctx, const gb2_report *report, const uint64_t *d_row_off, uint8_t *d_out, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

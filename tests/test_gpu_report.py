@@ -1,0 +1,91 @@
+"""GPU tests of K8 (csrc/report.cu): TSV / GFF3 bytes written from device-resident hit columns against the host
+writers (pandas to_csv / gff3_lines, which are pinned on reference-generated goldens) on the same rows."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import golden_util as gu
+import graph_util as gr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from grafimo_b200.engine import Context
+    return Context(0)
+
+
+class _Args:
+    def __init__(self, threshold=1.0, noqvalue=False, qvalueT=False, noreverse=False, recomb=True, outdir="out", text_only=True):
+        self.cores, self.threshold, self.noqvalue, self.qvalueT = 1, float(threshold), noqvalue, qvalueT
+        self.noreverse, self.recomb, self.verbose, self.outdir, self.text_only, self.top_graphs = noreverse, recomb, False, outdir, text_only, 0
+
+
+def _motif(tmp_path, key="ctcf_meme"):
+    from grafimo_b200 import motif_ops as mo
+    p = tmp_path / f"{key}.meme"
+    p.write_text(gu.fixtures()[key])
+    return mo.build_motif_meme(str(p), "unfrm_dst", 0.1, False, 1, False, True)[0]
+
+
+@pytest.mark.parametrize("opts", [dict(threshold=1.0), dict(threshold=0.05, recomb=False), dict(threshold=0.3, noreverse=True),
+                                  dict(threshold=1.0, qvalueT=True), dict(threshold=0.02, noqvalue=True)])
+def test_device_writer_equals_host_writers(ctx, tmp_path, opts):
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.extract_regions import DeviceGraph
+    from grafimo_b200.res_writer import write_results, write_results_device
+    ss._ctx = ctx
+    motif = _motif(tmp_path)
+    ref, vs, gt = gr.random_case(77, length=5000, n_var=250, n_hap=40)
+    rows = [DeviceGraph.build(ctx, "7", ref, vs, gt=gt).extract([(0, 2100), (2000, 5000)], 19)]
+    ref2, vs2, gt2 = gr.random_case(78, length=1500, n_var=60, n_hap=40)
+    rows.append(DeviceGraph.build(ctx, "X", ref2, vs2, gt=gt2).extract([(10, 1500)], 19))
+    a_host = _Args(outdir=str(tmp_path / "host"), **opts)
+    a_dev = _Args(outdir=str(tmp_path / "dev"), **opts)
+    df = ss.compute_results_rows(motif, rows, True, a_host)
+    write_results(df, motif, 1, a_host, True)
+    report = ss.scan_rows_device(motif, rows, True, a_dev)
+    assert report.n == len(df) > 20
+    write_results_device(report, motif, 1, a_dev, True)
+    for ext in ("tsv", "gff"):
+        host = (tmp_path / "host" / f"grafimo_out.{ext}").read_text().split("\n")
+        dev = (tmp_path / "dev" / f"grafimo_out.{ext}").read_text().split("\n")
+        assert host[0] == dev[0] and host[-1] == dev[-1] == "" and len(host) == len(dev) == len(df) + 2
+        if ext == "tsv":  # the index column follows the row order, which differs between the two paths only inside p-value ties
+            assert [ln.split("\t", 1)[0] for ln in dev[1:-1]] == [str(i) for i in range(len(df))]
+            strip = lambda ln: ln.split("\t", 1)[1]  # noqa: E731
+            assert sorted(map(strip, host[1:-1])) == sorted(map(strip, dev[1:-1]))
+            pcol = 8
+            p = np.array([float(ln.split("\t")[pcol]) for ln in dev[1:-1]])
+            assert (np.diff(p) >= 0).all()
+        else:
+            assert sorted(host[1:-1]) == sorted(dev[1:-1])
+    # the DataFrame view of the device report is the same table
+    d2 = report.to_df()
+    gu.assert_tables_equal({c: d2[c].to_numpy() for c in d2.columns}, {c: df[c].to_numpy() for c in df.columns}, list(df.columns))
+    assert list(d2.columns) == list(df.columns)
+
+
+def test_device_writer_large_and_long_motif(ctx, tmp_path):
+    """Every window reported (-t 1) for a w = 30 motif on a denser graph: 1e5+ rows, all bytes equal to the host writers."""
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.extract_regions import DeviceGraph
+    from grafimo_b200.res_writer import gff3_lines
+    ss._ctx = ctx
+    motif = _motif(tmp_path, "synth_w30_meme")
+    ref, vs, gt = gr.random_case(5, length=40000, n_var=1500, n_hap=64, indel=0.3)
+    rows = DeviceGraph.build(ctx, "3", ref, vs, gt=gt).extract([(0, 40000)], 30)
+    a = _Args(threshold=1.0, recomb=True)
+    report = ss.scan_rows_device(motif, rows, True, a)
+    assert report.n > 100_000
+    df = report.to_df()
+    tsv_dev = report.render(0).decode().split("\n")
+    import io
+    buf = io.StringIO()
+    df.to_csv(buf, sep="\t", encoding="utf-8")
+    tsv_host = buf.getvalue().split("\n")
+    assert tsv_host[1:] == tsv_dev  # same order here: both come from the device report
+    assert tsv_host[0] + "\n" == report.tsv_header().decode()
+    gff_dev = report.render(1).decode()
+    assert gff_dev == "".join(gff3_lines(df, False, True))

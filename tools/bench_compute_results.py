@@ -11,6 +11,7 @@ from grafimo_b200.score_sequences import compute_results
 from grafimo_b200.workflow import Findmotif
 
 mrows = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+threshold = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-4   # 1 = report every row (the paper's `-t 1` runs)
 n_kmers = int(mrows * 1e6 / 2)
 tmp = tempfile.mkdtemp(prefix="gb2_cr_")
 meme = os.path.join(tmp, "MA0139.1.meme"); open(meme, "w").write(gu.fixtures()["ctcf_meme"])
@@ -35,7 +36,7 @@ with open(os.path.join(d, "chr7.tsv"), "wb") as fh:   # vectorised writer: both 
         fh.write("".join(np.stack([plus, minus], 1).ravel().tolist()).encode())
 size = os.path.getsize(os.path.join(d, "chr7.tsv"))
 print(f"TSV: {2 * n_kmers} rows, {size / 1e9:.2f} GB, generated in {time.time() - t0:.1f}s")
-wf = Findmotif(motif=[meme], kmers_dir=os.path.join(tmp, "kmers"), threshold=1e-4, verbose=True)
+wf = Findmotif(motif=[meme], kmers_dir=os.path.join(tmp, "kmers"), threshold=threshold, recomb=True, verbose=True)
 for rep in range(3):
     t = time.time()
     with contextlib.redirect_stdout(io.StringIO()) as out:
@@ -43,6 +44,12 @@ for rep in range(3):
     dt = time.time() - t
     print(f"compute_results run {rep}: {dt:.3f}s  {2 * n_kmers / dt / 1e6:.1f} M rows/s  ({size / dt / 1e9:.2f} GB/s of text)  hits={len(df)}")
 print(out.getvalue().strip().replace("\n\n", "\n"))
+if threshold >= 1.0:
+    from grafimo_b200.res_writer import write_results
+    wf2 = Findmotif(motif=[meme], kmers_dir=os.path.join(tmp, "kmers"), threshold=threshold, out=os.path.join(tmp, "out"), text_only=True, verbose=True)
+    t = time.time()
+    write_results(df, motif, 1, wf2, True)
+    print(f"write_results (TSV + GFF3, no HTML): {time.time() - t:.2f}s for {len(df)} rows")
 from oracle import oracle as orc
 k = 200000
 rows = np.ascontiguousarray(np.concatenate([fwd[:k], rc[:k]]))
