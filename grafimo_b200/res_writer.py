@@ -162,7 +162,8 @@ class DeviceReport:
         return blob, off, first
 
     def render(self, layout):
-        """-> bytes of the body rows of the TSV (layout 0) or GFF3 (layout 1) file."""
+        """-> uint8 array (a bytes-like view of pinned memory) with the body rows of the TSV (layout 0) or GFF3
+        (layout 1) file."""
         import ctypes
 
         import torch
@@ -170,7 +171,7 @@ class DeviceReport:
         from ._lib import Report, check
         ctx = self.ctx
         if self.n == 0:
-            return b""
+            return np.zeros(0, dtype=np.uint8)
         blob, off, first = self._tables(layout)
         with torch.cuda.stream(ctx.stream):
             d_blob = torch.from_numpy(blob.copy()).to(ctx.device)
@@ -192,11 +193,12 @@ class DeviceReport:
             out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=ctx.device)
         check(ctx.lib.gb2_report_write(ctx.h, ctypes.byref(r), ctypes.c_void_p(row_off.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                        nbytes), "gb2_report_write", ctx.h)
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)  # pinned: the copy back runs at PCIe speed
         with torch.cuda.stream(ctx.stream):
-            host = out[:nbytes].cpu()
+            host.copy_(out[:nbytes], non_blocking=True)
         ctx.sync()
         ctx.leave()
-        return host.numpy().tobytes()
+        return host.numpy()
 
     def to_df(self) -> pd.DataFrame:
         """The same rows as a DataFrame with the reference's columns (resultsTmp.py:269-301), in the device's order."""

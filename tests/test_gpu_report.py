@@ -80,12 +80,12 @@ def test_device_writer_large_and_long_motif(ctx, tmp_path):
     report = ss.scan_rows_device(motif, rows, True, a)
     assert report.n > 100_000
     df = report.to_df()
-    tsv_dev = report.render(0).decode().split("\n")
+    tsv_dev = report.render(0).tobytes().decode().split("\n")
     import io
     buf = io.StringIO()
     df.to_csv(buf, sep="\t", encoding="utf-8")
     tsv_host = buf.getvalue().split("\n")
     assert tsv_host[1:] == tsv_dev  # same order here: both come from the device report
     assert tsv_host[0] + "\n" == report.tsv_header().decode()
-    gff_dev = report.render(1).decode()
+    gff_dev = report.render(1).tobytes().decode()
     assert gff_dev == "".join(gff3_lines(df, False, True))

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--regions", type=int, default=1, help="split the region into this many BED-like regions")
     ap.add_argument("--indel-frac", type=float, default=0.1)
     ap.add_argument("--density", type=float, default=1.0 / 40.0)
+    ap.add_argument("--dense", action="store_true", help="also time the unthresholded report (-t 1): K8 device writer vs DataFrame + host writers")
     a = ap.parse_args()
     import torch
     from grafimo_b200 import engine, synth
@@ -98,6 +99,43 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             df = ss.compute_results_rows(motif, r2, True, Args) if a.width == 19 else None
         tt.append(time.perf_counter() - t0)
+    dense = None
+    if a.dense and a.width == 19:
+        from grafimo_b200.res_writer import write_results, write_results_device
+
+        class Dense:
+            cores, threshold, noqvalue, qvalueT, noreverse, recomb, verbose, text_only, top_graphs = 1, 1.0, False, False, False, True, False, True, 0
+            outdir = os.path.join(tmp, "dense_dev")
+        r2 = dg.extract(regions, a.width)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            rep = ss.scan_rows_device(motif, r2, True, Dense)
+        ctx.sync()
+        t_scan = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            write_results_device(rep, motif, 1, Dense, True)
+        t_write = time.perf_counter() - t0
+        sizes = [os.path.getsize(os.path.join(Dense.outdir, f)) for f in ("grafimo_out.tsv", "grafimo_out.gff")]
+        t0 = time.perf_counter()
+        tsv = rep.render(0)
+        t_render_tsv = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        gff = rep.render(1)
+        t_render_gff = time.perf_counter() - t0
+        Dense.outdir = os.path.join(tmp, "dense_host")
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            dfd = ss.compute_results_rows(motif, r2, True, Dense)
+        t_df = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            write_results(dfd, motif, 1, Dense, True)
+        t_hostw = time.perf_counter() - t0
+        dense = {"rows_reported": rep.n, "scan_to_device_report_s": t_scan, "device_writer_tsv_gff_files_s": t_write,
+                 "render_tsv_s": t_render_tsv, "render_gff_s": t_render_gff, "tsv_bytes": sizes[0], "gff_bytes": sizes[1],
+                 "dataframe_path_s": t_df, "host_writers_tsv_gff_s": t_hostw}
+        del tsv, gff, dfd
     # CPU beside it: the oracle (oracle/graph_oracle.py, pure Python: every haplotype spelled out) on a bounded sample
     from oracle import graph_oracle as go
     samp = 3000
@@ -123,7 +161,7 @@ def main():
         "rows_per_s": n / min(te), "scored_windows_equiv_per_s": 2 * n / min(te),
         "freq_sum_invariant_ok": invariant_ok,
         "graph_to_table_s_best": min(tt), "hits": None if df is None else int(len(df)),
-        "launches_total": ctx.launches,
+        "launches_total": ctx.launches, "dense_report": dense,
     }
     print(json.dumps(out))
 
