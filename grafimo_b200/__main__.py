@@ -13,7 +13,7 @@ import sys
 
 from .motif_ops import get_motif_pwm
 from .res_writer import print_results, write_results, write_results_device
-from .score_sequences import compute_results, scan_rows_device
+from .score_sequences import compute_results, scan_dir_device, scan_rows_device
 from .utils import DEFAULT_OUTDIR, UNIF
 from .workflow import Findmotif
 
@@ -60,6 +60,11 @@ def findmotif(wf: Findmotif, debug: bool) -> None:
             else:
                 write_results_device(report, motif, len(motifs), wf, debug)
             continue
+        if not wf.text_only:  # files straight from the device columns (K8) when the input allows it
+            report = scan_dir_device(motif, wf.kmers_dir, debug, wf)
+            if report is not None:
+                write_results_device(report, motif, len(motifs), wf, debug)
+                continue
         res = compute_results(motif, wf.kmers_dir, debug, wf)
         if wf.text_only:
             print_results(res, debug)

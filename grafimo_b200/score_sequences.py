@@ -107,9 +107,10 @@ def device_motif(motif: Motif, ctx=None):
 _CHUNK_BYTES = 1 << 30  # TSV text is parsed on the device in chunks of at most 1 GiB (cut at line boundaries)
 
 
-def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
+def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES, segments: Optional[list] = None):
     """Yields (pinned) uint8 tensors holding whole lines of the concatenated files; every file is
-    newline-terminated, chunks are cut at line boundaries."""
+    newline-terminated, chunks are cut at line boundaries.  When `segments` is a list, one entry per yielded chunk is
+    appended to it: [(file index, byte offset in the chunk where that file's lines begin), ...]."""
     import torch
     pin = torch.cuda.is_available()
     sizes = [os.stat(f).st_size for f in files]
@@ -121,7 +122,9 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
         view = buf.numpy()
         jobs, off = [], 0
         seg = 32 << 20
-        for fn, sz in zip(files, sizes):
+        segs = []
+        for fi, (fn, sz) in enumerate(zip(files, sizes)):
+            segs.append((fi, off))
             for lo in range(0, sz, seg):
                 jobs.append((fn, lo, min(seg, sz - lo), off + lo))
             view[off + sz] = 10
@@ -148,6 +151,8 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
             for j in jobs:
                 read(j)
         if off > 0:
+            if segments is not None:
+                segments.append(segs)
             yield buf[:off]
         return
 
@@ -157,7 +162,9 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
 
     buf, view = new_buf(0)
     fill = 0
-    for fn in files:
+    segs = []
+    for fi, fn in enumerate(files):
+        segs.append((fi, fill))
         with open(fn, "rb") as fh:
             while True:
                 room = view.shape[0] - fill - 1  # one spare byte for a file-terminating newline
@@ -168,10 +175,13 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
                         raise ValueError(f"{fn}: a line longer than the chunk size / 1 MiB")
                     cut += lo + 1
                     carry = view[cut:fill].copy()
+                    if segments is not None:
+                        segments.append([sg for sg in segs if sg[1] < cut])
                     yield buf[:cut]
                     buf, view = new_buf(len(carry))
                     view[:len(carry)] = carry
                     fill = len(carry)
+                    segs = [(fi, 0)]  # the current file goes on in the new chunk
                     continue
                 got = fh.readinto(memoryview(view)[fill:fill + room])
                 if not got:
@@ -183,6 +193,8 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES):
             fill += 1
         left -= 1
     if fill > 0:
+        if segments is not None:
+            segments.append(segs)
         yield buf[:fill]
 
 
@@ -568,6 +580,127 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
     span = int(dm.span)
     score_by_bin = (np.arange(span, dtype=np.int64) + int(dm.lo)) / np.float64(motif.scale) + np.float64(width) * np.float64(motif.offset)
     return DeviceReport(ctx, motif, width, not no_qvalue, *cols, seqnames, score_by_bin, dm.ptable,
+                        qtab[:span] if qtab is not None else None)
+
+
+def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
+    """compute_results with the report left on the device: the `vg find` TSVs under `<sequence_loc>/width_<w>/` are
+    parsed, scored and finalized on the GPU and the hit columns stay there -> res_writer.DeviceReport for
+    write_results_device (K8), no DataFrame.  Returns None when the input needs the general path (compute_results):
+    a file whose lines do not all carry the same region name (vg writes one file per region), lines with leading blanks,
+    a reference column that is neither `ref` nor `non.ref`, lower-case or non-ACGTN k-mers, or more than one process.  Rows are ordered by (p-value, row, strand)."""
+    import torch
+    import torch.distributed as tdist
+    from .res_writer import DeviceReport
+    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+        return None
+    if not isinstance(motif, Motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    if not os.path.isdir(sequence_loc):
+        exception_handler(FileNotFoundError, f"Unable to locate {sequence_loc}.\n", debug)
+    threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+    no_reverse, recomb = args_obj.noreverse, args_obj.recomb
+    if not motif.is_scaled:
+        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    width = motif.width
+    files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
+    files = [f for f in files if os.stat(f).st_size > 0]
+    ctx = _context()
+    dev = ctx.device
+    dm = device_motif(motif, ctx)
+    segments, chunks, names, n = [], [], [], 0
+    name_of_file = {}
+    for text in _text_chunks(files, _CHUNK_BYTES, segments) if files else ():
+        rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
+        st = rows.stats()
+        if st["malformed"]:
+            exception_handler(ValueError, f"{st['malformed']} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
+                              "symbols are required).\n", debug)
+        if st["bad_rows"] or (rows.n and bool((rows.ref[:rows.n] == 2).any().item())):
+            return None
+        host = text.numpy()
+        segs = segments[-1]
+        with torch.cuda.stream(ctx.stream):
+            seg_start = torch.tensor([o for _, o in segs], dtype=torch.int64, device=dev)
+            file_of_row = torch.bucketize(rows.line_off[:rows.n], seg_start, right=True) - 1  # index into segs
+            # every line of a file must begin with the name its first line has (vg writes one file per region)
+            if rows.n:
+                first_row = torch.full((len(segs),), rows.n, dtype=torch.int64, device=dev)
+                first_row.scatter_reduce_(0, file_of_row, torch.arange(rows.n, device=dev), reduce="amin")
+                has = first_row < rows.n
+                fr = first_row.clamp(max=max(rows.n - 1, 0))
+                nl = rows.name_len[:rows.n].to(torch.int64)
+                off = rows.line_off[:rows.n]
+                ok = bool((nl == nl[fr][file_of_row]).all().item())
+                first_byte = rows.d_text[off]
+                ok = ok and not bool(((first_byte == 32) | (first_byte == 9)).any().item())  # leading blanks: general path
+                if ok:  # k-mers are printed from their packed form, i.e. in upper case: lower-case input takes the general path
+                    kcol = torch.arange(width, device=dev)[None, :]
+                    kb = rows.d_text[(off + rows.seq_off[:rows.n].to(torch.int64))[:, None] + kcol]
+                    ok = not bool((kb >= 97).any().item())
+                if ok:
+                    mx = int(nl.max().item())
+                    col = torch.arange(mx, device=dev)[None, :]
+                    a = rows.d_text[(off[:, None] + col).clamp(max=rows.d_text.shape[0] - 1)]
+                    b = rows.d_text[(off[fr][file_of_row][:, None] + col).clamp(max=rows.d_text.shape[0] - 1)]
+                    ok = bool(((a == b) | (col >= nl[:, None])).all().item())
+                if not ok:
+                    return None
+                fr_h, has_h = fr.cpu().numpy(), has.cpu().numpy()
+                off_h, nl_h = off[fr].cpu().numpy(), nl[fr].cpu().numpy()
+                local = np.full(len(segs), -1, dtype=np.int64)
+                for k, (fi, _) in enumerate(segs):
+                    if not has_h[k]:
+                        continue
+                    nm = bytes(host[off_h[k]:off_h[k] + nl_h[k]]).decode("ascii")
+                    if fi in name_of_file and names[name_of_file[fi]] != nm:
+                        return None
+                    if fi not in name_of_file:
+                        name_of_file[fi] = len(names)
+                        names.append(nm)
+                    local[k] = name_of_file[fi]
+                name_id = torch.from_numpy(local).to(dev)[file_of_row].to(torch.int32)
+            else:
+                name_id = torch.zeros(0, dtype=torch.int32, device=dev)
+        rows.d_text = None
+        rows.name_id = name_id
+        chunks.append((rows, n, st))
+        n += rows.n
+    print_scoring_msg(motif, no_reverse, debug)
+    if n == 0:
+        errmsg = "No result retrieved. Unable to proceed.\n"
+        errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
+        exception_handler(ValueError, errmsg, debug)
+    cap = max(1, n if threshold >= 0.25 else min(n, max(1 << 20, n // 8)))
+    while True:
+        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        for rows, base, st in chunks:
+            if rows.n:
+                scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=base)
+        found = scan.n_hits()
+        if found <= cap:
+            break
+        cap = found
+    kept = scan.finalize_device(q_filter=bool(qval_t))
+    if not no_qvalue:
+        print("\nComputing q-values...\n")
+    print(f"Scanned sequences:\t{n}")
+    print(f"Scanned nucleotides:\t{n * width}")
+    with torch.cuda.stream(ctx.stream):
+        row = scan.out["row"][:kept]
+        bin_ = (scan.out["iscore"][:kept] - int(dm.lo)).to(torch.int32)
+        cat = lambda name, dt: torch.cat([getattr(r, name)[:r.n].to(dt) for r, _, _ in chunks])  # noqa: E731
+        kmer, start, stop = cat("packed", torch.int64)[row], cat("start", torch.int64)[row], cat("stop", torch.int64)[row]
+        freq, refc, strand = cat("freq", torch.int64)[row], cat("ref", torch.uint8)[row], cat("strand", torch.uint8)[row]
+        name_id = cat("name_id", torch.int32)[row]
+        ref = ((refc == 1) & ((stop - start).abs() == width)).to(torch.uint8)  # score_sequences.py:305-307
+        keep = torch.ones_like(ref, dtype=torch.bool) if recomb else freq > 0  # resultsTmp.py:309-310
+        cols = [c[keep].contiguous() for c in (kmer, strand, start, stop, freq, ref, bin_, name_id)]
+        qtab = scan.qtab.cpu().numpy() if not no_qvalue else None
+    ctx.sync()
+    span = int(dm.span)
+    score_by_bin = (np.arange(span, dtype=np.int64) + int(dm.lo)) / np.float64(motif.scale) + np.float64(width) * np.float64(motif.offset)
+    return DeviceReport(ctx, motif, width, not no_qvalue, *cols, names, score_by_bin, dm.ptable,
                         qtab[:span] if qtab is not None else None)
 
 

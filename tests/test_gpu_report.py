@@ -89,3 +89,72 @@ def test_device_writer_large_and_long_motif(ctx, tmp_path):
     assert tsv_host[0] + "\n" == report.tsv_header().decode()
     gff_dev = report.render(1).tobytes().decode()
     assert gff_dev == "".join(gff3_lines(df, False, True))
+
+
+@pytest.mark.parametrize("tag", ["fixture_testmode", "fixture_t05_norecomb", "fixture_plus_N_2files", "fixture_qvalT", "synth_w8"])
+def test_tsv_directory_to_files_on_device(ctx, tmp_path, tag):
+    """`vg find` TSV directory -> K1b/K2/K5/K6 -> K8 files == compute_results + host writers on the reference-generated
+    golden cases (same line sets; the order differs only inside p-value ties)."""
+    from grafimo_b200 import motif_ops as mo
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.res_writer import write_results, write_results_device
+    ss._ctx = ctx
+    tags = gu.scoring_tags()
+    if tag not in tags:
+        pytest.skip(f"no golden case {tag}")
+    c = gu.load_scoring(tag)
+    g = gu.load_motif(c["motif_tag"])
+    fx = gu.fixtures()
+    key = g["source"] if g["source"].endswith("_" + g["fmt"]) else g["source"] + "_meme"
+    (tmp_path / "m.meme").write_text(fx[key])
+    (tmp_path / "bg_nt").write_text(fx["bg_nt"])
+    bg = "unfrm_dst" if g["bgfile"] == "unif" else str(tmp_path / "bg_nt")
+    m = mo.build_motif_meme(str(tmp_path / "m.meme"), bg, g["pseudo"], g["no_reverse"], 1, False, True)[0]
+    d = tmp_path / "seqs" / f"width_{m.width}"
+    d.mkdir(parents=True)
+    for k, lines in enumerate(c["files"]):
+        # one file per region name, as vg writes them
+        by_name = {}
+        for ln in lines:
+            by_name.setdefault(ln.split()[0], []).append(ln)
+        for j, (nm, ls) in enumerate(by_name.items()):
+            (d / f"region_{k}_{j}.tsv").write_text("\n".join(ls) + "\n")
+    o = c["options"] if tag != "fixture_testmode" else dict(threshold=1.0, noqvalue=False, qvalueT=False, noreverse=False, recomb=True)
+    a_host = _Args(outdir=str(tmp_path / "host"), threshold=o["threshold"], noqvalue=o["noqvalue"], qvalueT=o["qvalueT"],
+                   noreverse=o["noreverse"], recomb=o["recomb"])
+    a_dev = _Args(outdir=str(tmp_path / "dev"), threshold=o["threshold"], noqvalue=o["noqvalue"], qvalueT=o["qvalueT"],
+                  noreverse=o["noreverse"], recomb=o["recomb"])
+    df = ss.compute_results(m, str(tmp_path / "seqs"), True, a_host)
+    gu.assert_tables_equal({col: df[col].to_numpy() for col in df.columns}, c["table"], c["columns"])  # still the reference's table
+    write_results(df, m, 1, a_host, True)
+    report = ss.scan_dir_device(m, str(tmp_path / "seqs"), True, a_dev)
+    lower = any(ln.split()[1] != ln.split()[1].upper() for f in c["files"] for ln in f)
+    if lower:  # lower-case k-mers keep their case in the report: the general path must be asked for
+        assert report is None
+        return
+    assert report is not None and report.n == len(df)
+    write_results_device(report, m, 1, a_dev, True)
+    for ext in ("tsv", "gff"):
+        host = (tmp_path / "host" / f"grafimo_out.{ext}").read_text().split("\n")
+        dev = (tmp_path / "dev" / f"grafimo_out.{ext}").read_text().split("\n")
+        assert host[0] == dev[0] and len(host) == len(dev)
+        strip = (lambda ln: ln.split("\t", 1)[1]) if ext == "tsv" else (lambda ln: ln)
+        assert sorted(map(strip, host[1:-1])) == sorted(map(strip, dev[1:-1]))
+
+
+def test_tsv_directory_fallback_conditions(ctx, tmp_path):
+    from grafimo_b200 import score_sequences as ss
+    ss._ctx = ctx
+    m = _motif(tmp_path)
+    d = tmp_path / "k" / "width_19"
+    d.mkdir(parents=True)
+    lines = [ln for ln in gu.fixtures()["scoring_input_tsv"].split("\n") if ln][:50]
+    (d / "a.tsv").write_text("\n".join(lines) + "\n")
+    a = _Args(threshold=1.0)
+    assert ss.scan_dir_device(m, str(tmp_path / "k"), True, a) is not None
+    mixed = lines[:25] + [ln.replace(ln.split()[0], "other:1-2", 1) for ln in lines[25:]]
+    (d / "a.tsv").write_text("\n".join(mixed) + "\n")
+    assert ss.scan_dir_device(m, str(tmp_path / "k"), True, a) is None  # two region names in one file
+    low = [ln.split("\t")[0] + "\t" + ln.split("\t")[1].lower() + "\t" + "\t".join(ln.split("\t")[2:]) for ln in lines]
+    (d / "a.tsv").write_text("\n".join(low) + "\n")
+    assert ss.scan_dir_device(m, str(tmp_path / "k"), True, a) is None  # lower-case k-mers keep their case in the general path
