@@ -199,21 +199,93 @@ def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES, segments: Op
 
 
 def _fixed_strings(text: np.ndarray, offs: np.ndarray, length: int) -> np.ndarray:
-    if len(offs) == 0:
+    """Object array of the ASCII strings text[o:o+length]: one gather, one decode, one slicing pass."""
+    n = len(offs)
+    if n == 0:
         return np.array([], dtype=object)
     idx = offs[:, None] + np.arange(length, dtype=np.int64)[None, :]
-    return np.char.decode(np.ascontiguousarray(text[idx]).view(f"S{length}").ravel(), "ascii").astype(object)
+    flat = np.ascontiguousarray(text[idx]).tobytes().decode("ascii")
+    out = np.empty(n, dtype=object)
+    out[:] = [flat[i:i + length] for i in range(0, n * length, length)]
+    return out
 
 
 def _var_strings(text: np.ndarray, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
-    if len(offs) == 0:
+    """Object array of text[o:o+l].  Region names repeat in long runs (one name per vg file), so rows are compared
+    with their predecessor in offset order and only the heads of the runs are decoded."""
+    n = len(offs)
+    if n == 0:
         return np.array([], dtype=object)
-    mx = int(lens.max())
+    order = np.argsort(offs, kind="stable")
+    o, l = offs[order], lens[order]
+    mx = int(l.max())
     col = np.arange(mx, dtype=np.int64)[None, :]
-    idx = np.minimum(offs[:, None] + col, text.shape[0] - 1)
-    chars = text[idx]
-    chars[col >= lens[:, None]] = 0
-    return np.char.decode(np.ascontiguousarray(chars).view(f"S{mx}").ravel(), "ascii").astype(object)
+    chars = text[np.minimum(o[:, None] + col, text.shape[0] - 1)]
+    chars[col >= l[:, None]] = 0
+    head = np.ones(n, dtype=bool)
+    if n > 1:
+        head[1:] = (l[1:] != l[:-1]) | (chars[1:] != chars[:-1]).any(axis=1)
+    heads = np.nonzero(head)[0]
+    names = np.empty(len(heads), dtype=object)
+    names[:] = [bytes(chars[h, :l[h]]).decode("ascii") for h in heads.tolist()]
+    out = np.empty(n, dtype=object)
+    out[order] = names[np.cumsum(head) - 1]
+    return out
+
+
+def _report_order(pval, start, stop, strand, seq):
+    """Row order of the report: p-value ascending, ties -- which the reference leaves undefined -- by (start, stop,
+    strand, matched_sequence).  Numeric keys first; the sequence strings are only compared inside groups that tie on
+    all of them."""
+    n = len(pval)
+    if n < 2:
+        return np.arange(n)
+    minus = (strand == "-")
+    other = ~minus & (strand != "+")
+    scode = minus.astype(np.int8) * 2 + other.astype(np.int8) * 3  # '+' < '-' < anything else, like the characters
+    order = np.lexsort((scode, stop, start, pval))
+    p, a, b, c = pval[order], start[order], stop[order], scode[order]
+    same = (p[1:] == p[:-1]) & (a[1:] == a[:-1]) & (b[1:] == b[:-1]) & (c[1:] == c[:-1])
+    if same.any():
+        grp = np.concatenate([[0], np.cumsum(~same)])
+        tied = np.zeros(n, dtype=bool)
+        tied[1:] |= same
+        tied[:-1] |= same
+        idx = np.nonzero(tied)[0]
+        sub = np.lexsort((seq[order][idx].astype(str), grp[idx]))
+        order[idx] = order[idx][sub]
+    return order
+
+
+def _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world):
+    """The 12-column table (resultsTmp.py:269-313) from per-hit arrays: filter, merge over ranks, order, DataFrame."""
+    arrays = [seqname, start, stop, strand, score, pval, qval, seq, freq, ref]
+    if not keep.all():
+        arrays = [None if a is None else a[keep] for a in arrays]
+    if world > 1:  # every rank returns the whole table
+        import torch.distributed as tdist
+        parts = [None] * world
+        tdist.all_gather_object(parts, arrays)
+        arrays = [None if parts[0][k] is None else np.concatenate([p[k] for p in parts]) for k in range(len(arrays))]
+    seqname, start, stop, strand, score, pval, qval, seq, freq, ref = arrays
+    order = _report_order(pval, start, stop, strand, seq)
+    n = len(order)
+    cols = {
+        "motif_id": np.full(n, motif.motif_id, dtype=object),
+        "motif_alt_id": np.full(n, motif.motif_name, dtype=object),
+        "sequence_name": seqname[order],
+        "start": start[order],
+        "stop": stop[order],
+        "strand": strand[order],
+        "score": score[order],
+        "p-value": pval[order],
+    }
+    if not no_qvalue:
+        cols["q-value"] = qval[order]
+    cols["matched_sequence"] = seq[order]
+    cols["haplotype_frequency"] = freq[order]
+    cols["reference"] = ref[order]
+    return pd.DataFrame(cols)
 
 
 def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
@@ -347,30 +419,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         ref[m] = r
     keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     ref[(ref == "ref") & (np.abs(stop - start) != width)] = "non.ref"  # score_sequences.py:305-307
-    cols = {
-        "motif_id": [motif.motif_id] * int(keep.sum()),
-        "motif_alt_id": [motif.motif_name] * int(keep.sum()),
-        "sequence_name": seqname[keep],
-        "start": start[keep],
-        "stop": stop[keep],
-        "strand": strand[keep],
-        "score": score[keep],
-        "p-value": pval[keep],
-    }
-    if not no_qvalue:
-        cols["q-value"] = qval[keep]
-    cols["matched_sequence"] = seq[keep]
-    cols["haplotype_frequency"] = freq[keep]
-    cols["reference"] = ref[keep]
-    df = pd.DataFrame(cols)
-    if world > 1:  # every rank returns the whole table
-        parts = [None] * world
-        tdist.all_gather_object(parts, df)
-        df = pd.concat(parts, ignore_index=True)
-    if len(df) > 1:  # deterministic tie order on top of the device's p-ascending order
-        order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
-                            df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
-        df = df.iloc[order].reset_index(drop=True)
+    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df
@@ -485,30 +534,8 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         isref[m] = g["isref"].astype(bool)
     ref = np.where(isref & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
     keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
-    cols = {
-        "motif_id": [motif.motif_id] * int(keep.sum()),
-        "motif_alt_id": [motif.motif_name] * int(keep.sum()),
-        "sequence_name": seqname[keep],
-        "start": start[keep],
-        "stop": stop[keep],
-        "strand": np.where(minus, "-", "+").astype(object)[keep],
-        "score": score[keep],
-        "p-value": pval[keep],
-    }
-    if not no_qvalue:
-        cols["q-value"] = qval[keep]
-    cols["matched_sequence"] = seq[keep]
-    cols["haplotype_frequency"] = freq[keep]
-    cols["reference"] = ref[keep]
-    df = pd.DataFrame(cols)
-    if world > 1:  # every rank returns the whole table
-        parts = [None] * world
-        tdist.all_gather_object(parts, df)
-        df = pd.concat(parts, ignore_index=True)
-    if len(df) > 1:
-        order = np.lexsort((df["matched_sequence"].to_numpy().astype(str), df["strand"].to_numpy().astype(str),
-                            df["stop"].to_numpy(), df["start"].to_numpy(), df["p-value"].to_numpy()))
-        df = df.iloc[order].reset_index(drop=True)
+    strand = np.where(minus, "-", "+").astype(object)
+    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df

@@ -50,6 +50,18 @@ if threshold >= 1.0:
     t = time.time()
     write_results(df, motif, 1, wf2, True)
     print(f"write_results (TSV + GFF3, no HTML): {time.time() - t:.2f}s for {len(df)} rows")
+    from grafimo_b200.res_writer import write_results_device
+    from grafimo_b200.score_sequences import scan_dir_device
+    wf3 = Findmotif(motif=[meme], kmers_dir=os.path.join(tmp, "kmers"), threshold=threshold, recomb=True, out=os.path.join(tmp, "out_dev"), text_only=True, verbose=True)
+    for rep in range(2):
+        t = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            report = scan_dir_device(motif, os.path.join(tmp, "kmers"), True, wf3)
+        t1 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            write_results_device(report, motif, 1, wf3, True)
+        t2 = time.time()
+        print(f"device report path run {rep}: TSV dir -> device columns {t1 - t:.2f}s, K8 TSV + GFF3 files {t2 - t1:.2f}s for {report.n} rows")
 from oracle import oracle as orc
 k = 200000
 rows = np.ascontiguousarray(np.concatenate([fwd[:k], rc[:k]]))
