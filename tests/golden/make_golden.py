@@ -259,6 +259,13 @@ def main():
                                  (30, 0.1, 4000), (32, 0.2, 500)):
         synth[f"synth_w{width}"] = synth_meme(rng, width, alpha, nsites, f"SYN{width:02d}.1")
     fixtures.update({k + "_meme": v for k, v in synth.items()})
+    # motifs wider than one 64-bit packed word (JASPAR 2022 CORE holds 34/35-bp CTCF profiles): own generator, so that
+    # the vectors above do not change
+    rng_wide = np.random.default_rng(20244)
+    synth_wide = {}
+    for width, alpha, nsites in ((33, 0.3, 900), (35, 0.2, 2000), (48, 0.5, 400), (64, 0.3, 1500)):
+        synth_wide[f"synth_w{width}"] = synth_meme(rng_wide, width, alpha, nsites, f"SYN{width:02d}.1")
+    fixtures.update({k + "_meme": v for k, v in synth_wide.items()})
     with open(os.path.join(HERE, "fixtures.json"), "w") as fh:
         json.dump(fixtures, fh, indent=0, sort_keys=True)
 
@@ -292,6 +299,9 @@ def main():
             add_meme(f"{k}_meme__bgnt", fixtures[k + "_meme"], bg_nt, False)
         add_meme("synth_w8_meme__unif", fixtures["synth_w8_meme"], UNIF, False)
         add_meme("synth_w30_meme__bgnt_norev", fixtures["synth_w30_meme"], bg_nt, True)
+        for k in synth_wide:
+            add_meme(f"{k}_meme__bgnt", fixtures[k + "_meme"], bg_nt, False)
+        add_meme("synth_w35_meme__unif_norev", fixtures["synth_w35_meme"], UNIF, True)
         for fmt, fn in (("jaspar", build_motif_jaspar), ("transfac", build_motif_transfac), ("pfm", build_motif_pfm)):
             for bgtag, bg in (("unif", UNIF), ("bgnt", bg_nt)):
                 tag = f"ctcf_{fmt}__{bgtag}"
@@ -360,6 +370,16 @@ def main():
                 recomb=True)
     add_scoring("synth_w32", "synth_w32_meme__bgnt", [rows_w32], 32, threshold=1.0, recomb=True)
     add_scoring("synth_w6", "synth_w6_meme__bgnt", [rows_w6], 6, threshold=1.0, recomb=True)
+    rng_wide = np.random.default_rng(20245)
+    rows_w33 = synth_rows(rng_wide, 1200, 33, chrom="5", with_n=4)
+    rows_w35 = synth_rows(rng_wide, 2500, 35, chrom="11", with_n=6, lower=5)
+    rows_w48 = synth_rows(rng_wide, 800, 48, chrom="2", with_n=2)
+    rows_w64 = synth_rows(rng_wide, 600, 64, chrom="X", with_n=3)
+    add_scoring("synth_w33", "synth_w33_meme__bgnt", [rows_w33], 33, threshold=1.0, recomb=True)
+    add_scoring("synth_w35", "synth_w35_meme__bgnt", [rows_w35[:2000], rows_w35[2000:]], 35, threshold=0.05, recomb=False)
+    add_scoring("synth_w35_norev", "synth_w35_meme__unif_norev", [rows_w35], 35, threshold=0.5, noreverse=True, recomb=True)
+    add_scoring("synth_w48", "synth_w48_meme__bgnt", [rows_w48], 48, threshold=1.0, recomb=True)
+    add_scoring("synth_w64", "synth_w64_meme__bgnt", [rows_w64], 64, threshold=1.0, qvalueT=True, recomb=True)
     print("scoring goldens:", scoring)
     shutil.rmtree(scratch, ignore_errors=True)
 
