@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libgrafimo_b200.so")
 
 GB2_OK = 0
 GB2_ERR_CAPACITY = 4
-MAX_WIDTH = 32
+NARROW_WIDTH = 32  # widest k-mer that fits one packed word
+MAX_WIDTH = 64
 RANGE = 1000
 
 
@@ -117,7 +118,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.gb2_abi_version() != 1:
+    if lib.gb2_abi_version() != 2:
         raise GrafimoB200Error(-1, "grafimo_b200", "ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -229,16 +229,27 @@ extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const do
     for (int64_t k = 1; k < span; ++k)
         if (m->h_ptab[(size_t)k] > m->h_ptab[(size_t)k - 1]) { m->monotone = 0; break; }
 
-    // ---- shared-memory plan of the scoring kernel: replicated LUT + u32 histogram
+    // ---- shared-memory plan of the scoring kernel: replicated LUT + u32 histogram.  Wide motifs whose span does not
+    //      fit next to even one copy of the tables keep the histogram in global memory (hist_global).
     const int64_t budget = (int64_t)ctx->max_smem_optin - 1024;
-    const int64_t hist_bytes = (span + 1) * 4;
-    int R = 32;
-    while (R > 1 && (int64_t)m->n_chunks * 1024 * R + hist_bytes > budget) R >>= 1;
-    if ((int64_t)m->n_chunks * 1024 * R + hist_bytes > budget) {
-        GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld does not fit shared memory", (long long)span);
+    int64_t hist_bytes = (span + 1) * 4;
+    if (span > 65535) {  // the two strands travel as 16-bit fields of one register
+        GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld exceeds 65535", (long long)span);
         gb2_motif_destroy(m);
         return GB2_ERR_MOTIF;
     }
+    m->hist_global = 0;
+    if ((int64_t)m->n_chunks * 1024 + hist_bytes > budget) {
+        if (w <= GB2_NARROW_WIDTH) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld does not fit shared memory", (long long)span);
+            gb2_motif_destroy(m);
+            return GB2_ERR_MOTIF;
+        }
+        m->hist_global = 1;
+        hist_bytes = 0;
+    }
+    int R = 32;
+    while (R > 1 && (int64_t)m->n_chunks * 1024 * R + hist_bytes > budget) R >>= 1;
     m->replicas = R;
     m->smem_bytes = (int64_t)m->n_chunks * 1024 * R + hist_bytes;
     *out = m;

@@ -22,6 +22,8 @@ __device__ __forceinline__ uint32_t base_code(uint32_t c)
     return acgt ? code : (c == 'N' ? 4u : 5u);
 }
 
+// WIDE: 32 < w <= 64, two packed words per row (bases 0..31, 32..w-1)
+template <bool WIDE>
 __global__ void __launch_bounds__(ENC_ROWS) gb2_encode_kernel(const uint8_t *__restrict__ ascii, int64_t n, int w,
                                                              int64_t stride, uint64_t *__restrict__ packed,
                                                              uint32_t *__restrict__ nmask,
@@ -62,10 +64,10 @@ __global__ void __launch_bounds__(ENC_ROWS) gb2_encode_kernel(const uint8_t *__r
         const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (addr >> 2);
         const uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
         const int nwords = (w + 3) >> 2;
-        uint32_t lo = 0, hi = 0, bad = 0;
+        uint32_t lo = 0, hi = 0, lo2 = 0, hi2 = 0, bad = 0;
         uint32_t cur = sw[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < (WIDE ? 16 : 8); ++j) {
             if (j < nwords) {
                 const uint32_t nxt = sw[j + 1];
                 uint32_t v = __byte_perm(cur, nxt, sel);  // bytes 4j .. 4j+3 of the row
@@ -84,19 +86,23 @@ __global__ void __launch_bounds__(ENC_ROWS) gb2_encode_kernel(const uint8_t *__r
                 bad |= u ^ letters;
                 const uint32_t four = (c * 0x01041040u) >> 24;  // codes of the 4 symbols in 8 bits
                 if (j < 4) lo |= four << (8 * j);
-                else hi |= four << (8 * (j - 4));
+                else if (j < 8) hi |= four << (8 * (j - 4));
+                else if (j < 12) lo2 |= four << (8 * (j - 8));
+                else hi2 |= four << (8 * (j - 12));
             }
         }
         x = ((uint64_t)hi << 32) | lo;
+        uint64_t x2 = ((uint64_t)hi2 << 32) | lo2;
         if (bad) {  // rare: find out whether it is an N or a symbol the reference does not define
             const uint8_t *sb = stage + addr;
             for (int i = 0; i < w; ++i) {
                 const uint32_t code = base_code(sb[i]);
                 flag |= (code >= 4u ? 1u : 0u) | (code == 5u ? 2u : 0u);
             }
-            if (flag) x = 0;
+            if (flag) x = x2 = 0;
         }
-        packed[row0 + tid] = x;
+        if (WIDE) reinterpret_cast<ulonglong2 *>(packed)[row0 + tid] = make_ulonglong2(x, x2);
+        else packed[row0 + tid] = x;
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, flag & 1u);
     const unsigned mb = __ballot_sync(0xFFFFFFFFu, flag & 2u);
@@ -120,13 +126,16 @@ extern "C" int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n,
     if (n == 0) return GB2_OK;
     GB2_REQUIRE(ctx, d_ascii && d_packed && d_nmask, "gb2_encode_kmers: null buffer");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)ENC_ROWS * (size_t)stride + 48;
+    const bool wide = w > GB2_NARROW_WIDTH;
+    GB2_REQUIRE(ctx, !wide || ((uintptr_t)d_packed & 15u) == 0, "gb2_encode_kmers: wide k-mers need a 16-byte aligned output");
+    const size_t smem = (size_t)ENC_ROWS * (size_t)stride + 48 + (wide ? 32 : 0);
+    auto kern = wide ? gb2_encode_kernel<true> : gb2_encode_kernel<false>;
     if (smem > 48 * 1024)
-        GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = gb2_div_up(n, ENC_ROWS);
     GB2_REQUIRE(ctx, blocks < ((int64_t)1 << 31), "gb2_encode_kmers: too many rows for one launch");
-    gb2_encode_kernel<<<(unsigned)blocks, ENC_ROWS, smem, ctx->stream>>>(d_ascii, n, w, stride, d_packed, d_nmask,
-                                                                        (unsigned long long *)d_counts);
+    kern<<<(unsigned)blocks, ENC_ROWS, smem, ctx->stream>>>(d_ascii, n, w, stride, d_packed, d_nmask,
+                                                            (unsigned long long *)d_counts);
     GB2_LAUNCH_CHECK(ctx);
     return GB2_OK;
 }

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <new>
+#include <type_traits>
 
 #include "internal.cuh"
 
@@ -63,7 +64,7 @@ struct RowsOut {
     int32_t *freq;
     uint8_t *isref;
     uint32_t *region;
-    uint32_t *walk;      // [capacity][GB2_MAX_WIDTH] node indices, or nullptr
+    uint32_t *walk;      // [capacity][32] ([capacity][64] when w > 32) node indices, or nullptr
     uint8_t *walk_len;   // nodes in the walk
     uint8_t *walk_off;   // offset of the first base in the first node
     unsigned long long capacity;
@@ -125,7 +126,8 @@ __device__ __forceinline__ int32_t walk_frequency(const GraphView &g, const uint
     return total;
 }
 
-template <bool WRITE>
+// MAXW = 32: k-mers of one packed word; MAXW = 64: wide k-mers (two words per row, 64-deep stacks)
+template <bool WRITE, int MAXW>
 __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const GraphView g, const QueryView q, int64_t n_threads,
                                                                       uint32_t *__restrict__ counts,
                                                                       const unsigned long long *__restrict__ offsets,
@@ -144,12 +146,15 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
     const int64_t start = min(g.node_a0[node0] + off0, g.node_clamp[node0]);
     uint32_t n_found = 0;
     if (start >= rs && start < re) {
-        // depth-first traversal; every node on the stack contributes at least one base, so depth < w <= 32
-        uint32_t st_node[GB2_MAX_WIDTH], st_edge[GB2_MAX_WIDTH], st_cons[GB2_MAX_WIDTH];
-        uint8_t st_have[GB2_MAX_WIDTH];  // bases collected before the node at this depth
-        unsigned long long packed = 0;
-        uint32_t nbits = 0;              // bit i: base i of the k-mer is not ACGT
-        uint32_t nonref = 0;             // bit d: node at depth d is off the reference path
+        // depth-first traversal; every node on the stack contributes at least one base, so depth < w <= MAXW
+        constexpr bool WIDE = MAXW > 32;
+        typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type mask_t;
+        uint32_t st_node[MAXW], st_edge[MAXW], st_cons[MAXW];
+        uint8_t st_have[MAXW];           // bases collected before the node at this depth
+        unsigned long long packed = 0;   // bases 0..31
+        unsigned long long packed_hi = 0;  // bases 32..63 (WIDE)
+        mask_t nbits = 0;                // bit i: base i of the k-mer is not ACGT
+        mask_t nonref = 0;               // bit d: node at depth d is off the reference path
         int depth = 0, have = 0;
         st_node[0] = (uint32_t)node0;
         st_have[0] = 0;
@@ -170,19 +175,26 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                         unsigned long long bits = ((unsigned long long)nb.y << 32) | nb.x;
                         bits >>= 2 * o;
                         if (take < 32) bits &= (1ull << (2 * take)) - 1ull;
-                        packed |= bits << (2 * have);
+                        if (!WIDE || have < 32) {
+                            packed |= bits << (2 * have);
+                            if (WIDE && have > 0) packed_hi |= bits >> (64 - 2 * have);
+                        } else {
+                            packed_hi |= bits << (2 * (have - 32));
+                        }
                         uint32_t bad = __ldg(g.node_nbits + n) >> o;
                         if (take < 32) bad &= (1u << take) - 1u;
-                        nbits |= bad << have;
+                        nbits |= (mask_t)bad << have;
                     } else {
                         for (int k = 0; k < take; ++k) {
                             const uint32_t c = g.seq[b0 + o + k];
-                            if (c < 4u) packed |= (unsigned long long)c << (2 * (have + k));
-                            else nbits |= 1u << (have + k);
+                            const int at = have + k;
+                            if (c >= 4u) nbits |= (mask_t)1 << at;
+                            else if (!WIDE || at < 32) packed |= (unsigned long long)c << (2 * at);
+                            else packed_hi |= (unsigned long long)c << (2 * (at - 32));
                         }
                     }
                 }
-                if (g.node_flags[n] & 1u) nonref &= ~(1u << depth); else nonref |= 1u << depth;
+                if (g.node_flags[n] & 1u) nonref &= ~((mask_t)1 << depth); else nonref |= (mask_t)1 << depth;
                 have += take;
                 if (have < w) {  // node used up: go on through its edges
                     st_edge[depth] = g.edge_off[n];
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                     if (WRITE) {
                         const unsigned long long row = row0 + n_found;
                         if (row < out.capacity) {
-                            uint32_t cons[GB2_MAX_WIDTH];
+                            uint32_t cons[MAXW];
                             int nc = 0;
                             if (depth == 0) {
                                 if (st_cons[0] != GB2_NO_CONS) cons[nc++] = st_cons[0];
@@ -203,7 +215,8 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                                 for (int d = 1; d <= depth; ++d)
                                     if (st_cons[d] != GB2_NO_CONS) cons[nc++] = st_cons[d];
                             }
-                            out.packed[row] = packed;
+                            if (WIDE) reinterpret_cast<ulonglong2 *>(out.packed)[row] = make_ulonglong2(packed, packed_hi);
+                            else out.packed[row] = packed;
                             out.start[row] = start;
                             out.stop[row] = stop;
                             if (nc == 0 || nc > FREQ_MAX_CONS || g.n_hap == 0) {
@@ -213,14 +226,14 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                                 for (int c = 0; c < nc; ++c) out.cons8[row * FREQ_MAX_CONS + c] = cons[c];
                                 out.ncons[row] = (uint8_t)nc;
                             }
-                            out.isref[row] = (nonref & ((2u << depth) - 1u)) == 0 ? 1 : 0;
+                            out.isref[row] = (nonref & (((mask_t)2 << depth) - (mask_t)1)) == 0 ? 1 : 0;
                             out.region[row] = (uint32_t)r;
                             if (nbits) {
                                 atomicOr(out.nmask + (row >> 5), 1u << (row & 31));
                                 atomicAdd(out.counts, 1ull);
                             }
                             if (out.walk != nullptr) {
-                                for (int d = 0; d <= depth; ++d) out.walk[row * GB2_MAX_WIDTH + d] = st_node[d];
+                                for (int d = 0; d <= depth; ++d) out.walk[row * MAXW + d] = st_node[d];
                                 out.walk_len[row] = (uint8_t)(depth + 1);
                                 out.walk_off[row] = (uint8_t)off0;
                             }
@@ -252,8 +265,13 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                 --depth;
                 entering = false;
                 if (WRITE) {
-                    packed &= (1ull << (2 * have)) - 1ull;  // have < w <= 32 here
-                    nbits &= (1u << have) - 1u;
+                    if (!WIDE || have < 32) {  // have < w here
+                        packed &= (1ull << (2 * have)) - 1ull;
+                        packed_hi = 0;
+                    } else {
+                        packed_hi &= (1ull << (2 * (have - 32))) - 1ull;
+                    }
+                    nbits &= ((mask_t)1 << have) - (mask_t)1;
                 }
             }
         }
@@ -499,7 +517,10 @@ extern "C" int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *g, int32_t n_regions, 
     const int64_t grid = gb2_div_up(T, WALK_THREADS);
     GB2_REQUIRE(ctx, grid < ((int64_t)1 << 31), "gb2_graph_prepare: too many candidate bases (%lld)", (long long)T);
     RowsOut none{};
-    gb2_graph_walk_kernel<false><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, g->d_counts, nullptr, none, g->d_flag);
+    if (w > GB2_NARROW_WIDTH)
+        gb2_graph_walk_kernel<false, 64><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, g->d_counts, nullptr, none, g->d_flag);
+    else
+        gb2_graph_walk_kernel<false, 32><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, g->d_counts, nullptr, none, g->d_flag);
     GB2_LAUNCH_CHECK(ctx);
     // exclusive scan over T+1 counts (the extra zero makes offsets[T] the total)
     size_t cub_bytes = 0;
@@ -557,7 +578,12 @@ extern "C" int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *g, uint64_t capacity, 
     GB2_CUDA(ctx, cudaMemsetAsync(d_nmask, 0, (size_t)gb2_div_up((int64_t)g->q_total, 32) * sizeof(uint32_t), ctx->stream));
     const int64_t T = g->q_threads;
     const int64_t grid = gb2_div_up(T, WALK_THREADS);
-    gb2_graph_walk_kernel<true><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, nullptr, g->d_offsets, o, g->d_flag);
+    if (g->q.w > GB2_NARROW_WIDTH) {
+        GB2_REQUIRE(ctx, ((uintptr_t)d_packed & 15u) == 0, "gb2_graph_extract: wide k-mers need a 16-byte aligned output");
+        gb2_graph_walk_kernel<true, 64><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, nullptr, g->d_offsets, o, g->d_flag);
+    } else {
+        gb2_graph_walk_kernel<true, 32><<<(unsigned)grid, WALK_THREADS, 0, ctx->stream>>>(g->v, g->q, T, nullptr, g->d_offsets, o, g->d_flag);
+    }
     GB2_LAUNCH_CHECK(ctx);
     if (g->v.n_hap > 0) {
         const int64_t fgrid = gb2_div_up((int64_t)g->q_total * FREQ_GROUP, 256);

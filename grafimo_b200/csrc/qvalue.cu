@@ -35,7 +35,7 @@ __global__ void gb2_bh_keys_kernel(const double *__restrict__ ptab, uint32_t spa
 }
 
 #define BH_THREADS 1024
-// Single CTA: <= 32002 bins.  Each thread owns a contiguous run of sorted bins.
+// Single CTA: <= 65536 bins (w <= 64).  Each thread owns a contiguous run of sorted bins.
 __global__ void __launch_bounds__(BH_THREADS) gb2_bh_kernel(const double *__restrict__ sorted_p,
                                                             const uint32_t *__restrict__ sorted_bins,
                                                             const unsigned long long *__restrict__ hist, uint32_t nbins,

@@ -70,11 +70,15 @@ __device__ __forceinline__ void put_int(Sink &s, long long x)
     while (n) s.put(buf[--n]);
 }
 
+// k-mer of row i as letters; rows wider than 32 bases take two packed words (bases 0..31, 32..w-1)
 template <typename Sink>
-__device__ __forceinline__ void put_kmer(Sink &s, unsigned long long x, int w)
+__device__ __forceinline__ void put_kmer(Sink &s, const unsigned long long *kmer, unsigned long long i, int w)
 {
-    for (int i = 0; i < w; ++i) {
-        const uint32_t c = (uint32_t)(x >> (2 * i)) & 3u;
+    const bool wide = w > GB2_NARROW_WIDTH;
+    unsigned long long x = wide ? kmer[2 * i] : kmer[i];
+    for (int k = 0; k < w; ++k) {
+        if (k == 32) x = kmer[2 * i + 1];
+        const uint32_t c = (uint32_t)(x >> (2 * (k & 31))) & 3u;
         s.put((uint8_t)(c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : 'T'));
     }
 }
@@ -97,7 +101,7 @@ __device__ __forceinline__ void format_row(Sink &s, const ReportView &v, unsigne
         put_str(s, v, v.base_score + bin); s.put('\t');
         put_str(s, v, v.base_p + bin); s.put('\t');
         if (v.want_q) { put_str(s, v, v.base_q + bin); s.put('\t'); }
-        put_kmer(s, v.kmer[i], v.w); s.put('\t');
+        put_kmer(s, v.kmer, i, v.w); s.put('\t');
         put_int(s, v.freq[i]); s.put('\t');
         put_str(s, v, C + (v.ref[i] ? 2 : 3));
         s.put('\n');
@@ -128,7 +132,7 @@ __device__ __forceinline__ void format_row(Sink &s, const ReportView &v, unsigne
             put_str(s, v, v.base_q + bin);
         }
         put_str(s, v, C + 11);  // ";sequence=="
-        put_kmer(s, v.kmer[i], v.w);
+        put_kmer(s, v.kmer, i, v.w);
         put_str(s, v, C + 12);  // "=;\n"
     }
 }

@@ -33,7 +33,7 @@ extern "C" int gb2_scan_host(gb2_ctx *ctx, const gb2_motif *m, const uint8_t *h_
     const int64_t nb = m->span + 1;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_ascii = align((size_t)chunk_rows * (size_t)stride + 64);
-    const size_t b_packed = align((size_t)chunk_rows * 8);
+    const size_t b_packed = align((size_t)chunk_rows * (w > GB2_NARROW_WIDTH ? 16 : 8));
     const size_t b_mask = align((size_t)gb2_div_up(chunk_rows, 32) * 4);
     const size_t b_hist = align((size_t)nb * 8);
     const size_t b_small = 256;  // counters: [0]=N rows [1]=bad rows [2]=hit count [3]=kept [4]=total

@@ -272,6 +272,95 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Wide k-mers (32 < w <= 64, two packed words each): one 128-bit load = one k-mer, 9..16 chunk lookups.  Such motifs are
+// rare (the 34/35-bp CTCF profiles of JASPAR), so the chunk count and the replication factor are run-time values here
+// and one guarded loop serves full tiles and the tail.  Same tables, same packed 16-bit fields, same histogram / hit /
+// dense semantics as the narrow kernel; when the histogram does not fit shared memory next to the tables
+// (hist_in_smem == 0) it is counted with 64-bit global atomics.
+__global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int n_chunks, int R, int hist_in_smem)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *lut_s = smem;                        // [n_chunks*256][R]
+    uint32_t *hist_s = smem + n_chunks * 256 * R;  // [span+1] when hist_in_smem
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const bool do_hist = p.hist != nullptr;
+    const bool hist_smem = do_hist && hist_in_smem;
+
+    for (int i = tid; i < n_chunks * 256 * R; i += 1024) lut_s[i] = p.lut[i / R];
+    if (hist_smem)
+        for (uint32_t i = tid; i <= p.span; i += 1024) hist_s[i] = 0u;
+    __syncthreads();
+
+    const uint32_t lut32 = smem_u32(lut_s) + 4u * (lane & (uint32_t)(R - 1));
+    const uint32_t hist32 = smem_u32(hist_s);
+    const uint32_t rstride = (uint32_t)R * 4u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.packed);
+    const uint32_t nsent = (p.span << 16) | p.span;
+    const bool two = p.two_strands != 0;
+    constexpr int U = 4;
+    constexpr int64_t TILE = 1024 * U;
+    const int64_t ntiles = (p.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TILE + tid;
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = r0 + u * 1024;
+            v[u] = row < p.n ? ld_stream_u4(src + row) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t acc[U];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t a = 0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < n_chunks) {  // uniform
+                    const uint32_t b = (wd[c >> 2] >> (8 * (c & 3))) & 255u;
+                    uint32_t e;
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 256u + b) * rstride));
+                    a += e;
+                }
+            }
+            const int64_t row = r0 + u * 1024;
+            const bool ok = row < p.n;
+            if (ok && p.nmask != nullptr && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) a = nsent;
+            acc[u] = a;
+            if (ok) {
+                const uint32_t bf = a & 0xFFFFu, br = a >> 16;
+                if (hist_smem) {
+                    red_shared_inc(hist32 + 4u * bf);
+                    if (two) red_shared_inc(hist32 + 4u * br);
+                } else if (do_hist) {
+                    atomicAdd(p.hist + bf, 1ull);
+                    if (two) atomicAdd(p.hist + br, 1ull);
+                }
+                if (p.dense != nullptr) p.dense[row] = (a == nsent) ? 0xFFFFFFFFu : a;
+                any |= (bf >= p.cut) | (two & (br >= p.cut));
+            }
+        }
+        if (p.hits != nullptr && __any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t row = r0 + u * 1024;
+                const bool ok = row < p.n;
+                const uint32_t bf = acc[u] & 0xFFFFu, br = acc[u] >> 16;
+                append_hits(p, ok && bin_hits(p, bf), (uint64_t)row, bf, 0u, lane);
+                if (two) append_hits(p, ok && bin_hits(p, br), (uint64_t)row, br, 1u, lane);
+            }
+        }
+    }
+    if (hist_smem) {
+        __syncthreads();
+        for (uint32_t i = tid; i <= p.span; i += 1024) {
+            const uint32_t c = hist_s[i];
+            if (c) atomicAdd(p.hist + i, (unsigned long long)c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int NCHUNK, int R>
 static int launch_score(gb2_ctx *ctx, const ScoreParams &p, size_t smem, int grid)
 {
@@ -345,9 +434,16 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
         p.bitmap = m->d_bitmap;
     }
 
+    const size_t smem = (size_t)m->smem_bytes;
+    if (m->w > GB2_NARROW_WIDTH) {  // two packed words per k-mer
+        const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(n, 4096)));
+        GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_score_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb2_score_wide_kernel<<<grid, 1024, smem, ctx->stream>>>(p, m->n_chunks, m->replicas, m->hist_global ? 0 : 1);
+        GB2_LAUNCH_CHECK(ctx);
+        return GB2_OK;
+    }
     const int64_t npairs = n >> 1;
     int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(npairs, 4096)));
-    const size_t smem = (size_t)m->smem_bytes;
     switch (m->n_chunks) {
     case 1: return dispatch_r<1>(ctx, m->replicas, p, smem, grid);
     case 2: return dispatch_r<2>(ctx, m->replicas, p, smem, grid);

@@ -240,13 +240,14 @@ __global__ void __launch_bounds__(PARSE_ROWS) gb2_tsv_parse_kernel(const uint8_t
         name_len[r] = (uint32_t)(p - name_b);
         while (p < tn && is_ws(t[p])) ++p;
         seq_off[r] = (uint32_t)(p - b);
-        unsigned long long x = 0;
+        unsigned long long x = 0, x2 = 0;  // bases 0..31 / 32..w-1 (wide k-mers: two packed words per row)
         bool ok = true;
         for (int i = 0; i < w; ++i) {
             const uint8_t c = (p < tn) ? t[p] : 0;
             if (is_ws(c) || is_eol(c)) { ok = false; break; }
             const uint32_t code = tsv_base_code(c);
-            x |= (unsigned long long)(code & 3u) << (2 * i);
+            if (i < 32) x |= (unsigned long long)(code & 3u) << (2 * i);
+            else x2 |= (unsigned long long)(code & 3u) << (2 * (i - 32));
             flag |= (code >= 4u ? 1u : 0u) | (code == 5u ? 2u : 0u);
             ++p;
         }
@@ -280,7 +281,12 @@ __global__ void __launch_bounds__(PARSE_ROWS) gb2_tsv_parse_kernel(const uint8_t
             if (len == 0) ok = false;
         }
         if (!ok) flag |= 4u;
-        packed[r] = (flag & 1u) ? 0ull : x;
+        if (w > GB2_NARROW_WIDTH) {
+            packed[2 * r] = (flag & 1u) ? 0ull : x;
+            packed[2 * r + 1] = (flag & 1u) ? 0ull : x2;
+        } else {
+            packed[r] = (flag & 1u) ? 0ull : x;
+        }
         start[r] = v0;
         stop[r] = v1;
         strand[r] = s0;

@@ -22,6 +22,15 @@ def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def packed_rows(ctx, n, width):
+    """Device buffer for n packed k-mers: int64[n] (width <= 32) or int64[n, 2] = {bases 0..31, bases 32..} (wider),
+    16-byte aligned either way (include/grafimo_b200.h, "Data layout")."""
+    m = max(int(n), 1)
+    if width > _lib.NARROW_WIDTH:
+        return ctx.empty(2 * m, torch.int64).view(m, 2)
+    return ctx.empty(m + (m & 1), torch.int64)[:m]
+
+
 class Context:
     """One per (process, GPU): owns a CUDA stream and the library context bound to it."""
 
@@ -77,15 +86,15 @@ class Context:
 
     # -- K1 -----------------------------------------------------------------------------------
     def encode(self, ascii_rows, width=None):
-        """uint8 device tensor [n, stride] (ASCII k-mers) -> (packed int64[n] (uint64 bits), nmask int32[ceil(n/32)],
-        counts int64[2] = rows masked, rows with a non-ACGTN symbol)."""
+        """uint8 device tensor [n, stride] (ASCII k-mers) -> (packed int64[n] (uint64 bits; int64[n, 2] when the width is
+        above 32), nmask int32[ceil(n/32)], counts int64[2] = rows masked, rows with a non-ACGTN symbol)."""
         assert ascii_rows.is_cuda and ascii_rows.dtype == torch.uint8 and ascii_rows.dim() == 2
         assert ascii_rows.stride(1) == 1
         n, stride = ascii_rows.shape[0], ascii_rows.stride(0) if ascii_rows.shape[0] > 1 else ascii_rows.shape[1]
         w = ascii_rows.shape[1] if width is None else int(width)
         self.enter()
         ascii_rows.record_stream(self.stream)
-        packed = self.empty(n + (n & 1), torch.int64)[:n]
+        packed = packed_rows(self, n, w)[:n]
         nmask = self.zeros((n + 31) // 32, torch.int32)
         counts = self.zeros(2, torch.int64)
         check(self.lib.gb2_encode_kmers(self.h, _ptr(ascii_rows), n, w, stride, _ptr(packed), _ptr(nmask), _ptr(counts)),
@@ -176,7 +185,7 @@ class DeviceRows:
     def __init__(self, ctx, d_text, line_off, n, width):
         self.ctx, self.d_text, self.line_off, self.n, self.width = ctx, d_text, line_off, n, width
         m = max(n, 1)
-        self.packed = ctx.empty(m + (m & 1), torch.int64)[:m]
+        self.packed = packed_rows(ctx, m, width)
         self.nmask = ctx.zeros((m + 31) // 32, torch.int32)
         self.start = ctx.empty(m, torch.int64)
         self.stop = ctx.empty(m, torch.int64)
@@ -270,8 +279,13 @@ class Scan:
         self.row_limit = 0
 
     def score(self, packed, nmask=None, row_base=0, dense_out=None):
+        """packed: int64[n] device tensor, or int64[n, 2] for a motif wider than 32 (two words per k-mer)."""
         n = packed.shape[0]
         lib, ctx = self.ctx.lib, self.ctx
+        wide = self.motif.width > _lib.NARROW_WIDTH
+        if (packed.dim() == 2) != wide or (wide and (packed.shape[1] != 2 or not packed.is_contiguous())):
+            raise ValueError(f"k-mers of a width-{self.motif.width} motif must be packed as "
+                             f"{'int64[n, 2]' if wide else 'int64[n]'}")
         ctx.enter()
         check(lib.gb2_score(ctx.h, self.motif.h, _ptr(packed), _ptr(nmask), n, int(row_base), self.strands, self.threshold,
                             _ptr(self.hist), _ptr(self.hits), self.capacity, _ptr(self.counters), _ptr(dense_out)),

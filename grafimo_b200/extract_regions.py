@@ -19,11 +19,9 @@ from typing import Dict, List, Tuple
 import numpy as np
 import torch
 
-from ._lib import GraphInfo, check
+from ._lib import MAX_WIDTH, NARROW_WIDTH, GraphInfo, check
 from .utils import exception_handler
 from .vgraph import VariationGraph
-
-MAX_WIDTH = 32
 
 
 def get_regions_bed(bedfile: str, debug: bool) -> Tuple[Dict[str, List], int]:
@@ -192,10 +190,18 @@ _COMP = {65: 84, 67: 71, 71: 67, 84: 65, 78: 78}
 
 
 def decode_kmers(packed: np.ndarray, width: int) -> np.ndarray:
-    """uint64/int64 [n] packed k-mers -> uint8 [n, width] ASCII."""
+    """uint64/int64 [n] (or [n, 2] for widths above 32) packed k-mers -> uint8 [n, width] ASCII."""
     p = packed.astype(np.uint64)
+    if p.ndim == 2:
+        lo = decode_kmers(p[:, 0], NARROW_WIDTH)
+        return np.concatenate([lo, decode_kmers(p[:, 1], width - NARROW_WIDTH)], axis=1)
     sh = (2 * np.arange(width, dtype=np.uint64))[None, :]
     return _ASCII[((p[:, None] >> sh) & np.uint64(3)).astype(np.intp)]
+
+
+def walk_stride(width: int) -> int:
+    """Nodes reserved per row of the walk array of gb2_graph_extract."""
+    return NARROW_WIDTH if width <= NARROW_WIDTH else MAX_WIDTH
 
 
 class GraphRows:
@@ -205,7 +211,8 @@ class GraphRows:
     def __init__(self, ctx, chrom, regions, width, n, want_walks, n_hap):
         self.ctx, self.chrom, self.regions, self.width, self.n, self.n_hap = ctx, chrom, regions, width, n, n_hap
         m = max(n, 1)
-        self.packed = ctx.empty(m + (m & 1), torch.int64)[:m]
+        from .engine import packed_rows
+        self.packed = packed_rows(ctx, m, width)
         self.nmask = ctx.zeros((m + 31) // 32, torch.int32)
         self.start = ctx.empty(m, torch.int64)
         self.stop = ctx.empty(m, torch.int64)
@@ -213,7 +220,7 @@ class GraphRows:
         self.isref = ctx.empty(m, torch.uint8)
         self.region = ctx.empty(m, torch.int32)
         self.counts = ctx.zeros(2, torch.int64)
-        self.walk = ctx.empty(m * MAX_WIDTH, torch.int32) if want_walks else None
+        self.walk = ctx.empty(m * walk_stride(width), torch.int32) if want_walks else None
         self.walk_len = ctx.empty(m, torch.uint8) if want_walks else None
         self.walk_off = ctx.empty(m, torch.uint8) if want_walks else None
 
@@ -233,7 +240,7 @@ class GraphRows:
                        freq=self.freq[:n].cpu().numpy(), isref=self.isref[:n].cpu().numpy(), region=self.region[:n].cpu().numpy(),
                        nmask=self.nmask.cpu().numpy())
             if self.walk is not None:
-                out["walk"] = self.walk.cpu().numpy().reshape(-1, MAX_WIDTH)[:n]
+                out["walk"] = self.walk.cpu().numpy().reshape(-1, walk_stride(self.width))[:n]
                 out["walk_len"] = self.walk_len[:n].cpu().numpy()
                 out["walk_off"] = self.walk_off[:n].cpu().numpy()
         self.ctx.sync()

@@ -207,8 +207,8 @@ class DeviceReport:
             h = {k: getattr(self, k).cpu().numpy() for k in ("kmer", "strand", "start", "stop", "freq", "ref", "bin", "name")}
         self.ctx.sync()
         n, w = self.n, self.width
-        codes = ((h["kmer"].astype(np.uint64)[:, None] >> (2 * np.arange(w, dtype=np.uint64))[None, :]) & np.uint64(3)).astype(np.intp)
-        letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+        from .extract_regions import decode_kmers
+        letters = decode_kmers(h["kmer"], w)
         seq = np.char.decode(np.ascontiguousarray(letters).view(f"S{w}").ravel(), "ascii").astype(object) if n else np.array([], dtype=object)
         cols = {
             "motif_id": [self.motif.motif_id] * n, "motif_alt_id": [self.motif.motif_name] * n,

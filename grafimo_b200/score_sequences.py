@@ -541,6 +541,18 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     return df
 
 
+def _revcomp_packed(packed, width):
+    """Reverse complement of packed k-mers on the device: int64[n], or int64[n, 2] for widths above 32."""
+    import torch
+    wide = packed.dim() == 2
+    words = [packed[:, 0], packed[:, 1]] if wide else [packed]
+    out = [torch.zeros_like(w_) for w_ in words]
+    for i in range(width):
+        j = width - 1 - i
+        out[j >> 5] |= (3 - ((words[i >> 5] >> (2 * (i & 31))) & 3)) << (2 * (j & 31))
+    return torch.stack(out, dim=1) if wide else out[0]
+
+
 def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
     """The scoring of compute_results_rows with the report left on the device: -> res_writer.DeviceReport (hit columns
     in HBM + per-bin score / p / q values) for write_results_device (K8).  Same flags and semantics; rows are ordered by
@@ -590,11 +602,8 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
         name_base = np.concatenate([[0], np.cumsum([len(b.regions) for b in batches])])
         region = torch.cat([b.region[:b.n].to(torch.int32) + int(nb) for b, nb in zip(batches, name_base[:-1])])[row]
         # '-' hits: reverse complement of the k-mer, start/stop swapped
-        comp = ~packed
-        rc = torch.zeros_like(packed)
-        for i in range(width):
-            rc |= ((comp >> (2 * i)) & 3) << (2 * (width - 1 - i))
-        kmer = torch.where(minus, rc, packed)
+        rc = _revcomp_packed(packed, width)
+        kmer = torch.where(minus[:, None] if packed.dim() == 2 else minus, rc, packed)
         s2 = torch.where(minus, stop, start)
         e2 = torch.where(minus, start, stop)
         ref = (isref & ((e2 - s2).abs() == width)).to(torch.uint8)  # score_sequences.py:305-307

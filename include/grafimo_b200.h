@@ -23,8 +23,11 @@
  *     GB2_ERR_CUDA.
  *
  * Data layout
- *   packed k-mer  uint64: base i of the k-mer in bits [2i, 2i+1], A=0 C=1 G=2 T=3, bits >= 2w
- *                 are zero, w <= 32.
+ *   packed k-mer  w <= 32 ("narrow"): one uint64 per k-mer -- base i in bits [2i, 2i+1], A=0 C=1 G=2 T=3, bits >= 2w
+ *                 zero.  32 < w <= 64 ("wide"; the reference has no width limit and JASPAR holds 34/35-bp profiles):
+ *                 TWO consecutive uint64 per k-mer, {bases 0..31, bases 32..w-1}, i.e. arrays named d_packed / d_kmer
+ *                 hold 2n words and must be 16-byte aligned.  Which form an array has follows from the width given to
+ *                 (or stored in the motif / prepared query of) the call.
  *   N mask        uint32[ceil(n/32)]: bit (r & 31) of word (r >> 5) is set when row r holds a
  *                 symbol other than ACGTacgt (the reference scores such rows as `min_val`,
  *                 p-value 1: score_sequences.py:376-378).
@@ -41,8 +44,9 @@
 extern "C" {
 #endif
 
-#define GB2_ABI_VERSION 1
-#define GB2_MAX_WIDTH 32
+#define GB2_ABI_VERSION 2
+#define GB2_NARROW_WIDTH 32 /* widest k-mer that fits one packed word */
+#define GB2_MAX_WIDTH 64
 #define GB2_RANGE 1000 /* src/grafimo/utils.py:26 */
 
 enum {
@@ -98,7 +102,7 @@ int gb2_ctx_sm_count(const gb2_ctx *ctx);
 
 /* ---- K1: k-mer encoder ------------------------------------------------------------------ */
 /* Replaces the per-row string handling of score_seqs (score_sequences.py:279,286,375-386):
- * n ASCII k-mers of w bytes (row stride `stride` >= w bytes) -> packed uint64 + N mask.
+ * n ASCII k-mers of w bytes (row stride `stride` >= w bytes) -> packed uint64 (two per k-mer when w > 32) + N mask.
  * d_counts[0] += rows flagged in the mask, d_counts[1] += rows holding a symbol that is neither
  * ACGTacgt nor 'N' (undefined in the reference; scored like N here). d_counts may be NULL. */
 int gb2_encode_kmers(gb2_ctx *ctx, const uint8_t *d_ascii, int64_t n, int w, int64_t stride,
@@ -156,7 +160,9 @@ const double *gb2_motif_ptable_device(const gb2_motif *motif);
  *   d_hits / hit_capacity / d_hit_count: hit records appended at *d_hit_count (device counter,
  *                += hits found even when capacity is exceeded; excess records are dropped).
  *   d_dense      uint32[n] or NULL: per k-mer ((rc - lo) << 16 | (fwd - lo)); 0xFFFFFFFF for N rows.
- * d_packed must be 16-byte aligned.  row_base is added to the row index in hit records. */
+ * d_packed must be 16-byte aligned (uint64[n], or uint64[n][2] for a motif wider than 32).  row_base is added to the
+ * row index in hit records.  Motifs whose score span does not fit shared memory next to the lookup tables (w >~ 54)
+ * count their histogram with global atomics instead: same results, slower. */
 int gb2_score(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_packed, const uint32_t *d_nmask,
               int64_t n, uint64_t row_base, int strands, double p_threshold, uint64_t *d_hist,
               gb2_hit *d_hits, uint64_t hit_capacity, uint64_t *d_hit_count, uint32_t *d_dense);
@@ -262,11 +268,11 @@ int gb2_graph_prepare(gb2_ctx *ctx, gb2_graph *graph, int32_t n_regions, const i
                       int w, uint64_t *h_n_rows);
 /* Pass 2 of the prepared query (stream-ordered): rows in (region, first base, depth-first) order, forward strand only
  * (the '-' row vg prints for a walk is its reverse complement with start/stop swapped: score with strands = 2).
- *   d_packed uint64[cap] (16-byte aligned), d_nmask uint32[ceil(cap/32)], d_start/d_stop int64[cap], d_freq int32[cap]
+ *   d_packed uint64[cap] (uint64[cap][2] when w > 32; 16-byte aligned), d_nmask uint32[ceil(cap/32)], d_start/d_stop int64[cap], d_freq int32[cap]
  *   (haplotypes containing the walk's node sequence), d_isref uint8[cap] (1 = every node on the reference path; the
  *   reference rewrites it when |stop-start| != w, score_sequences.py:305-307), d_region uint32[cap] (index into the
- *   region arrays), optional d_walk uint32[cap][32] + d_walk_len + d_walk_off (node indices of the walk, offset of the
- *   first base) for writing vg's node-path column; d_counts[0] += rows holding a non-ACGT base. */
+ *   region arrays), optional d_walk uint32[cap][32] ([cap][64] when w > 32) + d_walk_len + d_walk_off (node indices of
+ *   the walk, offset of the first base) for writing vg's node-path column; d_counts[0] += rows holding a non-ACGT base. */
 int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *graph, uint64_t capacity, uint64_t *d_packed, uint32_t *d_nmask,
                       int64_t *d_start, int64_t *d_stop, int32_t *d_freq, uint8_t *d_isref, uint32_t *d_region,
                       uint32_t *d_walk, uint8_t *d_walk_len, uint8_t *d_walk_off, uint64_t *d_counts);
@@ -304,7 +310,8 @@ int gb2_vcf_parse_genotypes(gb2_ctx *ctx, const uint8_t *d_text, int64_t n_bytes
 typedef struct gb2_report {
     uint64_t n_rows, index_base;       /* index_base: value of the first row's index column (TSV) */
     int32_t width, layout, want_q, reserved; /* layout 0 = TSV rows, 1 = GFF3 rows; want_q 0 = no q-value column */
-    const uint64_t *d_kmer;            /* the k-mer as reported (reverse-complemented already for '-' hits) */
+    const uint64_t *d_kmer;            /* the k-mer as reported (reverse-complemented already for '-' hits); two words
+                                          per row when width > 32 */
     const uint8_t *d_strand;           /* '+' or '-' */
     const int64_t *d_start, *d_stop, *d_freq;
     const uint8_t *d_ref;              /* 1 = "ref", 0 = "non.ref" (after the |stop-start| != w rewrite) */

@@ -123,11 +123,12 @@ def test_c4_sharded_scan_gives_the_global_qvalues(ctx):
 
 
 def test_c5_long_motifs_both_strands_no_threshold(ctx):
-    """w = 25..32, threshold 1 (every window with p < 1 is reported), both strands, N rows included."""
+    """w = 25..64, threshold 1 (every window with p < 1 is reported), both strands, N rows included."""
     from grafimo_b200.engine import Scan
     orc = _orc()
     rng = np.random.default_rng(21)
-    for tag in ("synth_w25_meme__bgnt", "synth_w27_meme__bgnt", "synth_w30_meme__bgnt", "synth_w32_meme__bgnt"):
+    for tag in ("synth_w25_meme__bgnt", "synth_w27_meme__bgnt", "synth_w30_meme__bgnt", "synth_w32_meme__bgnt",
+                "synth_w35_meme__bgnt", "synth_w64_meme__bgnt"):
         m = gu.load_motif(tag)
         w, n = m["width"], 2500
         seqs = ["".join(rng.choice(list("ACGT"), size=w)) for _ in range(n)]

@@ -61,7 +61,7 @@ def test_extract_equals_oracle_random_graphs(ctx, seed, builder):
         dg.graph = VariationGraph.build("c", ref, vs, gt, max_node_len=m)  # host arrays, only to spell N rows as text
         assert (dg.info.n_nodes, dg.info.n_edges, dg.info.n_sets) == (dg.graph.n_nodes, dg.graph.n_edges, dg.graph.n_cons)
     regions = [(0, 600), (37, 301), (100, 250), (590, 600), (250, 250)]
-    for w in (5, 19, 32):
+    for w in (5, 19, 32, 33, 40) + ((64,) if seed == 1 else ()):  # above 32: two packed words per row, 64-deep stacks
         rows = dg.extract(regions, w, want_walks=True)
         got = _rows_as_tuples(rows, w)
         exp = []
@@ -96,15 +96,15 @@ def test_extract_without_haplotypes_and_errors(ctx):
     empty = dg.extract([], 11)
     assert empty.n == 0
     with pytest.raises(ValueError):
-        dg.extract([(0, 10)], 33)
+        dg.extract([(0, 10)], 65)
     with pytest.raises(GrafimoB200Error):
         dg.extract([(10, 0)], 11)
 
 
-def _motif(tmp_path):
+def _motif(tmp_path, key="ctcf_meme"):
     from grafimo_b200 import motif_ops as mo
-    p = tmp_path / "ctcf.meme"
-    p.write_text(gu.fixtures()["ctcf_meme"])
+    p = tmp_path / (key + ".meme")
+    p.write_text(gu.fixtures()[key])
     return mo.build_motif_meme(str(p), "unfrm_dst", 0.1, False, 1, False, True)[0]
 
 
@@ -115,22 +115,25 @@ class _Args:
 
 
 @pytest.mark.parametrize("opts", [dict(threshold=1.0), dict(threshold=0.05, recomb=False), dict(threshold=0.2, noreverse=True),
-                                  dict(threshold=0.5, qvalueT=True), dict(threshold=0.01, noqvalue=True)])
+                                  dict(threshold=0.5, qvalueT=True), dict(threshold=0.01, noqvalue=True),
+                                  dict(threshold=1.0, mkey="synth_w35_meme"), dict(threshold=0.3, recomb=False, mkey="synth_w48_meme")])
 def test_graph_to_table_equals_tsv_path_and_oracle(ctx, tmp_path, opts, capsys):
     """graph -> K7 -> K2/K5/K6 (no text) == compute_results on the vg-format TSVs of the same regions == the oracle's
-    scoring of those TSV rows (score, p, q bit-exact)."""
+    scoring of those TSV rows (score, p, q bit-exact).  The last two cases use motifs wider than one packed word."""
     from grafimo_b200 import score_sequences as ss
     from grafimo_b200.vgraph import VariationGraph
     from oracle import oracle as orc
     ss._ctx = ctx
-    motif = _motif(tmp_path)
+    opts = dict(opts)
+    motif = _motif(tmp_path, opts.pop("mkey", "ctcf_meme"))
+    W = motif.width
     ref, vs, gt = gr.random_case(321, length=3000, n_var=150, n_hap=40, n_frac=0.002)
     dg = VariationGraph.build("7", ref, vs, gt).to_device(ctx)
     regions = [(0, 1200), (1100, 3000)]
-    rows = dg.extract(regions, 19, want_walks=True)
+    rows = dg.extract(regions, W, want_walks=True)
     args = _Args(**opts)
     df = ss.compute_results_rows(motif, rows, True, args)
-    d = tmp_path / "seqs" / "width_19"
+    d = tmp_path / "seqs" / f"width_{W}"
     d.mkdir(parents=True)
     lines_all = []
     for r, lines in rows.to_vg_tsv().items():
@@ -144,7 +147,7 @@ def test_graph_to_table_equals_tsv_path_and_oracle(ctx, tmp_path, opts, capsys):
     assert out.count(f"Scanned sequences:\t{n}") == 2
     # the oracle on the TSV rows
     f = [ln.split("\t") for ln in lines_all if not (args.noreverse and ln.split("\t")[2][-1] == "-")]
-    a = orc.kmers_to_matrix([x[1] for x in f], 19)
+    a = orc.kmers_to_matrix([x[1] for x in f], W)
     _, lo, p = orc.score_rows(a, motif.score_matrix_acgt(), motif.pval_matrix, motif.min_val, motif.scale, float(motif.offset))
     q = orc.bh(p)
     start = np.array([int(x[2].split(":")[1][:-1]) for x in f]); stop = np.array([int(x[3].split(":")[1][:-1]) for x in f])
@@ -155,7 +158,7 @@ def test_graph_to_table_equals_tsv_path_and_oracle(ctx, tmp_path, opts, capsys):
     exp = {"start": start[keep], "stop": stop[keep], "strand": np.array([x[2][-1] for x in f], dtype=object)[keep],
            "score": lo[keep], "p-value": p[keep], "q-value": q[keep],
            "matched_sequence": np.array([x[1] for x in f], dtype=object)[keep], "haplotype_frequency": freq[keep],
-           "reference": np.array(["ref" if (x[5] == "ref" and abs(int(b) - int(a_)) == 19) else "non.ref"
+           "reference": np.array(["ref" if (x[5] == "ref" and abs(int(b) - int(a_)) == W) else "non.ref"
                                   for x, a_, b in zip(f, start, stop)], dtype=object)[keep]}
     cols = [c for c in df.columns if c in exp and not (c == "q-value" and args.noqvalue)]
     gu.assert_tables_equal({c: df[c].to_numpy() for c in df.columns}, exp, cols)

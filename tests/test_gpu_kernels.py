@@ -40,7 +40,7 @@ def test_k3_batched_dp_bit_exact(ctx):
 
 
 @pytest.mark.parametrize("tag", ["ctcf_meme__unif", "ctcf_meme__bgnt", "synth_w6_meme__bgnt", "synth_w30_meme__bgnt",
-                                 "synth_w32_meme__bgnt"])
+                                 "synth_w32_meme__bgnt", "synth_w33_meme__bgnt", "synth_w48_meme__bgnt", "synth_w64_meme__bgnt"])
 def test_k4_ptable_bit_exact(ctx, tag):
     m = gu.load_motif(tag)
     dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
@@ -53,7 +53,7 @@ def test_k4_ptable_bit_exact(ctx, tag):
 
 def test_k1_encoder(ctx):
     rng = np.random.default_rng(5)
-    for w in (1, 5, 19, 31, 32):
+    for w in (1, 5, 19, 31, 32, 33, 36, 47, 63, 64):  # above 32: two packed words per k-mer
         n = 1000 + w
         letters = np.array(list("ACGTacgt"))
         seqs = ["".join(rng.choice(letters, size=w)) for _ in range(n)]
@@ -64,6 +64,7 @@ def test_k1_encoder(ctx):
         a, d = _ascii_dev(seqs, w)
         packed, nmask, counts = ctx.encode(d)
         ctx.sync()
+        assert tuple(packed.shape) == ((n, 2) if w > 32 else (n,))
         packed = packed.cpu().numpy().view(np.uint64)
         nm = nmask.cpu().numpy().view(np.uint32)
         code = {"A": 0, "C": 1, "G": 2, "T": 3}
@@ -74,7 +75,10 @@ def test_k1_encoder(ctx):
                 x = 0
                 for i, ch in enumerate(s):
                     x |= code[ch.upper()] << (2 * i)
-                assert int(packed[r]) == x
+                if w > 32:
+                    assert int(packed[r, 0]) == x & ((1 << 64) - 1) and int(packed[r, 1]) == x >> 64
+                else:
+                    assert int(packed[r]) == x
         assert counts.cpu().numpy().tolist() == [4, 2]
 
 
@@ -129,7 +133,8 @@ def test_k2_both_strands_equals_reverse_complement_rows(ctx):
     orc = _orc()
     rng = np.random.default_rng(11)
     for tag, n in (("ctcf_meme__bgnt", 20001), ("synth_w30_meme__bgnt", 4097), ("synth_w6_meme__bgnt", 3000),
-                   ("synth_w32_meme__bgnt", 2049)):
+                   ("synth_w32_meme__bgnt", 2049), ("synth_w33_meme__bgnt", 4100), ("synth_w35_meme__bgnt", 3001),
+                   ("synth_w48_meme__bgnt", 1025), ("synth_w64_meme__bgnt", 1500)):
         m = gu.load_motif(tag)
         w = m["width"]
         seqs = ["".join(rng.choice(list("ACGT"), size=w)) for _ in range(n)]
@@ -160,10 +165,11 @@ def test_k2_both_strands_equals_reverse_complement_rows(ctx):
         assert np.array_equal(hist, exp_hist)
 
 
-def test_dense_output_and_no_hist(ctx):
+@pytest.mark.parametrize("tag", ["synth_w25_meme__bgnt", "synth_w35_meme__bgnt"])
+def test_dense_output_and_no_hist(ctx, tag):
     from grafimo_b200.engine import Scan
     orc = _orc()
-    m = gu.load_motif("synth_w25_meme__bgnt")
+    m = gu.load_motif(tag)
     w = m["width"]
     rng = np.random.default_rng(3)
     n = 5003
@@ -185,6 +191,27 @@ def test_dense_output_and_no_hist(ctx):
     assert dn[17] == 0xFFFFFFFF
     assert np.array_equal((dn[ok] & 0xFFFF).astype(np.int64) + dm.lo, isf[ok])
     assert np.array_equal((dn[ok] >> 16).astype(np.int64) + dm.lo, isr[ok])
+
+
+def test_scan_host_wide_motif(ctx):
+    """gb2_scan_host with a 48-bp motif: two packed words per k-mer through the chunked encode + score loop."""
+    from grafimo_b200.engine import scan_host
+    orc = _orc()
+    m = gu.load_motif("synth_w48_meme__bgnt")
+    rng = np.random.default_rng(48)
+    n, w = 3001, 48
+    seqs = ["".join(rng.choice(list("ACGT"), size=w)) for _ in range(n)]
+    seqs[5] = seqs[5][:40] + "N" + seqs[5][41:]
+    a = orc.kmers_to_matrix(seqs, w)
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    out = scan_host(ctx, dm, a, strands=1, threshold=0.2)
+    isc, lo, pv = orc.score_rows(a, m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    q = orc.bh(pv)
+    rows = out["row"].astype(np.int64)
+    assert sorted(rows.tolist()) == np.nonzero(pv < 0.2)[0].tolist()
+    assert np.array_equal(out["int_score"], isc[rows]) and np.array_equal(out["score"], lo[rows])
+    assert np.array_equal(out["p-value"], pv[rows]) and np.array_equal(out["q-value"], q[rows])
+    assert out["stats"]["n_rows"] == 1
 
 
 def test_scan_host_matches_device_path(ctx):
@@ -317,6 +344,18 @@ def test_k1b_device_tsv_reader(ctx):
             line = text[off[k]:].split(b"\n", 1)[0]
             assert line.split()[0].decode() == r["seqname"][k] and len(r["seqname"][k]) == nl[k]
             assert text[off[k] + so[k]:off[k] + so[k] + 19].decode() == r["seq"][k]
+    # k-mers wider than one packed word (reference-generated rows of the w = 35 golden)
+    c = gu.load_scoring("synth_w35")
+    lines = [ln for f in c["files"] for ln in f]
+    text = ("\n".join(lines) + "\n").encode()
+    rows = ctx.parse_kmer_tsv(torch.frombuffer(bytearray(text), dtype=torch.uint8), 35)
+    r = orc.parse_rows(lines, False)
+    assert rows.n == len(r["seq"]) and rows.stats()["malformed"] == 0
+    packed, nmask, counts = ctx.encode(torch.from_numpy(orc.kmers_to_matrix(r["seq"], 35)).cuda())
+    ctx.sync()
+    assert tuple(rows.packed.shape) == (rows.n, 2)
+    assert torch.equal(rows.packed, packed) and torch.equal(rows.nmask, nmask)
+    assert np.array_equal(rows.start.cpu().numpy(), r["start"]) and np.array_equal(rows.stop.cpu().numpy(), r["stop"])
     # malformed lines are counted, not silently scored
     bad = b"1:1-9\tACGT\t1:1+\t1:5+\t3\tref\t1+,\n1:1-9\tACGTACGTACGTACGTACG\t1:1+\t1:20+\tx\tref\t1+,\n1:1-9\tACGTACGTACGTACGTACG\t1:1+\n"
     rows = ctx.parse_kmer_tsv(torch.frombuffer(bytearray(bad), dtype=torch.uint8), 19)

@@ -1,4 +1,4 @@
-"""Randomised GPU parity: arbitrary integer score matrices of every width 1..32 (including degenerate ones) with
+"""Randomised GPU parity: arbitrary integer score matrices of every width 1..64 (including degenerate ones) with
 their oracle-computed score distributions; DP, p-table, both-strand scores, histogram, hits and q-values must be
 bit-exact against the CPU oracle."""
 import numpy as np
@@ -32,18 +32,23 @@ def _random_motif(rng, w, kind):
     return sm.astype(np.int64), bg
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", list(range(6)) + ["wide0", "wide1"])
 def test_random_motifs_all_widths(ctx, seed):
     from grafimo_b200.engine import Scan
     from oracle import oracle as orc
+    wide = isinstance(seed, str)  # widths 33..64: two packed words per k-mer, K2's wide kernel
+    if wide:
+        seed = 6 + int(seed[-1])
     rng = np.random.default_rng(1000 + seed)
-    widths = list(range(1, 33))
+    widths = list(range(33, 65)) if wide else list(range(1, 33))
     rng.shuffle(widths)
+    if wide:
+        widths = sorted(set(widths[:8] + ([33, 64] if seed == 6 else [34, 63])))
     motifs = []
-    for i, w in enumerate(widths[:12] if seed else widths):
+    for i, w in enumerate(widths if wide or not seed else widths[:12]):
         kind = ["uniformish", "spiky", "flat", "tiny"][(i + seed) % 4]
-        if w > 28 and kind == "uniformish":
-            kind = "spiky"
+        if 28 < w <= 32 and kind == "uniformish":
+            kind = "spiky"  # the span would not fit shared memory; above 32 such spans are counted in global memory
         motifs.append((w, kind) + _random_motif(rng, w, kind))
     # K3 batched, all motifs in one launch
     pvs = ctx.pval_dp_batched([m[2] for m in motifs], [m[3] for m in motifs])

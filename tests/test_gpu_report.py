@@ -30,17 +30,20 @@ def _motif(tmp_path, key="ctcf_meme"):
 
 
 @pytest.mark.parametrize("opts", [dict(threshold=1.0), dict(threshold=0.05, recomb=False), dict(threshold=0.3, noreverse=True),
-                                  dict(threshold=1.0, qvalueT=True), dict(threshold=0.02, noqvalue=True)])
+                                  dict(threshold=1.0, qvalueT=True), dict(threshold=0.02, noqvalue=True),
+                                  dict(threshold=1.0, mkey="synth_w35_meme"), dict(threshold=0.4, recomb=False, mkey="synth_w64_meme")])
 def test_device_writer_equals_host_writers(ctx, tmp_path, opts):
     from grafimo_b200 import score_sequences as ss
     from grafimo_b200.extract_regions import DeviceGraph
     from grafimo_b200.res_writer import write_results, write_results_device
     ss._ctx = ctx
-    motif = _motif(tmp_path)
+    opts = dict(opts)
+    motif = _motif(tmp_path, opts.pop("mkey", "ctcf_meme"))  # the last two: motifs wider than one packed word
+    W = motif.width
     ref, vs, gt = gr.random_case(77, length=5000, n_var=250, n_hap=40)
-    rows = [DeviceGraph.build(ctx, "7", ref, vs, gt=gt).extract([(0, 2100), (2000, 5000)], 19)]
+    rows = [DeviceGraph.build(ctx, "7", ref, vs, gt=gt).extract([(0, 2100), (2000, 5000)], W)]
     ref2, vs2, gt2 = gr.random_case(78, length=1500, n_var=60, n_hap=40)
-    rows.append(DeviceGraph.build(ctx, "X", ref2, vs2, gt=gt2).extract([(10, 1500)], 19))
+    rows.append(DeviceGraph.build(ctx, "X", ref2, vs2, gt=gt2).extract([(10, 1500)], W))
     a_host = _Args(outdir=str(tmp_path / "host"), **opts)
     a_dev = _Args(outdir=str(tmp_path / "dev"), **opts)
     df = ss.compute_results_rows(motif, rows, True, a_host)
@@ -91,7 +94,8 @@ def test_device_writer_large_and_long_motif(ctx, tmp_path):
     assert gff_dev == "".join(gff3_lines(df, False, True))
 
 
-@pytest.mark.parametrize("tag", ["fixture_testmode", "fixture_t05_norecomb", "fixture_plus_N_2files", "fixture_qvalT", "synth_w8"])
+@pytest.mark.parametrize("tag", ["fixture_testmode", "fixture_t05_norecomb", "fixture_plus_N_2files", "fixture_qvalT", "synth_w8",
+                                 "synth_w33", "synth_w64"])
 def test_tsv_directory_to_files_on_device(ctx, tmp_path, tag):
     """`vg find` TSV directory -> K1b/K2/K5/K6 -> K8 files == compute_results + host writers on the reference-generated
     golden cases (same line sets; the order differs only inside p-value ties)."""
