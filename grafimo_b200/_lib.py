@@ -39,6 +39,14 @@ class Report(ctypes.Structure):
                 ("first_const", ctypes.c_int32)]
 
 
+class GraphInput(ctypes.Structure):
+    """gb2_graph_input (include/grafimo_b200.h)."""
+    _fields_ = [("h_ref", ctypes.c_void_p), ("ref_len", ctypes.c_int64), ("n_variants", ctypes.c_int64),
+                ("h_var_pos", ctypes.c_void_p), ("h_var_ref_len", ctypes.c_void_p), ("h_alt_off", ctypes.c_void_p),
+                ("h_alt", ctypes.c_void_p), ("n_hap", ctypes.c_int32), ("words", ctypes.c_int32),
+                ("h_gt_bits", ctypes.c_void_p), ("max_node_len", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 class GraphInfo(ctypes.Structure):
     _fields_ = [("n_nodes", ctypes.c_int64), ("n_edges", ctypes.c_int64), ("n_bases", ctypes.c_int64),
                 ("n_sets", ctypes.c_int64), ("n_hap", ctypes.c_int32), ("words", ctypes.c_int32)]
@@ -84,12 +92,14 @@ SIGNATURES = {
     "gb2_qvalues_from_hist": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_bh_pvalues": (_int, [_vp, _vp, _i64, _vp]),
     "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_finalize_dense": (_int, [_vp, _vp, _vp, _u64, _int, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_tally_haplotypes": (_int, [_vp, _vp, _vp, _i64, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gb2_graph_create": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32,
                                 _i64, _vp, ctypes.POINTER(_vp)]),
     "gb2_graph_destroy": (_int, [_vp]),
     "gb2_graph_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_int32,
                                ctypes.POINTER(_vp)]),
+    "gb2_graph_build_batch": (_int, [_vp, ctypes.c_int32, _vp, ctypes.c_int32, ctypes.POINTER(_vp)]),
     "gb2_graph_get_info": (_int, [_vp, _vp]),
     "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _int, ctypes.POINTER(_u64)]),
     "gb2_graph_extract": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -13,7 +13,9 @@
 //     "every haplotype" is not stored.
 // One pass over the breakpoints, bit-set work proportional to (variants x words): ~10 ms per Mb at 2,504 haplotypes.
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <unordered_map>
 
 #include "internal.cuh"
@@ -82,6 +84,20 @@ inline void and_into(Bits &dst, const Bits &a, const uint32_t *b)
     for (size_t i = 0; i < dst.size(); ++i) dst[i] = a[i] & b[i];
 }
 
+// what the host pass produces: the flat arrays gb2_graph_create uploads
+struct HostGraph {
+    std::vector<uint32_t> node_off, node_cons, edge_off, edge_to, edge_cons, cons_bits;
+    std::vector<uint8_t> seq, flags;
+    std::vector<int64_t> a0, clamp;
+    int32_t n_hap = 0, words = 4;
+    int64_t n_cons = 0;
+};
+
+// error text of a host pass running on a worker thread (GB2_REQUIRE / GB2_SET_ERR only need an `err` array)
+struct ErrSink {
+    char err[512] = {0};
+};
+
 }  // namespace
 
 extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, const uint8_t *h_seq,
@@ -90,13 +106,11 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
                                 const uint32_t *h_edge_to, const uint32_t *h_edge_cons, int32_t n_hap, int32_t words,
                                 int64_t n_cons, const uint32_t *h_cons_bits, gb2_graph **out);
 
-extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants,
-                               const int64_t *h_var_pos, const int32_t *h_var_ref_len, const int64_t *h_alt_off,
-                               const uint8_t *h_alt, int32_t n_hap, int32_t words, const uint32_t *h_gt_bits,
-                               int32_t max_node_len, gb2_graph **out)
+// The host pass: pure CPU work on caller-owned arrays, no CUDA call -- several chromosomes run on several threads.
+static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
+                      const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
+                      int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, HostGraph &hg)
 {
-    if (!ctx || !out) return GB2_ERR_ARG;
-    *out = nullptr;
     GB2_REQUIRE(ctx, h_ref && ref_len >= 1, "gb2_graph_build: empty reference");
     GB2_REQUIRE(ctx, n_variants >= 0 && (n_variants == 0 || (h_var_pos && h_var_ref_len && h_alt_off && h_alt)),
                 "gb2_graph_build: null variant array");
@@ -133,9 +147,10 @@ extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_l
     const int64_t nb = (int64_t)bps.size() - 1;
     auto bp_index = [&](int64_t pos) { return (int64_t)(std::lower_bound(bps.begin(), bps.end(), pos) - bps.begin()); };
 
-    std::vector<uint32_t> node_off(1, 0u), node_cons;
-    std::vector<uint8_t> seq, flags;
-    std::vector<int64_t> a0, clamp;
+    std::vector<uint32_t> &node_off = hg.node_off, &node_cons = hg.node_cons;
+    std::vector<uint8_t> &seq = hg.seq, &flags = hg.flags;
+    std::vector<int64_t> &a0 = hg.a0, &clamp = hg.clamp;
+    node_off.assign(1, 0u);
     std::vector<Edge> edges;
     seq.reserve((size_t)L + (size_t)(nv ? h_alt_off[nv] : 0));
 
@@ -268,7 +283,8 @@ extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_l
     // ---- CSR: by (source, target); repeated structural edges (two deletions with the same ends) are merged
     const int64_t n_nodes = (int64_t)a0.size();
     std::sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.src != y.src ? x.src < y.src : x.dst < y.dst; });
-    std::vector<uint32_t> edge_off((size_t)n_nodes + 1, 0u), edge_to, edge_cons;
+    std::vector<uint32_t> &edge_off = hg.edge_off, &edge_to = hg.edge_to, &edge_cons = hg.edge_cons;
+    edge_off.assign((size_t)n_nodes + 1, 0u);
     edge_to.reserve(edges.size());
     edge_cons.reserve(edges.size());
     for (size_t e = 0; e < edges.size(); ++e) {
@@ -290,9 +306,91 @@ extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_l
     }
     for (int64_t n = 0; n < n_nodes; ++n) edge_off[(size_t)n + 1] += edge_off[(size_t)n];
     std::vector<Edge>().swap(edges);
-    const int64_t n_cons = sets.on ? (int64_t)(sets.flat.size() / (size_t)words) : 0;
+    hg.n_cons = sets.on ? (int64_t)(sets.flat.size() / (size_t)words) : 0;
+    hg.n_hap = sets.on ? n_hap : 0;
+    hg.words = words;
+    hg.cons_bits.swap(sets.flat);
+    return GB2_OK;
+}
+
+static int upload_host_graph(gb2_ctx *ctx, const HostGraph &hg, gb2_graph **out)
+{
     static const uint32_t dummy[4] = {0, 0, 0, 0};
-    return gb2_graph_create(ctx, n_nodes, node_off.data(), seq.data(), a0.data(), clamp.data(), flags.data(), node_cons.data(),
-                            (int64_t)edge_to.size(), edge_off.data(), edge_to.data(), edge_cons.data(), sets.on ? n_hap : 0, words,
-                            n_cons, n_cons ? sets.flat.data() : dummy, out);
+    return gb2_graph_create(ctx, (int64_t)hg.a0.size(), hg.node_off.data(), hg.seq.data(), hg.a0.data(), hg.clamp.data(),
+                            hg.flags.data(), hg.node_cons.data(), (int64_t)hg.edge_to.size(), hg.edge_off.data(),
+                            hg.edge_to.data(), hg.edge_cons.data(), hg.n_hap, hg.words, hg.n_cons,
+                            hg.n_cons ? hg.cons_bits.data() : dummy, out);
+}
+
+extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants,
+                               const int64_t *h_var_pos, const int32_t *h_var_ref_len, const int64_t *h_alt_off,
+                               const uint8_t *h_alt, int32_t n_hap, int32_t words, const uint32_t *h_gt_bits,
+                               int32_t max_node_len, gb2_graph **out)
+{
+    if (!ctx || !out) return GB2_ERR_ARG;
+    *out = nullptr;
+    HostGraph hg;
+    ErrSink es;
+    const int rc = build_host(&es, h_ref, ref_len, n_variants, h_var_pos, h_var_ref_len, h_alt_off, h_alt, n_hap, words,
+                              h_gt_bits, max_node_len, hg);
+    if (rc != GB2_OK) {
+        GB2_SET_ERR(ctx, "%s", es.err);
+        return rc;
+    }
+    return upload_host_graph(ctx, hg, out);
+}
+
+// Several chromosomes at once: the host passes run on up to n_threads worker threads (0 = one per hardware thread), each
+// finished graph is uploaded by the calling thread on the context's stream while the others are still being built.
+extern "C" int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_graph_input *inputs, int32_t n_threads,
+                                     gb2_graph **out)
+{
+    if (!ctx || !out || n_graphs < 0 || (n_graphs > 0 && !inputs)) return GB2_ERR_ARG;
+    for (int i = 0; i < n_graphs; ++i) out[i] = nullptr;
+    if (n_graphs == 0) return GB2_OK;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, (int)n_graphs));
+    std::vector<HostGraph> hgs((size_t)n_graphs);
+    std::vector<ErrSink> errs((size_t)n_graphs);
+    std::vector<int> rcs((size_t)n_graphs, GB2_OK);
+    std::vector<std::atomic<int>> ready((size_t)n_graphs);
+    for (auto &r : ready) r.store(0);
+    // largest inputs first, so that the longest chromosome does not start last
+    std::vector<int> order((size_t)n_graphs);
+    for (int i = 0; i < n_graphs; ++i) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return inputs[a].ref_len + 64 * inputs[a].n_variants > inputs[b].ref_len + 64 * inputs[b].n_variants;
+    });
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= n_graphs) return;
+            const int i = order[(size_t)k];
+            const gb2_graph_input &in = inputs[i];
+            rcs[(size_t)i] = build_host(&errs[(size_t)i], in.h_ref, in.ref_len, in.n_variants, in.h_var_pos, in.h_var_ref_len,
+                                        in.h_alt_off, in.h_alt, in.n_hap, in.words, in.h_gt_bits, in.max_node_len, hgs[(size_t)i]);
+            ready[(size_t)i].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(worker);
+    int rc = GB2_OK;
+    for (int k = 0; k < n_graphs; ++k) {  // upload in the order the workers take them
+        const int i = order[(size_t)k];
+        while (!ready[(size_t)i].load(std::memory_order_acquire)) std::this_thread::yield();
+        if (rc != GB2_OK) continue;  // still wait for every worker before leaving
+        if (rcs[(size_t)i] != GB2_OK) {
+            rc = rcs[(size_t)i];
+            GB2_SET_ERR(ctx, "graph %d: %s", i, errs[(size_t)i].err);
+            continue;
+        }
+        rc = upload_host_graph(ctx, hgs[(size_t)i], &out[i]);
+        hgs[(size_t)i] = HostGraph();  // free the host copy
+    }
+    for (auto &t : pool) t.join();
+    if (rc != GB2_OK)
+        for (int i = 0; i < n_graphs; ++i)
+            if (out[i]) { gb2_graph_destroy(out[i]); out[i] = nullptr; }
+    return rc;
 }

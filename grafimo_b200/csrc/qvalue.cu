@@ -316,6 +316,121 @@ extern "C" int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *m, const gb2_hit
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6, dense form: the report rows of an unselective scan (`-t 1`, what docs/paper_results/run_analysis.sh runs: every
+// scored window with p < 1 is reported) straight from K2's dense scores -- no hit records, no 64-bit sort keys.
+// Window i = k-mer i / strands, strand i % strands, i.e. the windows are already in (row, strand) order, so ONE
+// stable radix sort on the p-rank alone (<= 17 bits, 2-3 passes of 4-byte keys) gives the (p, row, strand) order the
+// hit path gets from sorting 41-bit keys.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dense_bin(const uint32_t *__restrict__ dense, uint64_t i, int strands, uint32_t span)
+{
+    const uint32_t d = __ldg(dense + (strands == 2 ? (i >> 1) : i));
+    if (d == 0xFFFFFFFFu) return span;  // N row: score = min_val, p = 1
+    return (strands == 2 && (i & 1ull)) ? (d >> 16) : (d & 0xFFFFu);
+}
+
+__global__ void gb2_dense_keys_kernel(const uint32_t *__restrict__ dense, uint64_t n_windows, int strands, uint32_t span,
+                                      const double *__restrict__ ptab, const double *__restrict__ qtab,
+                                      const uint32_t *__restrict__ rank, double p_thr, int q_filter, double q_thr,
+                                      uint32_t drop_key, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx,
+                                      unsigned long long *__restrict__ n_kept)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n_windows) {
+        const uint32_t bin = dense_bin(dense, i, strands, span);
+        const double p = bin < span ? ptab[bin] : 1.0;
+        keep = p < p_thr && (!q_filter || qtab[bin] < q_thr);  // strict, resultsTmp.py:305-307
+        keys[i] = keep ? rank[bin] : drop_key;
+        idx[i] = (uint32_t)i;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_kept, (unsigned long long)__popc(m));
+}
+
+__global__ void gb2_rank_inverse_kernel(const uint32_t *__restrict__ rank, uint32_t nbins, uint32_t *__restrict__ bin_of_rank)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) bin_of_rank[rank[b]] = b;
+}
+
+// The sorted key of a kept window IS its p-rank, so its bin comes from the (tiny) inverse rank table: every read of this
+// kernel is coalesced or cache-resident, nothing goes back to the dense scores.
+__global__ void gb2_dense_gather_kernel(const uint32_t *__restrict__ sorted_rank, const uint32_t *__restrict__ order,
+                                        const uint32_t *__restrict__ bin_of_rank,
+                                        const unsigned long long *__restrict__ n_kept, int strands, uint64_t row_base,
+                                        int32_t lo, int w, double scale, double offset,
+                                        const double *__restrict__ ptab, const double *__restrict__ qtab,
+                                        uint64_t *__restrict__ o_row, uint8_t *__restrict__ o_strand,
+                                        int32_t *__restrict__ o_iscore, double *__restrict__ o_score,
+                                        double *__restrict__ o_p, double *__restrict__ o_q)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_kept) return;
+    const uint64_t i = order[t];
+    const uint32_t bin = bin_of_rank[sorted_rank[t]];  // kept windows have bin < span
+    const int32_t sc = lo + (int32_t)bin;
+    o_row[t] = row_base + (strands == 2 ? (i >> 1) : i);
+    o_strand[t] = (uint8_t)(strands == 2 ? (i & 1ull) : 0ull);
+    o_iscore[t] = sc;
+    o_score[t] = __dadd_rn(__ddiv_rn((double)sc, scale), __dmul_rn((double)w, offset));  // score_sequences.py:393
+    o_p[t] = ptab[bin];
+    if (o_q != nullptr && qtab != nullptr) o_q[t] = qtab[bin];
+}
+
+extern "C" int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *m, const uint32_t *d_dense, uint64_t n_kmers, int strands,
+                                  uint64_t row_base, const double *d_qtab, const uint32_t *d_rank, double p_threshold,
+                                  int q_filter, double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore,
+                                  double *d_score, double *d_p, double *d_q, uint64_t *d_n_out)
+{
+    if (!ctx || !m) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, d_n_out != nullptr && d_rank != nullptr, "gb2_finalize_dense: null counter or rank table");
+    GB2_REQUIRE(ctx, strands == 1 || strands == 2, "gb2_finalize_dense: strands must be 1 or 2");
+    GB2_REQUIRE(ctx, !q_filter || d_qtab != nullptr, "gb2_finalize_dense: q filter needs the q table");
+    const uint64_t n_windows = n_kmers * (uint64_t)strands;
+    GB2_REQUIRE(ctx, n_windows < ((uint64_t)1 << 31), "gb2_finalize_dense: at most 2^31-1 windows per call");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB2_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), ctx->stream));
+    if (n_windows == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_dense && d_row && d_strand && d_iscore && d_score && d_p, "gb2_finalize_dense: null buffer");
+    const int n = (int)n_windows;
+    int rank_bits = 1;
+    while ((1ll << rank_bits) < m->span + 1) ++rank_bits;  // ranks are < span + 1 <= 2^rank_bits
+    const uint32_t drop_key = 1u << rank_bits;             // sorts after every kept window
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n, 0, rank_bits + 1, ctx->stream);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const uint32_t nbins = (uint32_t)m->span + 1;
+    const size_t need = align(cub_bytes) + 4 * align((size_t)n * 4) + align((size_t)nbins * 4);
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    uint32_t *k_in = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *k_out = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *v_in = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *v_out = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *bin_of_rank = (uint32_t *)base;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)gb2_div_up(n, threads);
+    gb2_rank_inverse_kernel<<<(nbins + 255) / 256, 256, 0, ctx->stream>>>(d_rank, nbins, bin_of_rank);
+    GB2_LAUNCH_CHECK(ctx);
+    gb2_dense_keys_kernel<<<blocks, threads, 0, ctx->stream>>>(d_dense, n_windows, strands, (uint32_t)m->span, m->d_ptab, d_qtab,
+                                                              d_rank, p_threshold, q_filter, q_threshold, drop_key, k_in, v_in,
+                                                              (unsigned long long *)d_n_out);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, n, 0, rank_bits + 1, ctx->stream));
+    ctx->launches += 1;
+    gb2_dense_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(k_out, v_out, bin_of_rank, (const unsigned long long *)d_n_out,
+                                                                strands, row_base, (int32_t)m->lo, m->w, (double)m->scale,
+                                                                m->offset, m->d_ptab, d_qtab, d_row, d_strand, d_iscore,
+                                                                d_score, d_p, d_q);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // haplotype tally
 // ---------------------------------------------------------------------------------------------
 __global__ void gb2_tally_heads_kernel(const unsigned long long *__restrict__ pos,

@@ -110,6 +110,17 @@ __device__ __forceinline__ void append_hits(const ScoreParams &p, bool pred, uin
     }
 }
 
+// dense scores of pair j (k-mers 2j, 2j+1): one 8-byte store when the buffer allows it
+__device__ __forceinline__ void store_dense_pair(uint32_t *dense, int64_t j, uint2 o, bool aligned8)
+{
+    if (aligned8) {
+        reinterpret_cast<uint2 *>(dense)[j] = o;
+    } else {
+        dense[2 * j] = o.x;
+        dense[2 * j + 1] = o.y;
+    }
+}
+
 __device__ __forceinline__ bool bin_hits(const ScoreParams &p, uint32_t bin)
 {
     if (bin < p.cut || bin >= p.span) return false;  // bin == span: N row, never a hit
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
     const uint32_t cut_hi = p.cut << 16;
     const bool two = p.two_strands != 0;
     const bool has_n = p.nmask != nullptr;
+    const bool dense8 = (reinterpret_cast<uintptr_t>(p.dense) & 7u) == 0;  // a batch may start at an odd row of a larger buffer
 
     // ---- full tiles: 1024*U pairs, no bounds checks; thread t owns pairs t, t+1024, ... of the tile,
     //      so every warp-wide load covers 512 contiguous bytes and U loads are in flight per thread
@@ -187,13 +199,12 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
             }
         }
         if (p.dense != nullptr) {
-            uint2 *d = reinterpret_cast<uint2 *>(p.dense) + j0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 uint2 o;
                 o.x = (acc[2 * u] == nsent) ? 0xFFFFFFFFu : acc[2 * u];
                 o.y = (acc[2 * u + 1] == nsent) ? 0xFFFFFFFFu : acc[2 * u + 1];
-                d[u * 1024] = o;
+                store_dense_pair(p.dense, j0 + u * 1024, o, dense8);
             }
         }
         // cheap screen: per-field maximum over the 2U k-mers (packed 16-bit max), one compare per strand
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
                     uint2 o;
                     o.x = (a0 == nsent) ? 0xFFFFFFFFu : a0;
                     o.y = (a1 == nsent) ? 0xFFFFFFFFu : a1;
-                    reinterpret_cast<uint2 *>(p.dense)[j] = o;
+                    store_dense_pair(p.dense, j, o, dense8);
                 }
             }
             if (p.hits != nullptr) emit_pair_hits(p, a0, a1, j, ok, two, lane);
@@ -397,7 +408,7 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     GB2_REQUIRE(ctx, d_packed != nullptr, "gb2_score: null k-mer buffer");
     GB2_REQUIRE(ctx, ((uintptr_t)d_packed & 15u) == 0, "gb2_score: packed k-mers must be 16-byte aligned");
     GB2_REQUIRE(ctx, d_hits == nullptr || d_hit_count != nullptr, "gb2_score: hit buffer without a counter");
-    GB2_REQUIRE(ctx, d_dense == nullptr || ((uintptr_t)d_dense & 7u) == 0, "gb2_score: dense buffer must be 8-byte aligned");
+    GB2_REQUIRE(ctx, d_dense == nullptr || ((uintptr_t)d_dense & 3u) == 0, "gb2_score: dense buffer must be 4-byte aligned");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
 
     ScoreParams p;

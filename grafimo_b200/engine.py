@@ -259,16 +259,23 @@ class Scan:
     int64 tensor so that multi-GPU runs can all-reduce it (the only cross-GPU traffic); finalize()
     turns the hits into the numeric columns of the report."""
 
-    def __init__(self, ctx, motif, strands=2, threshold=1e-4, want_q=True, hit_capacity=1 << 20, dense=False):
+    def __init__(self, ctx, motif, strands=2, threshold=1e-4, want_q=True, hit_capacity=1 << 20, dense_rows=0):
+        """dense_rows > 0: unselective scan (`-t 1`-like thresholds) of that many k-mers in all -- K2 writes dense scores
+        instead of hit records and the report rows come from gb2_finalize_dense (batches must be scored in row order,
+        each starting where the previous one ended; dense_rows * strands < 2^31)."""
         self.ctx, self.motif = ctx, motif
         self.strands, self.threshold, self.want_q = int(strands), float(threshold), bool(want_q)
-        self.capacity = int(hit_capacity)
+        self.dense_rows = int(dense_rows)
+        if self.dense_rows * self.strands >= (1 << 31):
+            raise ValueError("dense scans are limited to 2^31-1 windows")
+        self.capacity = self.dense_rows * self.strands if self.dense_rows else int(hit_capacity)
         self.hist = ctx.zeros(motif.span + 1, torch.int64) if want_q else None
-        self.hits = ctx.empty(max(self.capacity, 1) * _HIT_BYTES, torch.uint8)
+        self.hits = None if self.dense_rows else ctx.empty(max(self.capacity, 1) * _HIT_BYTES, torch.uint8)
+        self.dense = ctx.empty(self.dense_rows + 1, torch.int32) if self.dense_rows else None
         self.counters = ctx.zeros(4, torch.int64)  # [0] hits found, [1] kept, [2] total N
         self.rows_scored = 0
         self.row_limit = 0
-        self.dense = dense
+        self.first_row = None
 
     def reset(self):
         with torch.cuda.stream(self.ctx.stream):
@@ -277,6 +284,7 @@ class Scan:
             self.counters.zero_()
         self.rows_scored = 0
         self.row_limit = 0
+        self.first_row = None
 
     def score(self, packed, nmask=None, row_base=0, dense_out=None):
         """packed: int64[n] device tensor, or int64[n, 2] for a motif wider than 32 (two words per k-mer)."""
@@ -287,8 +295,15 @@ class Scan:
             raise ValueError(f"k-mers of a width-{self.motif.width} motif must be packed as "
                              f"{'int64[n, 2]' if wide else 'int64[n]'}")
         ctx.enter()
+        if self.dense_rows:
+            if self.first_row is None:
+                self.first_row = int(row_base)
+            if int(row_base) != self.first_row + self.rows_scored or self.rows_scored + n > self.dense_rows or dense_out is not None:
+                raise ValueError("dense scan: batches must be consecutive rows within dense_rows")
+            dense_out = self.dense[self.rows_scored:]
         check(lib.gb2_score(ctx.h, self.motif.h, _ptr(packed), _ptr(nmask), n, int(row_base), self.strands, self.threshold,
-                            _ptr(self.hist), _ptr(self.hits), self.capacity, _ptr(self.counters), _ptr(dense_out)),
+                            _ptr(self.hist), _ptr(self.hits), self.capacity if self.hits is not None else 0,
+                            _ptr(self.counters), _ptr(dense_out)),
               "gb2_score", ctx.h)
         self.rows_scored += n
         self.row_limit = max(self.row_limit, int(row_base) + n)
@@ -308,6 +323,8 @@ class Scan:
         return self.qtab, self.rank
 
     def n_hits(self):
+        if self.dense_rows:  # every window is a candidate; the kept count comes from finalize
+            return self.rows_scored * self.strands
         self.ctx.sync()
         return int(self.counters[0].item())
 
@@ -326,11 +343,19 @@ class Scan:
                            p=ctx.empty(cap, torch.float64), q=ctx.empty(cap, torch.float64) if self.want_q else None)
             self._out_cap = cap
         o = self._o
-        check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, int(self.row_limit),
-                                        _ptr(self.qtab) if self.want_q else None, _ptr(self.rank), self.threshold,
-                                        int(bool(q_filter)), self.threshold, _ptr(o["row"]), _ptr(o["strand"]),
-                                        _ptr(o["iscore"]), _ptr(o["score"]), _ptr(o["p"]), _ptr(o["q"]),
-                                        ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits", ctx.h)
+        if self.dense_rows:
+            check(ctx.lib.gb2_finalize_dense(ctx.h, self.motif.h, _ptr(self.dense), self.rows_scored, self.strands,
+                                             int(self.first_row or 0), _ptr(self.qtab) if self.want_q else None,
+                                             _ptr(self.rank), self.threshold, int(bool(q_filter)), self.threshold,
+                                             _ptr(o["row"]), _ptr(o["strand"]), _ptr(o["iscore"]), _ptr(o["score"]),
+                                             _ptr(o["p"]), _ptr(o["q"]), ctypes.c_void_p(self.counters.data_ptr() + 8)),
+                  "gb2_finalize_dense", ctx.h)
+        else:
+            check(ctx.lib.gb2_finalize_hits(ctx.h, self.motif.h, _ptr(self.hits), n, int(self.row_limit),
+                                            _ptr(self.qtab) if self.want_q else None, _ptr(self.rank), self.threshold,
+                                            int(bool(q_filter)), self.threshold, _ptr(o["row"]), _ptr(o["strand"]),
+                                            _ptr(o["iscore"]), _ptr(o["score"]), _ptr(o["p"]), _ptr(o["q"]),
+                                            ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits", ctx.h)
         ctx.sync()
         with torch.cuda.stream(ctx.stream):
             kept = int(self.counters[1].item())

@@ -82,11 +82,8 @@ class DeviceGraph:
         self.n_hap = int(info.n_hap)
 
     @staticmethod
-    def build(ctx, chrom, ref, variants, gt=None, gt_bits=None, max_node_len=32):
-        """Native builder (gb2_graph_build).  ref: str/bytes/uint8 array; variants: [(pos0, ref_allele, alt_allele)]
-        (reduced) or a dict of arrays {pos int64, ref_len int32, alt_off int64[n+1], alt uint8}; genotypes as
-        gt uint8 [n_variants, n_hap] or gt_bits uint32 [n_variants, words] + n_hap (tuple) -- None: no haplotype index.
-        Variants are put in position order (stable) like vgraph.VariationGraph.build does."""
+    def _build_inputs(ref, variants, gt=None, gt_bits=None):
+        """Host arrays of gb2_graph_build: (refa, pos, rlen, alt_off, alt, n_hap, words, bits)."""
         from .vgraph import pack_bits
         if isinstance(ref, str):
             ref = ref.encode("ascii")
@@ -125,12 +122,43 @@ class DeviceGraph:
         words = bits.shape[1] if bits is not None else 4
         if bits is not None and bits.shape[0] != nv:
             raise ValueError("one genotype row per variant is required")
-        h = ctypes.c_void_p()
         alt_p = alt if len(alt) else np.zeros(1, np.uint8)
-        check(ctx.lib.gb2_graph_build(ctx.h, _np_ptr(refa), len(refa), nv, _np_ptr(pos), _np_ptr(rlen), _np_ptr(alt_off),
+        return refa, pos, rlen, alt_off, alt_p, int(n_hap), int(words), bits
+
+    @staticmethod
+    def build(ctx, chrom, ref, variants, gt=None, gt_bits=None, max_node_len=32):
+        """Native builder (gb2_graph_build).  ref: str/bytes/uint8 array; variants: [(pos0, ref_allele, alt_allele)]
+        (reduced) or a dict of arrays {pos int64, ref_len int32, alt_off int64[n+1], alt uint8}; genotypes as
+        gt uint8 [n_variants, n_hap] or gt_bits uint32 [n_variants, words] + n_hap (tuple) -- None: no haplotype index.
+        Variants are put in position order (stable) like vgraph.VariationGraph.build does."""
+        refa, pos, rlen, alt_off, alt_p, n_hap, words, bits = DeviceGraph._build_inputs(ref, variants, gt, gt_bits)
+        h = ctypes.c_void_p()
+        check(ctx.lib.gb2_graph_build(ctx.h, _np_ptr(refa), len(refa), len(pos), _np_ptr(pos), _np_ptr(rlen), _np_ptr(alt_off),
                                       _np_ptr(alt_p), n_hap, words, _np_ptr(bits) if bits is not None else None,
                                       int(max_node_len), ctypes.byref(h)), "gb2_graph_build", ctx.h)
         return DeviceGraph(ctx, None, handle=h, chrom=chrom)
+
+    @staticmethod
+    def build_many(ctx, items, max_node_len=32, n_threads=0):
+        """Several chromosomes at once (gb2_graph_build_batch): items = [(chrom, ref, variants, gt, gt_bits)] with the
+        argument forms of build(); the host passes run on n_threads worker threads of the library (0 = all hardware
+        threads), uploads happen as graphs finish.  -> [DeviceGraph] in item order."""
+        from ._lib import GraphInput
+        n = len(items)
+        if n == 0:
+            return []
+        keep, arr = [], (GraphInput * n)()
+        for i, (chrom, ref, variants, gt, gt_bits) in enumerate(items):
+            a = DeviceGraph._build_inputs(ref, variants, gt, gt_bits)
+            keep.append(a)  # the arrays must outlive the call
+            refa, pos, rlen, alt_off, alt_p, n_hap, words, bits = a
+            arr[i] = GraphInput(refa.ctypes.data, len(refa), len(pos), pos.ctypes.data, rlen.ctypes.data, alt_off.ctypes.data,
+                                alt_p.ctypes.data, n_hap, words, bits.ctypes.data if bits is not None else None,
+                                int(max_node_len), 0)
+        outs = (ctypes.c_void_p * n)()
+        check(ctx.lib.gb2_graph_build_batch(ctx.h, n, ctypes.cast(arr, ctypes.c_void_p), int(n_threads),
+                                            ctypes.cast(outs, ctypes.POINTER(ctypes.c_void_p))), "gb2_graph_build_batch", ctx.h)
+        return [DeviceGraph(ctx, None, handle=ctypes.c_void_p(outs[i]), chrom=items[i][0]) for i in range(n)]
 
     @staticmethod
     def from_files(ctx, fasta, vcf, chrom, display_name=None, max_node_len=32, use_haplotypes=True):

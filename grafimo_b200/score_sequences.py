@@ -104,6 +104,12 @@ def device_motif(motif: Motif, ctx=None):
     return dm
 
 
+def _dense_rows(threshold, n_kmers, strands):
+    """Unselective thresholds (`-t 1` in docs/paper_results/run_analysis.sh) report a large share of the windows: K2 then
+    writes dense scores and gb2_finalize_dense builds the rows (no hit records, 4-byte sort keys).  -> dense_rows of Scan."""
+    return int(n_kmers) if (threshold >= 0.25 and 0 < n_kmers * strands < (1 << 31)) else 0
+
+
 _CHUNK_BYTES = 1 << 30  # TSV text is parsed on the device in chunks of at most 1 GiB (cut at line boundaries)
 
 
@@ -359,8 +365,9 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     # every row is scored as given: `vg find -E` already emits the reverse-strand rows.  The hit buffer starts
     # small for selective thresholds and the (cheap) scoring pass is repeated in the rare case it overflows.
     cap = n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8))
+    dense = _dense_rows(threshold, n_local, 1)
     while True:
-        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap, dense_rows=dense)
         for (_, rows, base), st in zip(chunks, stats):
             if rows.n:  # the N mask is only read by the kernel when some row of the chunk needs it
                 scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=rank_base + base)
@@ -479,8 +486,9 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     bases = (rank_base + np.concatenate([[0], np.cumsum([b.n for b in batches])])).astype(np.int64)
     n_local = n_kmers * strands
     cap = max(1, n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8)))
+    dense = _dense_rows(threshold, n_kmers, strands)
     while True:
-        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap, dense_rows=dense)
         for b, base in zip(batches, bases[:-1]):
             if b.n:
                 scan.score(b.packed, b.nmask if b.n_masked() else None, row_base=int(base))
@@ -578,8 +586,9 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
     dm = device_motif(motif, ctx)
     bases = np.concatenate([[0], np.cumsum([b.n for b in batches])]).astype(np.int64)
     cap = max(1, n if threshold >= 0.25 else min(n, max(1 << 20, n // 8)))
+    dense = _dense_rows(threshold, n_kmers, strands)
     while True:
-        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        scan = engine.Scan(ctx, dm, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap, dense_rows=dense)
         for b, base in zip(batches, bases[:-1]):
             if b.n:
                 scan.score(b.packed, b.nmask if b.n_masked() else None, row_base=int(base))
@@ -708,8 +717,9 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
         exception_handler(ValueError, errmsg, debug)
     cap = max(1, n if threshold >= 0.25 else min(n, max(1 << 20, n // 8)))
+    dense = _dense_rows(threshold, n, 1)
     while True:
-        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        scan = engine.Scan(ctx, dm, strands=1, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap, dense_rows=dense)
         for rows, base, st in chunks:
             if rows.n:
                 scan.score(rows.packed, rows.nmask if st["n_rows"] else None, row_base=base)

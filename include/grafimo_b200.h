@@ -159,7 +159,8 @@ const double *gb2_motif_ptable_device(const gb2_motif *motif);
  *   d_hist       uint64[span+1] or NULL (no q-values wanted): += per-score counts.
  *   d_hits / hit_capacity / d_hit_count: hit records appended at *d_hit_count (device counter,
  *                += hits found even when capacity is exceeded; excess records are dropped).
- *   d_dense      uint32[n] or NULL: per k-mer ((rc - lo) << 16 | (fwd - lo)); 0xFFFFFFFF for N rows.
+ *   d_dense      uint32[n] or NULL: per k-mer ((rc - lo) << 16 | (fwd - lo)); 0xFFFFFFFF for N rows (8-byte aligned
+ *                for the fastest stores).
  * d_packed must be 16-byte aligned (uint64[n], or uint64[n][2] for a motif wider than 32).  row_base is added to the
  * row index in hit records.  Motifs whose score span does not fit shared memory next to the lookup tables (w >~ 54)
  * count their histogram with global atomics instead: same results, slower. */
@@ -196,6 +197,16 @@ int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *motif, const gb2_hit *d_hit
                       const double *d_qtab, const uint32_t *d_rank, double p_threshold, int q_filter,
                       double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score,
                       double *d_p, double *d_q, uint64_t *d_n_out);
+
+/* The same step for an unselective scan (`-t 1`, docs/paper_results/run_analysis.sh:43: every window with p < 1 is a
+ * report row), from the dense scores gb2_score wrote for n_kmers consecutive k-mers (d_dense, see gb2_score) instead of
+ * hit records: window i = (k-mer i / strands, strand i % strands) is already in (row, strand) order, so one stable radix
+ * sort on the p-rank gives the same (p, row, strand) order with 4-byte keys.  Row indices = row_base + k-mer index.
+ * Outputs need room for n_kmers * strands entries; n_kmers * strands < 2^31. */
+int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *motif, const uint32_t *d_dense, uint64_t n_kmers, int strands,
+                       uint64_t row_base, const double *d_qtab, const uint32_t *d_rank, double p_threshold, int q_filter,
+                       double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score,
+                       double *d_p, double *d_q, uint64_t *d_n_out);
 
 /* ---- haplotype tally ---------------------------------------------------------------------------- */
 /* Per-haplotype windows -> vg-like deduplicated rows: sorts (position, packed k-mer) pairs and
@@ -254,6 +265,21 @@ int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h_node_off, 
 int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
                     const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
                     int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, gb2_graph **out);
+/* gb2_graph_build for several chromosomes at once (one gb2_graph_input each, fields as the arguments above): the host
+ * passes run on up to n_threads worker threads (0 = one per hardware thread), every finished graph is uploaded by the
+ * calling thread.  out[n_graphs]; on failure no graph is returned. */
+typedef struct gb2_graph_input {
+    const uint8_t *h_ref;
+    int64_t ref_len, n_variants;
+    const int64_t *h_var_pos;
+    const int32_t *h_var_ref_len;
+    const int64_t *h_alt_off;
+    const uint8_t *h_alt;
+    int32_t n_hap, words;
+    const uint32_t *h_gt_bits;
+    int32_t max_node_len, reserved;
+} gb2_graph_input;
+int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_graph_input *inputs, int32_t n_threads, gb2_graph **out);
 typedef struct gb2_graph_info {
     int64_t n_nodes, n_edges, n_bases, n_sets; /* n_sets: stored haplotype-set rows */
     int32_t n_hap, words;

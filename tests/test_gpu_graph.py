@@ -80,6 +80,29 @@ def test_extract_equals_oracle_random_graphs(ctx, seed, builder):
             assert text == want
 
 
+def test_batch_builder_equals_single_builds(ctx):
+    """gb2_graph_build_batch (host passes on worker threads) == gb2_graph_build per chromosome: same graphs, same rows."""
+    from grafimo_b200._lib import GrafimoB200Error
+    from grafimo_b200.extract_regions import DeviceGraph
+    cases = [gr.random_case(900 + k, length=400 + 300 * k, n_var=30 + 25 * k, n_hap=(0, 12, 70, 40, 33)[k]) for k in range(5)]
+    items = [(f"c{k}", ref, vs, gt if k else None, None) for k, (ref, vs, gt) in enumerate(cases)]
+    for threads in (0, 1, 3):
+        many = DeviceGraph.build_many(ctx, items, n_threads=threads)
+        assert [g.chrom for g in many] == [f"c{k}" for k in range(5)]
+        for k, (ref, vs, gt) in enumerate(cases):
+            one = DeviceGraph.build(ctx, f"c{k}", ref, vs, gt=gt if k else None)
+            assert (many[k].info.n_nodes, many[k].info.n_edges, many[k].info.n_sets, many[k].info.n_hap) == \
+                   (one.info.n_nodes, one.info.n_edges, one.info.n_sets, one.info.n_hap)
+            a, b = many[k].extract([(0, len(ref))], 21).host(), one.extract([(0, len(ref))], 21).host()
+            assert all(np.array_equal(a[c], b[c]) for c in a)
+    assert DeviceGraph.build_many(ctx, []) == []
+    bad = list(items)
+    bad[2] = ("x", cases[2][0], {"pos": np.array([5, 3], np.int64), "ref_len": np.array([1, 1], np.int32),
+                                 "alt_off": np.array([0, 1, 2], np.int64), "alt": np.frombuffer(b"AC", np.uint8)}, None, None)
+    with pytest.raises((GrafimoB200Error, ValueError)):
+        DeviceGraph.build_many(ctx, bad)
+
+
 def test_extract_without_haplotypes_and_errors(ctx):
     from grafimo_b200._lib import GrafimoB200Error
     from grafimo_b200.vgraph import VariationGraph

@@ -193,6 +193,48 @@ def test_dense_output_and_no_hist(ctx, tag):
     assert np.array_equal((dn[ok] >> 16).astype(np.int64) + dm.lo, isr[ok])
 
 
+@pytest.mark.parametrize("tag", ["ctcf_meme__bgnt", "synth_w35_meme__bgnt"])
+def test_dense_finalize_equals_hit_path(ctx, tag):
+    """Unselective thresholds: dense scores + gb2_finalize_dense == hit records + gb2_finalize_hits, row for row (same
+    (p, row, strand) order), for one and two strands, a q-value filter, N rows and batches that begin at odd rows."""
+    from grafimo_b200.engine import Scan
+    orc = _orc()
+    m = gu.load_motif(tag)
+    w = m["width"]
+    rng = np.random.default_rng(9)
+    n = 20001
+    seqs = ["".join(rng.choice(list("ACGT"), size=w)) for _ in range(n)]
+    for k in (0, 7000, 7001, n - 1):
+        seqs[k] = seqs[k][:3] + "N" + seqs[k][4:]
+    a = orc.kmers_to_matrix(seqs, w)
+    packed, nmask, _ = ctx.encode(torch.from_numpy(a).cuda())
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    for strands, thr, qf in ((2, 1.0, False), (1, 0.3, False), (2, 0.9, True)):
+        ref = Scan(ctx, dm, strands=strands, threshold=thr, hit_capacity=2 * n)
+        ref.score(packed, nmask, row_base=100)
+        exp = ref.finalize(q_filter=qf)
+        den = Scan(ctx, dm, strands=strands, threshold=thr, dense_rows=n)
+        cut = 7008  # the N mask of a batch starts at its own bit 0: split on a multiple of 32
+        den.score(packed[:cut], nmask[:cut // 32], row_base=100)
+        den.score(packed[cut:], nmask[cut // 32:], row_base=100 + cut)
+        got = den.finalize(q_filter=qf)
+        assert len(exp["row"]) > 100
+        for k in exp:
+            assert np.array_equal(np.asarray(got[k]), np.asarray(exp[k])), (strands, thr, qf, k)
+    # ... and an odd first batch (the dense pairs of the second batch are then 4-byte aligned only)
+    a2 = orc.kmers_to_matrix([s.replace("N", "A") for s in seqs], w)
+    packed2, _, _ = ctx.encode(torch.from_numpy(a2).cuda())
+    ref = Scan(ctx, dm, strands=2, threshold=1.0, hit_capacity=2 * n)
+    ref.score(packed2)
+    exp = ref.finalize()
+    den = Scan(ctx, dm, strands=2, threshold=1.0, dense_rows=n)
+    den.score(packed2[:7001].clone())
+    den.score(packed2[7001:].clone(), row_base=7001)  # clone: a 16-byte aligned k-mer buffer of its own
+    got = den.finalize()
+    for k in exp:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(exp[k])), k
+
+
 def test_scan_host_wide_motif(ctx):
     """gb2_scan_host with a 48-bp motif: two packed words per k-mer through the chunked encode + score loop."""
     from grafimo_b200.engine import scan_host

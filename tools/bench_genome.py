@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--haplotypes", type=int, default=5008)
     ap.add_argument("--width", type=int, default=19)
     ap.add_argument("--threshold", type=float, default=1e-4)
+    ap.add_argument("--build-threads", type=int, default=0, help="host threads of the graph builder (0 = cores / ranks)")
     a = ap.parse_args()
     import torch
     from grafimo_b200 import dist as gdist
@@ -53,17 +54,23 @@ def main():
 
     t = dict(gen=0.0, build=0.0, extract=0.0)
     rows, n_var, n_nodes, set_mb = [], 0, 0, 0.0
+    items = []
     for c in range(a.chroms_per_gpu):
         idx = rank * a.chroms_per_gpu + c
         t0 = time.perf_counter()
         ref, variants, gtb = synth.variant_arrays(a.chrom_len, a.haplotypes, 5000 + idx, device=ctx.device)
         t["gen"] += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        dg = DeviceGraph.build(ctx, str(idx + 1), ref, variants, gt_bits=gtb)
-        ctx.sync()
-        t["build"] += time.perf_counter() - t0
-        del gtb
-        n_var += len(variants["pos"]); n_nodes += int(dg.info.n_nodes); set_mb += dg.info.n_sets * dg.info.words * 4 / 1e6
+        items.append((str(idx + 1), ref, variants, None, gtb))
+        n_var += len(variants["pos"])
+    # host passes of all chromosomes of this rank on worker threads of the library, uploads as they finish
+    t0 = time.perf_counter()
+    threads = a.build_threads or max(1, (os.cpu_count() or 1) // world)
+    graphs = DeviceGraph.build_many(ctx, items, n_threads=threads)
+    ctx.sync()
+    t["build"] = time.perf_counter() - t0
+    del items
+    for dg in graphs:
+        n_nodes += int(dg.info.n_nodes); set_mb += dg.info.n_sets * dg.info.words * 4 / 1e6
         t0 = time.perf_counter()
         rows.append(dg.extract([(0, a.chrom_len)], motif.width))
         ctx.sync()
@@ -86,7 +93,7 @@ def main():
             "n_gpus": world, "genome_bp": L, "variants_rank0": n_var, "nodes_rank0": n_nodes, "haplotype_sets_mb_rank0": set_mb,
             "kmer_rows_total": tot_rows, "windows_scored_total": 2 * tot_rows,
             "haplotype_windows_equivalent": 2 * L * H,
-            "synth_gen_s": out["gen"], "graph_build_s": out["build"], "extract_s": out["extract"], "score_to_table_s": t_table,
+            "synth_gen_s": out["gen"], "graph_build_s": out["build"], "graph_build_threads": threads, "extract_s": out["extract"], "score_to_table_s": t_table,
             "extract_rows_per_s": tot_rows / out["extract"], "scan_s": out["extract"] + t_table,
             "haplotype_windows_equivalent_per_s": 2 * L * H / (out["extract"] + t_table), "hits": int(len(df))}))
     if world > 1:
