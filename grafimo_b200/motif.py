@@ -201,3 +201,24 @@ class Motif(object):
         if matrix not in chosen:
             raise ValueError("\n\nERROR: unable to print the requested matrix.\n")
         print(chosen[matrix])
+
+
+# ---- the reference's own Motif objects (src/grafimo/motif.py:18-483) carry the same properties: the seams accept them --
+_MOTIF_PROPS = ("score_matrix", "pval_matrix", "min_val", "scale", "width", "offset", "is_scaled", "motif_id", "motif_name",
+                "bg", "nucsmap")
+
+
+def is_motif(obj) -> bool:
+    """True for this package's Motif and for any object with the properties the path reads from the reference's
+    Motif (score_sequences.py:262-268, resultsTmp.py:272-273, motif_processing.pyx:583-587)."""
+    return isinstance(obj, Motif) or all(hasattr(obj, a) for a in _MOTIF_PROPS)
+
+
+def score_matrix_acgt(motif) -> np.ndarray:
+    """Integer matrix with rows in A,C,G,T order whatever row order the motif file used (nucsmap)."""
+    sm = np.asarray(motif.score_matrix)
+    return np.ascontiguousarray(np.stack([sm[motif.nucsmap[n]] for n in DNA_ALPHABET]), dtype=np.int64)
+
+
+def bg_acgt(motif) -> np.ndarray:
+    return np.array([motif.bg[n] for n in DNA_ALPHABET], dtype=np.float64)

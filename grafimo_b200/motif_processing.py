@@ -153,4 +153,5 @@ def comp_pval_mat_batched(motifs: List[Motif], debug: bool) -> List[np.ndarray]:
         if m.width * RANGE + 1 <= 0:
             exception_handler(MotifProcessingError, "Forbidden motif width.\n", debug)
     ctx = _context()
-    return ctx.pval_dp_batched([m.score_matrix_acgt() for m in motifs], [m.bg_acgt() for m in motifs])
+    from .motif import bg_acgt, score_matrix_acgt
+    return ctx.pval_dp_batched([score_matrix_acgt(m) for m in motifs], [bg_acgt(m) for m in motifs])

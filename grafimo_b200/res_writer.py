@@ -12,7 +12,7 @@ import numpy as np
 import pandas as pd
 
 from .grafimo_errors import FileWriteError, VGError
-from .motif import Motif
+from .motif import Motif, is_motif
 from .utils import DEFAULT_OUTDIR, PHASE, SOURCE, TP, dftolist, exception_handler
 
 
@@ -69,7 +69,7 @@ def write_results(results: pd.DataFrame, motif: Motif, motif_num: int, args_obj,
         exception_handler(TypeError, f"Expected DataFrame, got {type(results).__name__}.\n", debug)
     if len(results) == 0:
         exception_handler(ValueError, "No potential motif occurrence retreived.\n", debug)
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not isinstance(motif_num, int) or motif_num <= 0:
         exception_handler(ValueError, "No motif searched. Probably something went wrong.\n", debug)

@@ -19,7 +19,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .motif import Motif
+from .motif import Motif, is_motif, score_matrix_acgt
 from .utils import exception_handler
 
 COLUMNS = ["motif_id", "motif_alt_id", "sequence_name", "start", "stop", "strand", "score", "p-value", "q-value",
@@ -83,7 +83,7 @@ class KmerTable:
 
 
 def print_scoring_msg(motif: Motif, noreverse: bool, debug: bool) -> None:
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not isinstance(noreverse, bool):
         exception_handler(TypeError, f"Expected bool, got {type(noreverse).__name__}.\n", debug)
@@ -99,8 +99,11 @@ def device_motif(motif: Motif, ctx=None):
     cached = getattr(motif, "_gb2_device", None)
     if cached is not None and cached.ctx is ctx and cached.h:
         return cached
-    dm = ctx.motif(motif.score_matrix_acgt(), motif.pval_matrix, motif.min_val, motif.scale, float(motif.offset))
-    motif._gb2_device = dm
+    dm = ctx.motif(score_matrix_acgt(motif), motif.pval_matrix, motif.min_val, motif.scale, float(motif.offset))
+    try:
+        motif._gb2_device = dm
+    except AttributeError:  # an object that does not take new attributes: no cache
+        pass
     return dm
 
 
@@ -306,7 +309,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     come back, and only their two string fields are sliced from the host copy of the text.
     Rows are ordered by p-value ascending; ties -- whose order the reference leaves undefined -- by
     (start, stop, strand, matched_sequence)."""
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not isinstance(sequence_loc, str):
         exception_handler(TypeError, f"Expected str, got {type(sequence_loc).__name__}.\n", debug)
@@ -441,7 +444,7 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     row of both strands counts in the q-values, and the same flags apply (score_sequences.py:93-107).
     Under torchrun (one process per GPU, e.g. chromosomes sharded over the ranks) every rank passes its own rows: the
     score histograms are all-reduced so the q-values are global, and every rank returns the whole table."""
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not testmode:
         needed = ("threshold", "noqvalue", "qvalueT", "noreverse", "recomb", "verbose")
@@ -567,7 +570,7 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
     (p-value, row, strand) -- deterministic; the reference leaves ties unordered.  Single process (one GPU)."""
     import torch
     from .res_writer import DeviceReport
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
     no_reverse, recomb = args_obj.noreverse, args_obj.recomb
@@ -639,7 +642,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
     from .res_writer import DeviceReport
     if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
         return None
-    if not isinstance(motif, Motif):
+    if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
     if not os.path.isdir(sequence_loc):
         exception_handler(FileNotFoundError, f"Unable to locate {sequence_loc}.\n", debug)

@@ -101,6 +101,43 @@ def test_compute_results_reference_own_golden(tmp_path):
     assert got.equals(exp)  # the reference's own assertion (tests/grafimo_run_test.py:127-137)
 
 
+def test_seams_accept_reference_style_motif_objects(tmp_path):
+    """compute_results / comp_pval_mat with an object that only has the reference Motif's properties (src/grafimo/motif.py;
+    not an instance of this package's class, no extra methods, does not take new attributes) -- what the unmodified
+    reference hands over when `motif_processing` / `score_sequences` resolve to this repository."""
+    import motif_processing as top  # the top-level name the reference imports (setup.py:53)
+    from grafimo_b200.score_sequences import compute_results
+    fx = gu.fixtures()
+    m, _ = _build("ctcf_meme__bgnt", tmp_path)
+
+    class RefLikeMotif:
+        __slots__ = ("_m",)
+
+        def __init__(self, m):
+            self._m = m
+        score_matrix = property(lambda s: s._m.score_matrix)
+        pval_matrix = property(lambda s: s._m.pval_matrix)
+        min_val = property(lambda s: s._m.min_val)
+        scale = property(lambda s: s._m.scale)
+        width = property(lambda s: s._m.width)
+        offset = property(lambda s: s._m.offset)
+        is_scaled = property(lambda s: s._m.is_scaled)
+        motif_id = property(lambda s: s._m.motif_id)
+        motif_name = property(lambda s: s._m.motif_name)
+        bg = property(lambda s: s._m.bg)
+        nucsmap = property(lambda s: s._m.nucsmap)
+        alphabet = property(lambda s: s._m.alphabet)
+
+    r = RefLikeMotif(m)
+    assert np.array_equal(top.comp_pval_mat(r, True), m.pval_matrix)
+    d = tmp_path / "input" / "width_19"
+    d.mkdir(parents=True)
+    (d / "scoring_test_input.tsv").write_text(fx["scoring_input_tsv"])
+    a = compute_results(r, str(tmp_path / "input") + "/", True, None, testmode=True)
+    b = compute_results(m, str(tmp_path / "input") + "/", True, None, testmode=True)
+    assert a.equals(b) and len(a) == 704
+
+
 def test_compute_results_errors(tmp_path):
     from grafimo_b200.score_sequences import compute_results
     m, _ = _build("ctcf_meme__unif", tmp_path)

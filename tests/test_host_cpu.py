@@ -188,3 +188,28 @@ def test_text_chunks_cut_at_line_boundaries(tmp_path):
         assert [ln for ln in b"".join(chunks).split(b"\n") if ln] == [ln for ln in want.split(b"\n") if ln]
         for c in chunks[:-1]:
             assert c.endswith(b"\n")
+
+
+def test_top_level_motif_processing_module_and_duck_typed_motifs():
+    """The reference imports its Cython extension as the top-level module `motif_processing` (setup.py:53,
+    motif_ops.py:29-35): the same name resolves to this package's implementation, and the seams accept any object with
+    the reference Motif's properties (not only this package's class)."""
+    import importlib
+    mp = importlib.import_module("motif_processing")
+    for name in ("read_bg_file", "get_uniform_bg", "apply_pseudocount_jaspar_transfac_pfm", "apply_pseudocount_meme",
+                 "compute_log_odds", "comp_pval_mat"):
+        assert callable(getattr(mp, name))
+    from grafimo_b200.motif import bg_acgt, is_motif, score_matrix_acgt
+
+    class RefLikeMotif:  # the property set of src/grafimo/motif.py, rows in the file's own order (here T,G,C,A)
+        score_matrix = np.arange(12).reshape(4, 3)
+        pval_matrix = np.ones(3001)
+        min_val, scale, width, offset, is_scaled = 0, 10, 3, np.float64(-2.0), True
+        motif_id, motif_name = "M1", "m"
+        bg = {"A": 0.1, "T": 0.4, "C": 0.2, "G": 0.3}
+        nucsmap = {"T": 0, "G": 1, "C": 2, "A": 3}
+
+    m = RefLikeMotif()
+    assert is_motif(m) and not is_motif(object())
+    assert score_matrix_acgt(m).tolist() == [[9, 10, 11], [6, 7, 8], [3, 4, 5], [0, 1, 2]]
+    assert bg_acgt(m).tolist() == [0.1, 0.2, 0.3, 0.4]
