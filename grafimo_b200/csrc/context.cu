@@ -119,9 +119,7 @@ extern "C" int gb2_motif_destroy(gb2_motif *m)
 {
     if (!m) return GB2_OK;
     cudaSetDevice(m->device);
-    if (m->d_lut) cudaFree(m->d_lut);
-    if (m->d_ptab) cudaFree(m->d_ptab);
-    if (m->d_bitmap) cudaFree(m->d_bitmap);
+    if (m->d_block) cudaFree(m->d_block);  // d_lut, d_ptab and d_bitmap live in this one allocation
     delete m;
     return GB2_OK;
 }
@@ -188,16 +186,24 @@ extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const do
     }
     int rc_ = GB2_OK;
     double *d_pm = nullptr, *d_ctab = nullptr;
+    auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_ptab = align256((size_t)span * sizeof(double));
+    const size_t b_lut = align256(lut.size() * sizeof(uint32_t));
+    const size_t b_bitmap = align256((size_t)gb2_div_up(span + 1, 32) * sizeof(uint32_t));
     do {
-        if (cudaMalloc((void **)&m->d_lut, lut.size() * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMalloc((void **)&m->d_ptab, (size_t)span * sizeof(double)) != cudaSuccess ||
-            cudaMalloc((void **)&m->d_bitmap, (size_t)gb2_div_up(span + 1, 32) * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMalloc((void **)&d_pm, (size_t)span * sizeof(double)) != cudaSuccess ||
-            cudaMalloc((void **)&d_ctab, (size_t)span * sizeof(double)) != cudaSuccess) {
+        // one allocation for what the motif keeps; the two work arrays of K4 come from the context's scratch buffer
+        // (no cudaMalloc / cudaFree pair per motif: an 800-motif collection is uploaded in a fraction of a second)
+        if ((rc_ = gb2_scratch_reserve(ctx, 2 * b_ptab)) != GB2_OK) break;
+        d_pm = (double *)ctx->scratch;
+        d_ctab = (double *)((char *)ctx->scratch + b_ptab);
+        if (cudaMalloc((void **)&m->d_block, b_ptab + b_lut + b_bitmap) != cudaSuccess) {
             GB2_SET_ERR(ctx, "gb2_motif_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc_ = GB2_ERR_NOMEM;
             break;
         }
+        m->d_ptab = (double *)m->d_block;
+        m->d_lut = (uint32_t *)((char *)m->d_block + b_ptab);
+        m->d_bitmap = (uint32_t *)((char *)m->d_block + b_ptab + b_lut);
         cudaError_t e = cudaMemcpyAsync(m->d_lut, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(d_pm, h_pval_mat + lo, (size_t)span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
@@ -221,8 +227,6 @@ extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const do
         if (rc_ != GB2_OK) break;
         if (!(m->total > 0.0)) { GB2_SET_ERR(ctx, "gb2_motif_create: empty p-value matrix"); rc_ = GB2_ERR_MOTIF; break; }
     } while (0);
-    if (d_pm) cudaFree(d_pm);
-    if (d_ctab) cudaFree(d_ctab);
     if (rc_ != GB2_OK) { gb2_motif_destroy(m); return rc_; }
 
     m->monotone = 1;

@@ -36,6 +36,7 @@ struct gb2_motif {
     int64_t min_val = 0, scale = 0;
     double offset = 0.0, total = 0.0;
     int64_t smem_bytes = 0;
+    void *d_block = nullptr;       // the one device allocation holding the three arrays below
     uint32_t *d_lut = nullptr;     // [n_chunks][256]  (rc_rel << 16 | fwd_rel)
     double *d_ptab = nullptr;      // [span]  p-value of score lo+k
     uint32_t *d_bitmap = nullptr;  // [ceil(span/32)] hit bitmap for non-monotone tables

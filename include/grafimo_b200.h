@@ -212,7 +212,8 @@ int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *motif, const uint32_t *d_d
 /* Per-haplotype windows -> vg-like deduplicated rows: sorts (position, packed k-mer) pairs and
  * run-length encodes them (segmented reduction).  Gives what `vg find -E -H gbwt` reports in the
  * frequency and ref columns consumed at score_sequences.py:292-293.
- *   d_pos[n], d_packed[n]      per-haplotype windows (any order); both arrays are sorted in place
+ *   d_pos[n], d_packed[n]      per-haplotype windows (any order; one packed word each, i.e. w <= 32); both arrays are
+ *                              sorted in place
  *   d_ref_packed               reference window per position (indexed by pos - pos_base) or NULL
  *   outputs (capacity n): d_u_pos, d_u_packed, d_u_freq (haplotype count), d_u_isref (1 when equal
  *   to the reference window); *d_n_unique = number of distinct rows. */
