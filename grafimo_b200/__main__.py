@@ -51,9 +51,12 @@ def findmotif(wf: Findmotif, debug: bool) -> None:
     for mf in wf.motif:
         motifs += get_motif_pwm(mf, wf, wf.cores, debug)
     graphs = load_graphs(wf, debug) if wf.has_graph_inputs() else None
+    rows_of_width = {}  # one k-mer set per distinct motif width, like scan_graph (src/grafimo/extract_regions.py:131-134)
     for motif in motifs:
         if graphs is not None:  # scan_graph + compute_results + writers without text or a DataFrame in between
-            rows = [dg.extract(spans, motif.width) for dg, spans in graphs]
+            if motif.width not in rows_of_width:
+                rows_of_width[motif.width] = [dg.extract(spans, motif.width) for dg, spans in graphs]
+            rows = rows_of_width[motif.width]
             report = scan_rows_device(motif, rows, debug, wf)
             if wf.text_only:
                 print_results(report.to_df(), debug)
