@@ -352,21 +352,110 @@ class VariationGraph:
 # ---------------------------------------------------------------------------------------------------------
 # K9: the VCF read on the device (csrc/vcf.cu) -- same result as read_vcf, for files of 1000-Genomes size
 # ---------------------------------------------------------------------------------------------------------
-def _vcf_chunks(path, chunk_bytes):
-    """Yields uint8 tensors (views of ONE reusable pinned buffer) holding whole lines of a plain or gzipped VCF; the
-    consumer must be done with a chunk before it asks for the next."""
+def _bgzf_blocks(mm):
+    """Block table of a BGZF file (the blocked gzip `bgzip` writes; tabix-indexed VCFs such as the 1000 Genomes files are
+    BGZF): [(offset of the deflate data, its length, uncompressed size)], or None when the file is plain gzip."""
+    import struct
+    n = len(mm)
+    out, o = [], 0
+    while o < n:
+        if n - o < 18 or mm[o:o + 4] != b"\x1f\x8b\x08\x04":
+            return None
+        xlen = struct.unpack_from("<H", mm, o + 10)[0]
+        p, end, bsize = o + 12, o + 12 + xlen, None
+        while p + 4 <= end:
+            si1, si2, slen = mm[p], mm[p + 1], struct.unpack_from("<H", mm, p + 2)[0]
+            if si1 == 66 and si2 == 67 and slen == 2:
+                bsize = struct.unpack_from("<H", mm, p + 4)[0] + 1
+            p += 4 + slen
+        if bsize is None or o + bsize > n:
+            return None
+        isize = struct.unpack_from("<I", mm, o + bsize - 4)[0]
+        out.append((end, bsize - (12 + xlen) - 8, isize))
+        o += bsize
+    return out
+
+
+def _vcf_chunks(path, chunk_bytes, threads=None):
+    """Yields uint8 tensors (views of ONE reusable pinned buffer) holding whole lines of a plain, gzipped or BGZF VCF; the
+    consumer must be done with a chunk before it asks for the next.  BGZF blocks are independent deflate streams: they
+    are inflated by a thread pool (zlib releases the GIL) straight to their place in the buffer -- a single gzip stream
+    (~0.2 GB/s) would otherwise bound the whole graph path on real, compressed VCFs."""
+    import os
     import torch
     pin = torch.cuda.is_available()
-    op = gzip.open if str(path).endswith(".gz") else open
-    size = None
-    if not str(path).endswith(".gz"):
-        import os
-        size = os.stat(path).st_size
+    gz = str(path).endswith(".gz")
+    size = None if gz else os.stat(path).st_size
+    blocks = mm = None
+    if gz and os.stat(path).st_size > 0:
+        import mmap
+        fh_mm = open(path, "rb")
+        mm = mmap.mmap(fh_mm.fileno(), 0, access=mmap.ACCESS_READ)
+        blocks = _bgzf_blocks(mm)
+        if blocks is None:
+            mm.close()
+            fh_mm.close()
+            mm = None
+        else:
+            size = sum(b[2] for b in blocks)
     cap = int(chunk_bytes if size is None else min(chunk_bytes, size + 2))
     buf = torch.empty(max(cap, 2), dtype=torch.uint8, pin_memory=pin)
     view = buf.numpy()
     mv = memoryview(view)
     fill = 0
+
+    def cut_and_carry(fill, last):
+        """-> (bytes to yield, bytes carried to the front of the buffer)"""
+        if last:
+            if view[fill - 1] != 10:
+                view[fill] = 10
+                fill += 1
+            return fill, 0
+        lo = max(0, fill - (64 << 20))
+        cut = bytes(mv[lo:fill]).rfind(b"\n")
+        if cut < 0:
+            raise ValueError(f"{path}: a line longer than the chunk size / 64 MiB")
+        cut += lo + 1
+        return cut, fill - cut
+
+    if blocks is not None:
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        nthreads = int(threads or min(32, os.cpu_count() or 1))
+
+        def inflate(job):
+            (c0, clen, isize), dst = job
+            if isize:
+                raw = zlib.decompress(mm[c0:c0 + clen], -15)
+                if len(raw) != isize:
+                    raise ValueError(f"{path}: corrupt BGZF block at byte {c0}")
+                view[dst:dst + isize] = np.frombuffer(raw, dtype=np.uint8)
+
+        try:
+            with ThreadPoolExecutor(max_workers=nthreads) as ex:
+                k = 0
+                while k < len(blocks):
+                    jobs = []
+                    while k < len(blocks) and fill + blocks[k][2] <= view.shape[0] - 1:
+                        jobs.append((blocks[k], fill))
+                        fill += blocks[k][2]
+                        k += 1
+                    if not jobs:
+                        raise ValueError(f"{path}: a line longer than the chunk size")
+                    list(ex.map(inflate, jobs))
+                    if fill == 0:
+                        continue
+                    n_out, rest = cut_and_carry(fill, k == len(blocks))
+                    yield buf[:n_out]
+                    if rest:
+                        view[:rest] = view[n_out:n_out + rest].copy()
+                    fill = rest
+        finally:
+            mm.close()
+            fh_mm.close()
+        return
+
+    op = gzip.open if gz else open
     with op(path, "rb") as fh:
         while True:
             room = view.shape[0] - fill - 1
@@ -377,20 +466,11 @@ def _vcf_chunks(path, chunk_bytes):
                     continue  # keep filling (gzip returns short reads)
             if fill == 0:
                 break
-            if not got:  # end of file: terminate the last line
-                if view[fill - 1] != 10:
-                    view[fill] = 10
-                    fill += 1
-                yield buf[:fill]
+            n_out, rest = cut_and_carry(fill, not got)
+            yield buf[:n_out]
+            if not got:
                 break
-            lo = max(0, fill - (64 << 20))
-            cut = bytes(mv[lo:fill]).rfind(b"\n")
-            if cut < 0:
-                raise ValueError(f"{path}: a line longer than the chunk size / 64 MiB")
-            cut += lo + 1
-            yield buf[:cut]
-            rest = fill - cut
-            view[:rest] = view[cut:fill].copy()
+            view[:rest] = view[n_out:n_out + rest].copy()
             fill = rest
 
 

@@ -223,6 +223,52 @@ def test_cli_findmotif_from_fasta_vcf_bed(ctx, tmp_path):
     assert (out / "grafimo_out.gff").exists()
 
 
+def test_cli_many_motifs_share_one_extraction_per_width(ctx, tmp_path):
+    """A MEME file with three motifs (two of width 19, one of width 8): every motif gets its own report files, the k-mers
+    are extracted once per width, and the CTCF report equals the single-motif run."""
+    import gzip
+    import pandas as pd
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.__main__ import main
+    from grafimo_b200.extract_regions import DeviceGraph
+    ss._ctx = ctx
+    fx = gu.fixtures()
+    (tmp_path / "test.fa").write_text(fx["test_fa"])
+    with gzip.open(tmp_path / "test.vcf.gz", "wt") as fh:
+        fh.write(fx["test_vcf"])
+    (tmp_path / "r.bed").write_text("chrx\t0\t50\n")
+    ctcf = fx["ctcf_meme"]
+    block = ctcf[ctcf.index("MOTIF"):]
+    second = block.replace("MA0139.1", "MA0139.9").replace("CTCF", "CTCFB")
+    w8 = fx["synth_w8_meme"]
+    (tmp_path / "one.meme").write_text(ctcf)
+    (tmp_path / "three.meme").write_text(ctcf.rstrip("\n") + "\n\n" + second.rstrip("\n") + "\n\n" + w8[w8.index("MOTIF"):])
+    calls = []
+    orig = DeviceGraph.extract
+
+    def counting(self, regions, width, want_walks=False):
+        calls.append(width)
+        return orig(self, regions, width, want_walks)
+    DeviceGraph.extract = counting
+    try:
+        common = ["-l", str(tmp_path / "test.fa"), "-v", str(tmp_path / "test.vcf.gz"), "-b", str(tmp_path / "r.bed"), "-t", "1",
+                  "--recomb", "--debug"]
+        assert main(["findmotif", "-m", str(tmp_path / "three.meme"), "-o", str(tmp_path / "out3")] + common) == 0
+        assert sorted(calls) == [8, 19]
+        assert main(["findmotif", "-m", str(tmp_path / "one.meme"), "-o", str(tmp_path / "out1")] + common) == 0
+    finally:
+        DeviceGraph.extract = orig
+    files = sorted(p.name for p in (tmp_path / "out3").iterdir())
+    assert files == ["grafimo_out_MA0139.1.gff", "grafimo_out_MA0139.1.tsv", "grafimo_out_MA0139.9.gff", "grafimo_out_MA0139.9.tsv",
+                     "grafimo_out_SYN08.1.gff", "grafimo_out_SYN08.1.tsv"], files
+    a = pd.read_csv(tmp_path / "out3" / "grafimo_out_MA0139.1.tsv", sep="\t", index_col=0, float_precision="round_trip")
+    b = pd.read_csv(tmp_path / "out1" / "grafimo_out.tsv", sep="\t", index_col=0, float_precision="round_trip")
+    assert a.equals(b) and len(a) > 50
+    c = pd.read_csv(tmp_path / "out3" / "grafimo_out_MA0139.9.tsv", sep="\t", index_col=0, float_precision="round_trip")
+    assert c["motif_id"].unique().tolist() == ["MA0139.9"] and c.drop(columns=["motif_id", "motif_alt_id"]).equals(
+        a.drop(columns=["motif_id", "motif_alt_id"]))
+
+
 def test_graph_path_over_two_gpus(ctx, tmp_path):
     """Chromosomes sharded over two ranks (torchrun, NCCL all-reduce of the histogram) == one process with both."""
     import pickle

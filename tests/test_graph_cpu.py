@@ -97,3 +97,50 @@ def test_bed_reader(tmp_path):
     assert n == 3 and regions == {"chr1": [("10", "50"), ("100", "150")], "chr2": [("5", "9")]}
     with pytest.raises(FileNotFoundError):
         get_regions_bed(str(tmp_path / "none.bed"), True)
+
+
+def _write_bgzf(path, data, block=60000):
+    """Minimal BGZF writer (SAM spec 4.1): independent deflate blocks with the BC extra field + the empty EOF block."""
+    import struct
+    import zlib
+    with open(path, "wb") as fh:
+        for lo in list(range(0, len(data), block)) + [None]:
+            piece = b"" if lo is None else data[lo:lo + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            cdata = c.compress(piece) + c.flush()
+            bsize = 12 + 6 + len(cdata) + 8
+            fh.write(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1))
+            fh.write(cdata + struct.pack("<II", zlib.crc32(piece), len(piece)))
+
+
+def test_vcf_chunk_reader_bgzf_equals_gzip_and_plain(tmp_path):
+    """The chunked VCF reader: BGZF input (blocks inflated by a thread pool) == plain gzip == plain text, whole lines per
+    chunk, for chunk sizes smaller and larger than the file, with and without a trailing newline."""
+    import gzip
+    from grafimo_b200.vgraph import _bgzf_blocks, _vcf_chunks
+    rng = np.random.default_rng(4)
+    lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"S{i}" for i in range(300))]
+    for k in range(900):
+        gts = "\t".join(f"{a}|{b}" for a, b in rng.integers(0, 2, size=(300, 2)))
+        lines.append(f"1\t{100 + 7 * k}\t.\tA\tC\t.\tPASS\t.\tGT\t{gts}")
+    for tail in ("\n", ""):
+        data = ("\n".join(lines) + tail).encode()
+        (tmp_path / "a.vcf").write_bytes(data)
+        with gzip.open(tmp_path / "plain.vcf.gz", "wb") as fh:
+            fh.write(data)
+        _write_bgzf(tmp_path / "b.vcf.gz", data)
+        import mmap
+        with open(tmp_path / "b.vcf.gz", "rb") as fh:
+            assert len(_bgzf_blocks(mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ))) == (len(data) + 59999) // 60000 + 1
+        with open(tmp_path / "plain.vcf.gz", "rb") as fh:
+            assert _bgzf_blocks(mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)) is None
+        want = data if data.endswith(b"\n") else data + b"\n"
+        for chunk in (150_000, 1 << 22):
+            for name in ("a.vcf", "plain.vcf.gz", "b.vcf.gz"):
+                got = []
+                for t in _vcf_chunks(str(tmp_path / name), chunk, threads=4):
+                    b = t.numpy().tobytes()
+                    assert b.endswith(b"\n")
+                    got.append(b)
+                assert b"".join(got) == want, (name, chunk, tail)
+                assert len(got) > 1 or chunk > len(data)

@@ -115,6 +115,40 @@ def main():
     v, (fb, fh_), samples = read_vcf_device(ctx, path, "22")
     t_file = time.perf_counter() - t0
     ok_file = len(v["pos"]) == fl and bool(np.array_equal(fb.view(np.int32), bits[:fl].cpu().numpy())) and len(samples) == S
+    # the same file compressed: BGZF (independent 64 KB blocks, what bgzip/tabix-indexed 1000 Genomes VCFs are; inflated by
+    # a thread pool) and, on a quarter of the lines, one plain gzip stream (inflated by a single thread)
+    import gzip
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    raw = header.encode() + text[:fl].cpu().numpy().tobytes()
+
+    def bgzf_block(piece):
+        c = zlib.compressobj(1, zlib.DEFLATED, -15)
+        cdata = c.compress(piece) + c.flush()
+        return (b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(cdata) + 8 - 1)
+                + cdata + struct.pack("<II", zlib.crc32(piece), len(piece)))
+    bpath = os.path.join(tmp, "t.vcf.gz")
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex, open(bpath, "wb") as fh:
+        for blk in ex.map(bgzf_block, (raw[lo:lo + 65280] for lo in range(0, len(raw), 65280))):
+            fh.write(blk)
+        fh.write(bgzf_block(b""))
+    t0 = time.perf_counter()
+    v2, (fb2, _), _ = read_vcf_device(ctx, bpath, "22")
+    t_bgzf = time.perf_counter() - t0
+    ok_bgzf = len(v2["pos"]) == fl and bool(np.array_equal(fb2, fb))
+    bg_bytes = os.path.getsize(bpath)
+    os.unlink(bpath)
+    ql = max(1, fl // 4)
+    gpath = os.path.join(tmp, "q.vcf.gz")
+    with gzip.open(gpath, "wb", compresslevel=1) as fh:
+        fh.write(header.encode() + text[:ql].cpu().numpy().tobytes())
+    t0 = time.perf_counter()
+    v3, _, _ = read_vcf_device(ctx, gpath, "22")
+    t_gz = time.perf_counter() - t0
+    ok_gz = len(v3["pos"]) == ql
+    os.unlink(gpath)
+    del raw
     # plain-Python reader on a bounded sample
     pl = min(fl, 300)
     small = os.path.join(tmp, "s.vcf")
@@ -130,6 +164,9 @@ def main():
         "index_ms": best[0], "fields_ms": best[1], "genotypes_ms": best[2],
         "genotypes_GBps": n_bytes / best[2] / 1e6, "all_passes_GBps": n_bytes / sum(best) / 1e6, "bits_equal_source": ok,
         "file_route": {"lines": fl, "bytes": fl * L, "seconds": t_file, "GBps": fl * L / t_file / 1e9, "equal": ok_file},
+        "file_route_bgzf": {"lines": fl, "compressed_bytes": bg_bytes, "seconds": t_bgzf, "GBps_uncompressed": fl * L / t_bgzf / 1e9,
+                            "equal": ok_bgzf, "inflate_threads": min(32, os.cpu_count() or 1)},
+        "file_route_plain_gzip": {"lines": ql, "seconds": t_gz, "GBps_uncompressed": ql * L / t_gz / 1e9, "equal": ok_gz},
         "cpu_python_reader": {"lines": pl, "seconds": t_py, "lines_per_s": pl / t_py, "MBps": pl * L / t_py / 1e6},
     }))
 
