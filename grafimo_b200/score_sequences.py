@@ -107,6 +107,35 @@ def device_motif(motif: Motif, ctx=None):
     return dm
 
 
+# The reference calls compute_results once per motif on the same `width_<w>/*.tsv` files (src/grafimo/grafimo.py:177-179);
+# the parsed, device-resident rows of the most recent file set are kept so that the next motif of that width starts at
+# the scoring kernel instead of re-reading and re-parsing gigabytes of text.  One entry per path, bounded in size.
+_PARSED = {}
+_PARSED_MAX_BYTES = 16 << 30
+
+
+def _files_key(files, width, no_reverse, ctx):
+    st = [os.stat(f) for f in files]
+    return (tuple((f, t.st_ino, t.st_mtime_ns, t.st_ctime_ns, t.st_size) for f, t in zip(files, st)), int(width), bool(no_reverse), id(ctx))
+
+
+def _parsed_get(kind, key):
+    e = _PARSED.get(kind)
+    return e[1] if e is not None and e[0] == key else None
+
+
+def _parsed_put(kind, key, value, n_bytes):
+    if n_bytes <= _PARSED_MAX_BYTES:
+        _PARSED[kind] = (key, value)
+    else:
+        _PARSED.pop(kind, None)
+
+
+def clear_parsed_cache():
+    """Drops the cached k-mer rows (host text and device arrays) of the last compute_results / scan_dir_device call."""
+    _PARSED.clear()
+
+
 def _dense_rows(threshold, n_kmers, strands):
     """Unselective thresholds (`-t 1` in docs/paper_results/run_analysis.sh) report a large share of the windows: K2 then
     writes dense scores and gb2_finalize_dense builds the rows (no hit records, 4-byte sort keys).  -> dense_rows of Scan."""
@@ -343,13 +372,19 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     t0 = time.time()
     ctx = _context()
     dm = device_motif(motif, ctx)
-    chunks = []  # (host text, DeviceRows, first local row)
-    n_local = 0
-    for text in _text_chunks(files, _CHUNK_BYTES) if files else ():
-        rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
-        rows.d_text = None  # the device copy of the text is only needed while parsing
-        chunks.append((text.numpy(), rows, n_local))
-        n_local += rows.n
+    key = _files_key(files, width, no_reverse, ctx)
+    cached = _parsed_get("table", key)
+    if cached is not None:
+        chunks, n_local = cached
+    else:
+        chunks = []  # (host text, DeviceRows, first local row)
+        n_local = 0
+        for text in _text_chunks(files, _CHUNK_BYTES) if files else ():
+            rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
+            rows.d_text = None  # the device copy of the text is only needed while parsing
+            chunks.append((text.numpy(), rows, n_local))
+            n_local += rows.n
+        _parsed_put("table", key, (chunks, n_local), sum(c[0].nbytes for c in chunks))
     if world > 1:
         counts = [None] * world
         tdist.all_gather_object(counts, n_local)
@@ -631,31 +666,14 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
                         qtab[:span] if qtab is not None else None)
 
 
-def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
-    """compute_results with the report left on the device: the `vg find` TSVs under `<sequence_loc>/width_<w>/` are
-    parsed, scored and finalized on the GPU and the hit columns stay there -> res_writer.DeviceReport for
-    write_results_device (K8), no DataFrame.  Returns None when the input needs the general path (compute_results):
-    a file whose lines do not all carry the same region name (vg writes one file per region), lines with leading blanks,
-    a reference column that is neither `ref` nor `non.ref`, lower-case or non-ACGTN k-mers, or more than one process.  Rows are ordered by (p-value, row, strand)."""
+_GENERAL = "general path"  # cached verdict of _parse_dir_for_report: the input needs compute_results
+
+
+def _parse_dir_for_report(files, width, no_reverse, ctx, debug):
+    """Parses the TSV files for scan_dir_device: -> (chunks [(DeviceRows with .name_id, first row, stats)], region names,
+    number of rows), or _GENERAL when the input needs the DataFrame path."""
     import torch
-    import torch.distributed as tdist
-    from .res_writer import DeviceReport
-    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
-        return None
-    if not is_motif(motif):
-        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
-    if not os.path.isdir(sequence_loc):
-        exception_handler(FileNotFoundError, f"Unable to locate {sequence_loc}.\n", debug)
-    threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
-    no_reverse, recomb = args_obj.noreverse, args_obj.recomb
-    if not motif.is_scaled:
-        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
-    width = motif.width
-    files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
-    files = [f for f in files if os.stat(f).st_size > 0]
-    ctx = _context()
     dev = ctx.device
-    dm = device_motif(motif, ctx)
     segments, chunks, names, n = [], [], [], 0
     name_of_file = {}
     for text in _text_chunks(files, _CHUNK_BYTES, segments) if files else ():
@@ -665,7 +683,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
             exception_handler(ValueError, f"{st['malformed']} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
                               "symbols are required).\n", debug)
         if st["bad_rows"] or (rows.n and bool((rows.ref[:rows.n] == 2).any().item())):
-            return None
+            return _GENERAL
         host = text.numpy()
         segs = segments[-1]
         with torch.cuda.stream(ctx.stream):
@@ -693,7 +711,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
                     b = rows.d_text[(off[fr][file_of_row][:, None] + col).clamp(max=rows.d_text.shape[0] - 1)]
                     ok = bool(((a == b) | (col >= nl[:, None])).all().item())
                 if not ok:
-                    return None
+                    return _GENERAL
                 fr_h, has_h = fr.cpu().numpy(), has.cpu().numpy()
                 off_h, nl_h = off[fr].cpu().numpy(), nl[fr].cpu().numpy()
                 local = np.full(len(segs), -1, dtype=np.int64)
@@ -702,7 +720,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
                         continue
                     nm = bytes(host[off_h[k]:off_h[k] + nl_h[k]]).decode("ascii")
                     if fi in name_of_file and names[name_of_file[fi]] != nm:
-                        return None
+                        return _GENERAL
                     if fi not in name_of_file:
                         name_of_file[fi] = len(names)
                         names.append(nm)
@@ -714,6 +732,43 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
         rows.name_id = name_id
         chunks.append((rows, n, st))
         n += rows.n
+    return chunks, names, n
+
+
+def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
+    """compute_results with the report left on the device: the `vg find` TSVs under `<sequence_loc>/width_<w>/` are
+    parsed, scored and finalized on the GPU and the hit columns stay there -> res_writer.DeviceReport for
+    write_results_device (K8), no DataFrame.  Returns None when the input needs the general path (compute_results):
+    a file whose lines do not all carry the same region name (vg writes one file per region), lines with leading blanks,
+    a reference column that is neither `ref` nor `non.ref`, lower-case or non-ACGTN k-mers, or more than one process.  Rows are ordered by (p-value, row, strand)."""
+    import torch
+    import torch.distributed as tdist
+    from .res_writer import DeviceReport
+    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+        return None
+    if not is_motif(motif):
+        exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)
+    if not os.path.isdir(sequence_loc):
+        exception_handler(FileNotFoundError, f"Unable to locate {sequence_loc}.\n", debug)
+    threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+    no_reverse, recomb = args_obj.noreverse, args_obj.recomb
+    if not motif.is_scaled:
+        exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    width = motif.width
+    files = sorted(glob.glob(os.path.join(sequence_loc, f"width_{width}", "*.tsv")))
+    files = [f for f in files if os.stat(f).st_size > 0]
+    ctx = _context()
+    dev = ctx.device
+    dm = device_motif(motif, ctx)
+    key = _files_key(files, width, no_reverse, ctx)
+    parsed = _parsed_get("report", key)
+    if parsed is None:
+        parsed = _parse_dir_for_report(files, width, no_reverse, ctx, debug)
+        nbytes = 0 if parsed is _GENERAL else sum(r.packed.numel() * 8 + r.n * 40 for r, _, _ in parsed[0])
+        _parsed_put("report", key, parsed, nbytes)
+    if parsed is _GENERAL:
+        return None
+    chunks, names, n = parsed
     print_scoring_msg(motif, no_reverse, debug)
     if n == 0:
         errmsg = "No result retrieved. Unable to proceed.\n"

@@ -138,6 +138,41 @@ def test_seams_accept_reference_style_motif_objects(tmp_path):
     assert a.equals(b) and len(a) == 704
 
 
+def test_parsed_rows_are_reused_across_motifs_and_flags(tmp_path):
+    """compute_results is called once per motif on the same files (grafimo.py:177-179): the parsed device rows of the
+    last file set are reused (no second read / parse), a changed file is read again, and the tables stay the goldens."""
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.engine import Context
+    c1, c2 = gu.load_scoring("fixture_default"), gu.load_scoring("fixture_t05_norecomb")  # same motif, same input rows
+    m, _ = _build(c1["motif_tag"], tmp_path)
+    d = tmp_path / "seqs" / f"width_{m.width}"
+    d.mkdir(parents=True)
+    (d / "region_0.tsv").write_text("\n".join(c1["files"][0]) + "\n")
+    calls = []
+    orig = Context.parse_kmer_tsv
+
+    def counting(self, text, width, skip_minus=False):
+        calls.append(int(text.shape[0]))
+        return orig(self, text, width, skip_minus)
+    Context.parse_kmer_tsv = counting
+    try:
+        ss.clear_parsed_cache()
+        for c in (c1, c2, c1):
+            df = ss.compute_results(m, str(tmp_path / "seqs"), True, _Args(c["options"]))
+            gu.assert_tables_equal({col: df[col].to_numpy() for col in df.columns}, c["table"], c["columns"])
+        assert len(calls) == 1
+        lines = c1["files"][0]
+        (d / "region_0.tsv").write_text("\n".join(lines[: len(lines) // 2]) + "\n")  # the file changes: parsed again
+        df = ss.compute_results(m, str(tmp_path / "seqs"), True, _Args(c1["options"]))
+        assert len(calls) == 2 and len(df) <= len(c1["table"]["start"])
+        ss.clear_parsed_cache()
+        ss.compute_results(m, str(tmp_path / "seqs"), True, _Args(c1["options"]))
+        assert len(calls) == 3
+    finally:
+        Context.parse_kmer_tsv = orig
+        ss.clear_parsed_cache()
+
+
 def test_compute_results_errors(tmp_path):
     from grafimo_b200.score_sequences import compute_results
     m, _ = _build("ctcf_meme__unif", tmp_path)
