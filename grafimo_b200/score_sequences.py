@@ -145,110 +145,143 @@ def _dense_rows(threshold, n_kmers, strands):
 _CHUNK_BYTES = 1 << 30  # TSV text is parsed on the device in chunks of at most 1 GiB (cut at line boundaries)
 
 
-def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES, segments: Optional[list] = None):
-    """Yields (pinned) uint8 tensors holding whole lines of the concatenated files; every file is
-    newline-terminated, chunks are cut at line boundaries.  When `segments` is a list, one entry per yielded chunk is
-    appended to it: [(file index, byte offset in the chunk where that file's lines begin), ...]."""
+_STAGING = [None, None]  # two pinned buffers reused by every call: pinning costs ~0.45 s per GB, reading ~0.1 s per GB
+
+
+def _staging_buffer(slot: int, nbytes: int, pin: bool):
     import torch
+    buf = _STAGING[slot]
+    if buf is None or buf.shape[0] < nbytes or buf.is_pinned() != pin:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, pin_memory=pin)
+        _STAGING[slot] = buf
+    return buf[:nbytes]
+
+
+def _text_chunks(files: List[str], chunk_bytes: int = _CHUNK_BYTES, segments: Optional[list] = None, reuse: bool = False):
+    """Yields (pinned) uint8 tensors holding whole lines of the concatenated files; a newline follows every file (the
+    blank line this may add is ignored by the line index), chunks are cut at line boundaries and hold at most
+    chunk_bytes.  The byte ranges of a chunk are read with a small thread pool (os.preadv releases the GIL).  When
+    `segments` is a list, one entry per yielded chunk is appended to it: [(file index, byte offset in the chunk where
+    that file's lines begin), ...].
+    reuse=True: the chunks are views of two alternating, process-wide pinned staging buffers -- the consumer must be done
+    with chunk k (its host-to-device copy complete) before it asks for chunk k + 2."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
     pin = torch.cuda.is_available()
+    slot = [0]
+
+    def alloc(nbytes):
+        if not reuse:
+            return torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+        slot[0] ^= 1
+        return _staging_buffer(slot[0], nbytes, pin)
+
     sizes = [os.stat(f).st_size for f in files]
-    left = sum(sizes) + len(files)
-    if left + 1 <= chunk_bytes:
-        # everything fits one chunk: place the files back to back (a newline after each; an extra blank line is
-        # ignored by the line index) and read them with a small thread pool -- os.preadv releases the GIL
-        buf = torch.empty(left + 1, dtype=torch.uint8, pin_memory=pin)
-        view = buf.numpy()
-        jobs, off = [], 0
-        seg = 32 << 20
-        segs = []
-        for fi, (fn, sz) in enumerate(zip(files, sizes)):
-            segs.append((fi, off))
-            for lo in range(0, sz, seg):
-                jobs.append((fn, lo, min(seg, sz - lo), off + lo))
-            view[off + sz] = 10
-            off += sz + 1
+    left = sum(sizes) + len(files)  # bytes still to deliver, file-terminating newlines included
+    piece = 32 << 20
+    cur_f, cur_pos = 0, 0
+    carry, carry_file = b"", 0
+    pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
 
-        def read(job):
-            fn, lo, nbytes, dst = job
-            fd = os.open(fn, os.O_RDONLY)
-            try:
-                done = 0
-                while done < nbytes:
-                    got = os.preadv(fd, [memoryview(view)[dst + done:dst + nbytes]], lo + done)
-                    if got <= 0:
-                        raise IOError(f"short read on {fn}")
-                    done += got
-            finally:
-                os.close(fd)
+    def read(job):
+        fn, lo, nbytes, dst, view = job
+        fd = os.open(fn, os.O_RDONLY)
+        try:
+            done = 0
+            while done < nbytes:
+                got = os.preadv(fd, [memoryview(view)[dst + done:dst + nbytes]], lo + done)
+                if got <= 0:
+                    raise IOError(f"short read on {fn}")
+                done += got
+        finally:
+            os.close(fd)
 
-        if len(jobs) > 1:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=min(8, len(jobs), os.cpu_count() or 1)) as ex:
-                list(ex.map(read, jobs))
-        else:
-            for j in jobs:
-                read(j)
-        if off > 0:
-            if segments is not None:
-                segments.append(segs)
-            yield buf[:off]
-        return
-
-    def new_buf(carry_len):
-        t = torch.empty(max(2, min(chunk_bytes, left + carry_len + 1)), dtype=torch.uint8, pin_memory=pin)
-        return t, t.numpy()
-
-    buf, view = new_buf(0)
-    fill = 0
-    segs = []
-    for fi, fn in enumerate(files):
-        segs.append((fi, fill))
-        with open(fn, "rb") as fh:
-            while True:
-                room = view.shape[0] - fill - 1  # one spare byte for a file-terminating newline
-                if room <= 0:  # buffer full: emit the whole lines, carry the partial one
-                    lo = max(0, fill - (1 << 20))
-                    cut = bytes(memoryview(view)[lo:fill]).rfind(b"\n")
-                    if cut < 0:
-                        raise ValueError(f"{fn}: a line longer than the chunk size / 1 MiB")
-                    cut += lo + 1
-                    carry = view[cut:fill].copy()
-                    if segments is not None:
-                        segments.append([sg for sg in segs if sg[1] < cut])
-                    yield buf[:cut]
-                    buf, view = new_buf(len(carry))
-                    view[:len(carry)] = carry
-                    fill = len(carry)
-                    segs = [(fi, 0)]  # the current file goes on in the new chunk
-                    continue
-                got = fh.readinto(memoryview(view)[fill:fill + room])
-                if not got:
+    try:
+        while cur_f < len(files) or carry:
+            cap = max(2, min(int(chunk_bytes), left + len(carry) + 1))
+            if len(carry) + 2 > cap:
+                raise ValueError(f"{files[carry_file]}: a line longer than the chunk size")
+            buf = alloc(cap)
+            view = buf.numpy()
+            fill = len(carry)
+            segs = []
+            if fill:
+                view[:fill] = np.frombuffer(carry, dtype=np.uint8)
+            if cur_pos > 0:  # the file being read goes on in this chunk (a carried partial line is always its own)
+                segs.append((cur_f, 0))
+            jobs = []
+            while cur_f < len(files):
+                room = cap - fill - 1  # one spare byte for the file-terminating newline
+                if room <= 0:
                     break
-                fill += got
-                left -= got
-        if fill > 0 and view[fill - 1] != 10:
-            view[fill] = 10
-            fill += 1
-        left -= 1
-    if fill > 0:
-        if segments is not None:
-            segments.append(segs)
-        yield buf[:fill]
+                if cur_pos == 0:
+                    segs.append((cur_f, fill))
+                n = min(sizes[cur_f] - cur_pos, room)
+                for lo in range(0, n, piece):
+                    jobs.append((files[cur_f], cur_pos + lo, min(piece, n - lo), fill + lo, view))
+                fill += n
+                cur_pos += n
+                left -= n
+                if cur_pos == sizes[cur_f]:
+                    view[fill] = 10
+                    fill += 1
+                    left -= 1
+                    cur_f += 1
+                    cur_pos = 0
+            if len(jobs) > 1:
+                list(pool.map(read, jobs))
+            else:
+                for job in jobs:
+                    read(job)
+            if cur_f >= len(files):  # everything is in: the last chunk
+                carry = b""
+                if segments is not None:
+                    segments.append(segs)
+                yield buf[:fill]
+                break
+            lo = max(0, fill - (1 << 20))  # emit the whole lines, carry the partial one
+            cut = bytes(memoryview(view)[lo:fill]).rfind(b"\n")
+            if cut < 0:
+                raise ValueError(f"{files[cur_f]}: a line longer than the chunk size / 1 MiB")
+            cut += lo + 1
+            carry, carry_file = bytes(memoryview(view)[cut:fill]), cur_f
+            if segments is not None:
+                segments.append([sg for sg in segs if sg[1] < cut])
+            if cut:
+                yield buf[:cut]
+    finally:
+        pool.shutdown(wait=True)
 
 
-def _fixed_strings(text: np.ndarray, offs: np.ndarray, length: int) -> np.ndarray:
+def _gather_rows(text, offs: np.ndarray, length: int) -> np.ndarray:
+    """uint8 [n, length] = text[offs[i] + j] (indices clamped to the text).  `text` is the host copy of the bytes (numpy)
+    or the device copy (torch tensor: the gather runs on the GPU, in slices, and only the selected bytes come back)."""
+    n = len(offs)
+    last = text.shape[0] - 1
+    if isinstance(text, np.ndarray):
+        return text[np.minimum(offs[:, None] + np.arange(length, dtype=np.int64)[None, :], last)]
+    import torch
+    out = np.empty((n, length), dtype=np.uint8)
+    col = torch.arange(length, device=text.device, dtype=torch.int64)[None, :]
+    step = max(1, (64 << 20) // max(1, length))
+    for lo in range(0, n, step):
+        o = torch.from_numpy(np.ascontiguousarray(offs[lo:lo + step], dtype=np.int64)).to(text.device)
+        out[lo:lo + step] = text[(o[:, None] + col).clamp_(max=last)].cpu().numpy()
+    return out
+
+
+def _fixed_strings(text, offs: np.ndarray, length: int) -> np.ndarray:
     """Object array of the ASCII strings text[o:o+length]: one gather, one decode, one slicing pass."""
     n = len(offs)
     if n == 0:
         return np.array([], dtype=object)
-    idx = offs[:, None] + np.arange(length, dtype=np.int64)[None, :]
-    flat = np.ascontiguousarray(text[idx]).tobytes().decode("ascii")
+    flat = np.ascontiguousarray(_gather_rows(text, offs, length)).tobytes().decode("ascii")
     out = np.empty(n, dtype=object)
     out[:] = [flat[i:i + length] for i in range(0, n * length, length)]
     return out
 
 
-def _var_strings(text: np.ndarray, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
+def _var_strings(text, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
     """Object array of text[o:o+l].  Region names repeat in long runs (one name per vg file), so rows are compared
     with their predecessor in offset order and only the heads of the runs are decoded."""
     n = len(offs)
@@ -258,7 +291,7 @@ def _var_strings(text: np.ndarray, offs: np.ndarray, lens: np.ndarray) -> np.nda
     o, l = offs[order], lens[order]
     mx = int(l.max())
     col = np.arange(mx, dtype=np.int64)[None, :]
-    chars = text[np.minimum(o[:, None] + col, text.shape[0] - 1)]
+    chars = _gather_rows(text, o, mx)
     chars[col >= l[:, None]] = 0
     head = np.ones(n, dtype=bool)
     if n > 1:
@@ -377,14 +410,15 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     if cached is not None:
         chunks, n_local = cached
     else:
-        chunks = []  # (host text, DeviceRows, first local row)
+        chunks = []  # (device text, DeviceRows, first local row)
         n_local = 0
-        for text in _text_chunks(files, _CHUNK_BYTES) if files else ():
+        # the text goes through two reusable pinned staging buffers and stays on the device: the string columns of the
+        # reported rows are gathered there, the host keeps no copy
+        for text in _text_chunks(files, _CHUNK_BYTES, reuse=True) if files else ():
             rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
-            rows.d_text = None  # the device copy of the text is only needed while parsing
-            chunks.append((text.numpy(), rows, n_local))
+            chunks.append((rows.d_text, rows, n_local))
             n_local += rows.n
-        _parsed_put("table", key, (chunks, n_local), sum(c[0].nbytes for c in chunks))
+        _parsed_put("table", key, (chunks, n_local), sum(int(c[0].shape[0]) for c in chunks))
     if world > 1:
         counts = [None] * world
         tdist.all_gather_object(counts, n_local)
@@ -446,13 +480,13 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         # leading blanks of a line belong to no field: the name starts at the first non-blank byte
         lead = np.zeros(len(m), dtype=np.int64)
         if len(off):
-            first = text[off]
+            first = _gather_rows(text, off, 1)[:, 0]
             while True:
                 blank = (first == 32) | (first == 9)
                 if not blank.any():
                     break
                 lead[blank] += 1
-                first = text[np.minimum(off + lead, text.shape[0] - 1)]
+                first = _gather_rows(text, off + lead, 1)[:, 0]
         seqname[m] = _var_strings(text, off + lead, g["name_len"].astype(np.int64))
         seq[m] = _fixed_strings(text, off + g["seq_off"].astype(np.int64), width)
         strand[m] = np.char.decode(g["strand"].view("S1"), "ascii").astype(object)
@@ -460,7 +494,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         r = np.where(g["ref"] == 1, "ref", "non.ref").astype(object)
         other = np.nonzero(g["ref"] == 2)[0]
         for i in other:  # a sixth field that is neither "ref" nor "non.ref" is passed through verbatim
-            r[i] = bytes(text[off[i]:off[i] + 4096]).split(b"\n", 1)[0].split()[5].decode("ascii")
+            r[i] = bytes(_gather_rows(text, off[i:i + 1], 4096)[0]).split(b"\n", 1)[0].split()[5].decode("ascii")
         ref[m] = r
     keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     ref[(ref == "ref") & (np.abs(stop - start) != width)] = "non.ref"  # score_sequences.py:305-307
@@ -676,7 +710,7 @@ def _parse_dir_for_report(files, width, no_reverse, ctx, debug):
     dev = ctx.device
     segments, chunks, names, n = [], [], [], 0
     name_of_file = {}
-    for text in _text_chunks(files, _CHUNK_BYTES, segments) if files else ():
+    for text in _text_chunks(files, _CHUNK_BYTES, segments, reuse=True) if files else ():
         rows = ctx.parse_kmer_tsv(text, width, skip_minus=no_reverse)
         st = rows.stats()
         if st["malformed"]:

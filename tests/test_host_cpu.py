@@ -181,8 +181,18 @@ def test_text_chunks_cut_at_line_boundaries(tmp_path):
         p.write_bytes(body)
         files.append(str(p))
         want += body if body.endswith(b"\n") else body + b"\n"
-    for chunk_bytes in (128, 1000, 1 << 20):
-        chunks = [bytes(c.numpy()) for c in _text_chunks(files, chunk_bytes)]
+    for chunk_bytes, reuse in ((128, False), (128, True), (1000, True), (1000, False), (1 << 20, False), (1 << 20, True)):
+        segments = []
+        chunks = [bytes(c.numpy()) for c in _text_chunks(files, chunk_bytes, segments, reuse=reuse)]
+        assert len(segments) == len(chunks)
+        # segments name the file every line of a chunk comes from
+        whole = [p.read_bytes() for p in map(type(tmp_path), files)]
+        for c, segs in zip(chunks, segments):
+            assert segs and segs[0][1] == 0 and [o for _, o in segs] == sorted(o for _, o in segs)
+            for k, (fi, off) in enumerate(segs):
+                end = segs[k + 1][1] if k + 1 < len(segs) else len(c)
+                for ln in c[off:end].split(b"\n"):
+                    assert ln == b"" or ln in whole[fi].split(b"\n")
         assert all(c.endswith(b"\n") and len(c) <= chunk_bytes for c in chunks)
         # blank lines may be added between files (the device line index skips them); the lines themselves are intact
         assert [ln for ln in b"".join(chunks).split(b"\n") if ln] == [ln for ln in want.split(b"\n") if ln]

@@ -37,12 +37,16 @@ with open(os.path.join(d, "chr7.tsv"), "wb") as fh:   # vectorised writer: both 
 size = os.path.getsize(os.path.join(d, "chr7.tsv"))
 print(f"TSV: {2 * n_kmers} rows, {size / 1e9:.2f} GB, generated in {time.time() - t0:.1f}s")
 wf = Findmotif(motif=[meme], kmers_dir=os.path.join(tmp, "kmers"), threshold=threshold, recomb=True, verbose=True)
-for rep in range(3):
+from grafimo_b200.score_sequences import clear_parsed_cache
+for rep in range(4):
+    if rep < 3:
+        clear_parsed_cache()  # runs 0-2 read and parse the files; run 3 is the "next motif of the same width" (rows reused)
     t = time.time()
     with contextlib.redirect_stdout(io.StringIO()) as out:
         df = compute_results(motif, os.path.join(tmp, "kmers"), True, wf)
     dt = time.time() - t
-    print(f"compute_results run {rep}: {dt:.3f}s  {2 * n_kmers / dt / 1e6:.1f} M rows/s  ({size / dt / 1e9:.2f} GB/s of text)  hits={len(df)}")
+    print(f"compute_results run {rep}{' (parsed rows reused)' if rep == 3 else ''}: {dt:.3f}s  {2 * n_kmers / dt / 1e6:.1f} M rows/s  "
+          f"({size / dt / 1e9:.2f} GB/s of text)  hits={len(df)}")
 print(out.getvalue().strip().replace("\n\n", "\n"))
 if threshold >= 1.0:
     from grafimo_b200.res_writer import write_results
