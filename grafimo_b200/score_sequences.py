@@ -142,7 +142,8 @@ def _dense_rows(threshold, n_kmers, strands):
     return int(n_kmers) if (threshold >= 0.25 and 0 < n_kmers * strands < (1 << 31)) else 0
 
 
-_CHUNK_BYTES = 1 << 30  # TSV text is parsed on the device in chunks of at most 1 GiB (cut at line boundaries)
+_CHUNK_BYTES = 256 << 20  # TSV text goes to the device in chunks of at most 256 MiB (cut at line boundaries): two pinned
+# staging buffers of that size are all the host memory the route needs, whatever the input size
 
 
 _STAGING = [None, None]  # two pinned buffers reused by every call: pinning costs ~0.45 s per GB, reading ~0.1 s per GB
