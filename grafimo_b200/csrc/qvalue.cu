@@ -35,76 +35,72 @@ __global__ void gb2_bh_keys_kernel(const double *__restrict__ ptab, uint32_t spa
 }
 
 #define BH_THREADS 1024
-// Single CTA: <= 65536 bins (w <= 64).  Each thread owns a contiguous run of sorted bins.
-__global__ void __launch_bounds__(BH_THREADS) gb2_bh_kernel(const double *__restrict__ sorted_p,
-                                                            const uint32_t *__restrict__ sorted_bins,
-                                                            const unsigned long long *__restrict__ hist, uint32_t nbins,
-                                                            double *__restrict__ qtab, uint32_t *__restrict__ rank,
-                                                            unsigned long long *__restrict__ total_out)
+// K5 runs as three small kernels so that the 2 x (span + 1) fp64 divisions -- the bulk of the work -- spread over the
+// whole GPU instead of queueing on one SM (a single-CTA version took 26 us at span 7,424 and 90 us at 22,805):
+//   count  one CTA: rank of every bin, cumulative row count C at every sorted position (block scan, exact integers)
+//   raw    grid:    raw = p / (C / float(N)) with IEEE div.rn, +inf for empty bins
+//   min    one CTA: reverse running minimum (block min-scan, exact), clip at 1, scatter to the bins
+__global__ void __launch_bounds__(BH_THREADS) gb2_bh_count_kernel(const uint32_t *__restrict__ sorted_bins,
+                                                                  const unsigned long long *__restrict__ hist, uint32_t nbins,
+                                                                  uint32_t *__restrict__ rank,
+                                                                  unsigned long long *__restrict__ cum,
+                                                                  unsigned long long *__restrict__ total_out)
 {
     typedef cub::BlockScan<unsigned long long, BH_THREADS> ScanU64;
-    typedef cub::BlockScan<double, BH_THREADS> ScanF64;
-    __shared__ union {
-        typename ScanU64::TempStorage u;
-        typename ScanF64::TempStorage f;
-    } tmp;
-    __shared__ unsigned long long s_total;
+    __shared__ typename ScanU64::TempStorage tmp;
     const uint32_t tid = threadIdx.x;
     const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
     const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
-
-    // rank of every bin in p-ascending order
-    for (uint32_t i = beg; i < end; ++i) rank[sorted_bins[i]] = i;
+    for (uint32_t i = beg; i < end; ++i) rank[sorted_bins[i]] = i;  // position of every bin in p-ascending order
     if (hist == nullptr) return;  // rank-only call (no q-values wanted)
-
     unsigned long long local = 0;
     for (uint32_t i = beg; i < end; ++i) local += hist[sorted_bins[i]];
     unsigned long long prefix, total;
-    ScanU64(tmp.u).ExclusiveSum(local, prefix, total);
-    if (tid == 0) { s_total = total; *total_out = total; }
-    __syncthreads();
-    const double dn = (double)s_total;
-
-    // reverse running minimum of raw = p / (C / N): thread t's run is reduced right-to-left, runs are
-    // combined with an inclusive min-scan over reversed thread order.
-    double run_min = CUDART_INF;
-    {
-        unsigned long long c = prefix;
-        // first pass: cumulative counts forward to get each raw; store raw temporarily in qtab by position
-        for (uint32_t i = beg; i < end; ++i) {
-            const unsigned long long cnt = hist[sorted_bins[i]];
-            c += cnt;
-            double raw = CUDART_INF;
-            if (cnt != 0ull) raw = __ddiv_rn(sorted_p[i], __ddiv_rn((double)c, dn));
-            run_min = fmin(run_min, raw);
-        }
+    ScanU64(tmp).ExclusiveSum(local, prefix, total);
+    if (tid == 0) *total_out = total;
+    unsigned long long c = prefix;
+    for (uint32_t i = beg; i < end; ++i) {
+        c += hist[sorted_bins[i]];
+        cum[i] = c;
     }
-    // suffix-min over threads: reverse the thread order and take an inclusive min-scan
+}
+
+__global__ void gb2_bh_raw_kernel(const double *__restrict__ sorted_p, const unsigned long long *__restrict__ cum,
+                                  uint32_t nbins, double *__restrict__ raw)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbins) return;
+    const unsigned long long c = cum[i], before = i ? cum[i - 1] : 0ull;
+    const double dn = (double)cum[nbins - 1];
+    raw[i] = c != before ? __ddiv_rn(sorted_p[i], __ddiv_rn((double)c, dn)) : CUDART_INF;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) gb2_bh_min_kernel(const double *__restrict__ raw,
+                                                                const uint32_t *__restrict__ sorted_bins, uint32_t nbins,
+                                                                double *__restrict__ qtab)
+{
+    typedef cub::BlockScan<double, BH_THREADS> ScanF64;
+    __shared__ typename ScanF64::TempStorage tmp;
     __shared__ double s_run[BH_THREADS];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
+    const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
+    double run_min = CUDART_INF;
+    for (uint32_t i = beg; i < end; ++i) run_min = fmin(run_min, raw[i]);
+    // suffix-min over threads: reverse the thread order and take an inclusive min-scan
+    double scanned;
     s_run[BH_THREADS - 1 - tid] = run_min;
     __syncthreads();
-    double rev = s_run[tid];
-    double scanned;
-    ScanF64(tmp.f).InclusiveScan(rev, scanned, cub::Min());
+    const double rev = s_run[tid];
+    ScanF64(tmp).InclusiveScan(rev, scanned, cub::Min());
     __syncthreads();
     s_run[tid] = scanned;  // s_run[j] = min over original threads >= BH_THREADS-1-j
     __syncthreads();
-    // minimum over all runs strictly to the right of this thread's run
-    double right = (tid + 1 < BH_THREADS) ? s_run[BH_THREADS - 2 - tid] : CUDART_INF;
-    {
-        // second pass right-to-left inside the run
-        unsigned long long c = prefix;
-        for (uint32_t i = beg; i < end; ++i) c += hist[sorted_bins[i]];
-        double m = right;
-        for (uint32_t i = end; i > beg; --i) {
-            const uint32_t k = i - 1;
-            const unsigned long long cnt = hist[sorted_bins[k]];
-            double raw = CUDART_INF;
-            if (cnt != 0ull) raw = __ddiv_rn(sorted_p[k], __ddiv_rn((double)c, dn));
-            m = fmin(m, raw);
-            qtab[sorted_bins[k]] = m > 1.0 ? 1.0 : m;
-            c -= cnt;
-        }
+    // minimum over all runs strictly to the right of this thread's run, then right-to-left inside the run
+    double m = (tid + 1 < BH_THREADS) ? s_run[BH_THREADS - 2 - tid] : CUDART_INF;
+    for (uint32_t i = end; i > beg; --i) {
+        m = fmin(m, raw[i - 1]);
+        qtab[sorted_bins[i - 1]] = m > 1.0 ? 1.0 : m;
     }
 }
 
@@ -120,13 +116,15 @@ extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uin
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const double *)nullptr, (double *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)nb, 0, 64, ctx->stream);
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t need = align(cub_bytes) + 2 * align(nb * sizeof(double)) + 2 * align(nb * sizeof(uint32_t));
+    const size_t need = align(cub_bytes) + 4 * align(nb * sizeof(double)) + 2 * align(nb * sizeof(uint32_t));
     int rc = gb2_scratch_reserve(ctx, need);
     if (rc != GB2_OK) return rc;
     char *base = (char *)ctx->scratch;
     void *d_tmp = base; base += align(cub_bytes);
     double *k_in = (double *)base; base += align(nb * sizeof(double));
     double *k_out = (double *)base; base += align(nb * sizeof(double));
+    unsigned long long *cum = (unsigned long long *)base; base += align(nb * sizeof(double));
+    double *raw = (double *)base; base += align(nb * sizeof(double));
     uint32_t *v_in = (uint32_t *)base; base += align(nb * sizeof(uint32_t));
     uint32_t *v_out = (uint32_t *)base;
     if (m->monotone) {
@@ -139,9 +137,15 @@ extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uin
         GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, (int)nb, 0, 64, ctx->stream));
         ctx->launches += 1;
     }
-    gb2_bh_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(k_out, v_out, (const unsigned long long *)d_hist, nb, d_qtab, d_rank,
-                                                     (unsigned long long *)d_total);
+    gb2_bh_count_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(v_out, (const unsigned long long *)d_hist, nb, d_rank, cum,
+                                                           (unsigned long long *)d_total);
     GB2_LAUNCH_CHECK(ctx);
+    if (d_hist != nullptr) {
+        gb2_bh_raw_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(k_out, cum, nb, raw);
+        GB2_LAUNCH_CHECK(ctx);
+        gb2_bh_min_kernel<<<1, BH_THREADS, 0, ctx->stream>>>(raw, v_out, nb, d_qtab);
+        GB2_LAUNCH_CHECK(ctx);
+    }
     return GB2_OK;
 }
 
