@@ -361,11 +361,13 @@ extern "C" int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_g
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return inputs[a].ref_len + 64 * inputs[a].n_variants > inputs[b].ref_len + 64 * inputs[b].n_variants;
     });
-    std::atomic<int> next(0);
+    std::atomic<int> next(0), uploaded(0);
     auto worker = [&]() {
         for (;;) {
             const int k = next.fetch_add(1);
             if (k >= n_graphs) return;
+            // bound the host copies alive at once: do not run more than nt graphs ahead of the uploader
+            while (k > uploaded.load(std::memory_order_acquire) + nt) std::this_thread::yield();
             const int i = order[(size_t)k];
             const gb2_graph_input &in = inputs[i];
             rcs[(size_t)i] = build_host(&errs[(size_t)i], in.h_ref, in.ref_len, in.n_variants, in.h_var_pos, in.h_var_ref_len,
@@ -379,14 +381,14 @@ extern "C" int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_g
     for (int k = 0; k < n_graphs; ++k) {  // upload in the order the workers take them
         const int i = order[(size_t)k];
         while (!ready[(size_t)i].load(std::memory_order_acquire)) std::this_thread::yield();
-        if (rc != GB2_OK) continue;  // still wait for every worker before leaving
-        if (rcs[(size_t)i] != GB2_OK) {
+        if (rc == GB2_OK && rcs[(size_t)i] != GB2_OK) {
             rc = rcs[(size_t)i];
             GB2_SET_ERR(ctx, "graph %d: %s", i, errs[(size_t)i].err);
-            continue;
+        } else if (rc == GB2_OK) {
+            rc = upload_host_graph(ctx, hgs[(size_t)i], &out[i]);
         }
-        rc = upload_host_graph(ctx, hgs[(size_t)i], &out[i]);
         hgs[(size_t)i] = HostGraph();  // free the host copy
+        uploaded.store(k + 1, std::memory_order_release);  // after a failure the rest is still waited for, then dropped
     }
     for (auto &t : pool) t.join();
     if (rc != GB2_OK)
