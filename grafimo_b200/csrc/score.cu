@@ -287,9 +287,12 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 // rare (the 34/35-bp CTCF profiles of JASPAR), so the chunk count and the replication factor are run-time values here
 // and one guarded loop serves full tiles and the tail.  Same tables, same packed 16-bit fields, same histogram / hit /
 // dense semantics as the narrow kernel; when the histogram does not fit shared memory next to the tables
-// (hist_in_smem == 0) it is counted with 64-bit global atomics.
-__global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int n_chunks, int R, int hist_in_smem)
+// (hist_in_smem == 0) it is counted with 64-bit global atomics.  NCHUNK is a template parameter (9..16) so that the
+// lookups are straight-line code; R stays a run-time value.
+template <int NCHUNK>
+__global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int R, int hist_in_smem)
 {
+    constexpr int n_chunks = NCHUNK;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *lut_s = smem;                        // [n_chunks*256][R]
     uint32_t *hist_s = smem + n_chunks * 256 * R;  // [span+1] when hist_in_smem
@@ -326,13 +329,11 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScorePara
             const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             uint32_t a = 0;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                if (c < n_chunks) {  // uniform
-                    const uint32_t b = (wd[c >> 2] >> (8 * (c & 3))) & 255u;
-                    uint32_t e;
-                    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 256u + b) * rstride));
-                    a += e;
-                }
+            for (int c = 0; c < NCHUNK; ++c) {
+                const uint32_t b = __byte_perm(wd[c >> 2], 0u, 0x4440u + (uint32_t)(c & 3));  // byte c of the k-mer
+                uint32_t e;
+                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 256u + b) * rstride));
+                a += e;
             }
             const int64_t row = r0 + u * 1024;
             const bool ok = row < p.n;
@@ -448,8 +449,19 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     const size_t smem = (size_t)m->smem_bytes;
     if (m->w > GB2_NARROW_WIDTH) {  // two packed words per k-mer
         const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(n, 4096)));
-        GB2_CUDA(ctx, cudaFuncSetAttribute(gb2_score_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gb2_score_wide_kernel<<<grid, 1024, smem, ctx->stream>>>(p, m->n_chunks, m->replicas, m->hist_global ? 0 : 1);
+        void (*kern)(const ScoreParams, int, int) = nullptr;
+        switch (m->n_chunks) {
+        case 9: kern = gb2_score_wide_kernel<9>; break;
+        case 10: kern = gb2_score_wide_kernel<10>; break;
+        case 11: kern = gb2_score_wide_kernel<11>; break;
+        case 12: kern = gb2_score_wide_kernel<12>; break;
+        case 13: kern = gb2_score_wide_kernel<13>; break;
+        case 14: kern = gb2_score_wide_kernel<14>; break;
+        case 15: kern = gb2_score_wide_kernel<15>; break;
+        default: kern = gb2_score_wide_kernel<16>; break;
+        }
+        GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 1024, smem, ctx->stream>>>(p, m->replicas, m->hist_global ? 0 : 1);
         GB2_LAUNCH_CHECK(ctx);
         return GB2_OK;
     }
