@@ -7,9 +7,11 @@
 //
 //   gb2_vcf_parse_fields     one thread per line: the eight fixed columns + FORMAT -> kind (header / data / malformed),
 //                            POS, byte ranges of CHROM / REF / ALT, number of ALT alleles, where the samples start;
-//   gb2_vcf_parse_genotypes  one CTA per data line: 2 KB tiles, tab ordinals by a block scan, every call "a|b" / "a/b" /
-//                            "a" parsed where its tab is found, bit (sample * ploidy + j) set in the row of allele a --
-//                            the rows are the haplotype bit sets gb2_graph_build takes (h_gt_bits).
+//   gb2_vcf_parse_genotypes  one CTA per data line.  Fixed-shape lines (plain GT, every call "d|d": 1000-Genomes style)
+//                            are read as 32-bit call words at computed positions; any other line goes through 4 KB
+//                            tiles, tab ordinals by a block scan, every call "a|b" / "a/b" / "a" parsed where its tab is
+//                            found.  Bit (sample * ploidy + j) is set in the row of allele a -- the rows are the
+//                            haplotype bit sets gb2_graph_build takes (h_gt_bits).
 // Line starts come from gb2_tsv_index_lines (csrc/tsv.cu).
 #include <cub/cub.cuh>
 
@@ -123,6 +125,61 @@ __global__ void __launch_bounds__(GT_THREADS) gb2_vcf_gt_kernel(const uint8_t *_
         const int64_t end = lo + line_len[line];
         uint32_t carry = 0;                   // tabs seen in earlier tiles == index of the next sample
         unsigned long long bad = 0;
+        // ---- fixed-shape lines: FORMAT is plain GT and every call is "d|d" (or "d/d", '.' for a digit) -- every line of a
+        //      1000-Genomes-style file.  Then call s sits at first + 1 + 4 s: no TAB search, no scan, no barrier per
+        //      tile; a thread checks four calls per step as 32-bit words ("0|0\t" is one compare) and only calls that
+        //      carry an alternative allele touch shared memory.  Any call of another shape sends the whole line to the
+        //      general path below.
+        const int n_samples = ploidy == 2 ? n_hap / 2 : 0;
+        if (n_samples >= 1 && end - (first + 1) == 4ll * n_samples - 1 && first + 1 + 4ll * n_samples + 16 <= n_bytes) {
+            bool ok = true;
+            const int64_t q0 = first + 1;
+            const int sh = 8 * (int)(q0 & 3);
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(text + (q0 & ~(int64_t)3));
+            auto take = [&](uint32_t rec, int smp, bool last) {
+                const uint32_t c0 = rec & 0xFFu, c1 = (rec >> 8) & 0xFFu, c2 = (rec >> 16) & 0xFFu, c3 = rec >> 24;
+                const bool d0 = c0 - '0' <= 9u, d2 = c2 - '0' <= 9u;
+                if (!((c1 == '|' || c1 == '/') && (d0 || c0 == '.') && (d2 || c2 == '.') && (last || c3 == '\t'))) {
+                    ok = false;
+                    return;
+                }
+                const int v0 = d0 ? (int)(c0 - '0') : 0, v1 = d2 ? (int)(c2 - '0') : 0;
+                const int h = 2 * smp;
+                if (v0 >= 1) {
+                    if (v0 <= na) atomicOr(&rows_s[(v0 - 1) * words + (h >> 5)], 1u << (h & 31));
+                    else ++bad;
+                }
+                if (v1 >= 1) {
+                    if (v1 <= na) atomicOr(&rows_s[(v1 - 1) * words + ((h + 1) >> 5)], 1u << ((h + 1) & 31));
+                    else ++bad;
+                }
+            };
+            const int n_full = n_samples - 1;  // the last call has no TAB behind it: checked on its own
+            for (int r0 = 4 * (int)threadIdx.x; r0 < n_full; r0 += 4 * GT_THREADS) {
+                uint32_t wv[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) wv[k] = __ldg(w32 + r0 + k);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (r0 + j < n_full) {
+                        const uint32_t rec = __funnelshift_r(wv[j], wv[j + 1], sh);
+                        if (rec != 0x09307C30u) take(rec, r0 + j, false);  // "0|0\t": nothing to record
+                    }
+                }
+            }
+            if (threadIdx.x == 0) {
+                const int64_t q = q0 + 4ll * n_full;
+                take((uint32_t)text[q] | ((uint32_t)text[q + 1] << 8) | ((uint32_t)text[q + 2] << 16), n_full, true);
+            }
+            if (__syncthreads_and(ok ? 1 : 0)) {
+                if (bad) atomicAdd(counts + 1, bad);
+                for (int k = threadIdx.x; k < na * words; k += GT_THREADS) bits[(size_t)base * words + k] = rows_s[k];
+                return;
+            }
+            bad = 0;  // another shape somewhere in the line: start again on the general path
+            for (int k = threadIdx.x; k < na * words; k += GT_THREADS) rows_s[k] = 0u;
+            __syncthreads();
+        }
         // tiles start on a 16-byte boundary so that every thread reads its 32 bytes as two 128-bit loads
         for (int64_t tile = first & ~(int64_t)15; tile < end; tile += GT_THREADS * GT_BYTES_PER_THREAD) {
             const int64_t b0 = tile + (int64_t)threadIdx.x * GT_BYTES_PER_THREAD;

@@ -76,7 +76,12 @@ def test_device_reader_special_cases(ctx, tmp_path):
              "x\t20\t.\tA\tg\t.\t.\t.\tGT\t1\t.\t0|1",
              "x\t25\t.\tT\t.\t.\t.\t.\tGT\t0|0\t0|0\t0|0",
              "y\t3\t.\tA\tC\t.\t.\t.\tGT\t1|1\t1|1\t1|1",
-             "x\t30\t.\tAC\tGT\t.\t.\t.\tGT\t0|1\t1|0\t1|1"]
+             "x\t30\t.\tAC\tGT\t.\t.\t.\tGT\t0|1\t1|0\t1|1",
+             # fixed-shape lines (the kernel's fast path): missing alleles, unphased separators, two ALT alleles ...
+             "x\t40\t.\tA\tC\t.\t.\t.\tGT\t.|1\t1/0\t./.",
+             "x\t42\t.\tG\tC,T\t.\t.\t.\tGT\t2|1\t0/2\t1|.",
+             # ... and a line of the same length with one call of another shape: the general path takes the whole line
+             "x\t45\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1:9\t1|1"]
     p = tmp_path / "s.vcf"
     p.write_text("\n".join(lines) + "\n")
     pv, pgt, ps = read_vcf(str(p), "x")
