@@ -273,7 +273,10 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "gb2_score_kernel<5,32,4>", "kernel_ms": k2_ms,
-                "kernel_share_of_step": k2_ms / ms_step, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}
+                "kernel_share_of_step": k2_ms / ms_step, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                "limiter": "shared-memory data pipe 95.9 % busy (ncu --set full, profiles/r01_score_kernel_ncu_full.txt): per 32 k-mers "
+                           "5 conflict-free LDS + 2 ATOMS x 4.17 wavefronts for the exact q-value histogram; the same kernel "
+                           "without the histogram (--no-qvalue) runs at 0.99 of this peak (DESIGN.md sections 6-7)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
