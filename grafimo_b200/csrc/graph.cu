@@ -30,6 +30,7 @@
 #define WALK_LIMIT (1u << 24)  // walks from one first base; beyond this the region is reported as too dense
 #define FREQ_MAX_CONS 8        // walks with more haplotype sets than this are counted by their own thread (rare)
 #define FREQ_GROUP 8           // lanes that share one row in the frequency pass
+#define FREQ_IN_POOL 0xFFu     // ncons marker: the row's set list lives in the overflow pool
 
 struct GraphView {
     int64_t n_nodes;
@@ -45,6 +46,11 @@ struct GraphView {
     const uint32_t *edge_off;   // [n_nodes+1] CSR
     const uint32_t *edge_to;
     const uint32_t *edge_cons;  // haplotype-set row of the edge or GB2_NO_CONS
+    const uint4 *edge_rec;      // [n_edges][3]: everything the walk needs about the edge's TARGET node, so that a step
+                                // along an edge is ONE dependent load instead of two (edge target, then node arrays):
+                                //   [0] = {target, haplotype-set row of the edge, node word x, node word y}
+                                //   [1] = {non-ACGT bits, length, first out-edge, out-degree | on-reference-path << 31}
+                                //   [2] = {a0 lo, a0 hi, clamp lo, clamp hi}
     const uint32_t *cons_bits;  // [n_cons][words]
     int32_t n_hap, words;
 };
@@ -70,7 +76,10 @@ struct RowsOut {
     unsigned long long capacity;
     unsigned long long *counts;  // [0] += rows with a non-ACGT base
     uint32_t *cons8;     // scratch [capacity][FREQ_MAX_CONS]: haplotype-set rows of the walk, for the frequency pass
-    uint8_t *ncons;      // scratch [capacity]: how many (0 = frequency already final)
+    uint8_t *ncons;      // scratch [capacity]: how many (0 = frequency already final, FREQ_IN_POOL = list is in `pool`)
+    uint32_t *pool;      // scratch: haplotype-set rows of the walks with more than FREQ_MAX_CONS of them, back to back;
+    unsigned long long pool_cap;    // such a row keeps {offset lo, offset hi, count} in its cons8 slots
+    unsigned long long *pool_used;
 };
 
 struct gb2_graph {
@@ -94,6 +103,8 @@ struct gb2_graph {
     int64_t q_cap_threads = 0;
     uint32_t *d_cons8 = nullptr;       // frequency-pass scratch, per row
     uint8_t *d_ncons = nullptr;
+    uint32_t *d_pool = nullptr;        // overflow lists of the frequency pass + their fill counter
+    unsigned long long *d_pool_used = nullptr;
     unsigned long long q_cap_rows = 0;
     uint32_t *d_flag = nullptr;        // [0] != 0: a first base exceeded WALK_LIMIT
 };
@@ -156,24 +167,33 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
         mask_t nbits = 0;                // bit i: base i of the k-mer is not ACGT
         mask_t nonref = 0;               // bit d: node at depth d is off the reference path
         int depth = 0, have = 0;
+        uint32_t st_eend[MAXW];  // one past the last out-edge of the node at this depth
         st_node[0] = (uint32_t)node0;
         st_have[0] = 0;
         st_cons[0] = g.node_cons[node0];
         bool entering = true;
         const unsigned long long row0 = WRITE ? offsets[t] : 0ull;
+        // the node being entered: from the node arrays for the start node, from the edge record (already loaded) below
+        uint32_t cur_len = g.node_off[node0 + 1] - g.node_off[node0], cur_flags = g.node_flags[node0];
+        uint32_t cur_eb = g.edge_off[node0], cur_ee = g.edge_off[node0 + 1], cur_nbits = 0;
+        unsigned long long cur_bits = 0;
+        long long cur_a0 = g.node_a0[node0], cur_clamp = g.node_clamp[node0];
+        if (WRITE && g.node_bits != nullptr) {
+            const uint2 nb = __ldg(g.node_bits + node0);
+            cur_bits = ((unsigned long long)nb.y << 32) | nb.x;
+            cur_nbits = __ldg(g.node_nbits + node0);
+        }
+        uint32_t cur_edge = 0;  // edge that led to the node being entered (its record holds a0 / clamp)
         while (true) {
             bool pop = false;
             if (entering) {
                 const uint32_t n = st_node[depth];
                 const int o = depth == 0 ? off0 : 0;
-                const uint32_t b0 = g.node_off[n];
-                const int len = (int)(g.node_off[n + 1] - b0);
+                const int len = (int)cur_len;
                 const int take = min(len - o, w - have);
                 if (WRITE) {
-                    if (g.node_bits != nullptr) {  // one 8-byte load: the node's bases, shifted into place
-                        const uint2 nb = __ldg(g.node_bits + n);
-                        unsigned long long bits = ((unsigned long long)nb.y << 32) | nb.x;
-                        bits >>= 2 * o;
+                    if (g.node_bits != nullptr) {  // the node's bases, shifted into place
+                        unsigned long long bits = cur_bits >> (2 * o);
                         if (take < 32) bits &= (1ull << (2 * take)) - 1ull;
                         if (!WIDE || have < 32) {
                             packed |= bits << (2 * have);
@@ -181,10 +201,11 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                         } else {
                             packed_hi |= bits << (2 * (have - 32));
                         }
-                        uint32_t bad = __ldg(g.node_nbits + n) >> o;
+                        uint32_t bad = cur_nbits >> o;
                         if (take < 32) bad &= (1u << take) - 1u;
                         nbits |= (mask_t)bad << have;
                     } else {
+                        const uint32_t b0 = g.node_off[n];
                         for (int k = 0; k < take; ++k) {
                             const uint32_t c = g.seq[b0 + o + k];
                             const int at = have + k;
@@ -194,15 +215,21 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                         }
                     }
                 }
-                if (g.node_flags[n] & 1u) nonref &= ~((mask_t)1 << depth); else nonref |= (mask_t)1 << depth;
+                if (cur_flags & 1u) nonref &= ~((mask_t)1 << depth); else nonref |= (mask_t)1 << depth;
                 have += take;
                 if (have < w) {  // node used up: go on through its edges
-                    st_edge[depth] = g.edge_off[n];
+                    st_edge[depth] = cur_eb;
+                    st_eend[depth] = cur_ee;
                     entering = false;
                     continue;
                 }
                 // a complete walk ending at base o + take - 1 of node n
-                const int64_t stop = min(g.node_a0[n] + (o + take), g.node_clamp[n]);
+                if (depth > 0) {
+                    const uint4 r2 = __ldg(g.edge_rec + 3ull * cur_edge + 2);
+                    cur_a0 = (long long)(((unsigned long long)r2.y << 32) | r2.x);
+                    cur_clamp = (long long)(((unsigned long long)r2.w << 32) | r2.z);
+                }
+                const int64_t stop = min((int64_t)cur_a0 + (o + take), (int64_t)cur_clamp);
                 if (stop <= re) {
                     if (WRITE) {
                         const unsigned long long row = row0 + n_found;
@@ -219,7 +246,21 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                             else out.packed[row] = packed;
                             out.start[row] = start;
                             out.stop[row] = stop;
-                            if (nc == 0 || nc > FREQ_MAX_CONS || g.n_hap == 0) {
+                            unsigned long long pool_at = ~0ull;
+                            if (nc > FREQ_MAX_CONS && g.n_hap != 0) {
+                                // walks through dense variant clusters: too many sets for the fixed slots.  Counting them
+                                // here, one thread reading nc x words, made a few CTAs run several times longer than
+                                // the rest of the grid (ncu: one SM busy for the whole kernel, the average SM for 25 %).
+                                pool_at = atomicAdd(out.pool_used, (unsigned long long)nc);
+                                if (pool_at + nc > out.pool_cap) pool_at = ~0ull;
+                            }
+                            if (pool_at != ~0ull) {
+                                for (int c = 0; c < nc; ++c) out.pool[pool_at + c] = cons[c];
+                                out.cons8[row * FREQ_MAX_CONS + 0] = (uint32_t)pool_at;
+                                out.cons8[row * FREQ_MAX_CONS + 1] = (uint32_t)(pool_at >> 32);
+                                out.cons8[row * FREQ_MAX_CONS + 2] = (uint32_t)nc;
+                                out.ncons[row] = (uint8_t)FREQ_IN_POOL;
+                            } else if (nc == 0 || nc > FREQ_MAX_CONS || g.n_hap == 0) {
                                 out.freq[row] = walk_frequency(g, cons, nc);
                                 out.ncons[row] = 0;
                             } else {  // counted by gb2_graph_freq_kernel, FREQ_GROUP lanes per row, coalesced
@@ -246,13 +287,23 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
                 }
                 pop = true;
             } else {  // next edge of the node at `depth` (its bases are already in the k-mer)
-                const uint32_t n = st_node[depth];
                 const uint32_t e = st_edge[depth];
-                if (e < g.edge_off[n + 1]) {
+                if (e < st_eend[depth]) {
                     st_edge[depth] = e + 1;
                     ++depth;
-                    st_node[depth] = g.edge_to[e];
-                    st_cons[depth] = g.edge_cons[e];
+                    const uint4 r1 = __ldg(g.edge_rec + 3ull * e + 1);
+                    cur_nbits = r1.x;
+                    cur_len = r1.y;
+                    cur_eb = r1.z;
+                    cur_ee = r1.z + (r1.w & 0x7FFFFFFFu);
+                    cur_flags = r1.w >> 31;
+                    cur_edge = e;
+                    if (WRITE) {
+                        const uint4 r0 = __ldg(g.edge_rec + 3ull * e);
+                        st_node[depth] = r0.x;
+                        st_cons[depth] = r0.y;
+                        cur_bits = ((unsigned long long)r0.w << 32) | r0.z;
+                    }
                     st_have[depth] = (uint8_t)have;
                     entering = true;
                 } else {
@@ -283,7 +334,8 @@ __global__ void __launch_bounds__(WALK_THREADS) gb2_graph_walk_kernel(const Grap
 // neighbouring 16-byte pieces of the same set) and add up the population counts.
 __global__ void __launch_bounds__(256) gb2_graph_freq_kernel(const GraphView g, unsigned long long n_rows,
                                                              const uint32_t *__restrict__ cons8,
-                                                             const uint8_t *__restrict__ ncons, int32_t *__restrict__ freq)
+                                                             const uint8_t *__restrict__ ncons,
+                                                             const uint32_t *__restrict__ pool, int32_t *__restrict__ freq)
 {
     const unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const unsigned long long row = t / FREQ_GROUP;
@@ -291,11 +343,23 @@ __global__ void __launch_bounds__(256) gb2_graph_freq_kernel(const GraphView g, 
     int nc = 0;
     if (row < n_rows) nc = ncons[row];
     int32_t total = 0;
-    if (nc) {
+    const int nq = g.words >> 2;
+    if (nc == (int)FREQ_IN_POOL) {  // long list in the overflow pool
+        const unsigned long long at = ((unsigned long long)cons8[row * FREQ_MAX_CONS + 1] << 32) | cons8[row * FREQ_MAX_CONS];
+        const int n = (int)cons8[row * FREQ_MAX_CONS + 2];
+        const uint32_t *ids = pool + at;
+        for (int q = sub; q < nq; q += FREQ_GROUP) {
+            uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[0] * g.words) + q);
+            for (int c = 1; c < n; ++c) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[c] * g.words) + q);
+                acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
+            }
+            total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
+        }
+    } else if (nc) {
         uint32_t ids[FREQ_MAX_CONS];
 #pragma unroll
         for (int c = 0; c < FREQ_MAX_CONS; ++c) ids[c] = c < nc ? cons8[row * FREQ_MAX_CONS + c] : 0u;
-        const int nq = g.words >> 2;
         for (int q = sub; q < nq; q += FREQ_GROUP) {
             uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[0] * g.words) + q);
 #pragma unroll
@@ -339,6 +403,8 @@ extern "C" int gb2_graph_destroy(gb2_graph *g)
     if (g->d_flag) cudaFree(g->d_flag);
     if (g->d_cons8) cudaFree(g->d_cons8);
     if (g->d_ncons) cudaFree(g->d_ncons);
+    if (g->d_pool) cudaFree(g->d_pool);
+    if (g->d_pool_used) cudaFree(g->d_pool_used);
     delete g;
     return GB2_OK;
 }
@@ -416,6 +482,28 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
         if ((rc = upload(ctx, g, h_edge_off, (size_t)n_nodes + 1, &g->v.edge_off)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_edge_to, (size_t)n_edges, &g->v.edge_to)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_edge_cons, (size_t)n_edges, &g->v.edge_cons)) != GB2_OK) break;
+        {   // edge records: what a walk needs about the edge's target, in one place (see GraphView::edge_rec)
+            std::vector<uint4> rec((size_t)n_edges * 3);
+            for (int64_t e = 0; e < n_edges; ++e) {
+                const uint32_t t = h_edge_to[e];
+                const uint32_t len = h_node_off[t + 1] - h_node_off[t];
+                unsigned long long bits = 0;
+                uint32_t bad = 0;
+                if (len <= 32u) {
+                    for (uint32_t j = 0; j < len; ++j) {
+                        const uint8_t c = h_seq[h_node_off[t] + j];
+                        if (c < 4) bits |= (unsigned long long)c << (2 * j); else bad |= 1u << j;
+                    }
+                }
+                const uint32_t deg = h_edge_off[t + 1] - h_edge_off[t];
+                rec[(size_t)3 * e] = make_uint4(t, h_edge_cons[e], (uint32_t)bits, (uint32_t)(bits >> 32));
+                rec[(size_t)3 * e + 1] = make_uint4(bad, len, h_edge_off[t], deg | ((uint32_t)(h_node_flags[t] & 1u) << 31));
+                const unsigned long long a0 = (unsigned long long)h_node_a0[t], cl = (unsigned long long)h_node_clamp[t];
+                rec[(size_t)3 * e + 2] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)cl, (uint32_t)(cl >> 32));
+            }
+            if ((rc = upload(ctx, g, rec.data(), rec.size(), &g->v.edge_rec)) != GB2_OK) break;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // rec goes out of scope
+        }
         if ((rc = upload(ctx, g, h_cons_bits, (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
         if (cudaMalloc((void **)&g->d_flag, sizeof(uint32_t)) != cudaSuccess) { rc = GB2_ERR_NOMEM; break; }
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // host arrays may go away
@@ -568,13 +656,20 @@ extern "C" int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *g, uint64_t capacity, 
         GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (g->d_cons8) cudaFree(g->d_cons8);
         if (g->d_ncons) cudaFree(g->d_ncons);
-        g->d_cons8 = nullptr; g->d_ncons = nullptr; g->q_cap_rows = 0;
+        if (g->d_pool) cudaFree(g->d_pool);
+        g->d_cons8 = nullptr; g->d_ncons = nullptr; g->d_pool = nullptr; g->q_cap_rows = 0;
         GB2_CUDA(ctx, cudaMalloc((void **)&g->d_cons8, (size_t)g->q_total * FREQ_MAX_CONS * sizeof(uint32_t)));
         GB2_CUDA(ctx, cudaMalloc((void **)&g->d_ncons, (size_t)g->q_total));
+        GB2_CUDA(ctx, cudaMalloc((void **)&g->d_pool, ((size_t)g->q_total * 4 + 1024) * sizeof(uint32_t)));
         g->q_cap_rows = g->q_total;
     }
+    if (!g->d_pool_used) GB2_CUDA(ctx, cudaMalloc((void **)&g->d_pool_used, sizeof(unsigned long long)));
+    GB2_CUDA(ctx, cudaMemsetAsync(g->d_pool_used, 0, sizeof(unsigned long long), ctx->stream));
     o.cons8 = g->d_cons8;
     o.ncons = g->d_ncons;
+    o.pool = g->d_pool;
+    o.pool_cap = (unsigned long long)g->q_cap_rows * 4 + 1024;  // beyond it a walk is counted by its own thread (correct, slower)
+    o.pool_used = g->d_pool_used;
     GB2_CUDA(ctx, cudaMemsetAsync(d_nmask, 0, (size_t)gb2_div_up((int64_t)g->q_total, 32) * sizeof(uint32_t), ctx->stream));
     const int64_t T = g->q_threads;
     const int64_t grid = gb2_div_up(T, WALK_THREADS);
@@ -588,7 +683,7 @@ extern "C" int gb2_graph_extract(gb2_ctx *ctx, gb2_graph *g, uint64_t capacity, 
     if (g->v.n_hap > 0) {
         const int64_t fgrid = gb2_div_up((int64_t)g->q_total * FREQ_GROUP, 256);
         GB2_REQUIRE(ctx, fgrid < ((int64_t)1 << 31), "gb2_graph_extract: too many rows for one launch (%llu)", (unsigned long long)g->q_total);
-        gb2_graph_freq_kernel<<<(unsigned)fgrid, 256, 0, ctx->stream>>>(g->v, g->q_total, g->d_cons8, g->d_ncons, d_freq);
+        gb2_graph_freq_kernel<<<(unsigned)fgrid, 256, 0, ctx->stream>>>(g->v, g->q_total, g->d_cons8, g->d_ncons, g->d_pool, d_freq);
         GB2_LAUNCH_CHECK(ctx);
     }
     return GB2_OK;
