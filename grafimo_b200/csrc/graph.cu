@@ -51,7 +51,9 @@ struct GraphView {
                                 //   [0] = {target, haplotype-set row of the edge, node word x, node word y}
                                 //   [1] = {non-ACGT bits, length, first out-edge, out-degree | on-reference-path << 31}
                                 //   [2] = {a0 lo, a0 hi, clamp lo, clamp hi}
-    const uint32_t *cons_bits;  // [n_cons][words]
+    const uint32_t *cons_bits;  // [n_cons][words]; a row that holds more than half of the haplotypes is stored COMPLEMENTED
+    const uint2 *cons_meta;     // [n_cons] {x, y} = 64-bit mask of the 16-byte pieces of the stored row that are not all zero
+    const uint8_t *cons_neg;    // [n_cons] 1 = the stored row is the complement of the set
     int32_t n_hap, words;
 };
 
@@ -85,7 +87,7 @@ struct RowsOut {
 struct gb2_graph {
     int device = 0;
     GraphView v{};
-    void *blocks[16] = {nullptr};
+    void *blocks[24] = {nullptr};
     int n_blocks = 0;
     std::vector<uint32_t> h_node_off;  // host copy: threads per region without a device round trip
     // region -> candidate first nodes: two non-decreasing envelopes of the coordinates a node can report as a start
@@ -119,22 +121,58 @@ __device__ __forceinline__ int64_t upper_bound_dev(const T *a, int64_t lo, int64
     return lo;
 }
 
-// Haplotypes that follow the walk: AND of the listed bit-set rows, population count.
+// Haplotypes that follow a walk = |AND of its haplotype sets|.  Most sets are very sparse (the carriers of a rare
+// alternative allele) or the complement of a sparse set (everybody else, on the reference side of the site), so every row
+// is stored in its sparser polarity with a 64-bit mask of its non-zero 16-byte pieces, and only the pieces that can
+// contribute are read:
+//   some set stored as is   -> pieces where ALL such sets are non-zero;          elsewhere the AND is empty
+//   only complemented sets  -> pieces where ANY complement is non-zero;         elsewhere every haplotype of the piece counts
+// Lanes `sub`, `sub + step`, ... of a group share the pieces; the return value is this lane's share of the count
+// (all-complemented lists: of the haplotypes to SUBTRACT from n_hap -- *subtract is set).
+__device__ __forceinline__ uint32_t piece_valid_word(int n_hap, int word)
+{
+    const int left = n_hap - 32 * word;
+    return left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+__device__ __forceinline__ int32_t set_list_count(const GraphView &g, const uint32_t *ids, int n, int sub, int step, bool *subtract)
+{
+    const int nq = g.words >> 2;
+    unsigned long long all_pos = ~0ull, any_neg = 0ull;
+    bool has_pos = false;
+    for (int c = 0; c < n; ++c) {
+        const uint2 m = __ldg(g.cons_meta + ids[c]);
+        const unsigned long long mask = ((unsigned long long)m.y << 32) | m.x;
+        if (__ldg(g.cons_neg + ids[c])) any_neg |= mask;
+        else { all_pos &= mask; has_pos = true; }
+    }
+    *subtract = !has_pos;
+    const unsigned long long visit = has_pos ? all_pos : any_neg;
+    int32_t total = 0;
+    for (int q = sub; q < nq; q += step) {
+        if (q < 64 && !((visit >> q) & 1ull)) continue;  // pieces beyond 64 (more than 8,192 haplotypes) are always read
+        uint4 acc = make_uint4(piece_valid_word(g.n_hap, 4 * q), piece_valid_word(g.n_hap, 4 * q + 1),
+                               piece_valid_word(g.n_hap, 4 * q + 2), piece_valid_word(g.n_hap, 4 * q + 3));
+        const uint4 valid = acc;
+        for (int c = 0; c < n; ++c) {
+            uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[c] * g.words) + q);
+            if (__ldg(g.cons_neg + ids[c])) { x.x = ~x.x; x.y = ~x.y; x.z = ~x.z; x.w = ~x.w; }
+            acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
+        }
+        const int32_t kept = __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
+        total += has_pos ? kept : (__popc(valid.x) + __popc(valid.y) + __popc(valid.z) + __popc(valid.w)) - kept;
+    }
+    return total;
+}
+
+// one thread counts a whole list (walks whose list fits neither the per-row slots nor the overflow pool)
 __device__ __forceinline__ int32_t walk_frequency(const GraphView &g, const uint32_t *cons, int n_cons)
 {
     if (g.n_hap == 0) return 0;
     if (n_cons == 0) return g.n_hap;
-    int32_t total = 0;
-    const int nq = g.words >> 2;
-    for (int q = 0; q < nq; ++q) {
-        uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)cons[0] * g.words) + q);
-        for (int c = 1; c < n_cons; ++c) {
-            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)cons[c] * g.words) + q);
-            acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
-        }
-        total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
-    }
-    return total;
+    bool subtract;
+    const int32_t c = set_list_count(g, cons, n_cons, 0, 1, &subtract);
+    return subtract ? g.n_hap - c : c;
 }
 
 // MAXW = 32: k-mers of one packed word; MAXW = 64: wide k-mers (two words per row, 64-deep stacks)
@@ -343,39 +381,20 @@ __global__ void __launch_bounds__(256) gb2_graph_freq_kernel(const GraphView g, 
     int nc = 0;
     if (row < n_rows) nc = ncons[row];
     int32_t total = 0;
-    const int nq = g.words >> 2;
+    bool subtract = false;
     if (nc == (int)FREQ_IN_POOL) {  // long list in the overflow pool
         const unsigned long long at = ((unsigned long long)cons8[row * FREQ_MAX_CONS + 1] << 32) | cons8[row * FREQ_MAX_CONS];
-        const int n = (int)cons8[row * FREQ_MAX_CONS + 2];
-        const uint32_t *ids = pool + at;
-        for (int q = sub; q < nq; q += FREQ_GROUP) {
-            uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[0] * g.words) + q);
-            for (int c = 1; c < n; ++c) {
-                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[c] * g.words) + q);
-                acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
-            }
-            total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
-        }
+        total = set_list_count(g, pool + at, (int)cons8[row * FREQ_MAX_CONS + 2], sub, FREQ_GROUP, &subtract);
     } else if (nc) {
         uint32_t ids[FREQ_MAX_CONS];
 #pragma unroll
         for (int c = 0; c < FREQ_MAX_CONS; ++c) ids[c] = c < nc ? cons8[row * FREQ_MAX_CONS + c] : 0u;
-        for (int q = sub; q < nq; q += FREQ_GROUP) {
-            uint4 acc = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[0] * g.words) + q);
-#pragma unroll
-            for (int c = 1; c < FREQ_MAX_CONS; ++c) {
-                if (c < nc) {
-                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(g.cons_bits + (size_t)ids[c] * g.words) + q);
-                    acc.x &= x.x; acc.y &= x.y; acc.z &= x.z; acc.w &= x.w;
-                }
-            }
-            total += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
-        }
+        total = set_list_count(g, ids, nc, sub, FREQ_GROUP, &subtract);
     }
     // the FREQ_GROUP lanes of a row are neighbours inside one warp
 #pragma unroll
     for (int d = FREQ_GROUP / 2; d >= 1; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
-    if (nc && sub == 0) freq[row] = total;
+    if (nc && sub == 0) freq[row] = subtract ? g.n_hap - total : total;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -504,7 +523,34 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
             if ((rc = upload(ctx, g, rec.data(), rec.size(), &g->v.edge_rec)) != GB2_OK) break;
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // rec goes out of scope
         }
-        if ((rc = upload(ctx, g, h_cons_bits, (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
+        {   // every set in its sparser polarity + the mask of its non-zero 16-byte pieces (see set_list_count)
+            std::vector<uint32_t> bits(h_cons_bits, h_cons_bits + (size_t)n_cons * words);
+            std::vector<uint2> meta((size_t)n_cons);
+            std::vector<uint8_t> neg((size_t)n_cons, 0);
+            for (int64_t k = 0; k < n_cons; ++k) {
+                uint32_t *row = bits.data() + (size_t)k * words;
+                int64_t members = 0;
+                for (int wd = 0; wd < words; ++wd) members += __builtin_popcount(row[wd]);
+                if (2 * members > n_hap) {
+                    neg[(size_t)k] = 1;
+                    for (int wd = 0; wd < words; ++wd) {
+                        const int left = n_hap - 32 * wd;
+                        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                        row[wd] = ~row[wd] & valid;
+                    }
+                }
+                unsigned long long mask = 0;
+                for (int q = 0; q < words / 4; ++q) {
+                    const bool nz = (row[4 * q] | row[4 * q + 1] | row[4 * q + 2] | row[4 * q + 3]) != 0u;
+                    if (q < 64 && nz) mask |= 1ull << q;  // pieces beyond 64 are always read
+                }
+                meta[(size_t)k] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+            }
+            if ((rc = upload(ctx, g, bits.data(), (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
+            if ((rc = upload(ctx, g, meta.data(), (size_t)n_cons, &g->v.cons_meta)) != GB2_OK) break;
+            if ((rc = upload(ctx, g, neg.data(), (size_t)n_cons, &g->v.cons_neg)) != GB2_OK) break;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // the vectors go out of scope
+        }
         if (cudaMalloc((void **)&g->d_flag, sizeof(uint32_t)) != cudaSuccess) { rc = GB2_ERR_NOMEM; break; }
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // host arrays may go away
     } while (0);
