@@ -1,3 +1,5 @@
+# Profiling commands of round 1 (run on the GPU box from the repository root): launch lists of the bench step, of C5 (hit vs dense form)
+# and per-launch metrics of the wide scoring kernel -> gpurun_out/*.csv; the summaries under profiles/ are made from those files.
 set -x
 mkdir -p gpurun_out
 export GB2_PROFILE_RANGE=1
