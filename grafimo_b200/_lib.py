@@ -99,6 +99,8 @@ SIGNATURES = {
     "gb2_graph_destroy": (_int, [_vp]),
     "gb2_graph_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_int32,
                                ctypes.POINTER(_vp)]),
+    "gb2_graph_build_stats": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_int32,
+                                     ctypes.c_int32, _i64, _vp]),
     "gb2_graph_build_batch": (_int, [_vp, ctypes.c_int32, _vp, ctypes.c_int32, ctypes.POINTER(_vp)]),
     "gb2_graph_get_info": (_int, [_vp, _vp]),
     "gb2_graph_prepare": (_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _int, ctypes.POINTER(_u64)]),

@@ -12,8 +12,11 @@
 //   * one bit set per node (haplotypes through it) and per edge (haplotypes along it); identical sets share a row and
 //     "every haplotype" is not stored.
 // One pass over the breakpoints, bit-set work proportional to (variants x words): ~10 ms per Mb at 2,504 haplotypes.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <thread>
 #include <unordered_map>
@@ -43,16 +46,22 @@ struct SetTable {
         }
         return h;
     }
+    std::vector<uint64_t> hashes;  // per row: what `index` was keyed with (reused when ranges are stitched together)
     uint32_t id(const uint32_t *p)
     {
         if (!on) return GB2_NO_CONS;
         if (memcmp(p, full.data(), (size_t)words * 4) == 0) return GB2_NO_CONS;
-        const uint64_t h = hash(p, words);
+        return id_hashed(p, hash(p, words));
+    }
+    // the row is known not to be the full set and h == hash(p, words)
+    uint32_t id_hashed(const uint32_t *p, uint64_t h)
+    {
         auto range = index.equal_range(h);
         for (auto it = range.first; it != range.second; ++it)
             if (memcmp(p, flat.data() + (size_t)it->second * words, (size_t)words * 4) == 0) return it->second;
         const uint32_t k = (uint32_t)(flat.size() / (size_t)words);
         flat.insert(flat.end(), p, p + words);
+        hashes.push_back(h);
         index.emplace(h, k);
         return k;
     }
@@ -91,6 +100,7 @@ struct HostGraph {
     std::vector<int64_t> a0, clamp;
     int32_t n_hap = 0, words = 4;
     int64_t n_cons = 0;
+    int64_t n_ranges = 1;  // independent breakpoint ranges the host pass was cut into
 };
 
 // error text of a host pass running on a worker thread (GB2_REQUIRE / GB2_SET_ERR only need an `err` array)
@@ -106,53 +116,59 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
                                 const uint32_t *h_edge_to, const uint32_t *h_edge_cons, int32_t n_hap, int32_t words,
                                 int64_t n_cons, const uint32_t *h_cons_bits, gb2_graph **out);
 
-// The host pass: pure CPU work on caller-owned arrays, no CUDA call -- several chromosomes run on several threads.
-static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
-                      const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
-                      int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, HostGraph &hg)
-{
-    GB2_REQUIRE(ctx, h_ref && ref_len >= 1, "gb2_graph_build: empty reference");
-    GB2_REQUIRE(ctx, n_variants >= 0 && (n_variants == 0 || (h_var_pos && h_var_ref_len && h_alt_off && h_alt)),
-                "gb2_graph_build: null variant array");
-    GB2_REQUIRE(ctx, max_node_len >= 1, "gb2_graph_build: max_node_len must be positive");
-    GB2_REQUIRE(ctx, n_hap >= 0 && words >= 4 && (words & 3) == 0 && (int64_t)words * 32 >= n_hap,
-                "gb2_graph_build: haplotype bit sets need a multiple of 4 words covering %d haplotypes", n_hap);
-    const int64_t L = ref_len, nv = n_variants;
-    for (int64_t v = 0; v < nv; ++v) {
-        const int64_t s = h_var_pos[v], r = h_var_ref_len[v], a = h_alt_off[v + 1] - h_alt_off[v];
-        GB2_REQUIRE(ctx, s >= 0 && r >= 0 && a >= 0 && s + r <= L, "gb2_graph_build: variant %lld outside the reference", (long long)v);
-        GB2_REQUIRE(ctx, r > 0 || a > 0, "gb2_graph_build: variant %lld has two empty alleles", (long long)v);
-        GB2_REQUIRE(ctx, v == 0 || h_var_pos[v - 1] <= s, "gb2_graph_build: variants must be sorted by position");
-    }
+#define GB2_PREV_NODE 0xFFFFFFFFu  // chunk-local edge source: the last node of the previous chunk
+
+struct BuildInputs {
+    const uint8_t *h_ref;
+    int64_t ref_len, n_variants;
+    const int64_t *h_var_pos;
+    const int32_t *h_var_ref_len;
+    const int64_t *h_alt_off;
+    const uint8_t *h_alt;
+    int32_t n_hap, words;
+    const uint32_t *h_gt_bits;
+    int32_t max_node_len;
+};
+
+// What one range of breakpoints produces, with chunk-local node and set numbering.
+struct Chunk {
+    std::vector<uint32_t> node_off, node_cons;
+    std::vector<uint8_t> seq, flags;
+    std::vector<int64_t> a0, clamp;
+    std::vector<Edge> edges;
     SetTable sets;
+};
+
+// Breakpoints [i_lo, i_hi) of the graph.  A range may start at any breakpoint that no allele spans or ends at: there every
+// haplotype arrives and the only thing that ends is the reference segment before it -- the canonical state this function
+// starts from (`first` = the range begins at breakpoint 0, where nothing ends).  Ranges are therefore independent and run
+// on several threads; build_host stitches them together in order.
+static void build_range(const BuildInputs &in, const std::vector<int64_t> &bps, int64_t i_lo, int64_t i_hi, bool first, Chunk &ck)
+{
+    const int words = in.words;
+    const int64_t nv = in.n_variants;
+    const int64_t *h_var_pos = in.h_var_pos;
+    const int32_t *h_var_ref_len = in.h_var_ref_len;
+    const int64_t *h_alt_off = in.h_alt_off;
+    const uint8_t *h_alt = in.h_alt, *h_ref = in.h_ref;
+    const uint32_t *h_gt_bits = in.h_gt_bits;
+    const int32_t max_node_len = in.max_node_len;
+    SetTable &sets = ck.sets;
     sets.words = words;
-    sets.on = h_gt_bits != nullptr && n_hap > 0;
+    sets.on = h_gt_bits != nullptr && in.n_hap > 0;
     if (sets.on) {
         sets.full.assign((size_t)words, 0u);
-        for (int h = 0; h < n_hap; ++h) sets.full[(size_t)(h >> 5)] |= 1u << (h & 31);
+        for (int h = 0; h < in.n_hap; ++h) sets.full[(size_t)(h >> 5)] |= 1u << (h & 31);
     }
     const Bits none;  // stands for "no set" when sets are off
-
-    // breakpoints
-    std::vector<int64_t> bps;
-    bps.reserve((size_t)(2 * nv + 2));
-    bps.push_back(0);
-    bps.push_back(L);
-    for (int64_t v = 0; v < nv; ++v) {
-        bps.push_back(h_var_pos[v]);
-        bps.push_back(h_var_pos[v] + h_var_ref_len[v]);
-    }
-    std::sort(bps.begin(), bps.end());
-    bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
-    const int64_t nb = (int64_t)bps.size() - 1;
     auto bp_index = [&](int64_t pos) { return (int64_t)(std::lower_bound(bps.begin(), bps.end(), pos) - bps.begin()); };
 
-    std::vector<uint32_t> &node_off = hg.node_off, &node_cons = hg.node_cons;
-    std::vector<uint8_t> &seq = hg.seq, &flags = hg.flags;
-    std::vector<int64_t> &a0 = hg.a0, &clamp = hg.clamp;
+    std::vector<uint32_t> &node_off = ck.node_off, &node_cons = ck.node_cons;
+    std::vector<uint8_t> &seq = ck.seq, &flags = ck.flags;
+    std::vector<int64_t> &a0 = ck.a0, &clamp = ck.clamp;
+    std::vector<Edge> &edges = ck.edges;
     node_off.assign(1, 0u);
-    std::vector<Edge> edges;
-    seq.reserve((size_t)L + (size_t)(nv ? h_alt_off[nv] : 0));
+    seq.reserve((size_t)(bps[(size_t)i_hi] - bps[(size_t)i_lo]) + 64);
 
     // appends the chain of nodes of one item -> (first, last) node index; the haplotype set of the item is filled in by
     // set_item_cons once it is known (node ids must follow input order, the sets are computed insertions first)
@@ -181,13 +197,13 @@ static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64
 
     std::map<int64_t, Bits> arrive;                    // breakpoint index -> haplotypes arriving there
     std::map<int64_t, std::vector<Source>> sources;    // breakpoint index -> what ends there
-    if (sets.on) arrive[0] = sets.full;
+    if (sets.on) arrive[i_lo] = sets.full;
+    if (!first) sources[i_lo].push_back(Source{GB2_PREV_NODE, sets.on ? sets.full : none});
     Bits A, left, took, tmp;
     if (sets.on) { A.resize((size_t)words); left.resize((size_t)words); took.resize((size_t)words); tmp.resize((size_t)words); }
-    int64_t v_next = 0;
-    const size_t total_guard = (size_t)1 << 32;
+    int64_t v_next = std::lower_bound(h_var_pos, h_var_pos + nv, bps[(size_t)i_lo]) - h_var_pos;
 
-    for (int64_t i = 0; i < nb; ++i) {
+    for (int64_t i = i_lo; i < i_hi; ++i) {
         const int64_t b = bps[(size_t)i];
         const int64_t v_lo = v_next;
         while (v_next < nv && h_var_pos[v_next] == b) ++v_next;
@@ -274,12 +290,185 @@ static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64
             if (it == arrive.end()) arrive[i + 1] = left;
             else for (int k = 0; k < words; ++k) it->second[(size_t)k] |= left[(size_t)k];
         }
-        if (seq.size() >= total_guard || a0.size() >= ((size_t)1 << 31)) {
-            GB2_SET_ERR(ctx, "gb2_graph_build: graph too large for 32-bit base offsets");
-            return GB2_ERR_ARG;
+    }
+    // what is left in `arrive` / `sources` belongs to breakpoint i_hi: the canonical state the next range starts from
+}
+
+// The host pass: pure CPU work on caller-owned arrays, no CUDA call.  n_threads > 1 cuts the breakpoints of ONE chromosome
+// into independent ranges (see build_range) that run on worker threads; the result does not depend on the cut points --
+// node ids, edge order and the numbering of the haplotype sets are those of the single-range pass.  chunk_bps > 0 forces
+// the range size (tests).
+static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
+                      const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
+                      int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, HostGraph &hg, int n_threads = 1,
+                      int64_t chunk_bps = 0)
+{
+    GB2_REQUIRE(ctx, h_ref && ref_len >= 1, "gb2_graph_build: empty reference");
+    GB2_REQUIRE(ctx, n_variants >= 0 && (n_variants == 0 || (h_var_pos && h_var_ref_len && h_alt_off && h_alt)),
+                "gb2_graph_build: null variant array");
+    GB2_REQUIRE(ctx, max_node_len >= 1, "gb2_graph_build: max_node_len must be positive");
+    GB2_REQUIRE(ctx, n_hap >= 0 && words >= 4 && (words & 3) == 0 && (int64_t)words * 32 >= n_hap,
+                "gb2_graph_build: haplotype bit sets need a multiple of 4 words covering %d haplotypes", n_hap);
+    const int64_t L = ref_len, nv = n_variants;
+    for (int64_t v = 0; v < nv; ++v) {
+        const int64_t s = h_var_pos[v], r = h_var_ref_len[v], a = h_alt_off[v + 1] - h_alt_off[v];
+        GB2_REQUIRE(ctx, s >= 0 && r >= 0 && a >= 0 && s + r <= L, "gb2_graph_build: variant %lld outside the reference", (long long)v);
+        GB2_REQUIRE(ctx, r > 0 || a > 0, "gb2_graph_build: variant %lld has two empty alleles", (long long)v);
+        GB2_REQUIRE(ctx, v == 0 || h_var_pos[v - 1] <= s, "gb2_graph_build: variants must be sorted by position");
+    }
+    const BuildInputs in{h_ref, ref_len, n_variants, h_var_pos, h_var_ref_len, h_alt_off, h_alt, n_hap, words, h_gt_bits, max_node_len};
+
+    // breakpoints
+    std::vector<int64_t> bps;
+    bps.reserve((size_t)(2 * nv + 2));
+    bps.push_back(0);
+    bps.push_back(L);
+    for (int64_t v = 0; v < nv; ++v) {
+        bps.push_back(h_var_pos[v]);
+        bps.push_back(h_var_pos[v] + h_var_ref_len[v]);
+    }
+    std::sort(bps.begin(), bps.end());
+    bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+    const int64_t nb = (int64_t)bps.size() - 1;
+
+    // ---- ranges: cut only at breakpoints that no allele spans or ends at (the farthest end of the alleles that start
+    //      before the breakpoint lies before it)
+    std::vector<int64_t> cuts(1, 0);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, nb));
+    int64_t want = chunk_bps > 0 ? chunk_bps : (nt > 1 ? std::max<int64_t>(4096, nb / (4 * (int64_t)nt)) : nb + 1);
+    if (want <= nb) {
+        int64_t reach = -1, v = 0;
+        for (int64_t i = 1; i < nb; ++i) {
+            const int64_t b = bps[(size_t)i];
+            while (v < nv && h_var_pos[v] < b) { reach = std::max(reach, h_var_pos[v] + h_var_ref_len[v]); ++v; }
+            if (reach < b && i - cuts.back() >= want) cuts.push_back(i);
         }
     }
+    cuts.push_back(nb);
+    const int64_t n_chunks = (int64_t)cuts.size() - 1;
+    hg.n_ranges = n_chunks;
+    const bool timing = getenv("GB2_BUILD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_ranges = now();
+    std::vector<Chunk> chunks((size_t)n_chunks);
+    if (n_chunks == 1 || nt == 1) {
+        for (int64_t k = 0; k < n_chunks; ++k) build_range(in, bps, cuts[(size_t)k], cuts[(size_t)k + 1], k == 0, chunks[(size_t)k]);
+    } else {
+        std::atomic<int64_t> next(0);
+        auto worker = [&]() {
+            for (;;) {
+                const int64_t k = next.fetch_add(1);
+                if (k >= n_chunks) return;
+                build_range(in, bps, cuts[(size_t)k], cuts[(size_t)k + 1], k == 0, chunks[(size_t)k]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < std::min<int64_t>(nt, n_chunks); ++t) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
+    }
 
+    const double t_stitch = now();
+    // ---- stitch the ranges together in order: node ids and base offsets shift, set ids go through the global table in
+    //      order of first appearance (what one pass over all breakpoints would have assigned)
+    SetTable sets;
+    sets.words = words;
+    sets.on = h_gt_bits != nullptr && n_hap > 0;
+    if (sets.on) sets.full = chunks[0].sets.full;
+    std::vector<uint32_t> &node_off = hg.node_off, &node_cons = hg.node_cons;
+    std::vector<uint8_t> &seq = hg.seq, &flags = hg.flags;
+    std::vector<int64_t> &a0 = hg.a0, &clamp = hg.clamp;
+    std::vector<Edge> edges;
+    if (n_chunks == 1) {  // nothing to renumber
+        Chunk &c = chunks[0];
+        node_off.swap(c.node_off); node_cons.swap(c.node_cons); seq.swap(c.seq); flags.swap(c.flags);
+        a0.swap(c.a0); clamp.swap(c.clamp); edges.swap(c.edges);
+        sets.flat.swap(c.sets.flat); sets.index.swap(c.sets.index); sets.hashes.swap(c.sets.hashes);
+    } else {
+        // phase A (one thread, cheap): where every range goes, and the global id of every set -- looked up by the hash the
+        // range already computed; the rows themselves stay where they are until phase B
+        std::vector<size_t> node_base((size_t)n_chunks + 1, 0), seq_base((size_t)n_chunks + 1, 0), edge_base((size_t)n_chunks + 1, 0);
+        for (int64_t k = 0; k < n_chunks; ++k) {
+            node_base[(size_t)k + 1] = node_base[(size_t)k] + chunks[(size_t)k].a0.size();
+            seq_base[(size_t)k + 1] = seq_base[(size_t)k] + chunks[(size_t)k].seq.size();
+            edge_base[(size_t)k + 1] = edge_base[(size_t)k] + chunks[(size_t)k].edges.size();
+        }
+        std::vector<std::vector<uint32_t>> remap((size_t)n_chunks);
+        std::vector<const uint32_t *> row_ptr;  // global id -> the row, inside the range that saw it first
+        if (sets.on) {
+            size_t tot_sets = 0;
+            for (const Chunk &c : chunks) tot_sets += c.sets.hashes.size();
+            sets.index.reserve(tot_sets);
+            row_ptr.reserve(tot_sets);
+            for (int64_t k = 0; k < n_chunks; ++k) {
+                const SetTable &ls = chunks[(size_t)k].sets;
+                std::vector<uint32_t> &rm = remap[(size_t)k];
+                rm.resize(ls.hashes.size());
+                for (size_t r = 0; r < rm.size(); ++r) {
+                    const uint64_t h = ls.hashes[r];
+                    const uint32_t *p = ls.row((uint32_t)r);
+                    uint32_t gid = GB2_NO_CONS;
+                    auto range = sets.index.equal_range(h);
+                    for (auto it = range.first; it != range.second; ++it)
+                        if (memcmp(p, row_ptr[it->second], (size_t)words * 4) == 0) { gid = it->second; break; }
+                    if (gid == GB2_NO_CONS) {
+                        gid = (uint32_t)row_ptr.size();
+                        row_ptr.push_back(p);
+                        sets.hashes.push_back(h);
+                        sets.index.emplace(h, gid);
+                    }
+                    rm[r] = gid;
+                }
+            }
+            sets.flat.resize(row_ptr.size() * (size_t)words);
+        }
+        const size_t tot_nodes = node_base[(size_t)n_chunks], tot_seq = seq_base[(size_t)n_chunks], tot_edges = edge_base[(size_t)n_chunks];
+        node_off.resize(tot_nodes + 1); node_cons.resize(tot_nodes); flags.resize(tot_nodes); a0.resize(tot_nodes);
+        clamp.resize(tot_nodes); seq.resize(tot_seq); edges.resize(tot_edges);
+        node_off[0] = 0u;
+        // phase B (worker threads): every range copies itself -- and the set rows it saw first -- into place
+        auto place = [&](int64_t k) {
+            Chunk &c = chunks[(size_t)k];
+            const uint32_t nb0 = (uint32_t)node_base[(size_t)k], sb0 = (uint32_t)seq_base[(size_t)k];
+            const std::vector<uint32_t> &rm = remap[(size_t)k];
+            auto gid = [&](uint32_t cons) { return cons == GB2_NO_CONS ? GB2_NO_CONS : rm[cons]; };
+            if (!c.seq.empty()) memcpy(seq.data() + sb0, c.seq.data(), c.seq.size());
+            for (size_t n = 1; n < c.node_off.size(); ++n) node_off[nb0 + n] = c.node_off[n] + sb0;
+            for (size_t n = 0; n < c.node_cons.size(); ++n) node_cons[nb0 + n] = gid(c.node_cons[n]);
+            if (!c.flags.empty()) memcpy(flags.data() + nb0, c.flags.data(), c.flags.size());
+            if (!c.a0.empty()) memcpy(a0.data() + nb0, c.a0.data(), c.a0.size() * sizeof(int64_t));
+            if (!c.clamp.empty()) memcpy(clamp.data() + nb0, c.clamp.data(), c.clamp.size() * sizeof(int64_t));
+            Edge *eo = edges.data() + edge_base[(size_t)k];
+            for (size_t e = 0; e < c.edges.size(); ++e) {
+                const Edge &x = c.edges[e];
+                eo[e] = Edge{x.src == GB2_PREV_NODE ? nb0 - 1u : x.src + nb0, x.dst + nb0, gid(x.cons)};
+            }
+            for (size_t r = 0; r < rm.size(); ++r)
+                if (row_ptr[rm[r]] == c.sets.row((uint32_t)r))  // this range saw the set first: it owns the copy
+                    memcpy(sets.flat.data() + (size_t)rm[r] * words, c.sets.row((uint32_t)r), (size_t)words * 4);
+        };
+        if (nt == 1) {
+            for (int64_t k = 0; k < n_chunks; ++k) place(k);
+        } else {
+            std::atomic<int64_t> next(0);
+            auto worker = [&]() {
+                for (;;) {
+                    const int64_t k = next.fetch_add(1);
+                    if (k >= n_chunks) return;
+                    place(k);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 0; t < std::min<int64_t>(nt, n_chunks); ++t) pool.emplace_back(worker);
+            for (auto &t : pool) t.join();
+        }
+        chunks.clear();
+    }
+    if (seq.size() >= ((size_t)1 << 32) || a0.size() >= ((size_t)1 << 31)) {
+        GB2_SET_ERR(ctx, "gb2_graph_build: graph too large for 32-bit base offsets");
+        return GB2_ERR_ARG;
+    }
+
+    const double t_csr = now();
     // ---- CSR: by (source, target); repeated structural edges (two deletions with the same ends) are merged
     const int64_t n_nodes = (int64_t)a0.size();
     std::sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.src != y.src ? x.src < y.src : x.dst < y.dst; });
@@ -310,7 +499,17 @@ static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64
     hg.n_hap = sets.on ? n_hap : 0;
     hg.words = words;
     hg.cons_bits.swap(sets.flat);
+    if (timing)
+        fprintf(stderr, "gb2_graph_build host pass: %lld ranges on %d threads %.3f s, stitch %.3f s, CSR %.3f s\n", (long long)n_chunks, nt,
+                t_stitch - t_ranges, t_csr - t_stitch, now() - t_csr);
     return GB2_OK;
+}
+
+static int build_threads_default()
+{
+    const char *e = getenv("GB2_BUILD_THREADS");
+    const int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, n);
 }
 
 static int upload_host_graph(gb2_ctx *ctx, const HostGraph &hg, gb2_graph **out)
@@ -332,12 +531,42 @@ extern "C" int gb2_graph_build(gb2_ctx *ctx, const uint8_t *h_ref, int64_t ref_l
     HostGraph hg;
     ErrSink es;
     const int rc = build_host(&es, h_ref, ref_len, n_variants, h_var_pos, h_var_ref_len, h_alt_off, h_alt, n_hap, words,
-                              h_gt_bits, max_node_len, hg);
+                              h_gt_bits, max_node_len, hg, build_threads_default());
     if (rc != GB2_OK) {
         GB2_SET_ERR(ctx, "%s", es.err);
         return rc;
     }
     return upload_host_graph(ctx, hg, out);
+}
+
+// The host pass alone (no GPU, no context): sizes of the graph and a 64-bit digest of every array it would upload.  The
+// digest does not depend on n_threads / chunk_bps (how many worker threads cut the breakpoints into how large ranges):
+// tests/test_graph_cpu.py checks exactly that.  h_stats[6] = nodes, edges, bases, haplotype-set rows, ranges used, digest.
+extern "C" int gb2_graph_build_stats(const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
+                                     const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt,
+                                     int32_t n_hap, int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len,
+                                     int32_t n_threads, int64_t chunk_bps, uint64_t *h_stats)
+{
+    if (!h_stats) return GB2_ERR_ARG;
+    HostGraph hg;
+    ErrSink es;
+    const int rc = build_host(&es, h_ref, ref_len, n_variants, h_var_pos, h_var_ref_len, h_alt_off, h_alt, n_hap, words,
+                              h_gt_bits, max_node_len, hg, n_threads > 0 ? n_threads : build_threads_default(), chunk_bps);
+    if (rc != GB2_OK) return rc;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t bytes) {
+        const uint8_t *b = (const uint8_t *)p;
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        h ^= bytes; h *= 1099511628211ull;
+    };
+    mix(hg.node_off.data(), hg.node_off.size() * 4); mix(hg.seq.data(), hg.seq.size());
+    mix(hg.a0.data(), hg.a0.size() * 8); mix(hg.clamp.data(), hg.clamp.size() * 8);
+    mix(hg.flags.data(), hg.flags.size()); mix(hg.node_cons.data(), hg.node_cons.size() * 4);
+    mix(hg.edge_off.data(), hg.edge_off.size() * 4); mix(hg.edge_to.data(), hg.edge_to.size() * 4);
+    mix(hg.edge_cons.data(), hg.edge_cons.size() * 4); mix(hg.cons_bits.data(), hg.cons_bits.size() * 4);
+    h_stats[0] = hg.a0.size(); h_stats[1] = hg.edge_to.size(); h_stats[2] = hg.seq.size(); h_stats[3] = (uint64_t)hg.n_cons;
+    h_stats[4] = (uint64_t)hg.n_ranges; h_stats[5] = h;
+    return GB2_OK;
 }
 
 // Several chromosomes at once: the host passes run on up to n_threads worker threads (0 = one per hardware thread), each
@@ -349,7 +578,9 @@ extern "C" int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_g
     for (int i = 0; i < n_graphs; ++i) out[i] = nullptr;
     if (n_graphs == 0) return GB2_OK;
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    const int budget = std::max(1, nt);
     nt = std::max(1, std::min(nt, (int)n_graphs));
+    const int inner_threads = std::max(1, budget / nt);  // fewer chromosomes than threads: the rest cut each chromosome into ranges
     std::vector<HostGraph> hgs((size_t)n_graphs);
     std::vector<ErrSink> errs((size_t)n_graphs);
     std::vector<int> rcs((size_t)n_graphs, GB2_OK);
@@ -371,7 +602,8 @@ extern "C" int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_g
             const int i = order[(size_t)k];
             const gb2_graph_input &in = inputs[i];
             rcs[(size_t)i] = build_host(&errs[(size_t)i], in.h_ref, in.ref_len, in.n_variants, in.h_var_pos, in.h_var_ref_len,
-                                        in.h_alt_off, in.h_alt, in.n_hap, in.words, in.h_gt_bits, in.max_node_len, hgs[(size_t)i]);
+                                        in.h_alt_off, in.h_alt, in.n_hap, in.words, in.h_gt_bits, in.max_node_len, hgs[(size_t)i],
+                                        inner_threads);
             ready[(size_t)i].store(1, std::memory_order_release);
         }
     };

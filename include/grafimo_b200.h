@@ -281,6 +281,16 @@ typedef struct gb2_graph_input {
     int32_t max_node_len, reserved;
 } gb2_graph_input;
 int gb2_graph_build_batch(gb2_ctx *ctx, int32_t n_graphs, const gb2_graph_input *inputs, int32_t n_threads, gb2_graph **out);
+/* The host pass of gb2_graph_build alone (no GPU, no context): sizes of the graph and a 64-bit digest of every array it
+ * would upload.  With n_threads > 1 the breakpoints of the chromosome are cut into independent ranges (only where no
+ * allele spans or ends) that are built on worker threads and stitched together; the result -- node ids, edge order,
+ * numbering of the haplotype sets, hence the digest -- does not depend on n_threads or on chunk_bps (forced range size in
+ * breakpoints, 0 = automatic).  gb2_graph_build uses every hardware thread (GB2_BUILD_THREADS overrides).
+ * h_stats[6] = nodes, edges, bases, haplotype-set rows, ranges used, digest. */
+int gb2_graph_build_stats(const uint8_t *h_ref, int64_t ref_len, int64_t n_variants, const int64_t *h_var_pos,
+                          const int32_t *h_var_ref_len, const int64_t *h_alt_off, const uint8_t *h_alt, int32_t n_hap,
+                          int32_t words, const uint32_t *h_gt_bits, int32_t max_node_len, int32_t n_threads,
+                          int64_t chunk_bps, uint64_t *h_stats);
 typedef struct gb2_graph_info {
     int64_t n_nodes, n_edges, n_bases, n_sets; /* n_sets: stored haplotype-set rows */
     int32_t n_hap, words;

@@ -144,3 +144,35 @@ def test_vcf_chunk_reader_bgzf_equals_gzip_and_plain(tmp_path):
                     got.append(b)
                 assert b"".join(got) == want, (name, chunk, tail)
                 assert len(got) > 1 or chunk > len(data)
+
+
+def _build_stats(ref, vs, gt, threads, chunk_bps, max_node_len=32):
+    import ctypes
+    from grafimo_b200 import _lib
+    from grafimo_b200.extract_regions import DeviceGraph
+    refa, pos, rlen, alt_off, alt_p, n_hap, words, bits = DeviceGraph._build_inputs(ref, vs, gt)
+    lib = _lib.load()
+    out = np.zeros(6, np.uint64)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None  # noqa: E731
+    rc = lib.gb2_graph_build_stats(ptr(refa), len(refa), len(pos), ptr(pos), ptr(rlen), ptr(alt_off), ptr(alt_p), n_hap, words,
+                                   ptr(bits), max_node_len, threads, chunk_bps, ptr(out))
+    assert rc == 0
+    return out
+
+
+def test_graph_builder_ranges_do_not_change_the_graph():
+    """The host pass of gb2_graph_build cut into independent breakpoint ranges on worker threads (cuts only where no allele
+    spans or ends) gives, array for array, the graph of the single pass: same node ids, edges, haplotype-set numbering."""
+    for seed in range(8):
+        ref, vs, gt = gr.random_case(500 + seed, length=3000 + 700 * seed, n_var=250 + 60 * seed, n_hap=(0, 12, 70, 40)[seed % 4],
+                                     indel=0.4 if seed % 2 else 0.15)
+        gt_ = gt if seed % 4 else None
+        one = _build_stats(ref, vs, gt_, 1, 0)
+        assert one[4] == 1 and one[0] > len(vs)
+        for threads, chunk in ((4, 1), (3, 7), (8, 50), (2, 100000), (5, 0)):
+            many = _build_stats(ref, vs, gt_, threads, chunk)
+            assert many.tolist()[:4] == one.tolist()[:4] and many[5] == one[5], (seed, threads, chunk, one, many)
+            if chunk in (1, 7, 50):
+                assert many[4] > 3  # really cut into ranges
+        # a smaller node length (more chained nodes) as well
+        assert _build_stats(ref, vs, gt_, 4, 5, max_node_len=8)[5] == _build_stats(ref, vs, gt_, 1, 0, max_node_len=8)[5]
