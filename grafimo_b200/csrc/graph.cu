@@ -19,8 +19,12 @@
 // Rows come out in (region, first base, depth-first over ascending target node) order: deterministic.
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <memory>
 #include <new>
+#include <thread>
 #include <type_traits>
 
 #include "internal.cuh"
@@ -398,6 +402,23 @@ __global__ void __launch_bounds__(256) gb2_graph_freq_kernel(const GraphView g, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// host-side preparation loops of gb2_graph_create over nodes / edges / set rows: independent items, split over threads
+template <typename F>
+static void parallel_for(int64_t n, int64_t grain, F fn)
+{
+    const char *e = getenv("GB2_BUILD_THREADS");
+    int nt = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n / std::max<int64_t>(grain, 1)));
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t lo = t * per, hi = std::min(n, lo + per);
+        if (lo < hi) pool.emplace_back([=] { fn(lo, hi); });
+    }
+    for (auto &t : pool) t.join();
+}
+
 template <typename T>
 static int upload(gb2_ctx *ctx, gb2_graph *g, const T *h, size_t n, const T **d_out)
 {
@@ -462,13 +483,14 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
     do {
         if ((rc = upload(ctx, g, h_node_off, (size_t)n_nodes + 1, &g->v.node_off)) != GB2_OK) break;
         if ((rc = upload(ctx, g, h_seq, n_bases, &g->v.seq)) != GB2_OK) break;
-        {   // nodes of at most 32 bases (vg's default): their bases as one 64-bit word each
-            bool fits = true;
-            for (int64_t i = 0; i < n_nodes && fits; ++i) fits = h_node_off[i + 1] - h_node_off[i] <= 32u;
-            if (fits) {
-                std::vector<uint2> nb((size_t)n_nodes);
-                std::vector<uint32_t> bad((size_t)n_nodes);
-                for (int64_t i = 0; i < n_nodes; ++i) {
+        // nodes of at most 32 bases (vg's default): their bases as one 64-bit word each (also copied into the edge records)
+        bool fits = true;
+        for (int64_t i = 0; i < n_nodes && fits; ++i) fits = h_node_off[i + 1] - h_node_off[i] <= 32u;
+        std::vector<uint2> nb(fits ? (size_t)n_nodes : 0);
+        std::vector<uint32_t> bad(fits ? (size_t)n_nodes : 0);
+        if (fits) {
+            parallel_for(n_nodes, 1 << 16, [&](int64_t lo, int64_t hi) {
+                for (int64_t i = lo; i < hi; ++i) {
                     unsigned long long bits = 0;
                     uint32_t m = 0;
                     const uint32_t len = h_node_off[i + 1] - h_node_off[i];
@@ -479,10 +501,9 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
                     nb[(size_t)i] = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
                     bad[(size_t)i] = m;
                 }
-                if ((rc = upload(ctx, g, nb.data(), (size_t)n_nodes, &g->v.node_bits)) != GB2_OK) break;
-                if ((rc = upload(ctx, g, bad.data(), (size_t)n_nodes, &g->v.node_nbits)) != GB2_OK) break;
-                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // nb, bad go out of scope
-            }
+            });
+            if ((rc = upload(ctx, g, nb.data(), (size_t)n_nodes, &g->v.node_bits)) != GB2_OK) break;
+            if ((rc = upload(ctx, g, bad.data(), (size_t)n_nodes, &g->v.node_nbits)) != GB2_OK) break;
         }
         {
             std::vector<uint32_t> blk((n_bases + 31) / 32);
@@ -503,50 +524,51 @@ extern "C" int gb2_graph_create(gb2_ctx *ctx, int64_t n_nodes, const uint32_t *h
         if ((rc = upload(ctx, g, h_edge_cons, (size_t)n_edges, &g->v.edge_cons)) != GB2_OK) break;
         {   // edge records: what a walk needs about the edge's target, in one place (see GraphView::edge_rec)
             std::vector<uint4> rec((size_t)n_edges * 3);
-            for (int64_t e = 0; e < n_edges; ++e) {
-                const uint32_t t = h_edge_to[e];
-                const uint32_t len = h_node_off[t + 1] - h_node_off[t];
-                unsigned long long bits = 0;
-                uint32_t bad = 0;
-                if (len <= 32u) {
-                    for (uint32_t j = 0; j < len; ++j) {
-                        const uint8_t c = h_seq[h_node_off[t] + j];
-                        if (c < 4) bits |= (unsigned long long)c << (2 * j); else bad |= 1u << j;
-                    }
+            parallel_for(n_edges, 1 << 16, [&](int64_t lo, int64_t hi) {
+                for (int64_t e = lo; e < hi; ++e) {
+                    const uint32_t t = h_edge_to[e];
+                    const uint32_t len = h_node_off[t + 1] - h_node_off[t];
+                    const uint2 bits = fits ? nb[(size_t)t] : make_uint2(0u, 0u);
+                    const uint32_t nbad = fits ? bad[(size_t)t] : 0u;
+                    const uint32_t deg = h_edge_off[t + 1] - h_edge_off[t];
+                    rec[(size_t)3 * e] = make_uint4(t, h_edge_cons[e], bits.x, bits.y);
+                    rec[(size_t)3 * e + 1] = make_uint4(nbad, len, h_edge_off[t], deg | ((uint32_t)(h_node_flags[t] & 1u) << 31));
+                    const unsigned long long a0 = (unsigned long long)h_node_a0[t], cl = (unsigned long long)h_node_clamp[t];
+                    rec[(size_t)3 * e + 2] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)cl, (uint32_t)(cl >> 32));
                 }
-                const uint32_t deg = h_edge_off[t + 1] - h_edge_off[t];
-                rec[(size_t)3 * e] = make_uint4(t, h_edge_cons[e], (uint32_t)bits, (uint32_t)(bits >> 32));
-                rec[(size_t)3 * e + 1] = make_uint4(bad, len, h_edge_off[t], deg | ((uint32_t)(h_node_flags[t] & 1u) << 31));
-                const unsigned long long a0 = (unsigned long long)h_node_a0[t], cl = (unsigned long long)h_node_clamp[t];
-                rec[(size_t)3 * e + 2] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)cl, (uint32_t)(cl >> 32));
-            }
+            });
             if ((rc = upload(ctx, g, rec.data(), rec.size(), &g->v.edge_rec)) != GB2_OK) break;
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // rec goes out of scope
         }
         {   // every set in its sparser polarity + the mask of its non-zero 16-byte pieces (see set_list_count)
-            std::vector<uint32_t> bits(h_cons_bits, h_cons_bits + (size_t)n_cons * words);
+            std::unique_ptr<uint32_t[]> bits_mem(new (std::nothrow) uint32_t[std::max<size_t>((size_t)n_cons * words, 1)]);
+            if (!bits_mem) { rc = GB2_ERR_NOMEM; break; }
+            uint32_t *bits = bits_mem.get();  // filled by the worker threads below (no single-threaded copy or zero fill)
             std::vector<uint2> meta((size_t)n_cons);
             std::vector<uint8_t> neg((size_t)n_cons, 0);
-            for (int64_t k = 0; k < n_cons; ++k) {
-                uint32_t *row = bits.data() + (size_t)k * words;
-                int64_t members = 0;
-                for (int wd = 0; wd < words; ++wd) members += __builtin_popcount(row[wd]);
-                if (2 * members > n_hap) {
-                    neg[(size_t)k] = 1;
-                    for (int wd = 0; wd < words; ++wd) {
-                        const int left = n_hap - 32 * wd;
-                        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-                        row[wd] = ~row[wd] & valid;
+            parallel_for(n_cons, 4096, [&](int64_t lo, int64_t hi) {
+                for (int64_t k = lo; k < hi; ++k) {
+                    uint32_t *row = bits + (size_t)k * words;
+                    memcpy(row, h_cons_bits + (size_t)k * words, (size_t)words * sizeof(uint32_t));
+                    int64_t members = 0;
+                    for (int wd = 0; wd < words; ++wd) members += __builtin_popcount(row[wd]);
+                    if (2 * members > n_hap) {
+                        neg[(size_t)k] = 1;
+                        for (int wd = 0; wd < words; ++wd) {
+                            const int left = n_hap - 32 * wd;
+                            const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                            row[wd] = ~row[wd] & valid;
+                        }
                     }
+                    unsigned long long mask = 0;
+                    for (int q = 0; q < words / 4; ++q) {
+                        const bool nz = (row[4 * q] | row[4 * q + 1] | row[4 * q + 2] | row[4 * q + 3]) != 0u;
+                        if (q < 64 && nz) mask |= 1ull << q;  // pieces beyond 64 are always read
+                    }
+                    meta[(size_t)k] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
                 }
-                unsigned long long mask = 0;
-                for (int q = 0; q < words / 4; ++q) {
-                    const bool nz = (row[4 * q] | row[4 * q + 1] | row[4 * q + 2] | row[4 * q + 3]) != 0u;
-                    if (q < 64 && nz) mask |= 1ull << q;  // pieces beyond 64 are always read
-                }
-                meta[(size_t)k] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
-            }
-            if ((rc = upload(ctx, g, bits.data(), (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
+            });
+            if ((rc = upload(ctx, g, (const uint32_t *)bits, (size_t)n_cons * words, &g->v.cons_bits)) != GB2_OK) break;
             if ((rc = upload(ctx, g, meta.data(), (size_t)n_cons, &g->v.cons_meta)) != GB2_OK) break;
             if ((rc = upload(ctx, g, neg.data(), (size_t)n_cons, &g->v.cons_neg)) != GB2_OK) break;
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = GB2_ERR_CUDA; break; }  // the vectors go out of scope

@@ -47,10 +47,17 @@ struct SetTable {
         return h;
     }
     std::vector<uint64_t> hashes;  // per row: what `index` was keyed with (reused when ranges are stitched together)
+    bool index_stale = false;      // rows were placed without their index entries: rebuild before the next lookup
     uint32_t id(const uint32_t *p)
     {
         if (!on) return GB2_NO_CONS;
         if (memcmp(p, full.data(), (size_t)words * 4) == 0) return GB2_NO_CONS;
+        if (index_stale) {
+            index.clear();
+            index.reserve(hashes.size());
+            for (size_t k = 0; k < hashes.size(); ++k) index.emplace(hashes[k], (uint32_t)k);
+            index_stale = false;
+        }
         return id_hashed(p, hash(p, words));
     }
     // the row is known not to be the full set and h == hash(p, words)
@@ -395,30 +402,57 @@ static int build_host(ErrSink *ctx, const uint8_t *h_ref, int64_t ref_len, int64
         std::vector<std::vector<uint32_t>> remap((size_t)n_chunks);
         std::vector<const uint32_t *> row_ptr;  // global id -> the row, inside the range that saw it first
         if (sets.on) {
-            size_t tot_sets = 0;
-            for (const Chunk &c : chunks) tot_sets += c.sets.hashes.size();
-            sets.index.reserve(tot_sets);
-            row_ptr.reserve(tot_sets);
+            // Global ids in order of first appearance over (range, local id), without a hash-table insert per row: sort
+            // (hash, order), split every run of equal hashes into classes of equal rows (almost always one), the first
+            // member of a class represents it, ids count the representatives in order.
+            struct Ent { uint64_t hash; uint32_t ord; };
+            std::vector<size_t> set_base((size_t)n_chunks + 1, 0);
+            for (int64_t k = 0; k < n_chunks; ++k) set_base[(size_t)k + 1] = set_base[(size_t)k] + chunks[(size_t)k].sets.hashes.size();
+            const size_t tot_sets = set_base[(size_t)n_chunks];
+            std::vector<Ent> ents(tot_sets);
+            std::vector<const uint32_t *> local_ptr(tot_sets);
             for (int64_t k = 0; k < n_chunks; ++k) {
                 const SetTable &ls = chunks[(size_t)k].sets;
-                std::vector<uint32_t> &rm = remap[(size_t)k];
-                rm.resize(ls.hashes.size());
-                for (size_t r = 0; r < rm.size(); ++r) {
-                    const uint64_t h = ls.hashes[r];
-                    const uint32_t *p = ls.row((uint32_t)r);
-                    uint32_t gid = GB2_NO_CONS;
-                    auto range = sets.index.equal_range(h);
-                    for (auto it = range.first; it != range.second; ++it)
-                        if (memcmp(p, row_ptr[it->second], (size_t)words * 4) == 0) { gid = it->second; break; }
-                    if (gid == GB2_NO_CONS) {
-                        gid = (uint32_t)row_ptr.size();
-                        row_ptr.push_back(p);
-                        sets.hashes.push_back(h);
-                        sets.index.emplace(h, gid);
-                    }
-                    rm[r] = gid;
+                for (size_t r = 0; r < ls.hashes.size(); ++r) {
+                    const size_t o = set_base[(size_t)k] + r;
+                    ents[o] = Ent{ls.hashes[r], (uint32_t)o};
+                    local_ptr[o] = ls.row((uint32_t)r);
                 }
             }
+            std::sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.hash != b.hash ? a.hash < b.hash : a.ord < b.ord; });
+            std::vector<uint32_t> rep(tot_sets);  // order index of the representative of every row
+            for (size_t lo = 0; lo < tot_sets;) {
+                size_t hi = lo + 1;
+                while (hi < tot_sets && ents[hi].hash == ents[lo].hash) ++hi;
+                for (size_t a = lo; a < hi; ++a) {  // runs are tiny: first earlier member with the same bytes, else itself
+                    uint32_t r0 = ents[a].ord;
+                    for (size_t b = lo; b < a; ++b)
+                        if (rep[ents[b].ord] == ents[b].ord &&
+                            memcmp(local_ptr[ents[b].ord], local_ptr[ents[a].ord], (size_t)words * 4) == 0) { r0 = ents[b].ord; break; }
+                    rep[ents[a].ord] = r0;
+                }
+                lo = hi;
+            }
+            std::vector<uint32_t> gid_of(tot_sets);
+            for (size_t o = 0; o < tot_sets; ++o) {
+                if (rep[o] == (uint32_t)o) {
+                    gid_of[o] = (uint32_t)row_ptr.size();
+                    row_ptr.push_back(local_ptr[o]);
+                } else {
+                    gid_of[o] = gid_of[rep[o]];  // the representative comes earlier in order
+                }
+            }
+            sets.hashes.resize(row_ptr.size());
+            for (int64_t k = 0; k < n_chunks; ++k) {
+                std::vector<uint32_t> &rm = remap[(size_t)k];
+                const SetTable &ls = chunks[(size_t)k].sets;
+                rm.resize(ls.hashes.size());
+                for (size_t r = 0; r < rm.size(); ++r) {
+                    rm[r] = gid_of[set_base[(size_t)k] + r];
+                    sets.hashes[rm[r]] = ls.hashes[r];
+                }
+            }
+            sets.index_stale = true;  // rebuilt from `hashes` only if the CSR step has parallel edges to merge
             sets.flat.resize(row_ptr.size() * (size_t)words);
         }
         const size_t tot_nodes = node_base[(size_t)n_chunks], tot_seq = seq_base[(size_t)n_chunks], tot_edges = edge_base[(size_t)n_chunks];

@@ -176,3 +176,22 @@ def test_graph_builder_ranges_do_not_change_the_graph():
                 assert many[4] > 3  # really cut into ranges
         # a smaller node length (more chained nodes) as well
         assert _build_stats(ref, vs, gt_, 4, 5, max_node_len=8)[5] == _build_stats(ref, vs, gt_, 1, 0, max_node_len=8)[5]
+
+
+def test_graph_builder_ranges_with_parallel_edges_to_merge():
+    """Chained deletions that reach the same breakpoint by two routes give parallel edges whose haplotype sets are merged
+    after the ranges are stitched (a lookup in the global set table, rebuilt lazily): same digest for any range size."""
+    rng = np.random.default_rng(11)
+    ref = "".join(rng.choice(list("ACGT"), size=400))
+    vs = []
+    for p in (20, 90, 160, 230, 300):
+        vs += [(p, ref[p:p + 2], ""), (p + 2, ref[p + 2:p + 4], ""), (p, ref[p:p + 4], ""), (p + 30, ref[p + 30], "A" if ref[p + 30] != "A" else "C")]
+    gt = (rng.random((len(vs), 24)) < 0.3).astype(np.uint8)
+    one = _build_stats(ref, vs, gt, 1, 0)
+    for threads, chunk in ((4, 1), (2, 3), (8, 0)):
+        many = _build_stats(ref, vs, gt, threads, chunk)
+        assert many.tolist()[:4] == one.tolist()[:4] and many[5] == one[5]
+    assert _build_stats(ref, vs, gt, 4, 1)[4] > 3
+    # the merged edges exist: fewer CSR edges than a graph where the long deletions are left out
+    fewer = _build_stats(ref, [v for v in vs if len(v[1]) != 4], gt[[i for i, v in enumerate(vs) if len(v[1]) != 4]], 1, 0)
+    assert one[1] == fewer[1]
