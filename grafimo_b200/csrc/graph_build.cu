@@ -20,6 +20,7 @@
 #include <map>
 #include <thread>
 #include <unordered_map>
+#include <utility>
 
 #include "internal.cuh"
 
@@ -27,13 +28,25 @@
 
 namespace {
 
+// std::vector whose resize() leaves new elements uninitialised: the big arrays are sized once and then filled by worker
+// threads (a value-initialising resize would zero 1 GB on one thread first)
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { typedef NoInitAlloc<U> other; };
+    NoInitAlloc() = default;
+    template <typename U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    template <typename U> void construct(U *p) noexcept { ::new ((void *)p) U; }
+    template <typename U, typename... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+typedef std::vector<uint32_t, NoInitAlloc<uint32_t>> RowVec;
+
 typedef std::vector<uint32_t> Bits;
 
 struct SetTable {
     int words = 0;
     bool on = false;
     Bits full;
-    std::vector<uint32_t> flat;  // rows back to back
+    RowVec flat;                 // rows back to back
     std::unordered_multimap<uint64_t, uint32_t> index;
 
     static uint64_t hash(const uint32_t *p, int n)
@@ -102,7 +115,8 @@ inline void and_into(Bits &dst, const Bits &a, const uint32_t *b)
 
 // what the host pass produces: the flat arrays gb2_graph_create uploads
 struct HostGraph {
-    std::vector<uint32_t> node_off, node_cons, edge_off, edge_to, edge_cons, cons_bits;
+    std::vector<uint32_t> node_off, node_cons, edge_off, edge_to, edge_cons;
+    RowVec cons_bits;
     std::vector<uint8_t> seq, flags;
     std::vector<int64_t> a0, clamp;
     int32_t n_hap = 0, words = 4;
