@@ -92,6 +92,8 @@ SIGNATURES = {
     "gb2_qvalues_from_hist": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_bh_pvalues": (_int, [_vp, _vp, _i64, _vp]),
     "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_finalize_hits_many": (_int, [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _u64, _u64, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp]),
     "gb2_finalize_dense": (_int, [_vp, _vp, _vp, _u64, _int, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_tally_haplotypes": (_int, [_vp, _vp, _vp, _i64, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gb2_graph_create": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32,

@@ -10,6 +10,9 @@
 //   K6  src/grafimo/resultsTmp.py:303-313 (+ score_sequences.py:393 for the log-odds column).
 #include <math_constants.h>
 
+#include <algorithm>
+#include <vector>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/reverse_iterator.h>
 
@@ -446,6 +449,135 @@ extern "C" int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *m, const uint32
                                                                 strands, row_base, (int32_t)m->lo, m->w, (double)m->scale,
                                                                 m->offset, m->d_ptab, d_qtab, d_row, d_strand, d_iscore,
                                                                 d_score, d_p, d_q);
+    GB2_LAUNCH_CHECK(ctx);
+    return GB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 over many motifs at once (a JASPAR-sized collection scanned over the same k-mers): the hits of all motifs sit in
+// ONE buffer -- gb2_score was given row_base = motif index << 40 -- and are filtered, sorted and annotated by one key
+// kernel, one radix sort keyed by motif | p-rank | row | strand and one gather, instead of a sort and two host
+// round trips per motif (which cost more than the scoring itself when a motif has ~10^4 hits).
+// ---------------------------------------------------------------------------------------------
+struct ManyDesc {
+    const double *ptab, *qtab;
+    const uint32_t *rank;
+    int32_t lo;
+    uint32_t span;
+    int32_t w;
+    int32_t pad;
+    double scale, offset;
+};
+
+#define GB2_MANY_ROW_BITS 40
+
+__global__ void gb2_hit_keys_many_kernel(const gb2_hit *__restrict__ hits, uint64_t n, const ManyDesc *__restrict__ desc,
+                                         int n_motifs, double p_thr, int q_filter, double q_thr, int rank_bits, int row_bits,
+                                         unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx,
+                                         unsigned long long *__restrict__ n_kept)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        const gb2_hit h = hits[i];
+        const uint32_t m = (uint32_t)(h.row >> GB2_MANY_ROW_BITS);
+        unsigned long long key = ~0ull;
+        if (m < (uint32_t)n_motifs) {
+            const ManyDesc d = desc[m];
+            const uint32_t bin = (uint32_t)(h.score - d.lo);
+            const double p = bin < d.span ? d.ptab[bin] : 1.0;
+            keep = p < p_thr && (!q_filter || d.qtab[bin] < q_thr);
+            const unsigned long long row = h.row & ((1ull << row_bits) - 1ull);
+            key = ((unsigned long long)m << (rank_bits + row_bits + 1)) | ((unsigned long long)d.rank[bin] << (row_bits + 1)) |
+                  (row << 1) | (h.strand & 1u);
+        }
+        keys[i] = keep ? key : ~0ull;
+        idx[i] = (uint32_t)i;
+    }
+    block_count_add(keep ? 1u : 0u, n_kept);
+}
+
+__global__ void gb2_hit_gather_many_kernel(const gb2_hit *__restrict__ hits, const uint32_t *__restrict__ order,
+                                           const unsigned long long *__restrict__ n_kept, const ManyDesc *__restrict__ desc,
+                                           uint32_t *__restrict__ o_motif, uint64_t *__restrict__ o_row,
+                                           uint8_t *__restrict__ o_strand, int32_t *__restrict__ o_iscore,
+                                           double *__restrict__ o_score, double *__restrict__ o_p, double *__restrict__ o_q)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_kept) return;
+    const gb2_hit h = hits[order[i]];
+    const uint32_t m = (uint32_t)(h.row >> GB2_MANY_ROW_BITS);
+    const ManyDesc d = desc[m];
+    const uint32_t bin = (uint32_t)(h.score - d.lo);
+    o_motif[i] = m;
+    o_row[i] = h.row & ((1ull << GB2_MANY_ROW_BITS) - 1ull);
+    o_strand[i] = (uint8_t)h.strand;
+    o_iscore[i] = h.score;
+    o_score[i] = __dadd_rn(__ddiv_rn((double)h.score, d.scale), __dmul_rn((double)d.w, d.offset));  // score_sequences.py:393
+    o_p[i] = bin < d.span ? d.ptab[bin] : 1.0;
+    if (o_q != nullptr && d.qtab != nullptr) o_q[i] = d.qtab[bin];
+}
+
+extern "C" int gb2_finalize_hits_many(gb2_ctx *ctx, int32_t n_motifs, const gb2_motif *const *motifs, const double *const *d_qtabs,
+                                      const uint32_t *const *d_ranks, const gb2_hit *d_hits, uint64_t n_hits, uint64_t row_limit,
+                                      double p_threshold, int q_filter, double q_threshold, uint32_t *d_motif, uint64_t *d_row,
+                                      uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p, double *d_q,
+                                      uint64_t *d_n_out)
+{
+    if (!ctx || !motifs || !d_ranks) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, d_n_out != nullptr, "gb2_finalize_hits_many: null counter");
+    GB2_REQUIRE(ctx, n_motifs >= 1 && n_motifs <= (1 << 20), "gb2_finalize_hits_many: motif count out of range");
+    GB2_REQUIRE(ctx, !q_filter || d_qtabs != nullptr, "gb2_finalize_hits_many: q filter needs the q tables");
+    GB2_REQUIRE(ctx, n_hits < ((uint64_t)1 << 31), "gb2_finalize_hits_many: at most 2^31-1 hits per call");
+    GB2_REQUIRE(ctx, row_limit > 0 && row_limit <= ((uint64_t)1 << GB2_MANY_ROW_BITS), "gb2_finalize_hits_many: rows must be below 2^40");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB2_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), ctx->stream));
+    if (n_hits == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, d_hits && d_motif && d_row && d_strand && d_iscore && d_score && d_p, "gb2_finalize_hits_many: null buffer");
+    std::vector<ManyDesc> desc((size_t)n_motifs);
+    int64_t max_span = 1;
+    for (int m = 0; m < n_motifs; ++m) {
+        const gb2_motif *mo = motifs[m];
+        GB2_REQUIRE(ctx, mo != nullptr && d_ranks[m] != nullptr, "gb2_finalize_hits_many: null motif or rank table (%d)", m);
+        GB2_REQUIRE(ctx, mo->device == ctx->device, "gb2_finalize_hits_many: motif %d lives on another device", m);
+        desc[(size_t)m] = ManyDesc{mo->d_ptab, d_qtabs ? d_qtabs[m] : nullptr, d_ranks[m], (int32_t)mo->lo, (uint32_t)mo->span,
+                                   mo->w, 0, (double)mo->scale, mo->offset};
+        GB2_REQUIRE(ctx, !q_filter || desc[(size_t)m].qtab != nullptr, "gb2_finalize_hits_many: q filter needs the q table of motif %d", m);
+        max_span = std::max(max_span, mo->span);
+    }
+    int rank_bits = 1, row_bits = 1, motif_bits = 1;
+    while ((1ll << rank_bits) < max_span + 1) ++rank_bits;
+    while (row_bits < GB2_MANY_ROW_BITS && (1ull << row_bits) < row_limit) ++row_bits;
+    while ((1ll << motif_bits) < n_motifs) ++motif_bits;
+    const int end_bit = motif_bits + rank_bits + row_bits + 1;
+    GB2_REQUIRE(ctx, end_bit <= 63, "gb2_finalize_hits_many: %d motifs x %lld rows do not fit one 64-bit sort key", n_motifs, (long long)row_limit);
+    const int n = (int)n_hits;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 64, ctx->stream);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_desc = align(desc.size() * sizeof(ManyDesc));
+    const size_t need = align(cub_bytes) + b_desc + 2 * align((size_t)n * 8) + 2 * align((size_t)n * 4);
+    int rc = gb2_scratch_reserve(ctx, need);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    void *d_tmp = base; base += align(cub_bytes);
+    ManyDesc *d_desc = (ManyDesc *)base; base += b_desc;
+    unsigned long long *k_in = (unsigned long long *)base; base += align((size_t)n * 8);
+    unsigned long long *k_out = (unsigned long long *)base; base += align((size_t)n * 8);
+    uint32_t *v_in = (uint32_t *)base; base += align((size_t)n * 4);
+    uint32_t *v_out = (uint32_t *)base;
+    GB2_CUDA(ctx, cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(ManyDesc), cudaMemcpyHostToDevice, ctx->stream));
+    GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // desc is a stack-lifetime host buffer
+    const int threads = 256;
+    const unsigned blocks = (unsigned)gb2_div_up(n, threads);
+    gb2_hit_keys_many_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, n_hits, d_desc, n_motifs, p_threshold, q_filter, q_threshold,
+                                                                 rank_bits, row_bits, k_in, v_in, (unsigned long long *)d_n_out);
+    GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, cub_bytes, k_in, k_out, v_in, v_out, n, 0, end_bit + 1, ctx->stream));
+    ctx->launches += 1;
+    gb2_hit_gather_many_kernel<<<blocks, threads, 0, ctx->stream>>>(d_hits, v_out, (const unsigned long long *)d_n_out, d_desc, d_motif,
+                                                                   d_row, d_strand, d_iscore, d_score, d_p, d_q);
     GB2_LAUNCH_CHECK(ctx);
     return GB2_OK;
 }

@@ -379,6 +379,77 @@ class Scan:
         return out
 
 
+class ManyScan:
+    """One scan of MANY motifs over the same k-mers on one GPU (a JASPAR-sized collection, BASELINE config 3): every
+    motif has its own histogram / q-table, the hits of all motifs share one buffer (row_base = motif index << 40) and are
+    finalized by ONE sort (gb2_finalize_hits_many) -- no sort and no host round trip per motif.
+    score() and qvalues() only queue work; finalize_device() is the single synchronisation point."""
+
+    ROW_BITS = 40
+
+    def __init__(self, ctx, motifs, strands=2, threshold=1e-4, want_q=True, hit_capacity=1 << 22):
+        self.ctx, self.motifs = ctx, list(motifs)
+        self.strands, self.threshold, self.want_q = int(strands), float(threshold), bool(want_q)
+        self.capacity = int(hit_capacity)
+        sizes = [m.span + 1 for m in self.motifs]
+        self.off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        total = int(self.off[-1])
+        self.hist = ctx.zeros(total, torch.int64) if want_q else None
+        self.qtab = ctx.empty(total, torch.float64) if want_q else None
+        self.rank = ctx.empty(total, torch.int32)
+        self.totals = ctx.zeros(len(self.motifs), torch.int64)
+        self.hits = ctx.empty(max(self.capacity, 1) * _HIT_BYTES, torch.uint8)
+        self.counters = ctx.zeros(4, torch.int64)  # [0] hits found (all motifs), [1] kept
+        self.row_limit = 0
+
+    def _at(self, tensor, m, itemsize):
+        return ctypes.c_void_p(tensor.data_ptr() + int(self.off[m]) * itemsize) if tensor is not None else None
+
+    def score(self, m, packed, nmask=None):
+        """Queues K2 of motif number m over `packed` (rows 0..n-1 of the k-mer set of its width)."""
+        ctx, mo = self.ctx, self.motifs[m]
+        n = packed.shape[0]
+        if n >= (1 << self.ROW_BITS):
+            raise ValueError("at most 2^40 - 1 rows per motif")
+        ctx.enter()
+        check(ctx.lib.gb2_score(ctx.h, mo.h, _ptr(packed), _ptr(nmask), n, int(m) << self.ROW_BITS, self.strands, self.threshold,
+                                self._at(self.hist, m, 8), _ptr(self.hits), self.capacity, _ptr(self.counters), None),
+              "gb2_score", ctx.h)
+        self.row_limit = max(self.row_limit, n)
+
+    def qvalues(self):
+        """Queues K5 of every motif (its own histogram -> its own q-table and p-rank table)."""
+        ctx = self.ctx
+        ctx.enter()
+        for m, mo in enumerate(self.motifs):
+            check(ctx.lib.gb2_qvalues_from_hist(ctx.h, mo.h, self._at(self.hist, m, 8), self._at(self.qtab, m, 8), self._at(self.rank, m, 4),
+                                                ctypes.c_void_p(self.totals.data_ptr() + 8 * m)), "gb2_qvalues_from_hist", ctx.h)
+
+    def finalize_device(self, q_filter=False):
+        """One sort for all motifs -> self.out (device tensors: motif, row, strand, iscore, score, p, q), rows ordered by
+        (motif, p ascending, row, strand); returns the number of rows kept."""
+        ctx = self.ctx
+        ctx.sync()
+        n = int(self.counters[0].item())
+        if n > self.capacity:
+            raise GrafimoB200Error(_lib.GB2_ERR_CAPACITY, "ManyScan.finalize", f"{n} hits exceed the capacity {self.capacity}")
+        cap = max(n, 1)
+        o = dict(motif=ctx.empty(cap, torch.int32), row=ctx.empty(cap, torch.int64), strand=ctx.empty(cap, torch.uint8),
+                 iscore=ctx.empty(cap, torch.int32), score=ctx.empty(cap, torch.float64), p=ctx.empty(cap, torch.float64),
+                 q=ctx.empty(cap, torch.float64) if self.want_q else None)
+        k = len(self.motifs)
+        handles = (ctypes.c_void_p * k)(*[mo.h.value for mo in self.motifs])
+        ranks = (ctypes.c_void_p * k)(*[self.rank.data_ptr() + 4 * int(self.off[m]) for m in range(k)])
+        qtabs = (ctypes.c_void_p * k)(*[self.qtab.data_ptr() + 8 * int(self.off[m]) for m in range(k)]) if self.want_q else None
+        check(ctx.lib.gb2_finalize_hits_many(ctx.h, k, handles, qtabs, ranks, _ptr(self.hits), n, max(self.row_limit, 1), self.threshold,
+                                             int(bool(q_filter)), self.threshold, _ptr(o["motif"]), _ptr(o["row"]), _ptr(o["strand"]),
+                                             _ptr(o["iscore"]), _ptr(o["score"]), _ptr(o["p"]), _ptr(o["q"]),
+                                             ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits_many", ctx.h)
+        ctx.sync()
+        self.out = o
+        return int(self.counters[1].item())
+
+
 def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):
     """gb2_scan_host: numpy/pinned-torch uint8 [n, w] host k-mers -> dict of numpy columns (+ stats)."""
     if isinstance(ascii_rows, torch.Tensor):

@@ -208,6 +208,17 @@ int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *motif, const uint32_t *d_d
                        double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score,
                        double *d_p, double *d_q, uint64_t *d_n_out);
 
+/* The same step for MANY motifs at once (a motif collection scanned over the same k-mers, BASELINE config 3): the hits of
+ * all motifs are in one buffer -- gb2_score was called with row_base = (motif index << 40) and one shared hit counter --
+ * and are filtered, sorted by (motif, p ascending, row, strand) and annotated by one key kernel, one radix sort and one
+ * gather.  motifs / d_qtabs / d_ranks: host arrays of n_motifs pointers (d_qtabs may be NULL without q-values).
+ * row_limit: exclusive bound of the row indices (< 2^40).  d_motif receives the motif index of every kept hit; the rows
+ * of one motif are contiguous.  motif bits + rank bits + row bits + 1 must fit 63 bits. */
+int gb2_finalize_hits_many(gb2_ctx *ctx, int32_t n_motifs, const gb2_motif *const *motifs, const double *const *d_qtabs,
+                           const uint32_t *const *d_ranks, const gb2_hit *d_hits, uint64_t n_hits, uint64_t row_limit,
+                           double p_threshold, int q_filter, double q_threshold, uint32_t *d_motif, uint64_t *d_row,
+                           uint8_t *d_strand, int32_t *d_iscore, double *d_score, double *d_p, double *d_q, uint64_t *d_n_out);
+
 /* ---- haplotype tally ---------------------------------------------------------------------------- */
 /* Per-haplotype windows -> vg-like deduplicated rows: sorts (position, packed k-mer) pairs and
  * run-length encodes them (segmented reduction).  Gives what `vg find -E -H gbwt` reports in the

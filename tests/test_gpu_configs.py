@@ -53,6 +53,42 @@ def _rows_from_tally(u_pos, u_packed, u_freq, u_isref, w, chrom="5"):
     return lines
 
 
+def test_c3_many_motif_scan_equals_one_scan_per_motif(ctx):
+    """ManyScan (shared hit buffer, ONE sort for all motifs, gb2_finalize_hits_many) == a Scan per motif: same rows, same
+    columns, same (p, row, strand) order inside every motif; with and without the q-value filter."""
+    from grafimo_b200.engine import ManyScan, Scan
+    tags = ["ctcf_meme__unif", "synth_w8_meme__bgnt", "ctcf_meme__bgnt", "synth_w6_meme__bgnt", "synth_w30_meme__bgnt", "synth_w25_meme__bgnt",
+            "synth_w8_meme__unif"]
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    dms, sets = [], {}
+    for tag in tags:
+        m = gu.load_motif(tag)
+        dms.append(ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"]))
+        w = m["width"]
+        if w not in sets:
+            sets[w] = torch.randint(0, 1 << (2 * w), (200_003,), dtype=torch.int64, device="cuda", generator=g)
+    for thr, qf in ((0.01, False), (0.3, True)):
+        many = ManyScan(ctx, dms, strands=2, threshold=thr, hit_capacity=1 << 22)
+        for k, dm in enumerate(dms):
+            many.score(k, sets[dm.width])
+        many.qvalues()
+        kept = many.finalize_device(q_filter=qf)
+        out = {c: (t[:kept].cpu().numpy() if t is not None else None) for c, t in many.out.items()}
+        assert (np.diff(out["motif"]) >= 0).all()  # the rows of one motif are contiguous, motifs in order
+        total = 0
+        for k, dm in enumerate(dms):
+            one = Scan(ctx, dm, strands=2, threshold=thr, hit_capacity=1 << 20)
+            one.score(sets[dm.width])
+            exp = one.finalize(q_filter=qf)
+            sel = out["motif"] == k
+            total += len(exp["row"])
+            assert np.array_equal(out["row"][sel].astype(np.uint64), exp["row"].astype(np.uint64)), (k, thr)
+            assert np.array_equal(out["strand"][sel], exp["strand"]) and np.array_equal(out["iscore"][sel], exp["int_score"])
+            assert np.array_equal(out["score"][sel], exp["score"]) and np.array_equal(out["p"][sel], exp["p-value"])
+            assert np.array_equal(out["q"][sel], exp["q-value"])
+        assert total == kept > 1000
+
+
 def test_c2_parity_form_haplotypes_to_hit_table(ctx):
     """per-haplotype windows -> gb2_tally_haplotypes -> strands=2 scan of the deduplicated k-mers ==
     the oracle run on the equivalent vg-like TSV rows (frequency, ref flag, p, q, score)."""

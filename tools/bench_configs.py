@@ -104,6 +104,23 @@ if ONLY in ("", "c3"):
     assert tot2 == tot_hits
     print(f"    queued form (score + BH of all motifs first, then the hit tables): {dt2:.2f}s wall, {e0.elapsed_time(e1) / 1e3:.2f}s device "
           f"= {800 * 2 * n / dt2 / 1e9:.1f} G windows/s")
+    # one sort for all motifs: shared hit buffer, gb2_finalize_hits_many (engine.ManyScan)
+    from grafimo_b200.engine import ManyScan
+    for rep in range(2):
+        e0, e1 = ev(), ev()
+        e0.record(ctx.stream)
+        t0 = time.time()
+        many = ManyScan(ctx, dms, strands=2, threshold=1e-4, hit_capacity=1 << 24)
+        for k, m in enumerate(raw):
+            many.score(k, sets[m.width])
+        many.qvalues()
+        tot3 = many.finalize_device()
+        e1.record(ctx.stream); ctx.sync()
+        dt3 = time.time() - t0
+        del many
+    assert tot3 == tot_hits, (tot3, tot_hits)
+    print(f"    ManyScan (shared hit buffer, one sort for all motifs): {dt3:.2f}s wall, {e0.elapsed_time(e1) / 1e3:.2f}s device "
+          f"= {800 * 2 * n / dt3 / 1e9:.1f} G windows/s")
     del sets
 
 # ---------------------------------------------------------------- C5
