@@ -86,7 +86,7 @@ def test_c3_many_motif_scan_equals_one_scan_per_motif(ctx):
             assert np.array_equal(out["strand"][sel], exp["strand"]) and np.array_equal(out["iscore"][sel], exp["int_score"])
             assert np.array_equal(out["score"][sel], exp["score"]) and np.array_equal(out["p"][sel], exp["p-value"])
             assert np.array_equal(out["q"][sel], exp["q-value"])
-        assert total == kept > 1000
+        assert total == kept and (qf or kept > 1000)  # random k-mers: few rows survive the q-value filter
 
 
 def test_c2_parity_form_haplotypes_to_hit_table(ctx):
