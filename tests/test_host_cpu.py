@@ -223,3 +223,20 @@ def test_top_level_motif_processing_module_and_duck_typed_motifs():
     assert is_motif(m) and not is_motif(object())
     assert score_matrix_acgt(m).tolist() == [[9, 10, 11], [6, 7, 8], [3, 4, 5], [0, 1, 2]]
     assert bg_acgt(m).tolist() == [0.1, 0.2, 0.3, 0.4]
+
+
+def test_string_column_helpers_on_host_text():
+    """_gather_rows / _fixed_strings / _var_strings (the string columns of reported rows) on a numpy text buffer: the
+    same code gathers from the device copy of the text in compute_results."""
+    from grafimo_b200.score_sequences import _fixed_strings, _gather_rows, _var_strings
+    lines = [b"chr7:100-900\tACGTACG\tx", b"chr7:100-900\tTTTTGGG\ty", b"12:5-6\tCCCCAAA\tz", b"chr7:100-900\tGGGGGGG\tw"]
+    text = np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+    offs = np.cumsum([0] + [len(ln) + 1 for ln in lines[:-1]]).astype(np.int64)
+    name_len = np.array([ln.index(b"\t") for ln in lines], dtype=np.int64)
+    seq_off = name_len + 1
+    order = np.array([2, 0, 3, 1])  # rows come back in report order, not file order
+    assert _fixed_strings(text, (offs + seq_off)[order], 7).tolist() == ["CCCCAAA", "ACGTACG", "GGGGGGG", "TTTTGGG"]
+    assert _var_strings(text, offs[order], name_len[order]).tolist() == ["12:5-6", "chr7:100-900", "chr7:100-900", "chr7:100-900"]
+    g = _gather_rows(text, np.array([len(text) - 3], dtype=np.int64), 8)  # indices beyond the text are clamped
+    assert g.shape == (1, 8) and bytes(g[0, :3]) == b"\tw\n" and set(g[0, 3:].tolist()) == {10}
+    assert _fixed_strings(text, np.zeros(0, np.int64), 7).tolist() == [] and _var_strings(text, np.zeros(0, np.int64), np.zeros(0, np.int64)).tolist() == []
