@@ -182,6 +182,89 @@ def mem_available_bytes():
     return 8 << 30
 
 
+def kernel_label(info):
+    """Name of the K2 instantiation a motif runs (template arguments follow from the motif: csrc/score.cu dispatch)."""
+    if info.width > 32:
+        return f"gb2_score_wide_kernel<{info.n_chunks}> (R={info.lut_replicas})"
+    return f"gb2_score_kernel<{info.n_chunks},{info.lut_replicas},4>"
+
+
+def parity_multi_gpu(ctx, dm, rank, world):
+    """Hardware multi-GPU parity, run inside the bench so that the driver's N>1 launches carry correctness: a common
+    (same seed on every rank) sub-shard of >= 2^21 rows is split over the ranks by rows; every rank scores its part,
+    the histogram is all-reduced INSIDE the C ABI (gb2_allreduce_hist), every rank derives the q-table and finalizes its
+    own hits, the fixed-width hit columns are all-gathered (gb2_allgather_bytes) and merged; rank 0 also scans the whole
+    sub-shard alone and compares bit for bit: q-table of every rank, then (row, strand, integer score, p, q) of every hit.
+    What it replaces / must equal: the parent-side merge + BH over all rows, score_sequences.py:171-198."""
+    import torch
+    from grafimo_b200 import dist as gdist
+    from grafimo_b200 import engine, synth
+    w = dm.width
+    L, H, thr = (1 << 17) + w - 1, 16, 1e-3
+    with torch.cuda.stream(ctx.stream):
+        rows, _ = synth.haplotype_windows(L, H, w, SEED + 999, device=ctx.device, hap_batch=16)
+    n = rows.shape[0]
+    lo, hi = gdist.shard_bounds(n, rank, world)
+    part = engine.Scan(ctx, dm, strands=2, threshold=thr, want_q=True, hit_capacity=1 << 20)
+    part.score(rows[lo:hi], row_base=lo)
+    ctx.allreduce_hist(part.histogram())
+    qtab, _ = part.qvalues()
+    kept = part.finalize_device()
+    o = part.out
+    # fixed-width columns, padded to the largest per-rank count, gathered by the library
+    counts = ctx.allgather(torch.tensor([kept], dtype=torch.int64, device=ctx.device))
+    ctx.sync()
+    counts = counts.view(-1).cpu().tolist()
+    cap = max(max(counts), 1)
+    cols = {}
+    with torch.cuda.stream(ctx.stream):
+        for k, dt in (("row", torch.int64), ("strand", torch.uint8), ("iscore", torch.int32), ("p", torch.float64), ("q", torch.float64)):
+            buf = torch.zeros(cap, dtype=dt, device=ctx.device)
+            buf[:kept] = o[k][:kept]
+            cols[k] = buf
+    gathered = {k: ctx.allgather(v) for k, v in cols.items()}
+    all_q = ctx.allgather(qtab.contiguous())
+    ctx.sync()
+    res = {"ok": True, "ranks": world, "rows": int(n), "windows": int(2 * n), "threshold": thr,
+           "what": "rows split over the ranks, histogram all-reduced by gb2_allreduce_hist, per-rank finalize, columns merged "
+                   "by gb2_allgather_bytes == one single-GPU scan of the same rows: q-table of every rank and (row, strand, "
+                   "int score, p, q) of every hit, bit for bit"}
+    if rank == 0:
+        whole = engine.Scan(ctx, dm, strands=2, threshold=thr, want_q=True, hit_capacity=1 << 20)
+        whole.score(rows)
+        exp = whole.finalize()
+        exp_q = whole.qtab.cpu().numpy()
+        aq = all_q.cpu().numpy()
+        qt_ok = all(np.array_equal(aq[r], exp_q) for r in range(world))
+        parts = []
+        for r in range(world):
+            c = counts[r]
+            parts.append({"row": gathered["row"][r, :c].cpu().numpy(), "strand": gathered["strand"][r, :c].cpu().numpy(),
+                          "int_score": gathered["iscore"][r, :c].cpu().numpy(), "p-value": gathered["p"][r, :c].cpu().numpy(),
+                          "q-value": gathered["q"][r, :c].cpu().numpy()})
+        merged = gdist.merge_hit_tables(parts)
+        cols_ok = {k: bool(np.array_equal(merged[k], exp[k])) for k in ("row", "strand", "int_score", "p-value", "q-value")}
+        res.update(ok=bool(qt_ok and all(cols_ok.values())), hits=int(len(exp["row"])), hits_per_rank=counts,
+                   qtable_equal_on_every_rank=bool(qt_ok), columns_equal=cols_ok)
+    return res
+
+
+def parity_single_gpu(ctx, dm, windows, seq_batch, scan_hist, scan_hits):
+    """N=1 self-check at FULL size: the sequence form (windows formed in registers from the 2-bit haplotypes) must give
+    the histogram and the hit table of the k-mer form (one packed word per window) bit for bit."""
+    import torch
+    from grafimo_b200 import engine
+    sc = engine.Scan(ctx, dm, strands=2, threshold=THRESHOLD, want_q=True, hit_capacity=1 << 23)
+    sc.score_sequences(seq_batch)
+    got = sc.finalize()
+    hist_ok = bool(torch.equal(sc.histogram(), scan_hist))
+    cols_ok = {k: bool(np.array_equal(got[k], scan_hits[k])) for k in ("row", "strand", "int_score", "p-value", "q-value")}
+    return {"ok": bool(hist_ok and all(cols_ok.values())), "ranks": 1, "windows": int(2 * windows.shape[0]), "hits": int(len(got["row"])),
+            "what": "sequence-form scan (gb2_score_sequences on the 2-bit haplotypes) == k-mer-form scan (gb2_score on the expanded "
+                    "packed windows) at full size: score histogram and (row, strand, int score, p, q) of every hit, bit for bit",
+            "histogram_equal": hist_ok, "columns_equal": cols_ok}
+
+
 def run_ours(args):
     import torch
     from grafimo_b200 import dist as gdist
@@ -202,6 +285,7 @@ def run_ours(args):
     rank, world, local = info["rank"], info["world"], info["local"]
     torch.cuda.set_device(local)
     ctx = engine.Context(local)
+    gdist.init_comm(ctx)  # the library's own NCCL communicator; torch.distributed only carried the 128-byte id
     tmpdir = tempfile.mkdtemp(prefix="gb2_bench_")
     motif = build_ctcf(tmpdir)
     dm = device_motif(motif, ctx)
@@ -209,74 +293,85 @@ def run_ours(args):
     L, H = args.region_len, args.haplotypes
     per = L - w + 1
     n = per * H
+    host_ascii = torch.empty((H, L), dtype=torch.uint8, pin_memory=True)  # the e2e input: the haplotypes as ASCII text
     with torch.cuda.stream(ctx.stream):
         windows, model = synth.haplotype_windows(L, H, w, SEED + rank, device=ctx.device, hap_batch=32)
+        seq_words, _ = synth.haplotype_sequences(L, H, SEED + rank, device=ctx.device, hap_batch=32, ascii_out=host_ascii)
     ctx.sync()
+    seq_batch = engine.SeqBatch(ctx, np.full(H, L, dtype=np.int64), seq2=seq_words.view(-1))
     scan = engine.Scan(ctx, dm, strands=2, threshold=THRESHOLD, want_q=True, hit_capacity=1 << 23)
     ev_pairs = []
 
-    def step(timed):
+    def step(timed, form="kmers"):
         scan.reset()
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(ctx.stream)
-        scan.score(windows)
+        if form == "kmers":
+            scan.score(windows)
+        else:
+            scan.score_sequences(seq_batch)
         if timed:
             b.record(ctx.stream)
             ev_pairs.append((a, b))
         if world > 1:
-            with torch.cuda.stream(ctx.stream):
-                gdist.allreduce_histogram(scan.histogram())
+            ctx.allreduce_hist(scan.histogram())  # ncclAllReduce issued by the library on the context's stream
         scan.qvalues()
         return scan.finalize_device()
 
-    for _ in range(max(args.warmup, 3)):
-        kept = step(False)
-    ctx.sync()
-    if world > 1:
-        torch.distributed.barrier()
+    def timed_steps(form):
+        del ev_pairs[:]
+        for _ in range(max(args.warmup, 3)):
+            kept = step(False, form)
+        ctx.sync()
+        if world > 1:
+            torch.distributed.barrier()
+        launches0 = ctx.launches
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if os.environ.get("GB2_PROFILE_RANGE") == form:  # ncu --profile-from-start off: capture the timed region only
+            torch.cuda.profiler.start()
+        t0.record(ctx.stream)
+        for _ in range(args.steps):
+            kept = step(True, form)
+        t1.record(ctx.stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        if os.environ.get("GB2_PROFILE_RANGE") == form:
+            torch.cuda.profiler.stop()
+        ms_total = t0.elapsed_time(t1)
+        launches = ctx.launches - launches0
+        if world > 1:
+            torch.distributed.barrier()
+        ms_total = ctx.allreduce_max([ms_total])[0]
+        k_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
+        return ms_total / args.steps, k_ms, launches, kept
+
     sampler = ClockSampler(local)
-    launches0 = ctx.launches
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if os.environ.get("GB2_PROFILE_RANGE"):  # ncu --profile-from-start off: capture the timed region only
-        torch.cuda.profiler.start()
-    t0.record(ctx.stream)
-    for _ in range(args.steps):
-        kept = step(True)
-    t1.record(ctx.stream)
-    ctx.sync()
-    torch.cuda.synchronize()
-    if os.environ.get("GB2_PROFILE_RANGE"):
-        torch.cuda.profiler.stop()
-    ms_total = t0.elapsed_time(t1)
-    launches = ctx.launches - launches0
+    ms_step, k2_ms, launches, kept = timed_steps("kmers")
     clocks = sampler.stop()
-    if world > 1:
-        torch.distributed.barrier()
-    ms_total = gdist.allreduce_max(ms_total, device=ctx.device)
-    ms_step = ms_total / args.steps
     total_windows = 2 * n * world
     value = total_windows / (ms_step * 1e-3)
-    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
     n_hits = scan.n_hits()
-    algo_bytes = 8.0 * n + 16.0 * n_hits
+    hist_kmers = scan.histogram().clone()
+    hits_kmers = scan.finalize() if world == 1 else None
+    algo_bytes = 8.0 * n + 32.0 * n_hits  # 8 B read per k-mer + 32 B per survivor (16 B record + its report row)
     peak, peak_src = peaks()
     achieved = algo_bytes / (k2_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as fh:
             tj = json.load(fh)
-            if int(tj.get("n_kmers", -1)) == n:
-                traffic = tj["dram_bytes_per_launch"]
+            if int(tj.get("n_kmers", -1)) == n and tj.get("kernel") == kernel_label(dm.info):
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gb2_score_kernel<5,32,4>", "kernel_ms": k2_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_label(dm.info), "kernel_ms": k2_ms,
                 "kernel_share_of_step": k2_ms / ms_step, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                "limiter": "shared-memory data pipe 95.9 % busy (ncu --set full, profiles/r01_score_kernel_ncu_full.txt): per 32 k-mers "
-                           "5 conflict-free LDS + 2 ATOMS x 4.17 wavefronts for the exact q-value histogram; the same kernel "
-                           "without the histogram (--no-qvalue) runs at 0.99 of this peak (DESIGN.md sections 6-7)"}
+                "limiter": "shared-memory data pipe (ncu --set full, profiles/): per 32 k-mers n_chunks conflict-free LDS + 2 ATOMS "
+                           "x ~4.2 wavefronts for the exact q-value histogram; the same kernel without the histogram (--no-qvalue) "
+                           "runs at 0.99 of this peak (DESIGN.md sections 6-7)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -285,60 +380,98 @@ def run_ours(args):
         "config": {"workload": f"CTCF MA0139.1 (w=19, uniform bg) on a synthetic {L} bp region x {H} haplotype paths per GPU "
                                f"(1000G-like SNP/indel density), both strands, p<{THRESHOLD:g}, q-values on",
                    "kmers_per_gpu": n, "bytes_resident_per_gpu": 8 * n, "l2_policy": "inputs larger than L2 (no flush needed)",
-                   "parallelism": f"rows sharded by region over {world} GPU(s); one all-reduce of the score histogram",
+                   "parallelism": f"rows sharded by region over {world} GPU(s); one all-reduce of the score histogram, issued by "
+                                  "the library (gb2_allreduce_hist -> ncclAllReduce on the scan's stream)",
                    "hits_per_gpu": n_hits, "kept_after_finalize": kept,
                    "arithmetic": "integer scores as packed u16x2 adds in u32 (both strands per add); p/q-values f64"},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
     }
 
-    # ---- e2e: ASCII k-mers in pinned host memory through gb2_scan_host (rank-local; max over ranks) ----------
-    e2e_rows = n
-    budget = int(mem_available_bytes() * 0.30 / world)
-    if e2e_rows * w > budget:
-        e2e_rows = max(1 << 20, budget // w)
-    if args.e2e_rows:
-        e2e_rows = min(n, args.e2e_rows)
-    host = torch.empty((e2e_rows, w), dtype=torch.uint8, pin_memory=True)
-    chunk = 1 << 24
-    with torch.cuda.stream(ctx.stream):
-        for lo in range(0, e2e_rows, chunk):
-            hi = min(lo + chunk, e2e_rows)
-            host[lo:hi].copy_(synth.windows_to_ascii(windows[lo:hi], w), non_blocking=True)
-    ctx.sync()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    out = engine.scan_host(ctx, dm, host, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23)  # warm-up
-    if world > 1:
-        torch.distributed.barrier()
-    ts = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = engine.scan_host(ctx, dm, host, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23)
-    dt = (time.perf_counter() - ts) / e2e_steps
-    dt = gdist.allreduce_max(dt, device=ctx.device)
-    d2h = int(len(out["row"]) * (8 + 1 + 4 + 8 + 8 + 8) + 5 * 8 + 8)
-    line["e2e"] = {"value": 2.0 * e2e_rows * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(e2e_rows * w),
-                   "d2h_bytes_per_step": d2h, "rows_per_step_per_gpu": int(e2e_rows), "steps": e2e_steps,
-                   "ms_per_step": dt * 1e3, "api": "gb2_scan_host (ASCII k-mers, pinned host memory)",
-                   "hits": int(len(out["row"]))}
-    del host
+    # ---- the same step with the windows formed on the device from the 2-bit haplotype sequences (0.25 B per window of
+    #      HBM traffic instead of 8 B: no longer HBM-bound, the shared-memory pipe is the whole cost) ----------------------
+    ms_seq, kseq_ms, launches_seq, _ = timed_steps("sequences")
+    line["sequence_form"] = {
+        "what": "same step, K2 over 2-bit haplotype sequences (gb2_score_sequences: windows formed in registers by funnel shifts)",
+        "value": total_windows / (ms_seq * 1e-3), "unit": UNIT, "ms_per_step": ms_seq, "kernel_ms": kseq_ms,
+        "bytes_resident_per_gpu": int(seq_words.numel() * 8), "hbm_bytes_per_window": 0.125, "gpu_launches": int(launches_seq),
+        "speedup_vs_kmer_form": ms_step / ms_seq}
 
-    # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload ---------------
+    # ---- parity carried by the bench itself (N>1: across real GPUs; N=1: sequence form == k-mer form at full size) --------
+    if world > 1:
+        parity = parity_multi_gpu(ctx, dm, rank, world)
+    else:
+        parity = parity_single_gpu(ctx, dm, windows, seq_batch, hist_kmers, hits_kmers)
+    line["parity"] = parity
+
+    # ---- e2e: the haplotypes as ASCII text in pinned host memory through gb2_scan_host_sequences (rank-local; max over
+    #      ranks): host->device copy of every base + encode + score + BH + finalize + hit table back, all inside the timer --
+    offs = np.arange(H, dtype=np.int64) * L
+    lens = np.full(H, L, dtype=np.int64)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def time_host(fn):
+        out = fn()  # warm-up (grows the context's staging pool)
+        if world > 1:
+            torch.distributed.barrier()
+        ts = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = fn()
+        dt = (time.perf_counter() - ts) / e2e_steps
+        return ctx.allreduce_max([dt])[0], out
+
+    def hit_bytes(out):
+        return int(len(out["row"]) * (8 + 1 + 4 + 8 + 8 + 8) + 5 * 8 + 8)
+
+    dt, out = time_host(lambda: engine.scan_host_sequences(ctx, dm, host_ascii.view(-1), offs, lens, fmt="ascii", strands=2,
+                                                           threshold=THRESHOLD, hit_capacity=1 << 23))
+    if world == 1 and hits_kmers is not None:
+        parity["e2e_table_equal"] = bool(all(np.array_equal(out[k], hits_kmers[k]) for k in ("row", "strand", "int_score", "p-value", "q-value")))
+        parity["ok"] = bool(parity["ok"] and parity["e2e_table_equal"])
+    line["e2e"] = {"value": 2.0 * n * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(H * L), "d2h_bytes_per_step": hit_bytes(out),
+                   "windows_per_step_per_gpu": int(2 * n), "steps": e2e_steps, "ms_per_step": dt * 1e3,
+                   "api": "gb2_scan_host_sequences(format=ASCII): haplotype sequences as text in pinned host memory, 1 byte per "
+                          "window over PCIe; windows formed on the device", "hits": int(len(out["row"]))}
+    variants = {}
+    # (b) the same sequences already 2-bit packed on the host: 0.25 byte per window over PCIe
+    host_words = torch.empty(seq_words.shape, dtype=torch.int64, pin_memory=True)
+    with torch.cuda.stream(ctx.stream):
+        host_words.copy_(seq_words, non_blocking=True)
+    ctx.sync()
+    woffs = np.arange(H, dtype=np.int64) * seq_words.shape[1]
+    dt2, out2 = time_host(lambda: engine.scan_host_sequences(ctx, dm, host_words.view(-1), woffs, lens, fmt="2bit", strands=2,
+                                                             threshold=THRESHOLD, hit_capacity=1 << 23))
+    variants["sequences_2bit"] = {"value": 2.0 * n * world / dt2, "unit": UNIT, "ms_per_step": dt2 * 1e3,
+                                  "h2d_bytes_per_step": int(host_words.numel() * 8), "d2h_bytes_per_step": hit_bytes(out2),
+                                  "api": "gb2_scan_host_sequences(format=2-bit words)"}
+    del host_words
+    if world == 1 and not args.no_kmer_e2e:
+        # (c), (d): one k-mer per window from the host, as the reference's TSV rows hold them -- a bounded number of rows
+        rows_b = min(n, args.e2e_rows or (1 << 27))
+        host_packed = torch.empty(rows_b, dtype=torch.int64, pin_memory=True)
+        host_kmers = torch.empty((rows_b, w), dtype=torch.uint8, pin_memory=True)
+        chunk = 1 << 24
+        with torch.cuda.stream(ctx.stream):
+            host_packed.copy_(windows[:rows_b], non_blocking=True)
+            for lo in range(0, rows_b, chunk):
+                hi = min(lo + chunk, rows_b)
+                host_kmers[lo:hi].copy_(synth.windows_to_ascii(windows[lo:hi], w), non_blocking=True)
+        ctx.sync()
+        dt3, out3 = time_host(lambda: engine.scan_host_packed(ctx, dm, host_packed, None, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23))
+        variants["kmers_packed"] = {"value": 2.0 * rows_b / dt3, "unit": UNIT, "ms_per_step": dt3 * 1e3, "rows_per_step": int(rows_b),
+                                    "h2d_bytes_per_step": int(rows_b * 8), "d2h_bytes_per_step": hit_bytes(out3),
+                                    "api": "gb2_scan_host_packed (8 bytes per window over PCIe)"}
+        dt4, out4 = time_host(lambda: engine.scan_host(ctx, dm, host_kmers, strands=2, threshold=THRESHOLD, hit_capacity=1 << 23))
+        variants["kmers_ascii"] = {"value": 2.0 * rows_b / dt4, "unit": UNIT, "ms_per_step": dt4 * 1e3, "rows_per_step": int(rows_b),
+                                   "h2d_bytes_per_step": int(rows_b * w), "d2h_bytes_per_step": hit_bytes(out4),
+                                   "api": "gb2_scan_host (w = 19 ASCII bytes per window over PCIe; round 1's e2e entry)"}
+        del host_packed, host_kmers
+    line["e2e_variants"] = variants
+
+    # ---- cpu baseline (rank 0, N=1 only): a bounded sample of the same workload on the host cores ----------------------
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.build()
-        m = dict(score_matrix=motif.score_matrix_acgt(), pval_mat=motif.pval_matrix, min_val=motif.min_val,
-                 scale=motif.scale, offset=float(motif.offset))
-        threads = os.cpu_count() or 1
         with torch.cuda.stream(ctx.stream):
             fwd = synth.windows_to_ascii(windows[: 1 << 23], w).cpu().numpy()
-        calib = np.ascontiguousarray(np.concatenate([fwd[:10000], synth.revcomp_ascii(fwd[:10000])]))
-        rate = calib.shape[0] / time_oracle(calib, m, threads)
-        k = int(max(10000, min(fwd.shape[0], rate * 12.0 / 2)))  # ~12 s of CPU work
-        rows = np.ascontiguousarray(np.concatenate([fwd[:k], synth.revcomp_ascii(fwd[:k])]))
-        t = time_oracle(rows, m, threads)
-        line["cpu_baseline"] = {
-            "value": rows.shape[0] / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{rows.shape[0]} rows = first {k} forward 19-mers of the workload + their reverse-complement rows; "
-                      f"oracle C port of the reference's per-row scoring (incl. two pval_mat sums per row), {threads} threads, {t:.1f} s"}
+        line["cpu_baseline"] = cpu_baseline_block(motif, fwd)
     # ---- graph path (informational, N=1 only): the same region as a variation graph -- reference + phased variants ->
     #      K7 extraction of the haplotype-aware k-mers -> K2/K5/K6 -> report table, no `vg`, no text
     if world == 1 and not args.no_graph_path:
@@ -348,10 +481,33 @@ def run_ours(args):
             line["graph_path"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
+    ok = bool(line["parity"].get("ok", False)) if rank == 0 else True
     if world > 1:
         torch.distributed.barrier()
+        ctx.close()
         torch.distributed.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILED -- " + json.dumps(line["parity"]) + "\n")
+        return 1
     return 0
+
+
+def cpu_baseline_block(motif, fwd):
+    """oracle port on a bounded sample (about 12 s of CPU work) of the forward windows `fwd` + their reverse complements"""
+    from grafimo_b200 import synth
+    from oracle import oracle as orc
+    orc.build()
+    m = dict(score_matrix=motif.score_matrix_acgt(), pval_mat=motif.pval_matrix, min_val=motif.min_val,
+             scale=motif.scale, offset=float(motif.offset))
+    threads = os.cpu_count() or 1
+    calib = np.ascontiguousarray(np.concatenate([fwd[:10000], synth.revcomp_ascii(fwd[:10000])]))
+    rate = calib.shape[0] / time_oracle(calib, m, threads)
+    k = int(max(10000, min(fwd.shape[0], rate * 12.0 / 2)))
+    rows = np.ascontiguousarray(np.concatenate([fwd[:k], synth.revcomp_ascii(fwd[:k])]))
+    t = time_oracle(rows, m, threads)
+    return {"value": rows.shape[0] / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rows.shape[0]} rows = first {k} forward 19-mers of the workload + their reverse-complement rows; "
+                      f"oracle C port of the reference's per-row scoring (incl. two pval_mat sums per row), {threads} threads, {t:.1f} s"}
 
 
 def graph_path_numbers(ctx, motif, L, H):
@@ -401,6 +557,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph-path", action="store_true")
+    ap.add_argument("--no-kmer-e2e", action="store_true", help="skip the two k-mer-per-window host entries (e2e_variants)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -15,6 +15,7 @@ GB2_ERR_CAPACITY = 4
 NARROW_WIDTH = 32  # widest k-mer that fits one packed word
 MAX_WIDTH = 64
 RANGE = 1000
+NCCL_ID_BYTES = 128
 
 
 class GrafimoB200Error(RuntimeError):
@@ -113,6 +114,22 @@ SIGNATURES = {
     "gb2_report_write": (_int, [_vp, _vp, _vp, _vp, _u64]),
     "gb2_scan_host": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp,
                              _vp, ctypes.POINTER(_u64), _vp]),
+    "gb2_scan_host_packed": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    ctypes.POINTER(_u64), _vp]),
+    "gb2_comm_unique_id": (_int, [_vp]),
+    "gb2_comm_init": (_int, [_vp, _vp, _int, _int]),
+    "gb2_comm_destroy": (_int, [_vp]),
+    "gb2_comm_info": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+    "gb2_allreduce_hist": (_int, [_vp, _vp, _i64]),
+    "gb2_allreduce_max_f64": (_int, [_vp, _vp, _i64]),
+    "gb2_allgather_bytes": (_int, [_vp, _vp, _vp, _i64]),
+    "gb2_host_alloc": (_int, [_u64, ctypes.POINTER(_vp)]),
+    "gb2_host_free": (_int, [_vp]),
+    "gb2_encode_sequences": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_score_sequences": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _u64, _int, _dbl, _vp, _vp, _u64, _vp, _vp,
+                                   ctypes.POINTER(_u64)]),
+    "gb2_scan_host_sequences": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, ctypes.POINTER(_u64), _vp]),
 }
 
 _lib = None

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libgrafimo_b200.so")
-SOURCES = ["context.cu", "encode.cu", "tsv.cu", "score.cu", "pval.cu", "qvalue.cu", "scan_host.cu", "graph.cu", "graph_build.cu", "vcf.cu", "report.cu"]
+SOURCES = ["context.cu", "encode.cu", "tsv.cu", "score.cu", "pval.cu", "qvalue.cu", "scan_host.cu", "seqscan.cu", "graph.cu", "graph_build.cu", "vcf.cu", "report.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--fmad=true", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -39,7 +39,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "internal.cuh"), os.path.join(ROOT, "include", "grafimo_b200.h"), os.path.abspath(__file__)]
+    headers = [os.path.join(CSRC, "internal.cuh"), os.path.join(CSRC, "score_common.cuh"), os.path.join(CSRC, "scan_tail.cuh"), os.path.join(ROOT, "include", "grafimo_b200.h"), os.path.abspath(__file__)]
     jobs = []
     objs = []
     for src in SOURCES:
@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
                 if verbose and out:
                     print(out)
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         run(cmd)
     return LIB
 

@@ -1,4 +1,6 @@
 // context.cu -- context / motif lifetime of the grafimo_b200 C ABI (include/grafimo_b200.h).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 
@@ -65,7 +67,11 @@ extern "C" int gb2_ctx_destroy(gb2_ctx *ctx)
     if (!ctx) return GB2_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    gb2_comm_release(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pool) cudaFree(ctx->pool);
+    for (auto &d : ctx->desc)
+        if (d.d_ptr) cudaFree(d.d_ptr);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -109,6 +115,45 @@ int gb2_scratch_reserve(gb2_ctx *ctx, size_t bytes)
     size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
     GB2_CUDA(ctx, cudaMalloc(&ctx->scratch, want));
     ctx->scratch_bytes = want;
+    return GB2_OK;
+}
+
+int gb2_pool_reserve(gb2_ctx *ctx, size_t bytes, char **out)
+{
+    *out = nullptr;
+    if (bytes > ctx->pool_bytes) {
+        GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (ctx->pool) {
+            GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            GB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            GB2_CUDA(ctx, cudaFree(ctx->pool));
+            ctx->pool = nullptr;
+            ctx->pool_bytes = 0;
+        }
+        GB2_CUDA(ctx, cudaMalloc(&ctx->pool, bytes));
+        ctx->pool_bytes = bytes;
+    }
+    *out = (char *)ctx->pool;
+    return GB2_OK;
+}
+
+extern "C" int gb2_host_alloc(uint64_t bytes, void **out)
+{
+    if (!out) return GB2_ERR_ARG;
+    *out = nullptr;
+    if (cudaHostAlloc(out, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return GB2_ERR_NOMEM;
+    }
+    return GB2_OK;
+}
+
+extern "C" int gb2_host_free(void *ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return GB2_ERR_CUDA;
+    }
     return GB2_OK;
 }
 

@@ -23,6 +23,19 @@ struct gb2_ctx {
     size_t scratch_bytes = 0;
     // pinned host mailbox for small device->host reads
     uint64_t *h_mail = nullptr;
+    // grow-only device pool of the host-buffer entry points (gb2_scan_host*): staging + outputs
+    void *pool = nullptr;
+    size_t pool_bytes = 0;
+    // descriptor arrays of the sequence kernels (seqscan.cu), reused while the layout stays the same
+    struct DescSlot {
+        void *d_ptr = nullptr;
+        size_t bytes = 0;
+        uint64_t hash = 0;
+        int64_t n_seqs = -1, total_units = 0;
+    } desc[2];
+    // NCCL communicator of a multi-GPU run (comm.cu); null on one GPU
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 };
 
 struct gb2_motif {
@@ -73,6 +86,9 @@ struct gb2_motif {
 
 // grows the context scratch buffer (stream-ordered free of the old one)
 int gb2_scratch_reserve(gb2_ctx *ctx, size_t bytes);
+// grows the pool of the host-buffer entry points; *out = its base
+int gb2_pool_reserve(gb2_ctx *ctx, size_t bytes, char **out);
+void gb2_comm_release(gb2_ctx *ctx);  // comm.cu
 
 // kernels launched from other translation units
 int gb2_launch_ptable(gb2_ctx *ctx, const double *d_pval_mat, int64_t lo, int64_t span, double *d_ctab,

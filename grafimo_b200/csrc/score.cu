@@ -17,98 +17,7 @@
 //   * the histogram lives in shared memory (u32, one per CTA) and is flushed once per CTA with
 //     64-bit global atomics; hits are rare and are appended with one global atomic per warp;
 //   * persistent grid: one 1024-thread CTA per SM (the tables take most of the 227 KB).
-#include "internal.cuh"
-
-struct ScoreParams {
-    const uint64_t *packed;
-    const uint32_t *nmask;
-    int64_t n;
-    uint64_t row_base;
-    const uint32_t *lut;     // [n_chunks][256]
-    const uint32_t *bitmap;  // hit bitmap over bins, or nullptr when "bin >= cut" is the whole test
-    uint32_t span;           // number of score bins; bin `span` collects N rows
-    uint32_t cut;            // smallest bin that can be a hit
-    int32_t lo;              // absolute score of bin 0
-    int32_t two_strands;
-    unsigned long long *hist;  // global [span+1] or nullptr
-    gb2_hit *hits;
-    unsigned long long hit_capacity;
-    unsigned long long *hit_count;
-    uint32_t *dense;
-};
-
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int IMM>
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
-    return v;
-}
-
-// compiles to ATOMS.POPC.INC (same cost as ATOMS.ADD on B200: tools/ubench_atoms.cu, and merges same-address lanes)
-__device__ __forceinline__ void red_shared_inc(uint32_t addr)
-{
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-}
-
-// Both strands of one packed k-mer (w0 = bases 0..15, w1 = bases 16..31): one byte extract (PRMT), one
-// address add (LEA/IMAD) and one conflict-free LDS per 4-base chunk.  lut32 = shared-window address of
-// the replicated table + 4 * (lane & (R-1)); entry (c, b) sits at lut32 + (c*256 + b) * R * 4.
-template <int C, int NCHUNK, int R>
-struct ChunkSum {
-    static __device__ __forceinline__ uint32_t run(uint32_t w0, uint32_t w1, uint32_t lut32)
-    {
-        const uint32_t word = (C < 4) ? w0 : w1;
-        const uint32_t b = __byte_perm(word, 0u, 0x4440u + (uint32_t)(C & 3));  // PRMT: byte C of the k-mer
-        // table offset of chunk C rides in the LDS immediate; the entry offset is one IMAD/LEA
-        return lds_u32<C * 256 * R * 4>(lut32 + b * (uint32_t)(R * 4)) + ChunkSum<C + 1, NCHUNK, R>::run(w0, w1, lut32);
-    }
-};
-template <int NCHUNK, int R>
-struct ChunkSum<NCHUNK, NCHUNK, R> {
-    static __device__ __forceinline__ uint32_t run(uint32_t, uint32_t, uint32_t) { return 0u; }
-};
-
-template <int NCHUNK, int R>
-__device__ __forceinline__ uint32_t score_word(uint32_t w0, uint32_t w1, uint32_t lut32)
-{
-    return ChunkSum<0, NCHUNK, R>::run(w0, w1, lut32);
-}
-
-// Appends the hits of one (k-mer, strand) slot across the warp: one ballot, one global atomic.
-__device__ __forceinline__ void append_hits(const ScoreParams &p, bool pred, uint64_t row, uint32_t bin, uint32_t strand,
-                                            unsigned lane)
-{
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
-    if (m == 0) return;
-    const int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(p.hit_count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (pred) {
-        const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-        if (slot < p.hit_capacity) {
-            uint4 rec;
-            const uint64_t grow = p.row_base + row;
-            rec.x = (uint32_t)grow;
-            rec.y = (uint32_t)(grow >> 32);
-            rec.z = (uint32_t)(p.lo + (int32_t)bin);
-            rec.w = strand;
-            reinterpret_cast<uint4 *>(p.hits)[slot] = rec;
-        }
-    }
-}
+#include "score_common.cuh"
 
 // dense scores of pair j (k-mers 2j, 2j+1): one 8-byte store when the buffer allows it
 __device__ __forceinline__ void store_dense_pair(uint32_t *dense, int64_t j, uint2 o, bool aligned8)
@@ -119,13 +28,6 @@ __device__ __forceinline__ void store_dense_pair(uint32_t *dense, int64_t j, uin
         dense[2 * j] = o.x;
         dense[2 * j + 1] = o.y;
     }
-}
-
-__device__ __forceinline__ bool bin_hits(const ScoreParams &p, uint32_t bin)
-{
-    if (bin < p.cut || bin >= p.span) return false;  // bin == span: N row, never a hit
-    if (p.bitmap == nullptr) return true;
-    return (p.bitmap[bin >> 5] >> (bin & 31)) & 1u;
 }
 
 // Rare path, entered by the whole warp: exact per-bin test + warp-aggregated append for one pair.
@@ -396,6 +298,32 @@ static int dispatch_r(gb2_ctx *ctx, int R, const ScoreParams &p, size_t smem, in
     }
 }
 
+// p-value cut-off as an integer test: hit <=> ptab[bin] < threshold (strict, resultsTmp.py:305-307)
+int gb2_fill_score_params(gb2_ctx *ctx, const gb2_motif *m, double p_threshold, ScoreParams &p)
+{
+    p.lut = m->d_lut;
+    p.span = (uint32_t)m->span;
+    p.lo = (int32_t)m->lo;
+    const std::vector<double> &pt = m->h_ptab;
+    int64_t cut = m->span;
+    for (int64_t k = 0; k < m->span; ++k)
+        if (pt[(size_t)k] < p_threshold) { cut = k; break; }
+    bool simple = true;
+    for (int64_t k = cut; k < m->span; ++k)
+        if (!(pt[(size_t)k] < p_threshold)) { simple = false; break; }
+    p.cut = (uint32_t)cut;
+    p.bitmap = nullptr;
+    if (!simple) {  // p-value table not monotone across the cut: exact per-bin bitmap
+        std::vector<uint32_t> bm((size_t)gb2_div_up(m->span + 1, 32), 0u);
+        for (int64_t k = cut; k < m->span; ++k)
+            if (pt[(size_t)k] < p_threshold) bm[(size_t)(k >> 5)] |= 1u << (k & 31);
+        GB2_CUDA(ctx, cudaMemcpyAsync(m->d_bitmap, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // bm is a stack-lifetime host buffer
+        p.bitmap = m->d_bitmap;
+    }
+    return GB2_OK;
+}
+
 extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_packed, const uint32_t *d_nmask, int64_t n,
                          uint64_t row_base, int strands, double p_threshold, uint64_t *d_hist, gb2_hit *d_hits,
                          uint64_t hit_capacity, uint64_t *d_hit_count, uint32_t *d_dense)
@@ -417,33 +345,15 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     p.nmask = d_nmask;
     p.n = n;
     p.row_base = row_base;
-    p.lut = m->d_lut;
-    p.span = (uint32_t)m->span;
-    p.lo = (int32_t)m->lo;
     p.two_strands = strands == 2;
     p.hist = (unsigned long long *)d_hist;
     p.hits = d_hits;
     p.hit_capacity = hit_capacity;
     p.hit_count = (unsigned long long *)d_hit_count;
     p.dense = d_dense;
-
-    // p-value cut-off as an integer test: hit <=> ptab[bin] < threshold (strict, resultsTmp.py:305-307)
-    const std::vector<double> &pt = m->h_ptab;
-    int64_t cut = m->span;
-    for (int64_t k = 0; k < m->span; ++k)
-        if (pt[(size_t)k] < p_threshold) { cut = k; break; }
-    bool simple = true;
-    for (int64_t k = cut; k < m->span; ++k)
-        if (!(pt[(size_t)k] < p_threshold)) { simple = false; break; }
-    p.cut = (uint32_t)cut;
-    p.bitmap = nullptr;
-    if (!simple) {  // p-value table not monotone across the cut: exact per-bin bitmap
-        std::vector<uint32_t> bm((size_t)gb2_div_up(m->span + 1, 32), 0u);
-        for (int64_t k = cut; k < m->span; ++k)
-            if (pt[(size_t)k] < p_threshold) bm[(size_t)(k >> 5)] |= 1u << (k & 31);
-        GB2_CUDA(ctx, cudaMemcpyAsync(m->d_bitmap, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // bm is a stack-lifetime host buffer
-        p.bitmap = m->d_bitmap;
+    {
+        const int rc = gb2_fill_score_params(ctx, m, p_threshold, p);
+        if (rc != GB2_OK) return rc;
     }
 
     const size_t smem = (size_t)m->smem_bytes;

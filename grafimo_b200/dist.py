@@ -31,6 +31,21 @@ def init_from_env(backend: str = None) -> Dict[str, int]:
     return dict(rank=rank, world=world, local=local)
 
 
+def init_comm(ctx, group=None):
+    """Gives the library context `ctx` (engine.Context) its own NCCL communicator over the ranks of the current
+    torch.distributed job: rank 0 creates the NCCL unique id, the process group only carries those 128 bytes (the
+    rendezvous), and every later exchange of the scan runs inside the C ABI (gb2_allreduce_hist / gb2_allgather_bytes,
+    csrc/comm.cu).  No-op on one rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        ctx.comm_init(None, 0, 1)
+        return ctx
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(box[0], rank, world)
+    return ctx
+
+
 def shard_bounds(n_items: int, rank: int, world: int):
     """Contiguous, balanced split of n_items rows over the ranks (32-aligned so N-mask words are not shared)."""
     per = (n_items + world - 1) // world
@@ -51,8 +66,12 @@ def assign_chromosomes(lengths: Sequence[int], world: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
-def allreduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum the per-rank score histograms in place (int64[span+1], last bin = N rows).  No-op on one rank."""
+def allreduce_histogram(hist: torch.Tensor, group=None, ctx=None) -> torch.Tensor:
+    """Sum the per-rank score histograms in place (int64[span+1], last bin = N rows).  No-op on one rank.
+    With a context that owns a communicator (init_comm) the all-reduce is issued by the library on the context's
+    stream (gb2_allreduce_hist); otherwise torch.distributed does it (gloo in the CPU tests)."""
+    if ctx is not None and getattr(ctx, "world", 1) > 1:
+        return ctx.allreduce_hist(hist)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return hist

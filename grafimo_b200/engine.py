@@ -84,6 +84,48 @@ class Context:
         with torch.cuda.stream(self.stream):
             return torch.zeros(int(n), dtype=dtype, device=self.device)
 
+    # -- multi-GPU: NCCL communicator owned by the library context (csrc/comm.cu) -------------------
+    world = 1
+    rank = 0
+
+    def comm_unique_id(self):
+        buf = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
+        check(self.lib.gb2_comm_unique_id(buf), "gb2_comm_unique_id", self.h)
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        """Collective over the `world` contexts of a run (one per GPU); `unique_id` = rank 0's comm_unique_id()."""
+        buf = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        check(self.lib.gb2_comm_init(self.h, buf, int(rank), int(world)), "gb2_comm_init", self.h)
+        self.rank, self.world = int(rank), int(world)
+
+    def allreduce_hist(self, hist):
+        """In-place sum over the ranks of an int64 device tensor of score-histogram counters (stream-ordered)."""
+        assert hist.is_cuda and hist.dtype == torch.int64 and hist.is_contiguous()
+        self.enter()
+        hist.record_stream(self.stream)
+        check(self.lib.gb2_allreduce_hist(self.h, _ptr(hist), hist.numel()), "gb2_allreduce_hist", self.h)
+        return hist
+
+    def allreduce_max(self, values):
+        """Element-wise max over the ranks of a few host floats (device-timed durations) -> list of floats."""
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.device)
+        self.enter()
+        t.record_stream(self.stream)
+        check(self.lib.gb2_allreduce_max_f64(self.h, _ptr(t), t.numel()), "gb2_allreduce_max_f64", self.h)
+        self.sync()
+        return t.cpu().tolist()
+
+    def allgather(self, t):
+        """Concatenation over the ranks of equally shaped contiguous device tensors -> tensor [world, *t.shape]."""
+        assert t.is_cuda and t.is_contiguous()
+        self.enter()
+        t.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=self.device)
+        check(self.lib.gb2_allgather_bytes(self.h, _ptr(t), _ptr(out), t.numel() * t.element_size()), "gb2_allgather_bytes", self.h)
+        return out
+
     # -- K1 -----------------------------------------------------------------------------------
     def encode(self, ascii_rows, width=None):
         """uint8 device tensor [n, stride] (ASCII k-mers) -> (packed int64[n] (uint64 bits; int64[n, 2] when the width is
@@ -209,6 +251,74 @@ class DeviceRows:
         return out
 
 
+class SeqBatch:
+    """A batch of sequences on the device in the 2-bit layout of include/grafimo_b200.h ("K2 over sequences"):
+    seq2 int64[words] (32 bases per word), nbits int32[words] or None (1 bit per base: not A/C/G/T), and the host-side
+    layout arrays lens / word_off (int64[n_seqs])."""
+
+    def __init__(self, ctx, lens, seq2=None, nbits=None, word_off=None):
+        self.ctx = ctx
+        self.lens = np.ascontiguousarray(lens, dtype=np.int64)
+        self.n_seqs = int(self.lens.shape[0])
+        words = (self.lens + 31) // 32
+        if word_off is None:
+            word_off = np.concatenate([[0], np.cumsum(words)[:-1]]) if self.n_seqs else np.zeros(0)
+        self.word_off = np.ascontiguousarray(word_off, dtype=np.int64)
+        self.n_words = int((self.word_off + words).max()) if self.n_seqs else 0
+        self.seq2 = seq2 if seq2 is not None else ctx.empty(max(self.n_words, 1), torch.int64)
+        self.nbits = nbits
+
+    def n_windows(self, w):
+        return int(np.maximum(self.lens - int(w) + 1, 0).sum())
+
+    def window_base(self, w):
+        """int64[n_seqs + 1]: row index of the first window of every sequence (exclusive prefix of the window counts)."""
+        return np.concatenate([[0], np.cumsum(np.maximum(self.lens - int(w) + 1, 0))]).astype(np.int64)
+
+    @classmethod
+    def from_ascii(cls, ctx, text, text_off, lens, want_nbits=True):
+        """text: uint8 device tensor; sequence s = text[text_off[s] : text_off[s] + lens[s]] (ASCII, any case).
+        -> (SeqBatch, counts int64[2] device tensor = bases not ACGT, bases neither ACGT nor N)."""
+        assert text.is_cuda and text.dtype == torch.uint8 and text.dim() == 1 and text.is_contiguous()
+        b = cls(ctx, lens)
+        toff = np.ascontiguousarray(text_off, dtype=np.int64)
+        ctx.enter()
+        text.record_stream(ctx.stream)
+        b.nbits = ctx.empty(max(b.n_words, 1), torch.int32) if want_nbits else None
+        counts = ctx.zeros(2, torch.int64)
+        check(ctx.lib.gb2_encode_sequences(ctx.h, _ptr(text), text.shape[0], b.n_seqs, _np_ptr(toff), _np_ptr(b.lens),
+                                           _np_ptr(b.word_off), _ptr(b.seq2), _ptr(b.nbits), _ptr(counts)),
+              "gb2_encode_sequences", ctx.h)
+        ctx.leave()
+        return b, counts
+
+
+def pack_sequences_2bit(seqs):
+    """Host-side (numpy) packer of a list of ACGTN strings into the 2-bit layout: (words uint64, nbits uint32, word_off
+    int64, lens int64).  For callers / tests that hold sequences on the host; the device encoder is gb2_encode_sequences."""
+    lens = np.array([len(x) for x in seqs], dtype=np.int64)
+    nwords = (lens + 31) // 32
+    word_off = np.concatenate([[0], np.cumsum(nwords)[:-1]]).astype(np.int64) if len(seqs) else np.zeros(0, np.int64)
+    total = int(nwords.sum())
+    words = np.zeros(max(total, 1), dtype=np.uint64)
+    nbits = np.zeros(max(total, 1), dtype=np.uint32)
+    code = np.full(256, 4, dtype=np.uint8)
+    for k, ch in enumerate(b"ACGT"):
+        code[ch] = k
+        code[ch + 32] = k
+    for x, off, n in zip(seqs, word_off, lens):
+        if n == 0:
+            continue
+        c = code[np.frombuffer(x.encode("ascii"), dtype=np.uint8)]
+        pad = (-n) % 32
+        bad = np.concatenate([c > 3, np.zeros(pad, dtype=bool)]).reshape(-1, 32)
+        c2 = np.concatenate([np.where(c > 3, 0, c), np.zeros(pad, dtype=np.uint8)]).astype(np.uint64).reshape(-1, 32)
+        sh = (2 * np.arange(32, dtype=np.uint64))[None, :]
+        words[off:off + c2.shape[0]] = np.bitwise_or.reduce(c2 << sh, axis=1)
+        nbits[off:off + c2.shape[0]] = np.bitwise_or.reduce(bad.astype(np.uint32) << np.arange(32, dtype=np.uint32)[None, :], axis=1)
+    return words, nbits, word_off, lens
+
+
 class DeviceMotif:
     """Device-resident motif: chunk LUTs + the score -> p-value table (K4)."""
 
@@ -295,6 +405,9 @@ class Scan:
             raise ValueError(f"k-mers of a width-{self.motif.width} motif must be packed as "
                              f"{'int64[n, 2]' if wide else 'int64[n]'}")
         ctx.enter()
+        packed.record_stream(ctx.stream)  # the caller may free / reuse its tensors right after this asynchronous call
+        if nmask is not None:
+            nmask.record_stream(ctx.stream)
         if self.dense_rows:
             if self.first_row is None:
                 self.first_row = int(row_base)
@@ -307,6 +420,31 @@ class Scan:
               "gb2_score", ctx.h)
         self.rows_scored += n
         self.row_limit = max(self.row_limit, int(row_base) + n)
+
+    def score_sequences(self, batch, row_base=0):
+        """K2 over a SeqBatch (2-bit sequences on the device): every window of every sequence, formed in registers.
+        Window i of sequence s gets row index row_base + (windows of the sequences before s) + i."""
+        lib, ctx = self.ctx.lib, self.ctx
+        if self.motif.width > _lib.NARROW_WIDTH:
+            raise ValueError("sequence scoring takes motifs of at most 32 bp; wider motifs use packed k-mers")
+        n_win = batch.n_windows(self.motif.width)
+        ctx.enter()
+        dense_out = None
+        if self.dense_rows:
+            if self.first_row is None:
+                self.first_row = int(row_base)
+            if int(row_base) != self.first_row + self.rows_scored or self.rows_scored + n_win > self.dense_rows:
+                raise ValueError("dense scan: batches must be consecutive rows within dense_rows")
+            dense_out = self.dense[self.rows_scored:]
+        nw = ctypes.c_uint64(0)
+        check(lib.gb2_score_sequences(ctx.h, self.motif.h, _ptr(batch.seq2), _ptr(batch.nbits), batch.n_seqs, _np_ptr(batch.lens),
+                                      _np_ptr(batch.word_off), None, int(row_base), self.strands, self.threshold, _ptr(self.hist),
+                                      _ptr(self.hits), self.capacity if self.hits is not None else 0, _ptr(self.counters),
+                                      _ptr(dense_out), ctypes.byref(nw)), "gb2_score_sequences", ctx.h)
+        assert int(nw.value) == n_win
+        self.rows_scored += n_win
+        self.row_limit = max(self.row_limit, int(row_base) + n_win)
+        return n_win
 
     def histogram(self):
         return self.hist
@@ -412,6 +550,9 @@ class ManyScan:
         if n >= (1 << self.ROW_BITS):
             raise ValueError("at most 2^40 - 1 rows per motif")
         ctx.enter()
+        packed.record_stream(ctx.stream)
+        if nmask is not None:
+            nmask.record_stream(ctx.stream)
         check(ctx.lib.gb2_score(ctx.h, mo.h, _ptr(packed), _ptr(nmask), n, int(m) << self.ROW_BITS, self.strands, self.threshold,
                                 self._at(self.hist, m, 8), _ptr(self.hits), self.capacity, _ptr(self.counters), None),
               "gb2_score", ctx.h)
@@ -474,6 +615,65 @@ def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False,
         out["q-value"] = q[:k]
     out["stats"] = dict(windows=int(stats[0]), n_rows=int(stats[1]), bad_rows=int(stats[2]), hits=int(stats[3]))
     return out
+
+
+def _host_outputs(cap, want_q):
+    row = np.empty(cap, np.uint64); strand = np.empty(cap, np.uint8); isc = np.empty(cap, np.int32)
+    score = np.empty(cap, np.float64); p = np.empty(cap, np.float64); q = np.empty(cap, np.float64) if want_q else None
+    return row, strand, isc, score, p, q
+
+
+def _host_result(k, row, strand, isc, score, p, q, want_q, stats, names):
+    out = {"row": row[:k], "strand": strand[:k], "int_score": isc[:k], "score": score[:k], "p-value": p[:k]}
+    if want_q:
+        out["q-value"] = q[:k]
+    out["stats"] = {n: int(v) for n, v in zip(names, stats)}
+    return out
+
+
+def _host_base(a):
+    if isinstance(a, torch.Tensor):
+        assert not a.is_cuda and a.is_contiguous()
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def scan_host_packed(ctx, motif, packed, nmask=None, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):
+    """gb2_scan_host_packed: 2-bit packed k-mers in host memory (numpy uint64/int64 or pinned torch int64; [n] or [n, 2]
+    for a motif wider than 32) -> dict of numpy columns (+ stats)."""
+    n = int(packed.shape[0])
+    cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n * strands, 1 << 26)))
+    row, strand, isc, score, p, q = _host_outputs(cap, want_q)
+    nh = ctypes.c_uint64(0)
+    stats = np.zeros(4, np.uint64)
+    rc = ctx.lib.gb2_scan_host_packed(ctx.h, motif.h, ctypes.c_void_p(_host_base(packed)),
+                                      ctypes.c_void_p(_host_base(nmask)) if nmask is not None else None, n, int(strands),
+                                      float(threshold), int(bool(q_filter)), int(bool(want_q)), cap, _np_ptr(row), _np_ptr(strand),
+                                      _np_ptr(isc), _np_ptr(score), _np_ptr(p), _np_ptr(q) if want_q else None, ctypes.byref(nh),
+                                      _np_ptr(stats))
+    check(rc, "gb2_scan_host_packed", ctx.h)
+    return _host_result(int(nh.value), row, strand, isc, score, p, q, want_q, stats, ("windows", "n_rows", "bad_rows", "hits"))
+
+
+def scan_host_sequences(ctx, motif, data, offsets, lens, fmt="ascii", nbits=None, strands=1, threshold=1e-4, q_filter=False,
+                        want_q=True, hit_capacity=None):
+    """gb2_scan_host_sequences: whole sequences in host memory -> hit table.  fmt "ascii": data = uint8 bytes, offsets =
+    byte offset of every sequence; fmt "2bit": data = uint64/int64 words (32 bases each), offsets = word offsets, nbits =
+    optional uint32 per word.  Rows are window indices (sequence-major, see include/grafimo_b200.h)."""
+    offs = np.ascontiguousarray(offsets, dtype=np.int64)
+    ln = np.ascontiguousarray(lens, dtype=np.int64)
+    n_win = int(np.maximum(ln - motif.width + 1, 0).sum())
+    cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n_win * strands, 1 << 26)))
+    row, strand, isc, score, p, q = _host_outputs(cap, want_q)
+    nh = ctypes.c_uint64(0)
+    stats = np.zeros(4, np.uint64)
+    rc = ctx.lib.gb2_scan_host_sequences(ctx.h, motif.h, 0 if fmt == "ascii" else 1, ctypes.c_void_p(_host_base(data)),
+                                         ctypes.c_void_p(_host_base(nbits)) if nbits is not None else None, offs.shape[0],
+                                         _np_ptr(offs), _np_ptr(ln), int(strands), float(threshold), int(bool(q_filter)),
+                                         int(bool(want_q)), cap, _np_ptr(row), _np_ptr(strand), _np_ptr(isc), _np_ptr(score),
+                                         _np_ptr(p), _np_ptr(q) if want_q else None, ctypes.byref(nh), _np_ptr(stats))
+    check(rc, "gb2_scan_host_sequences", ctx.h)
+    return _host_result(int(nh.value), row, strand, isc, score, p, q, want_q, stats, ("windows", "n_bases", "bad_bases", "hits"))
 
 
 def bh_from_pvalues(ctx, pvalues):

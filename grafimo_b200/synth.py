@@ -76,6 +76,35 @@ def haplotype_windows(region_len, n_hap, w, seed, device="cpu", hap_batch=32, ou
     return out, model
 
 
+def pack_codes_2bit(codes):
+    """int64 [H, L] base codes -> int64 [H, ceil(L/32)] words of the 2-bit sequence layout (base i of a row in bits
+    2(i & 31) of word i >> 5; include/grafimo_b200.h, "K2 over sequences")."""
+    H, L = codes.shape
+    nw = (L + 31) // 32
+    pad = nw * 32 - L
+    if pad:
+        codes = torch.cat([codes, torch.zeros((H, pad), dtype=codes.dtype, device=codes.device)], dim=1)
+    sh = 2 * torch.arange(32, device=codes.device, dtype=torch.int64)
+    return ((codes.view(H, nw, 32) & 3) << sh[None, None, :]).sum(dim=2)  # disjoint bit fields: the sum is an OR
+
+
+def haplotype_sequences(region_len, n_hap, seed, device="cpu", hap_batch=32, ascii_out=None):
+    """The same haplotypes as `haplotype_windows` (same seed -> same bases) as whole sequences: int64 [n_hap, ceil(L/32)]
+    2-bit words on `device`; when `ascii_out` (uint8 [n_hap, region_len], e.g. pinned host memory) is given it receives
+    the ASCII letters as well."""
+    model = variant_model(region_len, n_hap, seed, device=device)
+    nw = (region_len + 31) // 32
+    words = torch.empty((n_hap, nw), dtype=torch.int64, device=device)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    for lo in range(0, n_hap, hap_batch):
+        hi = min(lo + hap_batch, n_hap)
+        codes = haplotype_codes(model, lo, hi)
+        words[lo:hi] = pack_codes_2bit(codes)
+        if ascii_out is not None:
+            ascii_out[lo:hi].copy_(lut[codes], non_blocking=True)
+    return words, model
+
+
 def windows_to_ascii(packed, w, out=None):
     """int64 [n] packed windows -> uint8 [n, w] ASCII k-mers (on the tensor's device)."""
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=packed.device)

@@ -48,6 +48,7 @@ extern "C" {
 #define GB2_NARROW_WIDTH 32 /* widest k-mer that fits one packed word */
 #define GB2_MAX_WIDTH 64
 #define GB2_RANGE 1000 /* src/grafimo/utils.py:26 */
+#define GB2_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
 
 enum {
     GB2_OK = 0,
@@ -99,6 +100,26 @@ const char *gb2_ctx_last_error(const gb2_ctx *ctx);
 int64_t gb2_ctx_launch_count(const gb2_ctx *ctx);
 int gb2_device_count(void);
 int gb2_ctx_sm_count(const gb2_ctx *ctx);
+
+/* ---- multi-GPU: the context owns the NCCL communicator ---------------------------------------------------- */
+/* Replaces the Manager-dict funnel and the parent-side merge that precede the q-value step in the reference
+ * (score_sequences.py:115-118,171-188,194-198): one process (or host thread) per GPU scores its own shard, then
+ *   gb2_allreduce_hist   sums the per-GPU score histograms in place (uint64[n], ncclAllReduce on the context's stream) --
+ *                        after it gb2_qvalues_from_hist gives the same, globally exact q-table on every GPU;
+ *   gb2_allgather_bytes  concatenates equally sized byte blocks of every rank (d_recv holds world * bytes_per_rank bytes,
+ *                        rank r's block at r * bytes_per_rank) -- used to merge the fixed-width hit columns on the device;
+ *   gb2_allreduce_max_f64 element-wise maximum of doubles (device-timed durations: "max over ranks").
+ * Rendezvous: rank 0 calls gb2_comm_unique_id and hands the 128 bytes to the other ranks by any means (file, MPI,
+ * torch.distributed store, ...); then every rank calls gb2_comm_init (collective).  With world == 1 gb2_comm_init needs
+ * no id and every collective is a no-op / local copy.  NCCL is bound at run time (libnccl.so.2 as already loaded by the
+ * process, else the system library; GB2_NCCL_LIB overrides); GB2_ERR_STATE when it cannot be found. */
+int gb2_comm_unique_id(uint8_t *id /* [GB2_NCCL_ID_BYTES] */);
+int gb2_comm_init(gb2_ctx *ctx, const uint8_t *id, int rank, int world);
+int gb2_comm_destroy(gb2_ctx *ctx);
+int gb2_comm_info(const gb2_ctx *ctx, int *rank, int *world);
+int gb2_allreduce_hist(gb2_ctx *ctx, uint64_t *d_hist, int64_t n);
+int gb2_allreduce_max_f64(gb2_ctx *ctx, double *d_values, int64_t n);
+int gb2_allgather_bytes(gb2_ctx *ctx, const void *d_send, void *d_recv, int64_t bytes_per_rank);
 
 /* ---- K1: k-mer encoder ------------------------------------------------------------------ */
 /* Replaces the per-row string handling of score_seqs (score_sequences.py:279,286,375-386):
@@ -246,6 +267,56 @@ int gb2_scan_host(gb2_ctx *ctx, const gb2_motif *motif, const uint8_t *h_ascii, 
                   int64_t stride, int strands, double p_threshold, int q_filter, int want_q,
                   uint64_t hit_capacity, uint64_t *h_row, uint8_t *h_strand, int32_t *h_iscore,
                   double *h_score, double *h_p, double *h_q, uint64_t *h_n_hits, uint64_t *h_stats);
+
+/* The same call for k-mers that are already 2-bit packed in host memory (8 bytes per k-mer instead of w; 16 when the
+ * motif is wider than 32): h_packed as d_packed of gb2_score, h_nmask the N mask (may be NULL = no N rows).
+ * h_stats[1], h_stats[2] are 0 (the caller made the mask). */
+int gb2_scan_host_packed(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *h_packed, const uint32_t *h_nmask,
+                         int64_t n, int strands, double p_threshold, int q_filter, int want_q, uint64_t hit_capacity,
+                         uint64_t *h_row, uint8_t *h_strand, int32_t *h_iscore, double *h_score, double *h_p, double *h_q,
+                         uint64_t *h_n_hits, uint64_t *h_stats);
+/* pinned (page-locked) host memory for the h_* inputs of the gb2_scan_host* calls: full PCIe bandwidth, and the copies
+ * overlap the kernels.  Any host memory works; pageable memory is staged by the driver. */
+int gb2_host_alloc(uint64_t bytes, void **out);
+int gb2_host_free(void *ptr);
+
+/* ---- K2 over sequences: windows formed on the device ------------------------------------------------------- */
+/* The reference scores one text row per window (score_seqs, score_sequences.py:273-321), so a base of a haplotype is
+ * read w times.  When the caller holds the SEQUENCES (every window of every haplotype is to be scored: the workload the
+ * headline metric is quoted on), these entry points take them as they are -- 2 bits or one ASCII byte per base -- and
+ * form the windows in registers: window i of sequence s is bases [i, i+w) and gets the row index
+ * row_base + (windows of sequences 0..s-1) + i (or row_base + h_row_base[s] + i), exactly the index it would have in the
+ * expanded list of k-mers given to gb2_score / gb2_scan_host.  Sequences shorter than w have no window.
+ *
+ * 2-bit layout: sequence s occupies words [h_word_off[s], h_word_off[s] + ceil(h_len[s] / 32)) of d_seq2; base i sits in
+ * bits [2(i & 31), 2(i & 31) + 1] of word h_word_off[s] + (i >> 5), A=0 C=1 G=2 T=3 (the packed k-mer layout).
+ * d_nbits (may be NULL: no such base) has one uint32 per word: bit (i & 31) set = base i is not A/C/G/T; a window touching
+ * such a base is an N row (score = min_val, p = 1, score_sequences.py:376-378; histogram bin `span`).
+ *
+ * gb2_encode_sequences: ASCII (any case) -> that layout.  Sequence s = bytes [h_text_off[s], h_text_off[s] + h_len[s]) of
+ * d_text.  d_counts[0] += bases that are not ACGTacgt, d_counts[1] += those that are not N/n either (undefined in the
+ * reference; treated like N).  d_nbits / d_counts may be NULL.
+ * gb2_score_sequences: as gb2_score (same histogram, hit records, dense scores indexed by window, thresholds), motif
+ * width <= 32.  *h_n_windows (may be NULL) = windows scored per strand. */
+int gb2_encode_sequences(gb2_ctx *ctx, const uint8_t *d_text, int64_t text_bytes, int64_t n_seqs, const int64_t *h_text_off,
+                         const int64_t *h_len, const int64_t *h_word_off, uint64_t *d_seq2, uint32_t *d_nbits,
+                         uint64_t *d_counts);
+int gb2_score_sequences(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_seq2, const uint32_t *d_nbits,
+                        int64_t n_seqs, const int64_t *h_len, const int64_t *h_word_off, const int64_t *h_row_base,
+                        uint64_t row_base, int strands, double p_threshold, uint64_t *d_hist, gb2_hit *d_hits,
+                        uint64_t hit_capacity, uint64_t *d_hit_count, uint32_t *d_dense, uint64_t *h_n_windows);
+/* gb2_scan_host for sequences in HOST memory.  format 0: h_data = ASCII bytes, h_off[s] = byte offset of sequence s
+ * (h_nbits must be NULL); format 1: h_data = 2-bit words (layout above), h_off[s] = word offset, h_nbits optional.
+ * Host->device traffic: one byte (format 0) or a quarter byte (format 1) per base, i.e. per window -- against w bytes
+ * per window for gb2_scan_host.  The batch is copied in chunks (long sequences are cut into pieces overlapping by w-1
+ * bases) while the previous chunk is encoded and scored.  Outputs as gb2_scan_host; h_row = window index as defined
+ * above; h_stats = {windows scored (both strands), non-ACGT bases, bases that are neither ACGT nor N, hits before the
+ * q filter} (the two base counts are 0 for format 1). */
+int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *motif, int format, const void *h_data, const uint32_t *h_nbits,
+                            int64_t n_seqs, const int64_t *h_off, const int64_t *h_len, int strands, double p_threshold,
+                            int q_filter, int want_q, uint64_t hit_capacity, uint64_t *h_row, uint8_t *h_strand,
+                            int32_t *h_iscore, double *h_score, double *h_p, double *h_q, uint64_t *h_n_hits,
+                            uint64_t *h_stats);
 
 /* ---- K7: k-mer extraction from a variation graph ---------------------------------- */
 /* Replaces the external `vg find -p REGION -x XG -H GBWT -K w -E` call the reference issues per BED region

@@ -12,13 +12,19 @@ recursion, every haplotype spelled out base by base) and is pinned on what the r
   * tests/test_data/input/test.fa + test.vcf.gz  ->  tests/test_data/expected_results/expected_seqs.tsv
     (`vg find -x test.xg -E -p x:0-20 -K 19`, tests/grafimo_run_test.py:49-63): all 32 lines, every field,
     including the node path column -- committed as tests/golden/fixtures.json["expected_seqs_tsv"];
-  * the structure of tests/test_data/input/width_19/scoring_test_input.tsv (SURVEY.md 8a "observed structure"):
-    '-' rows are mirrored '+' rows, walks with no haplotype support are emitted with frequency 0, the `ref` flag
-    is "every node of the walk lies on the reference path" (a walk through a deletion edge is flagged `ref`).
+  * tests/test_data/input/width_19/scoring_test_input.tsv -- REAL `vg find -K 19 -E -H gbwt` output for
+    22:19723256-19723526 of the 1000-Genomes graph (704 rows, 5096 haplotypes, five SNPs and a 2-bp deletion; the
+    reference's own test_scoring input).  tests/fixture_graph.py reconstructs that region's reference bases, alleles,
+    carrier counts and node layout from the rows themselves, and this oracle then prints EXACTLY those 704 lines:
+    sequence, start, stop, strand, haplotype frequency (5096 ... 1 and the 0 of the recombinant walk), `ref` flag
+    (the 36 walks through the deletion edge span 21 bp and are flagged `ref`, as vg does), and vg's node ids
+    (tests/test_graph_cpu.py::test_oracle_reproduces_real_vg_kmer_fixture; K7 is held to the same lines in
+    tests/test_gpu_graph.py::test_extract_equals_real_vg_kmer_fixture).
 
-Parity status: PINNED for SNP-only graphs (the fixture); the coordinates of walks that begin or end inside an
-inserted / multi-base alternative allele are a documented choice (nearest reference position, clamped to the allele's
-reference span), NOT pinned by anything in the reference tree.
+Parity status: PINNED on real vg output for SNPs, deletions (coordinates of walks through a deletion edge, their `ref`
+flag) and haplotype frequencies including 0.  NOT pinned by anything in the reference tree (no fixture holds one): the
+coordinates reported for walks that begin or end INSIDE an inserted / multi-base alternative allele -- a documented
+choice (nearest reference position, clamped to the allele's reference span).
 
 Model.  Variants are (pos0, ref_allele, alt_allele), already reduced (shared prefix/suffix removed); the graph is
 the reference cut at every allele boundary, one node per reference segment and per non-empty alternative allele

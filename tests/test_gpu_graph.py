@@ -45,6 +45,51 @@ def test_extract_equals_reference_vg_fixture(ctx):
 
 
 @pytest.mark.parametrize("builder", ["numpy", "native"])
+def test_extract_equals_real_vg_kmer_fixture(ctx, builder):
+    """K7 pinned on REAL vg output: the local graph of the reference's 704-row fixture (reconstructed from its own rows,
+    tests/fixture_graph.py) -> exactly those 704 lines: sequence, start, stop, strand, haplotype frequency (0 included),
+    ref flag, node path -- the 36 rows through the 2-bp deletion included."""
+    import fixture_graph as fg
+    from grafimo_b200.extract_regions import DeviceGraph
+    from grafimo_b200.vgraph import VariationGraph
+    c = fg.reconstruct(gu.fixtures()["scoring_input_tsv"])
+    if builder == "numpy":
+        dg = VariationGraph.build(c["chrom"], c["ref"], c["variants"], c["gt"]).to_device(ctx)
+    else:
+        dg = DeviceGraph.build(ctx, c["chrom"], c["ref"], c["variants"], gt=c["gt"])
+        dg.graph = VariationGraph.build(c["chrom"], c["ref"], c["variants"], c["gt"])
+    rows = dg.extract([c["local_region"]], c["w"], want_walks=True)
+    lines = fg.shift_lines(rows.to_vg_tsv()[0], c)
+    exp = [r["line"] for r in c["rows"]]
+    assert rows.n == 352 and sorted(lines) == sorted(exp)
+
+
+def test_real_vg_fixture_graph_to_reference_scoring_table(ctx, tmp_path):
+    """The whole replacement path on the reference's own data: reconstructed graph -> K7 -> K2/K5/K6 -> report table ==
+    tests/test_data/expected_results/scoring_results.tsv (what the unmodified reference made of vg's rows; its test_scoring
+    golden), after shifting the local coordinates back."""
+    import io
+    import pandas as pd
+    import fixture_graph as fg
+    from grafimo_b200 import score_sequences as ss
+    from grafimo_b200.extract_regions import DeviceGraph
+    ss._ctx = ctx
+    fx = gu.fixtures()
+    c = fg.reconstruct(fx["scoring_input_tsv"])
+    motif = _motif(tmp_path)
+    dg = DeviceGraph.build(ctx, c["chrom"], c["ref"], c["variants"], gt=c["gt"])
+    rows = dg.extract([c["local_region"]], c["w"])
+    df = ss.compute_results_rows(motif, rows, True, _Args(threshold=1.0, recomb=True))
+    exp = pd.read_csv(io.StringIO(fx["scoring_results_tsv"]), sep="\t", index_col=0, float_precision="round_trip")
+    assert len(df) == len(exp) == 704
+    got = {k: df[k].to_numpy() for k in df.columns}
+    got["start"] = got["start"] + c["offset"]
+    got["stop"] = got["stop"] + c["offset"]
+    cols = ["start", "stop", "strand", "score", "p-value", "q-value", "matched_sequence", "haplotype_frequency", "reference"]
+    gu.assert_tables_equal(got, {k: exp[k].to_numpy() for k in exp.columns}, cols)
+
+
+@pytest.mark.parametrize("builder", ["numpy", "native"])
 @pytest.mark.parametrize("seed", range(6))
 def test_extract_equals_oracle_random_graphs(ctx, seed, builder):
     """Both graph builders -- vgraph.VariationGraph.build (numpy, host arrays -> gb2_graph_create) and the library's

@@ -195,3 +195,39 @@ def test_graph_builder_ranges_with_parallel_edges_to_merge():
     # the merged edges exist: fewer CSR edges than a graph where the long deletions are left out
     fewer = _build_stats(ref, [v for v in vs if len(v[1]) != 4], gt[[i for i, v in enumerate(vs) if len(v[1]) != 4]], 1, 0)
     assert one[1] == fewer[1]
+
+
+# ---- pinned on REAL vg output: the reference's 704-row k-mer fixture ---------------------------------------------------
+def test_oracle_reproduces_real_vg_kmer_fixture():
+    """tests/test_data/input/width_19/scoring_test_input.tsv (what `vg find -K 19 -E -H` printed for
+    22:19723256-19723526 of the 1000-Genomes graph): the local graph is reconstructed from the rows themselves
+    (tests/fixture_graph.py) and the oracle must print exactly those 704 lines -- sequence, start, stop, strand, haplotype
+    frequency (0 for the recombinant walk included), ref flag, vg node ids -- including the 36 rows through the 2-bp
+    deletion (21-bp span, flagged `ref`: score_sequences.py:305-307 rewrites them later)."""
+    import fixture_graph as fg
+    c = fg.reconstruct(gu.fixtures()["scoring_input_tsv"])
+    assert sorted((p, r, a) for p, r, a in c["variants"]) == [(56, "C", "T"), (124, "C", "T"), (142, "G", "A"), (201, "G", "A"),
+                                                               (243, "TG", ""), (296, "C", "T")]
+    g = go.build_graph(c["ref"], c["variants"])
+    rows = go.extract_rows(g, [list(map(int, r)) for r in c["gt"]], c["local_region"], c["w"])
+    lines = fg.shift_lines(go.vg_tsv_lines(rows, c["chrom"], c["local_region"]), c)
+    exp = [r["line"] for r in c["rows"]]
+    assert len(exp) == 704 and sorted(lines) == sorted(exp)
+    spans = [abs(r["stop"] - r["start"]) for r in c["rows"]]
+    assert spans.count(21) == 36 and all(r["ref"] == "ref" for r in c["rows"] if abs(r["stop"] - r["start"]) == 21)
+    assert sum(r["freq"] == 0 for r in c["rows"]) == 2  # the recombinant walk, both orientations
+
+
+def test_builder_reproduces_real_vg_kmer_fixture():
+    """the host-side graph arrays (vgraph.VariationGraph.build -- what gb2_graph_create uploads) walked in plain Python:
+    the same 352 forward rows, node ids included"""
+    import fixture_graph as fg
+    from grafimo_b200.vgraph import VariationGraph
+    c = fg.reconstruct(gu.fixtures()["scoring_input_tsv"])
+    g = VariationGraph.build(c["chrom"], c["ref"], c["variants"], c["gt"])
+    got = gr.rows_from_arrays(g, c["local_region"], c["w"])
+    off, noff = c["offset"], c["node_offset"]
+    got = sorted((s + off, e + off, seq, f, "ref" if isref else "non.ref", tuple(n + noff for n in nodes))
+                 for s, e, seq, f, isref, nodes in got)
+    exp = sorted((r["start"], r["stop"], r["seq"], r["freq"], r["ref"], tuple(r["nodes"])) for r in c["rows"] if r["strand"] == "+")
+    assert len(exp) == 352 and got == exp
