@@ -20,6 +20,7 @@ host<->device copies inside the timed region).  `cpu_baseline` / `--impl referen
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -118,7 +119,69 @@ def time_oracle(rows, m, threads):
     return time.perf_counter() - t0
 
 
+def write_kmer_tsvs(rows, directory, n_files, width):
+    """The reference's input: `vg find -K w -E`-format TSVs (7 columns) under <directory>/width_<w>/, `rows` (uint8 [n, w],
+    forward k-mers followed by their reverse-complement rows) split over n_files files."""
+    d = os.path.join(directory, f"width_{width}")
+    os.makedirs(d, exist_ok=True)
+    n = rows.shape[0]
+    half = n // 2
+    kmers = np.ascontiguousarray(rows).view(f"S{width}").ravel()
+    per = (n + n_files - 1) // n_files
+    for f in range(n_files):
+        lo, hi = f * per, min(n, (f + 1) * per)
+        if lo >= hi:
+            break
+        with open(os.path.join(d, f"part{f:03d}.tsv"), "wb") as fh:
+            out = []
+            for i in range(lo, hi):
+                pos = i % half
+                if i < half:
+                    out.append(b"1:0-1000000\t%s\t1:%d+\t1:%d+\t1\tref\t1+,\n" % (kmers[i], pos, pos + width))
+                else:
+                    out.append(b"1:0-1000000\t%s\t1:%d-\t1:%d-\t1\tref\t1-,\n" % (kmers[i], pos + width, pos))
+            fh.write(b"".join(out))
+    return d
+
+
+def reference_objects(cores):
+    """(motif built by the reference's own build_motif_meme, Findmotif-like args, compute_results, warm-up) from oracle/_ref --
+    the UNMODIFIED reference, byte-compiled by oracle/build_ref.py -- or None when it is not available."""
+    from oracle import build_ref
+    if not build_ref.build():
+        return None
+    import contextlib
+    import io
+    from grafimo.motif_ops import build_motif_meme
+    from grafimo.score_sequences import compute_results, compute_score_seq
+    from grafimo.workflow import Findmotif
+    tmp = tempfile.mkdtemp(prefix="gb2_refarm_")
+    path = os.path.join(tmp, "MA0139.1.meme")
+    with open(path, "w") as fh:
+        fh.write(load_fixture_motif_text())
+    with contextlib.redirect_stdout(io.StringIO()):
+        motif = build_motif_meme(path, "unfrm_dst", 0.1, False, 1, False, True)[0]
+    wf = object.__new__(Findmotif)  # the attributes compute_results reads (score_sequences.py:93-99)
+    wf._cores, wf._thresh, wf._no_qvalue, wf._qvalueT, wf._no_rev, wf._recomb, wf._verbose = cores, THRESHOLD, False, False, False, False, False
+    # numba compiles compute_score_seq at its first call; do that once here, in the parent, so that the forked workers
+    # inherit the machine code (JIT time is not part of the measured rate, SURVEY.md 8d)
+    compute_score_seq("A" * motif.width, motif.score_matrix, motif.pval_matrix, motif.min_val, motif.scale, motif.width, motif.offset)
+    return motif, wf, compute_results
+
+
+def time_reference(compute_results, motif, wf, directory):
+    import contextlib
+    import io
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        df = compute_results(motif, directory, True, wf)
+    return time.perf_counter() - t0, len(df)
+
+
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores -- its compute_results
+    (numba scorer, one process per core, Manager funnel, statsmodels-style BH, pandas table) from oracle/_ref when that is
+    present (kind "reference"), else the C port of its algorithm (kind "port") -- on bounded samples of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -128,28 +191,62 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     calib = cpu_sample_rows(20000, SEED)
     t = time_oracle(calib, m, threads)
-    rate = calib.shape[0] / t
-    # bounded sample: the whole --steps K run should take about two minutes whatever K is
-    per_step_s = min(8.0, max(0.25, 120.0 / max(1, args.steps)))
-    rows_per_step = int(max(20000, min(rate * per_step_s, 8_000_000)))
-    rows = cpu_sample_rows(rows_per_step // 2, SEED + 1)
-    for _ in range(max(args.warmup, 0)):
-        time_oracle(rows[: max(2000, rows.shape[0] // 20)], m, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        time_oracle(rows, m, threads)
-    dt = (time.perf_counter() - t0) / args.steps
-    value = rows.shape[0] / dt
-    sample = (f"{rows.shape[0]} rows/step ({rows.shape[0] // 2} forward 19-mers of the synthetic haplotype workload + their "
-              f"reverse-complement rows), oracle C port of compute_score_seq incl. its two per-row pval_mat sums, {threads} threads")
+    port_rate = calib.shape[0] / t
+    ref = None
+    try:
+        ref = reference_objects(threads)
+    except Exception as e:  # a broken copy must not cost the line: fall back to the port and say so
+        sys.stderr.write(f"bench.py: oracle/_ref unusable ({e!r}); timing the port\n")
+    workload = "CTCF MA0139.1, synthetic 1 Mb region x 2504 haplotype paths, both strands, t=1e-4 (bounded sample per step)"
+    if ref is not None:
+        motif, wf, compute_results = ref
+        w = motif.width
+        # calibrate on 100 k rows, then size a step for about 6 s (the whole run stays within a few minutes)
+        tmp = tempfile.mkdtemp(prefix="gb2_refarm_rows_")
+        write_kmer_tsvs(cpu_sample_rows(50000, SEED), os.path.join(tmp, "calib"), threads, w)
+        t_cal, _ = time_reference(compute_results, motif, wf, os.path.join(tmp, "calib"))
+        rate = 100000 / t_cal
+        per_step_s = min(8.0, max(1.0, 150.0 / max(1, args.steps + args.warmup)))
+        rows_per_step = int(max(100000, min(rate * per_step_s, 6_000_000)))
+        rows = cpu_sample_rows(rows_per_step // 2, SEED + 1)
+        write_kmer_tsvs(rows, os.path.join(tmp, "step"), 4 * threads, w)
+        for _ in range(max(args.warmup, 0)):
+            time_reference(compute_results, motif, wf, os.path.join(tmp, "calib"))
+        ts, hits = [], 0
+        for _ in range(args.steps):
+            dt1, hits = time_reference(compute_results, motif, wf, os.path.join(tmp, "step"))
+            ts.append(dt1)
+        dt = float(np.mean(ts))
+        value = rows.shape[0] / dt
+        kind = "reference"
+        sample = (f"{rows.shape[0]} TSV rows/step ({rows.shape[0] // 2} forward 19-mers of the synthetic haplotype workload + their "
+                  f"reverse-complement rows, {4 * threads} files): the UNMODIFIED reference's compute_results (numba scorer, {threads} "
+                  f"processes = --cores {threads}, BH, DataFrame) from oracle/_ref; motif build and numba JIT excluded; {hits} rows reported")
+        # the C port of the same algorithm on the same rows, once: how conservative the port is as a stand-in
+        port_rate = rows.shape[0] / time_oracle(rows, m, threads)
+        shutil.rmtree(tmp, ignore_errors=True)
+    else:
+        per_step_s = min(8.0, max(0.25, 120.0 / max(1, args.steps)))
+        rows_per_step = int(max(20000, min(port_rate * per_step_s, 8_000_000)))
+        rows = cpu_sample_rows(rows_per_step // 2, SEED + 1)
+        for _ in range(max(args.warmup, 0)):
+            time_oracle(rows[: max(2000, rows.shape[0] // 20)], m, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            time_oracle(rows, m, threads)
+        dt = (time.perf_counter() - t0) / args.steps
+        value = rows.shape[0] / dt
+        kind = "port"
+        sample = (f"{rows.shape[0]} rows/step ({rows.shape[0] // 2} forward 19-mers of the synthetic haplotype workload + their "
+                  f"reverse-complement rows), oracle C port of compute_score_seq incl. its two per-row pval_mat sums, {threads} threads "
+                  "(oracle/_ref is absent: the reference itself could not be run)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64+f64", "data": "synthetic",
-        "config": {"workload": "CTCF MA0139.1, synthetic 1 Mb region x 2504 haplotype paths, both strands, t=1e-4 "
-                               "(bounded sample per step; the Python reference cannot travel to the GPU box, so this is "
-                               "the oracle port of its algorithm)", "rows_per_step": int(rows.shape[0])},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload, "rows_per_step": int(rows.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "port_value_same_rows": port_rate, "port_over_reference": (port_rate / value) if kind == "reference" else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -493,7 +590,8 @@ def run_ours(args):
 
 
 def cpu_baseline_block(motif, fwd):
-    """oracle port on a bounded sample (about 12 s of CPU work) of the forward windows `fwd` + their reverse complements"""
+    """The reference's CPU path on a bounded sample (10-20 s of CPU work) of the forward windows `fwd` + their reverse
+    complements: the unmodified reference from oracle/_ref when present (kind "reference"), else the oracle port."""
     from grafimo_b200 import synth
     from oracle import oracle as orc
     orc.build()
@@ -501,8 +599,29 @@ def cpu_baseline_block(motif, fwd):
              scale=motif.scale, offset=float(motif.offset))
     threads = os.cpu_count() or 1
     calib = np.ascontiguousarray(np.concatenate([fwd[:10000], synth.revcomp_ascii(fwd[:10000])]))
-    rate = calib.shape[0] / time_oracle(calib, m, threads)
-    k = int(max(10000, min(fwd.shape[0], rate * 12.0 / 2)))
+    port_rate = calib.shape[0] / time_oracle(calib, m, threads)
+    ref = None
+    try:
+        ref = reference_objects(threads)
+    except Exception as e:
+        sys.stderr.write(f"bench.py: oracle/_ref unusable ({e!r}); cpu_baseline from the port\n")
+    if ref is not None:
+        rmotif, wf, compute_results = ref
+        tmp = tempfile.mkdtemp(prefix="gb2_cpubase_")
+        c = np.ascontiguousarray(np.concatenate([fwd[:50000], synth.revcomp_ascii(fwd[:50000])]))
+        write_kmer_tsvs(c, os.path.join(tmp, "calib"), threads, rmotif.width)
+        t_cal, _ = time_reference(compute_results, rmotif, wf, os.path.join(tmp, "calib"))
+        k = int(max(50000, min(fwd.shape[0], (c.shape[0] / t_cal) * 10.0 / 2)))
+        rows = np.ascontiguousarray(np.concatenate([fwd[:k], synth.revcomp_ascii(fwd[:k])]))
+        write_kmer_tsvs(rows, os.path.join(tmp, "step"), 4 * threads, rmotif.width)
+        t, hits = time_reference(compute_results, rmotif, wf, os.path.join(tmp, "step"))
+        shutil.rmtree(tmp, ignore_errors=True)
+        return {"value": rows.shape[0] / t, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{rows.shape[0]} TSV rows = first {k} forward 19-mers of the workload + their reverse-complement rows in "
+                          f"{4 * threads} files; the UNMODIFIED reference's compute_results from oracle/_ref (numba scorer, --cores {threads}, "
+                          f"BH, DataFrame; motif build and JIT excluded), {t:.1f} s, {hits} rows reported",
+                "port_value": port_rate, "port_sample": "oracle C port of the same per-row algorithm, 20000 rows, same threads"}
+    k = int(max(10000, min(fwd.shape[0], port_rate * 12.0 / 2)))
     rows = np.ascontiguousarray(np.concatenate([fwd[:k], synth.revcomp_ascii(fwd[:k])]))
     t = time_oracle(rows, m, threads)
     return {"value": rows.shape[0] / t, "unit": UNIT, "cores": threads, "kind": "port",

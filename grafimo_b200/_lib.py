@@ -58,7 +58,8 @@ class MotifInfo(ctypes.Structure):
         ("width", ctypes.c_int32), ("n_chunks", ctypes.c_int32), ("lut_replicas", ctypes.c_int32),
         ("monotone", ctypes.c_int32), ("lo", ctypes.c_int64), ("hi", ctypes.c_int64), ("span", ctypes.c_int64),
         ("min_val", ctypes.c_int64), ("scale", ctypes.c_int64), ("offset", ctypes.c_double),
-        ("total", ctypes.c_double), ("smem_bytes", ctypes.c_int64),
+        ("total", ctypes.c_double), ("smem_bytes", ctypes.c_int64), ("chunk_bases", ctypes.c_int32),
+        ("hist_global", ctypes.c_int32),
     ]
 
 
@@ -85,12 +86,14 @@ SIGNATURES = {
     "gb2_tsv_parse_rows": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_pval_dp_batched": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "gb2_motif_create": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _dbl, ctypes.POINTER(_vp)]),
+    "gb2_motif_create_batched": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_motif_destroy": (_int, [_vp]),
     "gb2_motif_get_info": (_int, [_vp, ctypes.POINTER(MotifInfo)]),
     "gb2_motif_get_ptable": (_int, [_vp, _vp, _vp]),
     "gb2_motif_ptable_device": (_vp, [_vp]),
     "gb2_score": (_int, [_vp, _vp, _vp, _vp, _i64, _u64, _int, _dbl, _vp, _vp, _u64, _vp, _vp]),
     "gb2_qvalues_from_hist": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "gb2_qvalues_from_hist_many": (_int, [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_bh_pvalues": (_int, [_vp, _vp, _i64, _vp]),
     "gb2_finalize_hits": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_finalize_hits_many": (_int, [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _u64, _u64, _dbl, _int, _dbl, _vp, _vp, _vp, _vp, _vp,
@@ -149,7 +152,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.gb2_abi_version() != 2:
+    if lib.gb2_abi_version() != 3:
         raise GrafimoB200Error(-1, "grafimo_b200", "ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -160,34 +160,88 @@ extern "C" int gb2_host_free(void *ptr)
 // ---------------------------------------------------------------------------------------------
 // motif
 // ---------------------------------------------------------------------------------------------
+// Device memory of one or many motifs (p-value tables, chunk LUTs, hit bitmaps) is ONE allocation shared by the motifs
+// created together; it is freed when the last of them is destroyed.
+struct gb2_motif_block {
+    void *d_ptr = nullptr;
+    int refs = 0;
+    int device = 0;
+};
+
 extern "C" int gb2_motif_destroy(gb2_motif *m)
 {
     if (!m) return GB2_OK;
-    cudaSetDevice(m->device);
-    if (m->d_block) cudaFree(m->d_block);  // d_lut, d_ptab and d_bitmap live in this one allocation
+    if (m->block && --m->block->refs == 0) {
+        cudaSetDevice(m->block->device);
+        if (m->block->d_ptr) cudaFree(m->block->d_ptr);
+        delete m->block;
+    }
     delete m;
     return GB2_OK;
 }
 
-extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const double *h_pval_mat, int64_t min_val,
-                                int64_t scale, double offset, gb2_motif **out)
+namespace {
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Host-side facts of one motif: reachable score range and the chunk lookup tables.
+struct MotifPlan {
+    int w = 0, cb = 4, n_chunks = 0;
+    int64_t lo = 0, hi = 0, span = 0;
+    std::vector<uint32_t> lut;  // [n_chunks][4^cb]: (rc_rel << 16) | fwd_rel
+};
+
+// Expected shared-memory wavefronts of one lookup when the table is replicated R times (32 lanes, random entries):
+// R = 32 -> every lane has its own bank; below that, lanes sharing a replica collide (measured / simulated).
+double lookup_wavefronts(int R)
 {
-    if (!ctx || !out) return GB2_ERR_ARG;
-    *out = nullptr;
-    GB2_REQUIRE(ctx, sm && h_pval_mat, "gb2_motif_create: null matrix");
-    GB2_REQUIRE(ctx, w >= 1 && w <= GB2_MAX_WIDTH, "gb2_motif_create: width %d outside [1,%d]", w, GB2_MAX_WIDTH);
-    if (scale <= 0) {
-        GB2_SET_ERR(ctx, "gb2_motif_create: motif is not scaled (scale=%lld)", (long long)scale);
-        return GB2_ERR_MOTIF;
+    switch (R) {
+    case 32: return 1.0;
+    case 16: return 2.0;
+    case 8: return 3.0;
+    case 4: return 5.0;
+    case 2: return 8.0;
+    default: return 12.0;
     }
-    const int64_t L = (int64_t)GB2_RANGE * w + 1;
+}
+
+// Chunk size (bases per lookup) and replication for a motif: tables of 4^cb entries per chunk, ceil(w / cb) lookups per
+// k-mer; the smaller tables of cb = 3 replicate 32x where the 4-base tables no longer fit beside the histogram, which
+// makes every lookup one conflict-free wavefront (long motifs, large score spans).  Picks the smaller expected number of
+// shared-memory wavefronts per k-mer.  -> false when not even one copy of the tables fits with the histogram in shared
+// memory (then hist_global for wide motifs).
+bool plan_smem(int w, int64_t span, int64_t budget, bool allow_global_hist, int &cb, int &R, int &hist_global, int64_t &smem)
+{
+    const int64_t hist_bytes = (span + 1) * 4;
+    double best = 1e30;
+    bool found = false;
+    for (int c : {4, 3}) {
+        if (c == 3 && w < 19) continue;  // never wins below that width (and keeps the number of kernel variants down)
+        if (c == 4 && w > GB2_NARROW_WIDTH) continue;  // the wide kernel exists for 3-base chunks only (they always win there)
+        const int nch = (w + c - 1) / c;
+        const int64_t copy = (int64_t)nch * (c == 4 ? 1024 : 256);
+        for (int hg = 0; hg <= (allow_global_hist ? 1 : 0); ++hg) {
+            const int64_t hb = hg ? 0 : hist_bytes;
+            if (copy + hb > budget) continue;
+            int r = 32;
+            while (r > 1 && copy * r + hb > budget) r >>= 1;
+            if (w <= GB2_NARROW_WIDTH && c == 3 && r < 8) continue;  // narrow 3-base kernels exist for R = 32, 16, 8
+            // global-memory histogram updates are ~35x slower than shared-memory ones: only when nothing else fits
+            const double cost = nch * lookup_wavefronts(r) + (hg ? 300.0 : 0.0);
+            if (cost < best - 1e-9) { best = cost; cb = c; R = r; hist_global = hg; smem = copy * r + hb; found = true; }
+        }
+    }
+    return found;
+}
+
+int motif_plan(gb2_ctx *ctx, const int64_t *sm, int w, int cb, MotifPlan &pl, const char *who)
+{
     int64_t mincol[GB2_MAX_WIDTH], lo = 0, hi = 0;
     for (int j = 0; j < w; ++j) {
         int64_t mn = sm[j], mx = sm[j];
         for (int n = 0; n < 4; ++n) {
             int64_t v = sm[(int64_t)n * w + j];
             if (v < 0 || v > 60000) {
-                GB2_SET_ERR(ctx, "gb2_motif_create: scaled score %lld out of range", (long long)v);
+                GB2_SET_ERR(ctx, "%s: scaled score %lld out of range", who, (long long)v);
                 return GB2_ERR_MOTIF;
             }
             mn = std::min(mn, v);
@@ -197,112 +251,187 @@ extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const do
         lo += mn;
         hi += mx;
     }
-    if (hi >= L) {
-        GB2_SET_ERR(ctx, "gb2_motif_create: max score %lld exceeds the p-value matrix (%lld bins)", (long long)hi, (long long)L);
-        return GB2_ERR_MOTIF;
-    }
-    const int64_t span = hi - lo + 1;
-    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
-
-    gb2_motif *m = new (std::nothrow) gb2_motif();
-    if (!m) return GB2_ERR_NOMEM;
-    m->device = ctx->device;
-    m->w = w;
-    m->n_chunks = (w + 3) / 4;
-    m->lo = lo; m->hi = hi; m->span = span;
-    m->min_val = min_val; m->scale = scale; m->offset = offset;
-
-    // ---- 4-base chunk LUT: entry = (rc_rel << 16) | fwd_rel, both relative to the column minima so
-    //      that the accumulated fields are directly the histogram bins (score - lo).
-    std::vector<uint32_t> lut((size_t)m->n_chunks * 256);
-    for (int c = 0; c < m->n_chunks; ++c) {
-        for (int idx = 0; idx < 256; ++idx) {
+    pl.w = w; pl.cb = cb; pl.n_chunks = (w + cb - 1) / cb;
+    pl.lo = lo; pl.hi = hi; pl.span = hi - lo + 1;
+    // chunk LUT: entry = (rc_rel << 16) | fwd_rel, both relative to the column minima so that the accumulated fields
+    // are directly the histogram bins (score - lo).  Index bits beyond the motif's last base are ignored.
+    const int entries = 1 << (2 * cb);
+    pl.lut.assign((size_t)pl.n_chunks * entries, 0u);
+    for (int c = 0; c < pl.n_chunks; ++c) {
+        for (int idx = 0; idx < entries; ++idx) {
             uint32_t fwd = 0, rc = 0;
-            for (int j = 0; j < 4; ++j) {
-                int p = 4 * c + j;
+            for (int j = 0; j < cb; ++j) {
+                int p = cb * c + j;
                 if (p >= w) break;
                 int b = (idx >> (2 * j)) & 3;
                 fwd += (uint32_t)(sm[(int64_t)b * w + p] - mincol[p]);
                 int q = w - 1 - p;  // base at position p of x sits at position q of the reverse complement
                 rc += (uint32_t)(sm[(int64_t)(3 - b) * w + q] - mincol[q]);
             }
-            lut[(size_t)c * 256 + idx] = (rc << 16) | fwd;
+            pl.lut[(size_t)c * entries + idx] = (rc << 16) | fwd;
         }
     }
-    int rc_ = GB2_OK;
-    double *d_pm = nullptr, *d_ctab = nullptr;
-    auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_ptab = align256((size_t)span * sizeof(double));
-    const size_t b_lut = align256(lut.size() * sizeof(uint32_t));
-    const size_t b_bitmap = align256((size_t)gb2_div_up(span + 1, 32) * sizeof(uint32_t));
-    do {
-        // one allocation for what the motif keeps; the two work arrays of K4 come from the context's scratch buffer
-        // (no cudaMalloc / cudaFree pair per motif: an 800-motif collection is uploaded in a fraction of a second)
-        if ((rc_ = gb2_scratch_reserve(ctx, 2 * b_ptab)) != GB2_OK) break;
-        d_pm = (double *)ctx->scratch;
-        d_ctab = (double *)((char *)ctx->scratch + b_ptab);
-        if (cudaMalloc((void **)&m->d_block, b_ptab + b_lut + b_bitmap) != cudaSuccess) {
-            GB2_SET_ERR(ctx, "gb2_motif_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc_ = GB2_ERR_NOMEM;
-            break;
+    return GB2_OK;
+}
+}  // namespace
+
+// K4 over many motifs at once (pval.cu)
+int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const double *d_pm, double *d_ctab, double *d_ptab,
+                              double *d_totals);
+
+extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *h_score_mats,
+                                        const double *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
+                                        const double *h_offsets, gb2_motif **out)
+{
+    if (!ctx || !out) return GB2_ERR_ARG;
+    for (int i = 0; i < n_motifs; ++i) out[i] = nullptr;
+    GB2_REQUIRE(ctx, n_motifs >= 0, "gb2_motif_create_batched: negative motif count");
+    if (n_motifs == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, h_widths && h_score_mats && h_pval_mats && h_min_vals && h_scales && h_offsets,
+                "gb2_motif_create_batched: null argument");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t budget = (int64_t)ctx->max_smem_optin - 1024;
+    std::vector<MotifPlan> plans((size_t)n_motifs);
+    std::vector<gb2_motif *> ms((size_t)n_motifs, nullptr);
+    std::vector<int64_t> sm_off((size_t)n_motifs + 1, 0), pm_off((size_t)n_motifs + 1, 0), sp_off((size_t)n_motifs + 1, 0);
+    std::vector<size_t> lut_off((size_t)n_motifs + 1, 0), bm_off((size_t)n_motifs + 1, 0);
+    int rc = GB2_OK;
+    auto fail = [&](int code) {
+        for (gb2_motif *m : ms) delete m;
+        return code;
+    };
+    for (int i = 0; i < n_motifs; ++i) {
+        const int w = h_widths[i];
+        if (w < 1 || w > GB2_MAX_WIDTH) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: width %d outside [1,%d] (motif %d)", w, GB2_MAX_WIDTH, i);
+            return fail(GB2_ERR_ARG);
         }
-        m->d_ptab = (double *)m->d_block;
-        m->d_lut = (uint32_t *)((char *)m->d_block + b_ptab);
-        m->d_bitmap = (uint32_t *)((char *)m->d_block + b_ptab + b_lut);
-        cudaError_t e = cudaMemcpyAsync(m->d_lut, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(d_pm, h_pval_mat + lo, (size_t)span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) { GB2_SET_ERR(ctx, "gb2_motif_create: upload failed: %s", cudaGetErrorString(e)); rc_ = GB2_ERR_CUDA; break; }
-        // K4: p[s] = seqsum(pv[s:]) / seqsum(pv) -- mass outside [lo,hi] is exactly +0.0 and does not change a sum
-        rc_ = gb2_launch_ptable(ctx, d_pm, lo, span, d_ctab, m->d_ptab);
-        if (rc_ != GB2_OK) break;
-        m->h_ptab.resize((size_t)span);
-        e = cudaMemcpyAsync(m->h_ptab.data(), m->d_ptab, (size_t)span * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&m->total, d_ctab, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { GB2_SET_ERR(ctx, "gb2_motif_create: p-table failed: %s", cudaGetErrorString(e)); rc_ = GB2_ERR_CUDA; break; }
+        sm_off[(size_t)i + 1] = sm_off[(size_t)i] + 4 * (int64_t)w;
+        pm_off[(size_t)i + 1] = pm_off[(size_t)i] + (int64_t)GB2_RANGE * w + 1;
+        if (h_scales[i] <= 0) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: motif is not scaled (scale=%lld, motif %d)", (long long)h_scales[i], i);
+            return fail(GB2_ERR_MOTIF);
+        }
+        const int64_t *sm = h_score_mats + sm_off[(size_t)i];
+        MotifPlan probe;
+        if ((rc = motif_plan(ctx, sm, w, 4, probe, "gb2_motif_create")) != GB2_OK) return fail(rc);
+        const int64_t L = (int64_t)GB2_RANGE * w + 1;
+        if (probe.hi >= L) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: max score %lld exceeds the p-value matrix (%lld bins)", (long long)probe.hi, (long long)L);
+            return fail(GB2_ERR_MOTIF);
+        }
+        if (probe.span > 65535) {  // the two strands travel as 16-bit fields of one register
+            GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld exceeds 65535", (long long)probe.span);
+            return fail(GB2_ERR_MOTIF);
+        }
+        int cb = 4, R = 1, hg = 0;
+        int64_t smem = 0;
+        if (!plan_smem(w, probe.span, budget, w > GB2_NARROW_WIDTH, cb, R, hg, smem)) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld does not fit shared memory", (long long)probe.span);
+            return fail(GB2_ERR_MOTIF);
+        }
+        if (cb == 4) plans[(size_t)i] = std::move(probe);
+        else if ((rc = motif_plan(ctx, sm, w, cb, plans[(size_t)i], "gb2_motif_create")) != GB2_OK) return fail(rc);
+        const MotifPlan &pl = plans[(size_t)i];
         // mass outside the reachable range means the matrix and the p-value matrix do not belong together
+        const double *pm = h_pval_mats + pm_off[(size_t)i];
         for (int64_t k = 0; k < L; ++k) {
-            if ((k < lo || k > hi) && h_pval_mat[k] != 0.0) {
+            if ((k < pl.lo || k > pl.hi) && pm[k] != 0.0) {
                 GB2_SET_ERR(ctx, "gb2_motif_create: p-value matrix has mass at unreachable score %lld", (long long)k);
-                rc_ = GB2_ERR_MOTIF;
-                break;
+                return fail(GB2_ERR_MOTIF);
             }
         }
-        if (rc_ != GB2_OK) break;
-        if (!(m->total > 0.0)) { GB2_SET_ERR(ctx, "gb2_motif_create: empty p-value matrix"); rc_ = GB2_ERR_MOTIF; break; }
-    } while (0);
-    if (rc_ != GB2_OK) { gb2_motif_destroy(m); return rc_; }
-
-    m->monotone = 1;
-    for (int64_t k = 1; k < span; ++k)
-        if (m->h_ptab[(size_t)k] > m->h_ptab[(size_t)k - 1]) { m->monotone = 0; break; }
-
-    // ---- shared-memory plan of the scoring kernel: replicated LUT + u32 histogram.  Wide motifs whose span does not
-    //      fit next to even one copy of the tables keep the histogram in global memory (hist_global).
-    const int64_t budget = (int64_t)ctx->max_smem_optin - 1024;
-    int64_t hist_bytes = (span + 1) * 4;
-    if (span > 65535) {  // the two strands travel as 16-bit fields of one register
-        GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld exceeds 65535", (long long)span);
-        gb2_motif_destroy(m);
-        return GB2_ERR_MOTIF;
+        gb2_motif *m = new (std::nothrow) gb2_motif();
+        if (!m) return fail(GB2_ERR_NOMEM);
+        ms[(size_t)i] = m;
+        m->device = ctx->device;
+        m->w = w; m->chunk_bases = cb; m->n_chunks = pl.n_chunks;
+        m->lo = pl.lo; m->hi = pl.hi; m->span = pl.span;
+        m->min_val = h_min_vals[i]; m->scale = h_scales[i]; m->offset = h_offsets[i];
+        m->replicas = R; m->hist_global = hg; m->smem_bytes = smem;
+        sp_off[(size_t)i + 1] = sp_off[(size_t)i] + pl.span;
+        lut_off[(size_t)i + 1] = lut_off[(size_t)i] + align256(pl.lut.size() * sizeof(uint32_t));
+        bm_off[(size_t)i + 1] = bm_off[(size_t)i] + align256((size_t)gb2_div_up(pl.span + 1, 32) * sizeof(uint32_t));
     }
-    m->hist_global = 0;
-    if ((int64_t)m->n_chunks * 1024 + hist_bytes > budget) {
-        if (w <= GB2_NARROW_WIDTH) {
-            GB2_SET_ERR(ctx, "gb2_motif_create: score span %lld does not fit shared memory", (long long)span);
-            gb2_motif_destroy(m);
-            return GB2_ERR_MOTIF;
+    // ---- one allocation: [p-tables of all motifs][LUTs][bitmaps]; K4's two work arrays come from the scratch buffer
+    const int64_t total_span = sp_off[(size_t)n_motifs];
+    const size_t b_ptab = align256((size_t)total_span * sizeof(double));
+    const size_t b_lut = lut_off[(size_t)n_motifs], b_bm = bm_off[(size_t)n_motifs];
+    const size_t b_work = align256((size_t)total_span * sizeof(double));
+    const size_t b_tot = align256((size_t)n_motifs * sizeof(double));
+    if ((rc = gb2_scratch_reserve(ctx, 2 * b_work + b_tot)) != GB2_OK) return fail(rc);
+    double *d_pm = (double *)ctx->scratch;
+    double *d_ctab = (double *)((char *)ctx->scratch + b_work);
+    double *d_tot = (double *)((char *)ctx->scratch + 2 * b_work);
+    gb2_motif_block *blk = new (std::nothrow) gb2_motif_block();
+    if (!blk) return fail(GB2_ERR_NOMEM);
+    blk->device = ctx->device;
+    if (cudaMalloc(&blk->d_ptr, b_ptab + b_lut + b_bm) != cudaSuccess) {
+        GB2_SET_ERR(ctx, "gb2_motif_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete blk;
+        return fail(GB2_ERR_NOMEM);
+    }
+    char *base = (char *)blk->d_ptr;
+    // host staging of everything that goes up: one copy for the LUTs, one for the reachable slices of the p-value matrices
+    std::vector<uint8_t> h_lut(b_lut, 0);
+    std::vector<double> h_pm((size_t)total_span);
+    for (int i = 0; i < n_motifs; ++i) {
+        const MotifPlan &pl = plans[(size_t)i];
+        memcpy(h_lut.data() + lut_off[(size_t)i], pl.lut.data(), pl.lut.size() * sizeof(uint32_t));
+        memcpy(h_pm.data() + sp_off[(size_t)i], h_pval_mats + pm_off[(size_t)i] + pl.lo, (size_t)pl.span * sizeof(double));
+        gb2_motif *m = ms[(size_t)i];
+        m->d_ptab = (double *)base + sp_off[(size_t)i];
+        m->d_lut = (uint32_t *)(base + b_ptab + lut_off[(size_t)i]);
+        m->d_bitmap = (uint32_t *)(base + b_ptab + b_lut + bm_off[(size_t)i]);
+    }
+    std::vector<double> h_ptab_all((size_t)total_span), h_tot((size_t)n_motifs);
+    cudaError_t e = cudaMemcpyAsync(base + b_ptab, h_lut.data(), b_lut, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pm, h_pm.data(), (size_t)total_span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        // K4 for every motif in two launches: p[s] = seqsum(pv[s:]) / seqsum(pv) -- mass outside [lo,hi] is exactly +0.0
+        rc = gb2_launch_ptable_batched(ctx, n_motifs, sp_off.data(), d_pm, d_ctab, (double *)base, d_tot);
+        if (rc == GB2_OK) {
+            e = cudaMemcpyAsync(h_ptab_all.data(), base, (size_t)total_span * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot.data(), d_tot, (size_t)n_motifs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         }
-        m->hist_global = 1;
-        hist_bytes = 0;
     }
-    int R = 32;
-    while (R > 1 && (int64_t)m->n_chunks * 1024 * R + hist_bytes > budget) R >>= 1;
-    m->replicas = R;
-    m->smem_bytes = (int64_t)m->n_chunks * 1024 * R + hist_bytes;
-    *out = m;
+    if (e != cudaSuccess || rc != GB2_OK) {
+        if (e != cudaSuccess) { GB2_SET_ERR(ctx, "gb2_motif_create: upload / p-table failed: %s", cudaGetErrorString(e)); rc = GB2_ERR_CUDA; }
+        cudaFree(blk->d_ptr);
+        delete blk;
+        return fail(rc);
+    }
+    for (int i = 0; i < n_motifs; ++i) {
+        gb2_motif *m = ms[(size_t)i];
+        m->total = h_tot[(size_t)i];
+        if (!(m->total > 0.0)) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: empty p-value matrix (motif %d)", i);
+            cudaFree(blk->d_ptr);
+            delete blk;
+            return fail(GB2_ERR_MOTIF);
+        }
+        m->h_ptab.assign(h_ptab_all.begin() + sp_off[(size_t)i], h_ptab_all.begin() + sp_off[(size_t)i + 1]);
+        m->monotone = 1;
+        for (int64_t k = 1; k < m->span; ++k)
+            if (m->h_ptab[(size_t)k] > m->h_ptab[(size_t)k - 1]) { m->monotone = 0; break; }
+    }
+    for (int i = 0; i < n_motifs; ++i) {
+        ms[(size_t)i]->block = blk;
+        blk->refs++;
+        out[i] = ms[(size_t)i];
+    }
     return GB2_OK;
+}
+
+extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const double *h_pval_mat, int64_t min_val,
+                                int64_t scale, double offset, gb2_motif **out)
+{
+    if (!ctx || !out) return GB2_ERR_ARG;
+    *out = nullptr;
+    GB2_REQUIRE(ctx, sm && h_pval_mat, "gb2_motif_create: null matrix");
+    const int32_t w32 = w;
+    return gb2_motif_create_batched(ctx, 1, &w32, sm, h_pval_mat, &min_val, &scale, &offset, out);
 }
 
 extern "C" int gb2_motif_get_info(const gb2_motif *m, gb2_motif_info *info)
@@ -310,6 +439,8 @@ extern "C" int gb2_motif_get_info(const gb2_motif *m, gb2_motif_info *info)
     if (!m || !info) return GB2_ERR_ARG;
     info->width = m->w;
     info->n_chunks = m->n_chunks;
+    info->chunk_bases = m->chunk_bases;
+    info->hist_global = m->hist_global;
     info->lut_replicas = m->replicas;
     info->monotone = m->monotone;
     info->lo = m->lo; info->hi = m->hi; info->span = m->span;

@@ -38,9 +38,12 @@ struct gb2_ctx {
     int comm_rank = 0, comm_world = 1;
 };
 
+struct gb2_motif_block;  // shared device allocation of the motifs created together (context.cu)
+
 struct gb2_motif {
     int device = 0;
     int w = 0;
+    int chunk_bases = 4;           // bases per lookup-table chunk: 4 (256 entries) or 3 (64 entries)
     int n_chunks = 0;
     int replicas = 0;
     int monotone = 0;
@@ -49,8 +52,8 @@ struct gb2_motif {
     int64_t min_val = 0, scale = 0;
     double offset = 0.0, total = 0.0;
     int64_t smem_bytes = 0;
-    void *d_block = nullptr;       // the one device allocation holding the three arrays below
-    uint32_t *d_lut = nullptr;     // [n_chunks][256]  (rc_rel << 16 | fwd_rel)
+    gb2_motif_block *block = nullptr;  // owner of the device memory below (shared, reference-counted)
+    uint32_t *d_lut = nullptr;     // [n_chunks][4^chunk_bases]  (rc_rel << 16 | fwd_rel)
     double *d_ptab = nullptr;      // [span]  p-value of score lo+k
     uint32_t *d_bitmap = nullptr;  // [ceil(span/32)] hit bitmap for non-monotone tables
     std::vector<double> h_ptab;    // host copy of d_ptab
@@ -89,9 +92,5 @@ int gb2_scratch_reserve(gb2_ctx *ctx, size_t bytes);
 // grows the pool of the host-buffer entry points; *out = its base
 int gb2_pool_reserve(gb2_ctx *ctx, size_t bytes, char **out);
 void gb2_comm_release(gb2_ctx *ctx);  // comm.cu
-
-// kernels launched from other translation units
-int gb2_launch_ptable(gb2_ctx *ctx, const double *d_pval_mat, int64_t lo, int64_t span, double *d_ctab,
-                      double *d_ptab);
 
 static inline int64_t gb2_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -17,11 +17,38 @@
 // One thread per start score s; each walks pv[s..span) in ascending order.  Lanes of a warp read
 // consecutive addresses at every step (coalesced, L1-resident), the adds form one dependent chain
 // per thread as the contract requires.  Work is O(span^2/2) adds, latency-bound by the longest chain.
-__global__ void __launch_bounds__(128) gb2_ctab_kernel(const double *__restrict__ pv, int64_t span,
-                                                       double *__restrict__ ctab)
+// K4 for MANY motifs in two launches (a JASPAR-sized collection used to cost two launches, a D2H copy and a stream
+// synchronisation PER MOTIF).  The reachable slices of all p-value matrices lie back to back (motif m = elements
+// [off[m], off[m+1])); a CTA takes 128 consecutive start scores of one motif (tile -> motif by binary search over the
+// per-motif tile prefix).  Same dependent add chain per start score as above: bit-identical tables.
+struct PtabBatch {
+    const int64_t *off;       // [n+1] element offsets
+    const int64_t *tile_off;  // [n+1] tiles before motif m
+    int n;
+};
+
+__device__ __forceinline__ int ptab_find_motif(const PtabBatch &b, int64_t tile)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0, hi = b.n;  // tile_off[lo] <= tile < tile_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (b.tile_off[mid] <= tile) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) gb2_ctab_batched_kernel(const PtabBatch b, const double *__restrict__ pv_all,
+                                                               double *__restrict__ ctab_all)
+{
+    __shared__ int s_m;
+    if (threadIdx.x == 0) s_m = ptab_find_motif(b, blockIdx.x);
+    __syncthreads();
+    const int m = s_m;
+    const int64_t base = b.off[m], span = b.off[m + 1] - base;
+    const int64_t s = ((int64_t)blockIdx.x - b.tile_off[m]) * 128 + threadIdx.x;
     if (s >= span) return;
+    const double *pv = pv_all + base;
     double c = 0.0;
     int64_t k = s;
 #pragma unroll 1
@@ -33,25 +60,47 @@ __global__ void __launch_bounds__(128) gb2_ctab_kernel(const double *__restrict_
         for (int u = 0; u < 8; ++u) c = __dadd_rn(c, v[u]);
     }
     for (; k < span; ++k) c = __dadd_rn(c, pv[k]);
-    ctab[s] = c;
+    ctab_all[base + s] = c;
 }
 
-__global__ void gb2_ptab_div_kernel(const double *__restrict__ ctab, int64_t span, double *__restrict__ ptab)
+__global__ void __launch_bounds__(128) gb2_ptab_div_batched_kernel(const PtabBatch b, const double *__restrict__ ctab_all,
+                                                                   double *__restrict__ ptab_all, double *__restrict__ totals)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_m;
+    if (threadIdx.x == 0) s_m = ptab_find_motif(b, blockIdx.x);
+    __syncthreads();
+    const int m = s_m;
+    const int64_t base = b.off[m], span = b.off[m + 1] - base;
+    const int64_t s = ((int64_t)blockIdx.x - b.tile_off[m]) * 128 + threadIdx.x;
     if (s >= span) return;
-    ptab[s] = __ddiv_rn(ctab[s], ctab[0]);  // ctab[0] == seqsum over the whole matrix (zeros outside [lo,hi])
+    const double tot = ctab_all[base];  // seqsum over the whole matrix (zeros outside [lo,hi])
+    ptab_all[base + s] = __ddiv_rn(ctab_all[base + s], tot);
+    if (s == 0) totals[m] = tot;
 }
 
-int gb2_launch_ptable(gb2_ctx *ctx, const double *d_pm, int64_t lo, int64_t span, double *d_ctab, double *d_ptab)
+int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const double *d_pm, double *d_ctab, double *d_ptab,
+                              double *d_totals)
 {
-    (void)lo;
-    const int threads = 128;
-    const int blocks = (int)gb2_div_up(span, threads);
-    gb2_ctab_kernel<<<blocks, threads, 0, ctx->stream>>>(d_pm, span, d_ctab);
+    std::vector<int64_t> host((size_t)2 * (n + 1));
+    int64_t tiles = 0;
+    for (int m = 0; m <= n; ++m) {
+        host[(size_t)m] = h_off[m];
+        host[(size_t)(n + 1 + m)] = tiles;
+        if (m < n) tiles += gb2_div_up(h_off[m + 1] - h_off[m], 128);
+    }
+    GB2_REQUIRE(ctx, tiles > 0 && tiles < ((int64_t)1 << 31), "gb2_motif_create: too many score bins for one launch");
+    int64_t *d_idx = nullptr;  // tiny, lives until the kernels are done (stream-ordered free)
+    GB2_CUDA(ctx, cudaMallocAsync((void **)&d_idx, host.size() * sizeof(int64_t), ctx->stream));
+    GB2_CUDA(ctx, cudaMemcpyAsync(d_idx, host.data(), host.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    PtabBatch b;
+    b.off = d_idx;
+    b.tile_off = d_idx + (n + 1);
+    b.n = n;
+    gb2_ctab_batched_kernel<<<(unsigned)tiles, 128, 0, ctx->stream>>>(b, d_pm, d_ctab);
     GB2_LAUNCH_CHECK(ctx);
-    gb2_ptab_div_kernel<<<blocks, threads, 0, ctx->stream>>>(d_ctab, span, d_ptab);
+    gb2_ptab_div_batched_kernel<<<(unsigned)tiles, 128, 0, ctx->stream>>>(b, d_ctab, d_ptab, d_totals);
     GB2_LAUNCH_CHECK(ctx);
+    GB2_CUDA(ctx, cudaFreeAsync(d_idx, ctx->stream));
     return GB2_OK;
 }
 

@@ -152,6 +152,129 @@ extern "C" int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *m, const uin
     return GB2_OK;
 }
 
+// K5 for MANY motifs in one launch (a motif collection scanned over the same k-mers, BASELINE config 3): one CTA per
+// motif does what the three kernels above do -- the per-motif form costs three launches, two of them single-CTA, per
+// motif, and with 800 motifs the GPU is filled by the motifs themselves.  Motifs whose p-value table is monotone in the
+// score (all but pathological ones) need no sort: sorted position i is bin span-1-i, the N bin (p = 1) last.
+struct BhMotif {
+    const double *ptab;
+    long long bin_off;  // first bin of the motif in the concatenated hist / qtab / rank arrays
+    uint32_t span;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(BH_THREADS) gb2_bh_many_kernel(const BhMotif *__restrict__ ms,
+                                                                 const unsigned long long *__restrict__ hist_all,
+                                                                 double *__restrict__ qtab_all, uint32_t *__restrict__ rank_all,
+                                                                 unsigned long long *__restrict__ totals,
+                                                                 double *__restrict__ raw_all)
+{
+    typedef cub::BlockScan<unsigned long long, BH_THREADS> ScanU64;
+    typedef cub::BlockScan<double, BH_THREADS> ScanF64;
+    __shared__ union {
+        typename ScanU64::TempStorage u;
+        typename ScanF64::TempStorage f;
+    } tmp;
+    __shared__ double s_run[BH_THREADS];
+    const BhMotif m = ms[blockIdx.x];
+    const uint32_t span = m.span, nbins = span + 1u, tid = threadIdx.x;
+    const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
+    const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
+    uint32_t *rank = rank_all + m.bin_off;
+    auto bin_of = [&](uint32_t i) { return i < span ? span - 1u - i : span; };
+    for (uint32_t i = beg; i < end; ++i) rank[bin_of(i)] = i;
+    if (hist_all == nullptr) return;  // rank-only call (no q-values wanted)
+    const unsigned long long *hist = hist_all + m.bin_off;
+    double *qtab = qtab_all + m.bin_off, *raw = raw_all + m.bin_off;
+    unsigned long long local = 0;
+    for (uint32_t i = beg; i < end; ++i) local += hist[bin_of(i)];
+    unsigned long long prefix, total;
+    ScanU64(tmp.u).ExclusiveSum(local, prefix, total);
+    if (tid == 0) totals[blockIdx.x] = total;
+    const double dn = (double)total;
+    unsigned long long c = prefix;
+    double run_min = CUDART_INF;
+    for (uint32_t i = beg; i < end; ++i) {
+        const uint32_t b = bin_of(i);
+        const unsigned long long h = hist[b];
+        c += h;
+        const double p = i < span ? m.ptab[b] : 1.0;
+        const double r = h ? __ddiv_rn(p, __ddiv_rn((double)c, dn)) : CUDART_INF;  // raw = p / (C / float(N))
+        raw[i] = r;
+        run_min = fmin(run_min, r);
+    }
+    // suffix-min over threads: reverse the thread order and take an inclusive min-scan
+    double scanned;
+    s_run[BH_THREADS - 1 - tid] = run_min;
+    __syncthreads();
+    const double rev = s_run[tid];
+    ScanF64(tmp.f).InclusiveScan(rev, scanned, cub::Min());
+    __syncthreads();
+    s_run[tid] = scanned;  // s_run[j] = min over original threads >= BH_THREADS-1-j
+    __syncthreads();
+    double mn = (tid + 1 < BH_THREADS) ? s_run[BH_THREADS - 2 - tid] : CUDART_INF;
+    for (uint32_t i = end; i > beg; --i) {  // the thread re-reads only what it wrote itself
+        mn = fmin(mn, raw[i - 1]);
+        qtab[bin_of(i - 1)] = mn > 1.0 ? 1.0 : mn;
+    }
+}
+
+extern "C" int gb2_qvalues_from_hist_many(gb2_ctx *ctx, int32_t n_motifs, const gb2_motif *const *motifs,
+                                          const int64_t *h_bin_off, const uint64_t *d_hist, double *d_qtab, uint32_t *d_rank,
+                                          uint64_t *d_totals)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    GB2_REQUIRE(ctx, n_motifs >= 0, "gb2_qvalues_from_hist_many: negative motif count");
+    if (n_motifs == 0) return GB2_OK;
+    GB2_REQUIRE(ctx, motifs && h_bin_off && d_rank, "gb2_qvalues_from_hist_many: null argument");
+    GB2_REQUIRE(ctx, d_hist == nullptr || (d_qtab && d_totals), "gb2_qvalues_from_hist_many: histogram given without q/total buffers");
+    GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<BhMotif> fast;
+    std::vector<int> fast_idx, slow_idx;
+    for (int i = 0; i < n_motifs; ++i) {
+        const gb2_motif *m = motifs[i];
+        GB2_REQUIRE(ctx, m != nullptr && m->device == ctx->device, "gb2_qvalues_from_hist_many: bad motif %d", i);
+        GB2_REQUIRE(ctx, h_bin_off[i + 1] - h_bin_off[i] == m->span + 1, "gb2_qvalues_from_hist_many: motif %d needs %lld bins", i,
+                    (long long)(m->span + 1));
+        if (m->monotone) {
+            BhMotif b;
+            b.ptab = m->d_ptab; b.bin_off = h_bin_off[i]; b.span = (uint32_t)m->span; b.pad = 0;
+            fast.push_back(b);
+            fast_idx.push_back(i);
+        } else {
+            slow_idx.push_back(i);
+        }
+    }
+    for (int i : slow_idx) {  // p-value table not monotone: the sorting form, one motif at a time
+        const int64_t o = h_bin_off[i];
+        int rc = gb2_qvalues_from_hist(ctx, motifs[i], d_hist ? d_hist + o : nullptr, d_qtab ? d_qtab + o : nullptr, d_rank + o,
+                                       d_totals ? d_totals + i : nullptr);
+        if (rc != GB2_OK) return rc;
+    }
+    if (fast.empty()) return GB2_OK;
+    // per-motif totals of the fast group land in a compact array first (the kernel indexes by CTA), then go to their slots
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_desc = align(fast.size() * sizeof(BhMotif));
+    const size_t b_raw = align((size_t)h_bin_off[n_motifs] * sizeof(double));
+    const size_t b_tot = align(fast.size() * sizeof(uint64_t));
+    int rc = gb2_scratch_reserve(ctx, b_desc + b_raw + b_tot);
+    if (rc != GB2_OK) return rc;
+    char *base = (char *)ctx->scratch;
+    BhMotif *d_desc = (BhMotif *)base;
+    double *d_raw = (double *)(base + b_desc);
+    unsigned long long *d_tot = (unsigned long long *)(base + b_desc + b_raw);
+    GB2_CUDA(ctx, cudaMemcpyAsync(d_desc, fast.data(), fast.size() * sizeof(BhMotif), cudaMemcpyHostToDevice, ctx->stream));
+    const bool compact = (int)fast.size() != n_motifs;
+    gb2_bh_many_kernel<<<(unsigned)fast.size(), BH_THREADS, 0, ctx->stream>>>(
+        d_desc, (const unsigned long long *)d_hist, d_qtab, d_rank, compact ? d_tot : (unsigned long long *)d_totals, d_raw);
+    GB2_LAUNCH_CHECK(ctx);
+    if (compact && d_hist != nullptr) {
+        for (size_t k = 0; k < fast_idx.size(); ++k)
+            GB2_CUDA(ctx, cudaMemcpyAsync(d_totals + fast_idx[k], d_tot + k, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return GB2_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // B3: stand-alone Benjamini-Hochberg of an arbitrary p-value list (row-wise form of the same formula)
 // ---------------------------------------------------------------------------------------------

@@ -44,16 +44,17 @@ __device__ __forceinline__ void emit_pair_hits(const ScoreParams &p, uint32_t a0
     }
 }
 
-template <int NCHUNK, int R, int U>
+template <int CB, int NCHUNK, int R, int U>
 __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *lut_s = smem;                      // [NCHUNK*256][R]
-    uint32_t *hist_s = smem + NCHUNK * 256 * R;  // [span+1]
+    constexpr int LUT_WORDS = NCHUNK * ChunkGeom<CB>::ENTRIES * R;
+    uint32_t *lut_s = smem;               // [NCHUNK * 4^CB][R]
+    uint32_t *hist_s = smem + LUT_WORDS;  // [span+1]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool do_hist = p.hist != nullptr;
 
-    for (int i = tid; i < NCHUNK * 256 * R; i += 1024) lut_s[i] = p.lut[i / R];
+    for (int i = tid; i < LUT_WORDS; i += 1024) lut_s[i] = p.lut[i / R];
     if (do_hist)
         for (uint32_t i = tid; i <= p.span; i += 1024) hist_s[i] = 0u;
     __syncthreads();
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
         uint32_t acc[2 * U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            acc[2 * u] = score_word<NCHUNK, R>(v[u].x, v[u].y, lut32);
-            acc[2 * u + 1] = score_word<NCHUNK, R>(v[u].z, v[u].w, lut32);
+            acc[2 * u] = score_word<CB, NCHUNK, R>(v[u].x, v[u].y, lut32);
+            acc[2 * u + 1] = score_word<CB, NCHUNK, R>(v[u].z, v[u].w, lut32);
         }
         if (has_n) {
 #pragma unroll
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
             const bool ok = j < npairs;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (ok) v = ld_stream_u4(src + j);
-            uint32_t a0 = score_word<NCHUNK, R>(v.x, v.y, lut32);
-            uint32_t a1 = score_word<NCHUNK, R>(v.z, v.w, lut32);
+            uint32_t a0 = score_word<CB, NCHUNK, R>(v.x, v.y, lut32);
+            uint32_t a1 = score_word<CB, NCHUNK, R>(v.z, v.w, lut32);
             if (has_n && ok) {
                 const uint32_t nb = (__ldg(p.nmask + (j >> 4)) >> ((j & 15) * 2)) & 3u;
                 if (nb & 1u) a0 = nsent;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
             uint32_t a = 0;
             if (mine) {
                 const uint64_t x = p.packed[row];
-                a = score_word<NCHUNK, R>((uint32_t)x, (uint32_t)(x >> 32), lut32);
+                a = score_word<CB, NCHUNK, R>((uint32_t)x, (uint32_t)(x >> 32), lut32);
                 if (has_n && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) a = nsent;
                 if (do_hist) {
                     red_shared_inc(hist32 + 4u * (a & 0xFFFFu));
@@ -185,24 +186,25 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Wide k-mers (32 < w <= 64, two packed words each): one 128-bit load = one k-mer, 9..16 chunk lookups.  Such motifs are
-// rare (the 34/35-bp CTCF profiles of JASPAR), so the chunk count and the replication factor are run-time values here
-// and one guarded loop serves full tiles and the tail.  Same tables, same packed 16-bit fields, same histogram / hit /
-// dense semantics as the narrow kernel; when the histogram does not fit shared memory next to the tables
-// (hist_in_smem == 0) it is counted with 64-bit global atomics.  NCHUNK is a template parameter (9..16) so that the
-// lookups are straight-line code; R stays a run-time value.
+// Wide k-mers (32 < w <= 64, two packed words each): one 128-bit load = one k-mer.  3-base chunks (64-entry tables,
+// NCHUNK = ceil(w / 3) = 11..22 lookups): at 256 bytes per chunk the tables replicate 32x (16x at w >= 61 with the
+// largest spans) beside a histogram of up to 33 k bins, so a lookup stays at one or two wavefronts -- with 4-base
+// chunks (1 KB per chunk: R = 16 / 8 / 4 at w = 35 / 48 / 64) the shared-memory pipe was 88-96 % busy at 0.60 / 0.43 /
+// 0.34 of the HBM roofline (profiles/r02_wide_kernel_ncu_before.txt).  Same packed 16-bit fields, same histogram /
+// hit / dense semantics as the narrow kernel; when the histogram does not fit shared memory next to the tables
+// (hist_in_smem == 0) it is counted with 64-bit global atomics.  NCHUNK is a template parameter so that the lookups
+// are straight-line code; R is a run-time value.
 template <int NCHUNK>
 __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int R, int hist_in_smem)
 {
-    constexpr int n_chunks = NCHUNK;
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *lut_s = smem;                        // [n_chunks*256][R]
-    uint32_t *hist_s = smem + n_chunks * 256 * R;  // [span+1] when hist_in_smem
+    uint32_t *lut_s = smem;                     // [NCHUNK*64][R]
+    uint32_t *hist_s = smem + NCHUNK * 64 * R;  // [span+1] when hist_in_smem
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool do_hist = p.hist != nullptr;
     const bool hist_smem = do_hist && hist_in_smem;
 
-    for (int i = tid; i < n_chunks * 256 * R; i += 1024) lut_s[i] = p.lut[i / R];
+    for (int i = tid; i < NCHUNK * 64 * R; i += 1024) lut_s[i] = p.lut[i / R];
     if (hist_smem)
         for (uint32_t i = tid; i <= p.span; i += 1024) hist_s[i] = 0u;
     __syncthreads();
@@ -228,13 +230,14 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScorePara
         bool any = false;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const uint32_t wd[5] = {v[u].x, v[u].y, v[u].z, v[u].w, 0u};
             uint32_t a = 0;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
-                const uint32_t b = __byte_perm(wd[c >> 2], 0u, 0x4440u + (uint32_t)(c & 3));  // byte c of the k-mer
+                const int bit = 6 * c, q = bit >> 5, sh = bit & 31;  // constants after unrolling
+                const uint32_t x = (sh + 6 <= 32) ? (wd[q] >> sh) : __funnelshift_r(wd[q], wd[q + 1], sh);
                 uint32_t e;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 256u + b) * rstride));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 64u + (x & 63u)) * rstride));
                 a += e;
             }
             const int64_t row = r0 + u * 1024;
@@ -275,10 +278,10 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScorePara
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NCHUNK, int R>
+template <int CB, int NCHUNK, int R>
 static int launch_score(gb2_ctx *ctx, const ScoreParams &p, size_t smem, int grid)
 {
-    auto kern = gb2_score_kernel<NCHUNK, R, 4>;
+    auto kern = gb2_score_kernel<CB, NCHUNK, R, 4>;
     GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 1024, smem, ctx->stream>>>(p);
     GB2_LAUNCH_CHECK(ctx);
@@ -289,12 +292,23 @@ template <int NCHUNK>
 static int dispatch_r(gb2_ctx *ctx, int R, const ScoreParams &p, size_t smem, int grid)
 {
     switch (R) {
-    case 32: return launch_score<NCHUNK, 32>(ctx, p, smem, grid);
-    case 16: return launch_score<NCHUNK, 16>(ctx, p, smem, grid);
-    case 8: return launch_score<NCHUNK, 8>(ctx, p, smem, grid);
-    case 4: return launch_score<NCHUNK, 4>(ctx, p, smem, grid);
-    case 2: return launch_score<NCHUNK, 2>(ctx, p, smem, grid);
-    default: return launch_score<NCHUNK, 1>(ctx, p, smem, grid);
+    case 32: return launch_score<4, NCHUNK, 32>(ctx, p, smem, grid);
+    case 16: return launch_score<4, NCHUNK, 16>(ctx, p, smem, grid);
+    case 8: return launch_score<4, NCHUNK, 8>(ctx, p, smem, grid);
+    case 4: return launch_score<4, NCHUNK, 4>(ctx, p, smem, grid);
+    case 2: return launch_score<4, NCHUNK, 2>(ctx, p, smem, grid);
+    default: return launch_score<4, NCHUNK, 1>(ctx, p, smem, grid);
+    }
+}
+
+// 3-base chunks (narrow motifs of 19..32 bp whose 4-base tables would not replicate 32x): R = 32, 16 or 8
+template <int NCHUNK>
+static int dispatch_r3(gb2_ctx *ctx, int R, const ScoreParams &p, size_t smem, int grid)
+{
+    switch (R) {
+    case 32: return launch_score<3, NCHUNK, 32>(ctx, p, smem, grid);
+    case 16: return launch_score<3, NCHUNK, 16>(ctx, p, smem, grid);
+    default: return launch_score<3, NCHUNK, 8>(ctx, p, smem, grid);
     }
 }
 
@@ -357,18 +371,23 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     }
 
     const size_t smem = (size_t)m->smem_bytes;
-    if (m->w > GB2_NARROW_WIDTH) {  // two packed words per k-mer
+    if (m->w > GB2_NARROW_WIDTH) {  // two packed words per k-mer, 3-base chunks
+        GB2_REQUIRE(ctx, m->chunk_bases == 3 && m->n_chunks >= 11 && m->n_chunks <= 22, "gb2_score: bad chunk plan of a wide motif");
         const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(n, 4096)));
         void (*kern)(const ScoreParams, int, int) = nullptr;
         switch (m->n_chunks) {
-        case 9: kern = gb2_score_wide_kernel<9>; break;
-        case 10: kern = gb2_score_wide_kernel<10>; break;
         case 11: kern = gb2_score_wide_kernel<11>; break;
         case 12: kern = gb2_score_wide_kernel<12>; break;
         case 13: kern = gb2_score_wide_kernel<13>; break;
         case 14: kern = gb2_score_wide_kernel<14>; break;
         case 15: kern = gb2_score_wide_kernel<15>; break;
-        default: kern = gb2_score_wide_kernel<16>; break;
+        case 16: kern = gb2_score_wide_kernel<16>; break;
+        case 17: kern = gb2_score_wide_kernel<17>; break;
+        case 18: kern = gb2_score_wide_kernel<18>; break;
+        case 19: kern = gb2_score_wide_kernel<19>; break;
+        case 20: kern = gb2_score_wide_kernel<20>; break;
+        case 21: kern = gb2_score_wide_kernel<21>; break;
+        default: kern = gb2_score_wide_kernel<22>; break;
         }
         GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 1024, smem, ctx->stream>>>(p, m->replicas, m->hist_global ? 0 : 1);
@@ -377,6 +396,15 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     }
     const int64_t npairs = n >> 1;
     int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(npairs, 4096)));
+    if (m->chunk_bases == 3) {
+        switch (m->n_chunks) {
+        case 7: return dispatch_r3<7>(ctx, m->replicas, p, smem, grid);
+        case 8: return dispatch_r3<8>(ctx, m->replicas, p, smem, grid);
+        case 9: return dispatch_r3<9>(ctx, m->replicas, p, smem, grid);
+        case 10: return dispatch_r3<10>(ctx, m->replicas, p, smem, grid);
+        default: return dispatch_r3<11>(ctx, m->replicas, p, smem, grid);
+        }
+    }
     switch (m->n_chunks) {
     case 1: return dispatch_r<1>(ctx, m->replicas, p, smem, grid);
     case 2: return dispatch_r<2>(ctx, m->replicas, p, smem, grid);

@@ -46,28 +46,47 @@ __device__ __forceinline__ void red_shared_inc(uint32_t addr)
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-// Both strands of one packed k-mer (w0 = bases 0..15, w1 = bases 16..31): one byte extract (PRMT), one
-// address add (LEA/IMAD) and one conflict-free LDS per 4-base chunk.  lut32 = shared-window address of
-// the replicated table + 4 * (lane & (R-1)); entry (c, b) sits at lut32 + (c*256 + b) * R * 4.
-template <int C, int NCHUNK, int R>
+// Both strands of one packed k-mer (w0 = bases 0..15, w1 = bases 16..31): per CB-base chunk one index extract, one
+// address add and one conflict-free LDS.  lut32 = shared-window address of the replicated table + 4 * (lane & (R-1));
+// entry (c, b) sits at lut32 + (c * 4^CB + b) * R * 4.
+//   CB = 4: the chunk is a byte of the k-mer (PRMT), 256-entry tables;
+//   CB = 3: six bits at a time (shift / funnel shift + mask), 64-entry tables -- a quarter of the memory per chunk, so long
+//           motifs still replicate 32x and keep every lookup at one wavefront (context.cu plan_smem).
+template <int CB>
+struct ChunkGeom {
+    static constexpr int ENTRIES = 1 << (2 * CB);
+};
+
+template <int CB, int C, int NCHUNK, int R>
 struct ChunkSum {
     static __device__ __forceinline__ uint32_t run(uint32_t w0, uint32_t w1, uint32_t lut32)
     {
-        const uint32_t word = (C < 4) ? w0 : w1;
-        const uint32_t b = __byte_perm(word, 0u, 0x4440u + (uint32_t)(C & 3));  // PRMT: byte C of the k-mer
+        uint32_t b;
+        if (CB == 4) {
+            const uint32_t word = (C < 4) ? w0 : w1;
+            b = __byte_perm(word, 0u, 0x4440u + (uint32_t)(C & 3));  // PRMT: byte C of the k-mer
+        } else {
+            constexpr int bit = 2 * CB * C;
+            uint32_t v;
+            if (bit + 2 * CB <= 32) v = w0 >> bit;
+            else if (bit >= 32) v = w1 >> (bit - 32);
+            else v = __funnelshift_r(w0, w1, bit);
+            b = v & (uint32_t)(ChunkGeom<CB>::ENTRIES - 1);
+        }
         // table offset of chunk C rides in the LDS immediate; the entry offset is one IMAD/LEA
-        return lds_u32<C * 256 * R * 4>(lut32 + b * (uint32_t)(R * 4)) + ChunkSum<C + 1, NCHUNK, R>::run(w0, w1, lut32);
+        return lds_u32<C * ChunkGeom<CB>::ENTRIES * R * 4>(lut32 + b * (uint32_t)(R * 4)) +
+               ChunkSum<CB, C + 1, NCHUNK, R>::run(w0, w1, lut32);
     }
 };
-template <int NCHUNK, int R>
-struct ChunkSum<NCHUNK, NCHUNK, R> {
+template <int CB, int NCHUNK, int R>
+struct ChunkSum<CB, NCHUNK, NCHUNK, R> {
     static __device__ __forceinline__ uint32_t run(uint32_t, uint32_t, uint32_t) { return 0u; }
 };
 
-template <int NCHUNK, int R>
+template <int CB, int NCHUNK, int R>
 __device__ __forceinline__ uint32_t score_word(uint32_t w0, uint32_t w1, uint32_t lut32)
 {
-    return ChunkSum<0, NCHUNK, R>::run(w0, w1, lut32);
+    return ChunkSum<CB, 0, NCHUNK, R>::run(w0, w1, lut32);
 }
 
 // Appends the hits of one (k-mer, strand) slot across the warp: one ballot, one global atomic.

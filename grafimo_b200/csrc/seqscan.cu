@@ -68,18 +68,18 @@ __device__ __forceinline__ void window_words(uint32_t L0, uint32_t L1, uint32_t 
     }
 }
 
-template <int NCHUNK, int R, int ROUND, int K>
+template <int CB, int NCHUNK, int R, int ROUND, int K>
 struct RoundScore {
     static __device__ __forceinline__ void run(uint32_t L0, uint32_t L1, uint32_t H0, uint32_t H1, uint32_t lut32, uint32_t *acc)
     {
         uint32_t w0, w1;
         window_words<ROUND * 8 + K>(L0, L1, H0, H1, w0, w1);
-        acc[K] = score_word<NCHUNK, R>(w0, w1, lut32);
-        RoundScore<NCHUNK, R, ROUND, K + 1>::run(L0, L1, H0, H1, lut32, acc);
+        acc[K] = score_word<CB, NCHUNK, R>(w0, w1, lut32);
+        RoundScore<CB, NCHUNK, R, ROUND, K + 1>::run(L0, L1, H0, H1, lut32, acc);
     }
 };
-template <int NCHUNK, int R, int ROUND>
-struct RoundScore<NCHUNK, R, ROUND, 8> {
+template <int CB, int NCHUNK, int R, int ROUND>
+struct RoundScore<CB, NCHUNK, R, ROUND, 8> {
     static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t *) {}
 };
 
@@ -102,14 +102,14 @@ __device__ __noinline__ void emit_round_hits(const ScoreParams &p, uint32_t a0, 
 
 // One round = windows 8*ROUND .. 8*ROUND+7 of this lane's word.  GUARD: windows may be invalid (sequence tail) or
 // touch an N base; without it the round is straight-line code with no per-window predicate.
-template <int NCHUNK, int R, int ROUND, bool GUARD>
+template <int CB, int NCHUNK, int R, int ROUND, bool GUARD>
 __device__ __forceinline__ void score_round(const ScoreParams &p, uint32_t L0, uint32_t L1, uint32_t H0, uint32_t H1,
                                             uint64_t nn, uint64_t wmask, int nvalid, int64_t row_first, uint32_t lut32,
                                             uint32_t hist32, unsigned lane, bool do_hist, bool two, uint32_t nsent,
                                             uint32_t cut_hi)
 {
     uint32_t acc[8];
-    RoundScore<NCHUNK, R, ROUND, 0>::run(L0, L1, H0, H1, lut32, acc);
+    RoundScore<CB, NCHUNK, R, ROUND, 0>::run(L0, L1, H0, H1, lut32, acc);
     bool ok[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -158,38 +158,39 @@ __device__ __forceinline__ void score_round(const ScoreParams &p, uint32_t L0, u
     }
 }
 
-template <int NCHUNK, int R, bool GUARD>
+template <int CB, int NCHUNK, int R, bool GUARD>
 __device__ __forceinline__ void score_unit_body(const ScoreParams &p, uint64_t lo, uint64_t hi, uint64_t nn, uint64_t wmask,
                                            int nvalid, int64_t row_first, uint32_t lut32, uint32_t hist32, unsigned lane,
                                            bool do_hist, bool two, uint32_t nsent, uint32_t cut_hi)
 {
     const uint32_t L0 = (uint32_t)lo, L1 = (uint32_t)(lo >> 32), H0 = (uint32_t)hi, H1 = (uint32_t)(hi >> 32);
-    score_round<NCHUNK, R, 0, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
-    score_round<NCHUNK, R, 1, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
-    score_round<NCHUNK, R, 2, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
-    score_round<NCHUNK, R, 3, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+    score_round<CB, NCHUNK, R, 0, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+    score_round<CB, NCHUNK, R, 1, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+    score_round<CB, NCHUNK, R, 2, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+    score_round<CB, NCHUNK, R, 3, GUARD>(p, L0, L1, H0, H1, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
 }
 
 // the guarded form (sequence tails, units with N bases) is rare: out of line, its registers are its own
-template <int NCHUNK, int R>
+template <int CB, int NCHUNK, int R>
 __device__ __noinline__ void score_unit_guarded(const ScoreParams &p, uint64_t lo, uint64_t hi, uint64_t nn, uint64_t wmask,
                                                 int nvalid, int64_t row_first, uint32_t lut32, uint32_t hist32, unsigned lane,
                                                 bool do_hist, bool two, uint32_t nsent, uint32_t cut_hi)
 {
-    score_unit_body<NCHUNK, R, true>(p, lo, hi, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+    score_unit_body<CB, NCHUNK, R, true>(p, lo, hi, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
 }
 
-template <int NCHUNK, int R, int NT>
+template <int CB, int NCHUNK, int R, int NT>
 __global__ void __launch_bounds__(NT, 1) gb2_score_seq_kernel(const SeqScoreParams q)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const ScoreParams &p = q.sp;
-    uint32_t *lut_s = smem;                      // [NCHUNK*256][R]
-    uint32_t *hist_s = smem + NCHUNK * 256 * R;  // [span+1]
+    constexpr int LUT_WORDS = NCHUNK * ChunkGeom<CB>::ENTRIES * R;
+    uint32_t *lut_s = smem;               // [NCHUNK * 4^CB][R]
+    uint32_t *hist_s = smem + LUT_WORDS;  // [span+1]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool do_hist = p.hist != nullptr;
 
-    for (int i = tid; i < NCHUNK * 256 * R; i += NT) lut_s[i] = p.lut[i / R];
+    for (int i = tid; i < LUT_WORDS; i += NT) lut_s[i] = p.lut[i / R];
     if (do_hist)
         for (uint32_t i = tid; i <= p.span; i += NT) hist_s[i] = 0u;
     __syncthreads();
@@ -235,9 +236,9 @@ __global__ void __launch_bounds__(NT, 1) gb2_score_seq_kernel(const SeqScorePara
             const int64_t row_first = __ldg(&q.desc[s].row0) + wi * 32;
             const bool plain = (nvalid == 32) & (nn == 0ull);
             if (__all_sync(0xFFFFFFFFu, plain))
-                score_unit_body<NCHUNK, R, false>(p, lo, hi, 0ull, wmask, 32, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+                score_unit_body<CB, NCHUNK, R, false>(p, lo, hi, 0ull, wmask, 32, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
             else
-                score_unit_guarded<NCHUNK, R>(p, lo, hi, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
+                score_unit_guarded<CB, NCHUNK, R>(p, lo, hi, nn, wmask, nvalid, row_first, lut32, hist32, lane, do_hist, two, nsent, cut_hi);
         }
     }
 
@@ -432,24 +433,24 @@ static int upload_desc(gb2_ctx *ctx, int slot, int w_for_units, int64_t n_seqs, 
     return GB2_OK;
 }
 
-template <int NCHUNK, int R>
+template <int CB, int NCHUNK, int R>
 static int launch_seq(gb2_ctx *ctx, const SeqScoreParams &q, size_t smem, int grid)
 {
     // 32 warps per SM: measured 3.83 ms per 2.5e9 windows (CTCF, both strands) against 4.62 ms with 16 warps
-    auto kern = gb2_score_seq_kernel<NCHUNK, R, 1024>;
+    auto kern = gb2_score_seq_kernel<CB, NCHUNK, R, 1024>;
     GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 1024, smem, ctx->stream>>>(q);
     GB2_LAUNCH_CHECK(ctx);
     return GB2_OK;
 }
 
-template <int NCHUNK>
+template <int CB, int NCHUNK>
 static int dispatch_seq_r(gb2_ctx *ctx, int R, const SeqScoreParams &q, size_t smem, int grid)
 {
     switch (R) {
-    case 32: return launch_seq<NCHUNK, 32>(ctx, q, smem, grid);
-    case 16: return launch_seq<NCHUNK, 16>(ctx, q, smem, grid);
-    default: return launch_seq<NCHUNK, 8>(ctx, q, smem, grid);
+    case 32: return launch_seq<CB, NCHUNK, 32>(ctx, q, smem, grid);
+    case 16: return launch_seq<CB, NCHUNK, 16>(ctx, q, smem, grid);
+    default: return launch_seq<CB, NCHUNK, 8>(ctx, q, smem, grid);
     }
 }
 
@@ -459,15 +460,24 @@ static int gb2_launch_score_seq(gb2_ctx *ctx, const gb2_motif *m, const SeqScore
     const size_t smem = (size_t)m->smem_bytes;
     const int64_t per_cta = 32;  // warps per CTA
     const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(q.total_units, per_cta)));
+    if (m->chunk_bases == 3) {
+        switch (m->n_chunks) {
+        case 7: return dispatch_seq_r<3, 7>(ctx, m->replicas, q, smem, grid);
+        case 8: return dispatch_seq_r<3, 8>(ctx, m->replicas, q, smem, grid);
+        case 9: return dispatch_seq_r<3, 9>(ctx, m->replicas, q, smem, grid);
+        case 10: return dispatch_seq_r<3, 10>(ctx, m->replicas, q, smem, grid);
+        default: return dispatch_seq_r<3, 11>(ctx, m->replicas, q, smem, grid);
+        }
+    }
     switch (m->n_chunks) {
-    case 1: return dispatch_seq_r<1>(ctx, m->replicas, q, smem, grid);
-    case 2: return dispatch_seq_r<2>(ctx, m->replicas, q, smem, grid);
-    case 3: return dispatch_seq_r<3>(ctx, m->replicas, q, smem, grid);
-    case 4: return dispatch_seq_r<4>(ctx, m->replicas, q, smem, grid);
-    case 5: return dispatch_seq_r<5>(ctx, m->replicas, q, smem, grid);
-    case 6: return dispatch_seq_r<6>(ctx, m->replicas, q, smem, grid);
-    case 7: return dispatch_seq_r<7>(ctx, m->replicas, q, smem, grid);
-    default: return dispatch_seq_r<8>(ctx, m->replicas, q, smem, grid);
+    case 1: return dispatch_seq_r<4, 1>(ctx, m->replicas, q, smem, grid);
+    case 2: return dispatch_seq_r<4, 2>(ctx, m->replicas, q, smem, grid);
+    case 3: return dispatch_seq_r<4, 3>(ctx, m->replicas, q, smem, grid);
+    case 4: return dispatch_seq_r<4, 4>(ctx, m->replicas, q, smem, grid);
+    case 5: return dispatch_seq_r<4, 5>(ctx, m->replicas, q, smem, grid);
+    case 6: return dispatch_seq_r<4, 6>(ctx, m->replicas, q, smem, grid);
+    case 7: return dispatch_seq_r<4, 7>(ctx, m->replicas, q, smem, grid);
+    default: return dispatch_seq_r<4, 8>(ctx, m->replicas, q, smem, grid);
     }
 }
 

@@ -322,24 +322,49 @@ def pack_sequences_2bit(seqs):
 class DeviceMotif:
     """Device-resident motif: chunk LUTs + the score -> p-value table (K4)."""
 
-    def __init__(self, ctx, score_matrix, pval_mat, min_val, scale, offset):
+    def __init__(self, ctx, score_matrix, pval_mat, min_val, scale, offset, _handle=None):
         self.ctx = ctx
-        sm = np.ascontiguousarray(score_matrix, dtype=np.int64)
-        if sm.ndim != 2 or sm.shape[0] != 4:
-            raise ValueError("score_matrix must be int[4, w] with rows A,C,G,T")
-        w = sm.shape[1]
-        pm = np.ascontiguousarray(pval_mat, dtype=np.float64)
-        if pm.shape != (_lib.RANGE * w + 1,):
-            raise ValueError(f"pval_mat must have {_lib.RANGE * w + 1} entries for width {w}")
-        h = ctypes.c_void_p()
-        check(ctx.lib.gb2_motif_create(ctx.h, _np_ptr(sm), w, _np_ptr(pm), int(min_val), int(scale), float(offset),
-                                       ctypes.byref(h)), "gb2_motif_create", ctx.h)
-        self.h = h
+        if _handle is None:
+            _handle = DeviceMotif._create(ctx, [(score_matrix, pval_mat, min_val, scale, offset)])[0]
+        self.h = _handle
         info = MotifInfo()
-        check(ctx.lib.gb2_motif_get_info(h, ctypes.byref(info)), "gb2_motif_get_info")
+        check(ctx.lib.gb2_motif_get_info(self.h, ctypes.byref(info)), "gb2_motif_get_info")
         self.info = info
         self.width, self.lo, self.hi, self.span = info.width, info.lo, info.hi, info.span
         self._ptable = None
+
+    @staticmethod
+    def _create(ctx, items):
+        """gb2_motif_create_batched: one allocation, one upload, two K4 launches and one synchronisation for all items."""
+        sms, pms = [], []
+        for sm, pm, _, _, _ in items:
+            sm = np.ascontiguousarray(sm, dtype=np.int64)
+            if sm.ndim != 2 or sm.shape[0] != 4:
+                raise ValueError("score_matrix must be int[4, w] with rows A,C,G,T")
+            pm = np.ascontiguousarray(pm, dtype=np.float64)
+            if pm.shape != (_lib.RANGE * sm.shape[1] + 1,):
+                raise ValueError(f"pval_mat must have {_lib.RANGE * sm.shape[1] + 1} entries for width {sm.shape[1]}")
+            sms.append(sm)
+            pms.append(pm)
+        n = len(items)
+        widths = np.array([sm.shape[1] for sm in sms], dtype=np.int32)
+        sm_all = np.concatenate([sm.reshape(-1) for sm in sms]) if n > 1 else sms[0].reshape(-1)
+        pm_all = np.concatenate(pms) if n > 1 else pms[0]
+        mins = np.array([int(it[2]) for it in items], dtype=np.int64)
+        scales = np.array([int(it[3]) for it in items], dtype=np.int64)
+        offs = np.array([float(it[4]) for it in items], dtype=np.float64)
+        handles = (ctypes.c_void_p * n)()
+        check(ctx.lib.gb2_motif_create_batched(ctx.h, n, _np_ptr(widths), _np_ptr(sm_all), _np_ptr(pm_all), _np_ptr(mins),
+                                               _np_ptr(scales), _np_ptr(offs), handles), "gb2_motif_create_batched", ctx.h)
+        return [ctypes.c_void_p(h) for h in handles]
+
+    @classmethod
+    def create_many(cls, ctx, items):
+        """items: list of (score_matrix int[4, w], pval_mat, min_val, scale, offset) -> list of DeviceMotif, created together
+        (a motif collection: BASELINE config 3)."""
+        if not items:
+            return []
+        return [cls(ctx, None, None, None, None, None, _handle=h) for h in cls._create(ctx, items)]
 
     @property
     def ptable(self):
@@ -543,28 +568,30 @@ class ManyScan:
     def _at(self, tensor, m, itemsize):
         return ctypes.c_void_p(tensor.data_ptr() + int(self.off[m]) * itemsize) if tensor is not None else None
 
-    def score(self, m, packed, nmask=None):
-        """Queues K2 of motif number m over `packed` (rows 0..n-1 of the k-mer set of its width)."""
+    def score(self, m, packed, nmask=None, row_offset=0):
+        """Queues K2 of motif number m over `packed` (rows row_offset .. row_offset+n-1 of the k-mer set of its width)."""
         ctx, mo = self.ctx, self.motifs[m]
         n = packed.shape[0]
-        if n >= (1 << self.ROW_BITS):
+        if n + int(row_offset) >= (1 << self.ROW_BITS):
             raise ValueError("at most 2^40 - 1 rows per motif")
         ctx.enter()
         packed.record_stream(ctx.stream)
         if nmask is not None:
             nmask.record_stream(ctx.stream)
-        check(ctx.lib.gb2_score(ctx.h, mo.h, _ptr(packed), _ptr(nmask), n, int(m) << self.ROW_BITS, self.strands, self.threshold,
-                                self._at(self.hist, m, 8), _ptr(self.hits), self.capacity, _ptr(self.counters), None),
+        check(ctx.lib.gb2_score(ctx.h, mo.h, _ptr(packed), _ptr(nmask), n, (int(m) << self.ROW_BITS) + int(row_offset), self.strands,
+                                self.threshold, self._at(self.hist, m, 8), _ptr(self.hits), self.capacity, _ptr(self.counters), None),
               "gb2_score", ctx.h)
-        self.row_limit = max(self.row_limit, n)
+        self.row_limit = max(self.row_limit, n + int(row_offset))
 
     def qvalues(self):
-        """Queues K5 of every motif (its own histogram -> its own q-table and p-rank table)."""
+        """Queues K5 of every motif (its own histogram -> its own q-table and p-rank table): ONE launch, one CTA per
+        motif (gb2_qvalues_from_hist_many)."""
         ctx = self.ctx
         ctx.enter()
-        for m, mo in enumerate(self.motifs):
-            check(ctx.lib.gb2_qvalues_from_hist(ctx.h, mo.h, self._at(self.hist, m, 8), self._at(self.qtab, m, 8), self._at(self.rank, m, 4),
-                                                ctypes.c_void_p(self.totals.data_ptr() + 8 * m)), "gb2_qvalues_from_hist", ctx.h)
+        k = len(self.motifs)
+        handles = (ctypes.c_void_p * k)(*[mo.h.value for mo in self.motifs])
+        check(ctx.lib.gb2_qvalues_from_hist_many(ctx.h, k, handles, _np_ptr(self.off), _ptr(self.hist), _ptr(self.qtab),
+                                                 _ptr(self.rank), _ptr(self.totals)), "gb2_qvalues_from_hist_many", ctx.h)
 
     def finalize_device(self, q_filter=False):
         """One sort for all motifs -> self.out (device tensors: motif, row, strand, iscore, score, p, q), rows ordered by
@@ -588,7 +615,23 @@ class ManyScan:
                                              ctypes.c_void_p(self.counters.data_ptr() + 8)), "gb2_finalize_hits_many", ctx.h)
         ctx.sync()
         self.out = o
+        self.hits_found = n
         return int(self.counters[1].item())
+
+    def hits_overflowed(self):
+        """True when more hits were found than the buffer holds (the scan has to be repeated with hits_needed())."""
+        self.ctx.sync()
+        return int(self.counters[0].item()) > self.capacity
+
+    def hits_needed(self):
+        self.ctx.sync()
+        return int(self.counters[0].item())
+
+    def split_by_motif(self, kept):
+        """-> int64[n_motifs + 1] offsets of every motif's (contiguous) rows in self.out."""
+        with torch.cuda.stream(self.ctx.stream):
+            cnt = torch.bincount(self.out["motif"][:kept].to(torch.int64), minlength=len(self.motifs)).cpu().numpy()
+        return np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
 
 
 def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):

@@ -96,6 +96,26 @@ class DeviceGraph:
             if len(pos) > 1 and (np.diff(pos) < 0).any():
                 raise ValueError("variant arrays must be sorted by position")
             order = None
+            if variants.get("ref") is not None and len(pos):
+                # the REF alleles the VCF states must be what the FASTA holds there (a wrong assembly or an off-by-one in
+                # the chromosome naming would otherwise build -- and scan -- a wrong graph silently; `vg construct` rejects it)
+                rl = rlen.astype(np.int64)
+                ref_cat = np.ascontiguousarray(variants["ref"], np.uint8)
+                if len(ref_cat) != int(rl.sum()):
+                    raise ValueError("REF alleles do not match the ref_len column")
+                if (pos < 0).any() or (pos + rl > len(refa)).any():
+                    bad = int(np.nonzero((pos < 0) | (pos + rl > len(refa)))[0][0])
+                    raise ValueError(f"variant at position {int(pos[bad]) + 1} lies outside the reference sequence ({len(refa)} bp)")
+                starts = np.concatenate([[0], np.cumsum(rl)[:-1]])
+                idx = np.repeat(pos, rl) + (np.arange(len(ref_cat), dtype=np.int64) - np.repeat(starts, rl))
+                diff = (refa[idx] & 0xDF) != (ref_cat & 0xDF)
+                if diff.any():
+                    k = int(np.searchsorted(starts, np.nonzero(diff)[0][0], side="right") - 1)
+                    got = bytes(refa[int(pos[k]):int(pos[k]) + int(rl[k])]).decode("ascii", "replace")
+                    want = bytes(ref_cat[int(starts[k]):int(starts[k]) + int(rl[k])]).decode("ascii", "replace")
+                    raise ValueError(f"REF allele of the variant at position {int(pos[k]) + 1} is {want!r} in the VCF but the "
+                                     f"reference sequence holds {got!r} there ({int(diff.sum())} mismatching bases in all): "
+                                     "wrong assembly or chromosome?")
         else:
             nv = len(variants)
             pos = np.array([v[0] for v in variants], dtype=np.int64).reshape(nv)

@@ -26,6 +26,28 @@ COLUMNS = ["motif_id", "motif_alt_id", "sequence_name", "start", "stop", "strand
            "matched_sequence", "haplotype_frequency", "reference"]
 
 _ctx = None
+_LOCAL_ONLY = [False]
+
+
+class local_only:
+    """Inside this block the scoring seams ignore the other ranks of a torchrun job: used when a motif COLLECTION is
+    sharded over the GPUs by motif (every rank scans all the rows of its own motifs, so its q-values are already global
+    and there is nothing to exchange) -- as opposed to one motif whose rows are sharded over the ranks."""
+
+    def __enter__(self):
+        self.prev = _LOCAL_ONLY[0]
+        _LOCAL_ONLY[0] = True
+
+    def __exit__(self, *a):
+        _LOCAL_ONLY[0] = self.prev
+
+
+def _dist_world():
+    """(world, rank) of the scoring seams: the torchrun job, or (1, 0) on one process / inside local_only()."""
+    import torch.distributed as tdist
+    if _LOCAL_ONLY[0] or not (tdist.is_available() and tdist.is_initialized()):
+        return 1, 0
+    return tdist.get_world_size(), tdist.get_rank()
 
 
 def _context():
@@ -105,6 +127,21 @@ def device_motif(motif: Motif, ctx=None):
     except AttributeError:  # an object that does not take new attributes: no cache
         pass
     return dm
+
+
+def device_motifs(motifs, ctx=None):
+    """device_motif for a whole collection: the motifs not uploaded yet are created TOGETHER (gb2_motif_create_batched:
+    one allocation, one upload, two K4 launches, one synchronisation -- not one of each per motif)."""
+    ctx = ctx or _context()
+    todo = [m for m in motifs if not (getattr(m, "_gb2_device", None) is not None and m._gb2_device.ctx is ctx and m._gb2_device.h)]
+    made = engine.DeviceMotif.create_many(ctx, [(score_matrix_acgt(m), m.pval_matrix, m.min_val, m.scale, float(m.offset)) for m in todo])
+    for m, dm in zip(todo, made):
+        try:
+            m._gb2_device = dm
+        except AttributeError:
+            pass
+    lookup = {id(m): dm for m, dm in zip(todo, made)}
+    return [lookup.get(id(m)) or m._gb2_device for m in motifs]
 
 
 # The reference calls compute_results once per motif on the same `width_<w>/*.tsv` files (src/grafimo/grafimo.py:177-179);
@@ -400,8 +437,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     import torch
     import torch.distributed as tdist
     from . import dist as gdist
-    world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
-    rank = tdist.get_rank() if world > 1 else 0
+    world, rank = _dist_world()
     files = files[rank::world]
     t0 = time.time()
     ctx = _context()
@@ -432,9 +468,18 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         exception_handler(ValueError, errmsg, debug)
     stats = [c[1].stats() for c in chunks]
     bad = sum(st["malformed"] for st in stats)
+    odd = sum(st["bad_rows"] for st in stats)
+    if world > 1:  # every rank must fail together, or the others would wait in the exchange step until NCCL times out
+        both = [None] * world
+        tdist.all_gather_object(both, (bad, odd))
+        bad, odd = sum(b for b, _ in both), sum(o for _, o in both)
     if bad:
         exception_handler(ValueError, f"{bad} k-mer rows are malformed (six fields and a k-mer of exactly {width} "
                           "symbols are required).\n", debug)
+    if odd and rank == 0:
+        import warnings
+        warnings.warn(f"{odd} k-mer rows hold symbols other than A, C, G, T, N (IUPAC codes?): the reference leaves them "
+                      "undefined; they are scored like N rows (p-value 1)")
     # every row is scored as given: `vg find -E` already emits the reverse-strand rows.  The hit buffer starts
     # small for selective thresholds and the (cheap) scoring pass is repeated in the rare case it overflows.
     cap = n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8))
@@ -450,7 +495,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
         cap = found
     if world > 1 and not no_qvalue:  # the one exchange step: global score histogram -> global q-values
         with torch.cuda.stream(ctx.stream):
-            gdist.allreduce_histogram(scan.histogram())
+            gdist.allreduce_histogram(scan.histogram(), ctx=ctx)
     kept = scan.finalize_device(q_filter=bool(qval_t))
     if rank == 0:
         if verbose:
@@ -540,8 +585,7 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     n_kmers = sum(b.n for b in batches)
     import torch.distributed as tdist
     from . import dist as gdist
-    world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
-    rank = tdist.get_rank() if world > 1 else 0
+    world, rank = _dist_world()
     if world > 1:
         counts = [None] * world
         tdist.all_gather_object(counts, n_kmers)
@@ -571,7 +615,7 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         cap = found
     if world > 1 and not no_qvalue:  # the one exchange step: global score histogram -> global q-values
         with torch.cuda.stream(ctx.stream):
-            gdist.allreduce_histogram(scan.histogram())
+            gdist.allreduce_histogram(scan.histogram(), ctx=ctx)
     kept = scan.finalize_device(q_filter=bool(qval_t))
     if rank == 0:
         if verbose:
@@ -581,45 +625,102 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         print(f"Scanned sequences:\t{n}")
         print(f"Scanned nucleotides:\t{n * width}")
     t1 = time.time()
+    # ---- the fixed-width columns of this rank's hits, gathered on the device in hit order
+    wide = width > 32
     with torch.cuda.stream(ctx.stream):
         sel = scan.out["row"][:kept]
-        minus = scan.out["strand"][:kept].cpu().numpy().astype(bool)
-        score = scan.out["score"][:kept].cpu().numpy()
-        pval = scan.out["p"][:kept].cpu().numpy()
-        qval = scan.out["q"][:kept].cpu().numpy() if not no_qvalue else None
-        sel_h = sel.cpu().numpy().astype(np.int64)
-    which = np.searchsorted(bases, sel_h, side="right") - 1
-    seqname = np.empty(kept, dtype=object); seq = np.empty(kept, dtype=object)
-    start = np.empty(kept, dtype=np.int64); stop = np.empty(kept, dtype=np.int64); freq = np.empty(kept, dtype=np.int64)
-    isref = np.empty(kept, dtype=bool)
+        bases_dev = torch.from_numpy(bases[1:].copy()).to(ctx.device)
+        which = torch.bucketize(sel, bases_dev, right=True)
+        dev = {"packed": torch.empty((kept, 2) if wide else (kept,), dtype=torch.int64, device=ctx.device),
+               "start": torch.empty(kept, dtype=torch.int64, device=ctx.device), "stop": torch.empty(kept, dtype=torch.int64, device=ctx.device),
+               "freq": torch.empty(kept, dtype=torch.int64, device=ctx.device), "isref": torch.empty(kept, dtype=torch.uint8, device=ctx.device),
+               "region": torch.empty(kept, dtype=torch.int64, device=ctx.device)}
+        name_base = np.concatenate([[0], np.cumsum([len(b.regions) for b in batches])]).astype(np.int64)
+        for k, b in enumerate(batches):
+            if not b.n:
+                continue
+            m = torch.nonzero(which == k).view(-1)
+            if m.numel() == 0:
+                continue
+            idx = sel[m] - int(bases[k])
+            dev["packed"][m] = b.packed[idx]
+            dev["start"][m], dev["stop"][m] = b.start[idx], b.stop[idx]
+            dev["freq"][m] = b.freq[idx].to(torch.int64)
+            dev["isref"][m] = b.isref[idx].to(torch.uint8)
+            dev["region"][m] = b.region[idx].to(torch.int64) + int(name_base[k])
+        dev["minus"] = scan.out["strand"][:kept].to(torch.uint8)
+        dev["score"], dev["p"] = scan.out["score"][:kept], scan.out["p"][:kept]
+        if not no_qvalue:
+            dev["q"] = scan.out["q"][:kept]
+    names = [b.region_name(r) for b in batches for r in range(len(b.regions))]
+    if world > 1:
+        dev, names = _gather_hit_columns(ctx, dev, names, kept, world)
+    with torch.cuda.stream(ctx.stream):
+        host = {k: v.cpu().numpy() for k, v in dev.items()}
+    minus = host["minus"].astype(bool)
     from .extract_regions import decode_kmers
     comp = np.zeros(256, np.uint8)
     comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
-    for k, b in enumerate(batches):
-        m = np.nonzero(which == k)[0]
-        if len(m) == 0:
-            continue
-        with torch.cuda.stream(ctx.stream):
-            idx = torch.from_numpy(sel_h[m] - bases[k]).to(ctx.device)
-            g = {c: getattr(b, c)[idx].cpu().numpy() for c in ("packed", "start", "stop", "freq", "isref", "region")}
-        asc = decode_kmers(g["packed"], width)
-        rc = comp[asc][:, ::-1]
-        asc = np.where(minus[m][:, None], rc, asc)
-        seq[m] = np.char.decode(np.ascontiguousarray(asc).view(f"S{width}").ravel(), "ascii").astype(object)
-        names = np.array([b.region_name(r) for r in range(len(b.regions))], dtype=object)
-        seqname[m] = names[g["region"]]
-        # the '-' row of a walk starts where the walk stops
-        start[m] = np.where(minus[m], g["stop"], g["start"])
-        stop[m] = np.where(minus[m], g["start"], g["stop"])
-        freq[m] = g["freq"]
-        isref[m] = g["isref"].astype(bool)
-    ref = np.where(isref & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
-    keep = np.ones(kept, dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
+    asc = decode_kmers(host["packed"], width)
+    asc = np.where(minus[:, None], comp[asc][:, ::-1], asc)
+    seq = np.char.decode(np.ascontiguousarray(asc).view(f"S{width}").ravel(), "ascii").astype(object) if len(minus) else np.array([], dtype=object)
+    seqname = np.array(names, dtype=object)[host["region"]] if len(minus) else np.array([], dtype=object)
+    # the '-' row of a walk starts where the walk stops
+    start = np.where(minus, host["stop"], host["start"])
+    stop = np.where(minus, host["start"], host["stop"])
+    freq = host["freq"]
+    ref = np.where(host["isref"].astype(bool) & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
+    keep = np.ones(len(minus), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     strand = np.where(minus, "-", "+").astype(object)
-    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world)
+    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, host["score"], host["p"], host.get("q"), seq, freq, ref, 1)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df
+
+
+def _gather_hit_columns(ctx, dev, names, kept, world):
+    """Multi-rank merge of the report rows ON THE DEVICE: the fixed-width hit columns of every rank (packed k-mer, start,
+    stop, frequency, ref flag, region id, strand, score, p, q) are padded to the largest per-rank count, laid back to back
+    in one byte buffer and exchanged by ONE all-gather inside the library (gb2_allgather_bytes -> ncclAllGather; gloo /
+    torch.distributed when the context owns no communicator); the strings are decoded once from the gathered columns.
+    Replaces the pickled object arrays of all_gather_object (and the reference's Manager-dict funnel,
+    score_sequences.py:115-118,171-188).  Region ids become global (rank-major); -> (columns, all region names)."""
+    import torch
+    import torch.distributed as tdist
+    meta = [None] * world
+    tdist.all_gather_object(meta, (int(kept), list(names)))  # a few bytes per rank: counts and region names
+    counts = [m[0] for m in meta]
+    name_off = np.concatenate([[0], np.cumsum([len(m[1]) for m in meta])])
+    all_names = [nm for m in meta for nm in m[1]]
+    rank = tdist.get_rank()
+    cap = max(max(counts), 1)
+    keys = list(dev.keys())
+    with torch.cuda.stream(ctx.stream):
+        dev["region"] = dev["region"] + int(name_off[rank])
+        parts, layout = [], []
+        for k in keys:
+            v = dev[k].contiguous()
+            row_bytes = v.element_size() * (v.shape[1] if v.dim() == 2 else 1)
+            buf = torch.zeros(cap * row_bytes, dtype=torch.uint8, device=ctx.device)
+            buf[:kept * row_bytes] = v.view(torch.uint8).view(-1)
+            parts.append(buf)
+            layout.append((k, v.dtype, row_bytes, v.dim() == 2))
+        send = torch.cat(parts)
+    if getattr(ctx, "world", 1) == world:
+        gathered = ctx.allgather(send)
+    else:
+        gathered = torch.empty((world, send.numel()), dtype=torch.uint8, device=ctx.device)
+        with torch.cuda.stream(ctx.stream):
+            tdist.all_gather_into_tensor(gathered.view(-1), send)
+    out = {}
+    with torch.cuda.stream(ctx.stream):
+        off = 0
+        for k, dt, row_bytes, two in layout:
+            pieces = [gathered[r, off:off + counts[r] * row_bytes] for r in range(world)]
+            col = torch.cat(pieces).view(dt)
+            out[k] = col.view(-1, 2) if two else col
+            off += cap * row_bytes
+    return out, all_names
 
 
 def _revcomp_packed(packed, width):
@@ -675,9 +776,21 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
     print(f"Scanned sequences:\t{n}")
     print(f"Scanned nucleotides:\t{n * width}")
     with torch.cuda.stream(ctx.stream):
-        row = scan.out["row"][:kept]
-        minus = scan.out["strand"][:kept].to(torch.bool)
-        bin_ = (scan.out["iscore"][:kept] - int(dm.lo)).to(torch.int32)
+        qtab = scan.qtab.cpu().numpy() if not no_qvalue else None
+    return _device_report(ctx, motif, dm, batches, scan.out["row"][:kept], scan.out["strand"][:kept], scan.out["iscore"][:kept],
+                          qtab, recomb, no_qvalue)
+
+
+def _device_report(ctx, motif, dm, batches, row, strand_u8, iscore, qtab, recomb, no_qvalue):
+    """res_writer.DeviceReport from the device-resident hit columns of one motif (rows index the concatenation of
+    `batches`): side arrays gathered on the device, '-' hits reverse-complemented with start/stop swapped,
+    the ref rewrite of score_sequences.py:305-307 and the recomb filter of resultsTmp.py:309-310."""
+    import torch
+    from .res_writer import DeviceReport
+    dev, width = ctx.device, motif.width
+    with torch.cuda.stream(ctx.stream):
+        minus = strand_u8.to(torch.bool)
+        bin_ = (iscore - int(dm.lo)).to(torch.int32)
         cat = lambda name, dt: torch.cat([getattr(b, name)[:b.n].to(dt) for b in batches]) if len(batches) > 1 else getattr(batches[0], name)[:batches[0].n].to(dt)  # noqa: E731
         packed, start, stop = cat("packed", torch.int64)[row], cat("start", torch.int64)[row], cat("stop", torch.int64)[row]
         freq, isref = cat("freq", torch.int64)[row], cat("isref", torch.bool)[row]
@@ -692,13 +805,71 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
         strand = torch.where(minus, torch.tensor(45, dtype=torch.uint8, device=dev), torch.tensor(43, dtype=torch.uint8, device=dev))
         keep = torch.ones_like(minus) if recomb else freq > 0  # resultsTmp.py:309-310
         cols = [c[keep].contiguous() for c in (kmer, strand, s2, e2, freq, ref, bin_, region)]
-        qtab = scan.qtab.cpu().numpy() if not no_qvalue else None
     ctx.sync()
     seqnames = [b.region_name(r) for b in batches for r in range(len(b.regions))]
     span = int(dm.span)
     score_by_bin = (np.arange(span, dtype=np.int64) + int(dm.lo)) / np.float64(motif.scale) + np.float64(width) * np.float64(motif.offset)
     return DeviceReport(ctx, motif, width, not no_qvalue, *cols, seqnames, score_by_bin, dm.ptable,
                         qtab[:span] if qtab is not None else None)
+
+
+def scan_rows_device_many(motifs, rows_of_width, debug: bool, args_obj):
+    """scan_rows_device for a motif COLLECTION over the same k-mers (BASELINE config 3; replaces the per-motif loop of
+    src/grafimo/grafimo.py:177-183): the motifs are uploaded together (gb2_motif_create_batched), K2 of every motif is
+    queued into one shared hit buffer, K5 of all motifs is one launch and ONE sort finalizes the hits of all of them
+    (engine.ManyScan) -- no host round trip per motif.  `rows_of_width`: {width: [GraphRows, ...]}.  -> list of
+    DeviceReport, one per motif, each identical to what scan_rows_device returns for that motif alone.  Unselective
+    thresholds (>= 0.25: every window is a report row) take the per-motif dense route."""
+    import torch
+    threshold, no_qvalue, qval_t = args_obj.threshold, args_obj.noqvalue, args_obj.qvalueT
+    no_reverse, recomb = args_obj.noreverse, args_obj.recomb
+    if not motifs:
+        return []
+    if threshold >= 0.25 or len(motifs) == 1:
+        return [scan_rows_device(m, rows_of_width[m.width], debug, args_obj) for m in motifs]
+    for m in motifs:
+        if not is_motif(m):
+            exception_handler(TypeError, f"Expected Motif, got {type(m).__name__}.\n", debug)
+        if not m.is_scaled:
+            exception_handler(AssertionError, "The motif has not been scaled.\n", debug)
+    strands = 1 if no_reverse else 2
+    ctx = next(iter(rows_of_width.values()))[0].ctx
+    dms = device_motifs(motifs, ctx)
+    n_of_width = {w: sum(b.n for b in bs) for w, bs in rows_of_width.items()}
+    windows = sum(n_of_width[m.width] * strands for m in motifs)
+    if any(n_of_width[m.width] == 0 for m in motifs):
+        exception_handler(ValueError, "No result retrieved. Unable to proceed.\n", debug)
+    cap = max(1 << 20, min(windows, int(4.0 * threshold * windows) + (1 << 20)))
+    while True:
+        many = engine.ManyScan(ctx, dms, strands=strands, threshold=float(threshold), want_q=not no_qvalue, hit_capacity=cap)
+        for k, m in enumerate(motifs):
+            base = 0
+            for b in rows_of_width[m.width]:
+                if b.n:
+                    many.score(k, b.packed, b.nmask if b.n_masked() else None, row_offset=base)
+                base += b.n
+        if not many.hits_overflowed():
+            break
+        cap = many.hits_needed()
+    many.qvalues()
+    kept = many.finalize_device(q_filter=bool(qval_t))
+    off = many.split_by_motif(kept)
+    with torch.cuda.stream(ctx.stream):
+        qtab_all = many.qtab.cpu().numpy() if not no_qvalue else None
+    reports = []
+    for k, (m, dm) in enumerate(zip(motifs, dms)):
+        print_scoring_msg(m, no_reverse, debug)
+        if not no_qvalue:
+            print("\nComputing q-values...\n")
+        n = n_of_width[m.width] * strands
+        print(f"Scanned sequences:\t{n}")
+        print(f"Scanned nucleotides:\t{n * m.width}")
+        lo, hi = int(off[k]), int(off[k + 1])
+        o = many.out
+        qtab = qtab_all[int(many.off[k]):int(many.off[k + 1])] if qtab_all is not None else None
+        reports.append(_device_report(ctx, m, dm, rows_of_width[m.width], o["row"][lo:hi], o["strand"][lo:hi], o["iscore"][lo:hi],
+                                      qtab, recomb, no_qvalue))
+    return reports
 
 
 _GENERAL = "general path"  # cached verdict of _parse_dir_for_report: the input needs compute_results
@@ -779,7 +950,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
     import torch
     import torch.distributed as tdist
     from .res_writer import DeviceReport
-    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+    if _dist_world()[0] > 1:
         return None
     if not is_motif(motif):
         exception_handler(TypeError, f"Expected Motif, got {type(motif).__name__}.\n", debug)

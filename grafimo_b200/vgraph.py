@@ -474,6 +474,34 @@ def _vcf_chunks(path, chunk_bytes, threads=None):
             fill = rest
 
 
+VCF_MAX_ALT = 16  # csrc/vcf.cu: ALT alleles per line whose genotype rows the kernel builds
+
+
+def _host_genotype_rows(line: bytes, n_alts: int, ploidy: int, n_hap: int, words: int):
+    """Haplotype bit rows of one VCF data line, on the host (the general rule of gb2_vcf_parse_genotypes: bit
+    sample * ploidy + j of row a-1 is set when the j-th allele of the sample's call is a).  -> (uint32 [n_alts, words],
+    calls out of range)."""
+    rows = np.zeros((n_alts, words), dtype=np.uint32)
+    bad = 0
+    f = line.rstrip(b"\r\n").split(b"\t")
+    if len(f) < 10 or not f[8].startswith(b"GT"):
+        return rows, bad
+    for s_i, col in enumerate(f[9:]):
+        call = col.split(b":")[0].replace(b"/", b"|").split(b"|")
+        for j, a in enumerate(call):
+            if not a.isdigit():
+                continue
+            a = int(a)
+            if a == 0:
+                continue
+            hbit = s_i * ploidy + j
+            if a > n_alts or hbit >= n_hap or j >= ploidy:
+                bad += 1
+                continue
+            rows[a - 1, hbit >> 5] |= np.uint32(1 << (hbit & 31))
+    return rows, bad
+
+
 def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
     """Phased VCF -> ({pos int64, ref_len int32, alt_off int64[n+1], alt uint8}, (gt_bits uint32 [n, words], n_hap),
     samples): the arrays DeviceGraph.build / gb2_graph_build take, alleles reduced, one entry per ALT allele, in file
@@ -490,7 +518,7 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
 
     samples, ploidy = None, None
     want = None if chrom is None else np.frombuffer(str(chrom).encode("ascii"), dtype=np.uint8)
-    out_pos, out_rlen, out_alt, out_bits = [], [], [], []
+    out_pos, out_rlen, out_alt, out_bits, out_ref = [], [], [], [], []
     n_hap = words = 0
     skipped_many = bad_calls = 0
     ctx.enter()
@@ -556,13 +584,26 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
             bits = d_bits.cpu().numpy().view(np.uint32)
             cnt = d_counts.cpu().numpy()
         ctx.sync()
-        skipped_many += int(cnt[0]); bad_calls += int(cnt[1])
+        bad_calls += int(cnt[1])
+        if int(cnt[0]):  # lines with more ALT alleles than the kernel builds rows for (VCF_MAX_ALT): their genotype rows are
+            # filled here, on the host, so that no allele ever enters the graph with an empty haplotype set
+            bits = bits.copy()
+            for k in np.nonzero(h["nalt"][sel] > VCF_MAX_ALT)[0]:
+                i = int(sel[k])
+                lo = int(h["off"][i])
+                line = bytes(host[lo:lo + int(h["llen"][i])])
+                rows_k, bad_k = _host_genotype_rows(line, int(h["nalt"][i]), int(ploidy), n_hap, words)
+                b0 = int(row_base[i])
+                bits[b0:b0 + rows_k.shape[0]] = rows_k
+                bad_calls += bad_k
+                skipped_many += 1
         # alleles: single-base REF/ALT lines need no trimming and no per-line Python
         off = h["off"][sel].astype(np.int64)
         simple = (h["rlen"][sel] == 1) & (h["alen"][sel] == 1)
         rb = row_base[sel]
         pos0 = np.zeros(n_rows, dtype=np.int64); rl = np.zeros(n_rows, dtype=np.int32)
         alts = [None] * n_rows
+        refs = [b""] * n_rows
         keep = np.zeros(n_rows, dtype=bool)
         si = np.nonzero(simple)[0]
         if len(si):
@@ -574,8 +615,9 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
             rl[rows_i] = 1
             keep[rows_i] = ok
             letters = [bytes([c]) for c in range(256)]
-            for row, ch in zip(rows_i[ok].tolist(), (a_ & 0xDF)[ok].tolist()):
+            for row, ch, rc in zip(rows_i[ok].tolist(), (a_ & 0xDF)[ok].tolist(), (r & 0xDF)[ok].tolist()):
                 alts[row] = letters[ch]
+                refs[row] = letters[rc]
         for k in np.nonzero(~simple)[0]:
             lo = int(off[k])
             ref_s = bytes(host[lo + int(h["roff"][sel][k]):lo + int(h["roff"][sel][k]) + int(h["rlen"][sel][k])]).decode("ascii")
@@ -588,8 +630,10 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
                     continue
                 row = int(rb[k]) + j
                 pos0[row], rl[row], alts[row], keep[row] = s, len(r), a_.encode("ascii"), True
+                refs[row] = r.upper().encode("ascii")
         kept = np.nonzero(keep)[0]
         out_pos.append(pos0[kept]); out_rlen.append(rl[kept]); out_alt.extend(alts[i] for i in kept.tolist())
+        out_ref.extend(refs[i] for i in kept.tolist())
         out_bits.append(bits[kept])
     ctx.leave()
     if samples is None:
@@ -602,6 +646,12 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
     alt_list = [out_alt[i] for i in order.tolist()]
     alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alt_list])]).astype(np.int64)
     alt = np.frombuffer(b"".join(alt_list), dtype=np.uint8) if alt_list else np.zeros(0, np.uint8)
+    ref_cat = b"".join(out_ref[i] for i in order.tolist())  # REF alleles (reduced), back to back: checked against the FASTA
+    if bad_calls:
+        import warnings
+        warnings.warn(f"{path}: {bad_calls} genotype calls name an allele the line does not have (or a haplotype beyond the "
+                      "header's samples); they were read as the reference allele")
     variants = {"pos": np.ascontiguousarray(pos[order]), "ref_len": np.ascontiguousarray(rlen[order]), "alt_off": alt_off,
-                "alt": alt, "skipped_lines_with_many_alts": skipped_many, "calls_out_of_range": bad_calls}
+                "alt": alt, "ref": np.frombuffer(ref_cat, dtype=np.uint8), "lines_with_many_alts_read_on_host": skipped_many,
+                "calls_out_of_range": bad_calls}
     return variants, (np.ascontiguousarray(bits[order]), n_hap), samples

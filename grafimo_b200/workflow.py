@@ -29,6 +29,8 @@ class Findmotif(object):
         if bool(linear_genome) != bool(bedfile) or (vcf and not linear_genome):
             raise ValueError("\n\nERROR: scanning a graph built on the fly needs -l/--linear-genome and -b/--bedfile "
                              "(and -v/--vcf for the variants).\n")
+        if gpus < 1:
+            raise ValueError("\n\nERROR: --gpus must be at least 1.\n")
         if not (0 < threshold <= 1):
             raise ValueError("\n\nERROR: the threshold must be in (0, 1].\n")
         if qval_t and no_qvalue:

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GB2_ABI_VERSION 2
+#define GB2_ABI_VERSION 3
 #define GB2_NARROW_WIDTH 32 /* widest k-mer that fits one packed word */
 #define GB2_MAX_WIDTH 64
 #define GB2_RANGE 1000 /* src/grafimo/utils.py:26 */
@@ -74,7 +74,7 @@ typedef struct gb2_hit {
 /* Facts about an uploaded motif. */
 typedef struct gb2_motif_info {
     int32_t width;
-    int32_t n_chunks;      /* 4-base LUT chunks = ceil(width / 4) */
+    int32_t n_chunks;      /* lookup-table chunks = ceil(width / chunk_bases) */
     int32_t lut_replicas;  /* shared-memory replication factor chosen for the scoring kernel */
     int32_t monotone;      /* 1 when the p-value table is non-increasing in the score */
     int64_t lo, hi;        /* smallest / largest reachable integer score */
@@ -84,6 +84,8 @@ typedef struct gb2_motif_info {
     double offset;
     double total;          /* sequential sum of pval_mat (denominator of every p-value) */
     int64_t smem_bytes;    /* dynamic shared memory of the scoring kernel for this motif */
+    int32_t chunk_bases;   /* bases per lookup: 4 (256-entry tables) or 3 (64-entry tables: long motifs / large spans) */
+    int32_t hist_global;   /* 1: the histogram did not fit shared memory and is counted with global atomics */
 } gb2_motif_info;
 
 int gb2_abi_version(void);
@@ -163,6 +165,15 @@ int gb2_pval_dp_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, con
  * summation order (score_sequences.py:390-391).  Host pointers. */
 int gb2_motif_create(gb2_ctx *ctx, const int64_t *h_score_matrix, int w, const double *h_pval_mat,
                      int64_t min_val, int64_t scale, double offset, gb2_motif **out);
+/* The same for n_motifs motifs at once (a motif collection, BASELINE config 3; replaces the per-motif loop of
+ * motif_ops.py:303-335 / 971-1022 on the device side): arrays as gb2_pval_dp_batched takes them (h_widths[m]; concatenated
+ * int64[4][w_m] matrices; concatenated float64[1000*w_m+1] p-value matrices) plus min_val / scale / offset per motif.
+ * ONE device allocation, ONE upload, TWO kernel launches (K4 for every motif) and ONE synchronisation for the whole
+ * collection; out[n_motifs] receives the handles (each destroyed with gb2_motif_destroy; the shared allocation goes
+ * with the last one).  On failure no handle is returned. */
+int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *h_score_mats,
+                             const double *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
+                             const double *h_offsets, gb2_motif **out);
 int gb2_motif_destroy(gb2_motif *motif);
 int gb2_motif_get_info(const gb2_motif *motif, gb2_motif_info *info);
 /* copies the p-value table (span doubles, score lo..hi) to the host */
@@ -198,6 +209,12 @@ int gb2_score(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_packed, co
  *   d_total  uint64[1]       N = number of scored windows */
 int gb2_qvalues_from_hist(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_hist, double *d_qtab,
                           uint32_t *d_rank, uint64_t *d_total);
+
+/* The same step for MANY motifs in one launch (one CTA per motif): d_hist / d_qtab / d_rank are the per-motif arrays laid
+ * back to back, motif m owning bins [h_bin_off[m], h_bin_off[m+1]) (= span_m + 1 of them); d_totals[n_motifs].  d_hist may
+ * be NULL (ranks only).  Motifs with a non-monotone p-value table take the sorting form above, one at a time. */
+int gb2_qvalues_from_hist_many(gb2_ctx *ctx, int32_t n_motifs, const gb2_motif *const *motifs, const int64_t *h_bin_off,
+                               const uint64_t *d_hist, double *d_qtab, uint32_t *d_rank, uint64_t *d_totals);
 
 /* Stand-alone form of the same step for an arbitrary list of p-values (B3 seam: compute_qvalues takes a
  * list and returns a list, score_sequences.py:401-428): CUB radix sort, raw = p / (k / float(n)), reverse

@@ -38,6 +38,8 @@ def main():
     info = gdist.init_from_env("nccl")
     rank, world = info["rank"], info["world"]
     ctx = ss._context()
+    gdist.init_comm(ctx)  # histogram all-reduce and hit-column all-gather run inside the C ABI (csrc/comm.cu)
+    assert ctx.world == world and ctx.rank == rank
     motif = build_motif(os.path.join(tmp, f"r{rank}"))
     mine = [c for i, c in enumerate(chromosomes()) if i % world == rank]
     rows = []

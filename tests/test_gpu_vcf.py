@@ -59,7 +59,9 @@ def test_device_reader_equals_python_reader_and_source(ctx, tmp_path, fmt, gz):
     got_v, got_g = _as_lists(dv, bits, n_hap)
     assert got_v == [(s, len(r), a) for s, r, a in pv] == [(s, len(r), a) for s, r, a in variants]
     assert np.array_equal(got_g, pgt) and np.array_equal(got_g, gt)
-    assert dv["calls_out_of_range"] == 0 and dv["skipped_lines_with_many_alts"] == 0
+    assert dv["calls_out_of_range"] == 0 and dv["lines_with_many_alts_read_on_host"] == 0
+    # the REF alleles travel with the variants and are checked against the sequence the graph is built on
+    assert bytes(dv["ref"]).decode() == "".join(r for _, r, _ in pv)
     # no chromosome filter: the lines of the other chromosome come too
     dv2, _, _ = read_vcf_device(ctx, str(path), None, chunk_bytes=1 << 20)
     assert len(dv2["pos"]) > len(dv["pos"])
@@ -104,6 +106,50 @@ def test_device_reader_special_cases(ctx, tmp_path):
     bad.write_text("#CHROM\tPOS\nx\tnotanumber\t.\tA\tC\t.\t.\t.\n")
     with pytest.raises(ValueError):
         read_vcf_device(ctx, str(bad), "x")
+
+
+def test_lines_with_many_alt_alleles_and_bad_calls(ctx, tmp_path):
+    """A line with more ALT alleles than the genotype kernel builds rows for (16) is read on the host: its alleles get
+    their real haplotype sets (never empty ones), exactly what the plain-Python reader gives; a call naming an allele
+    the line does not have is counted and warned about."""
+    import warnings
+    from grafimo_b200.vgraph import read_vcf, read_vcf_device
+    alts = ["A" * k + "C" for k in range(1, 19)]  # 18 ALT alleles at one site (insertions of different lengths)
+    calls = ["17|18", "0|3", "18|1", "5|5"]
+    lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC\tD",
+             "x\t5\t.\tG\tT\t.\t.\t.\tGT\t1|0\t0|1\t0|0\t1|1",
+             "x\t9\t.\tC\t" + ",".join(alts) + "\t.\t.\t.\tGT\t" + "\t".join(calls),
+             "x\t20\t.\tA\tG\t.\t.\t.\tGT\t0|1\t1|0\t1|1\t0|0"]
+    p = tmp_path / "many.vcf"
+    p.write_text("\n".join(lines) + "\n")
+    pv, pgt, _ = read_vcf(str(p), "x")
+    dv, (bits, n_hap), _ = read_vcf_device(ctx, str(p), "x")
+    got_v, got_g = _as_lists(dv, bits, n_hap)
+    assert n_hap == 8 and dv["lines_with_many_alts_read_on_host"] == 1 and dv["calls_out_of_range"] == 0
+    assert got_v == [(s, len(r), a) for s, r, a in pv] and np.array_equal(got_g, pgt)
+    assert got_g.sum() == 4 + 7 + 4  # no carrier was lost: the 18-allele line contributes its 7 non-reference calls
+    q = tmp_path / "badcall.vcf"
+    q.write_text("\n".join(lines[:2] + ["x\t5\t.\tG\tT\t.\t.\t.\tGT\t1|0\t0|2\t0|0\t1|1"]) + "\n")
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        bv, _, _ = read_vcf_device(ctx, str(q), "x")
+    assert bv["calls_out_of_range"] == 1 and any("genotype calls" in str(w.message) for w in rec)
+
+
+def test_ref_allele_mismatch_is_rejected(ctx, tmp_path):
+    """FASTA and VCF that do not belong together (wrong assembly / shifted coordinates): the graph is not built"""
+    from grafimo_b200.extract_regions import DeviceGraph
+    ref = "ACGTACGTACGTACGTACGTACGTACGTAC"
+    good = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\nx\t3\t.\tG\tT\t.\t.\t.\tGT\t0|1\nx\t9\t.\tACG\tA\t.\t.\t.\tGT\t1|0\n"
+    (tmp_path / "g.vcf").write_text(good)
+    dg = DeviceGraph.from_files(ctx, {"x": ref}, str(tmp_path / "g.vcf"), "x")
+    assert dg.extract([(0, 30)], 5).n > 26
+    (tmp_path / "b.vcf").write_text(good.replace("x\t3\t.\tG\tT", "x\t4\t.\tG\tT"))  # REF says G, the sequence holds T there
+    with pytest.raises(ValueError, match="position 4"):
+        DeviceGraph.from_files(ctx, {"x": ref}, str(tmp_path / "b.vcf"), "x")
+    (tmp_path / "c.vcf").write_text(good.replace("x\t9\t.\tACG\tA", "x\t29\t.\tACG\tA"))  # runs past the end
+    with pytest.raises(ValueError):
+        DeviceGraph.from_files(ctx, {"x": ref}, str(tmp_path / "c.vcf"), "x")
 
 
 def test_graph_from_files_on_reference_fixture(ctx, tmp_path):

@@ -39,7 +39,7 @@ def test_abi_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().gb2_abi_version() == 2
+    assert _lib.load().gb2_abi_version() == 3
     assert _lib.load().gb2_error_string(2).decode().startswith("CUDA")
 
 

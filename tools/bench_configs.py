@@ -17,6 +17,17 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 ONLY = os.environ.get("GB2_ONLY", "")
+RESULTS = {}  # section -> list of records; written as JSON to $GB2_JSON (numbers for profiles/, not prose)
+import json, atexit
+def _dump():
+    if os.environ.get("GB2_JSON") and RESULTS:
+        with open(os.environ["GB2_JSON"], "w") as fh:
+            json.dump(RESULTS, fh, indent=1)
+atexit.register(_dump)
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
 g = torch.Generator(device="cuda"); g.manual_seed(3)
 if ONLY == "k1":
     print("K1 encoder")
@@ -144,6 +155,9 @@ if ONLY in ("", "c5"):
                 e2.record(ctx.stream); ctx.sync()
             print(f"    {tag}: w={w} span={dm.span} R={dm.info.lut_replicas} [{mode}]: K2 {e0.elapsed_time(e1):.2f} ms, K5+K6 {e1.elapsed_time(e2):.2f} ms, "
                   f"{kept} rows reported of {2 * n5}; {2 * n5 / (e0.elapsed_time(e2) * 1e-3) / 1e9:.2f} G windows/s")
+            RESULTS.setdefault("c5", []).append(dict(motif=tag, width=w, span=int(dm.span), chunk_bases=int(dm.info.chunk_bases), n_chunks=int(dm.info.n_chunks),
+                replicas=int(dm.info.lut_replicas), mode=mode, kmers=n5, rows_reported=int(kept), k2_ms=e0.elapsed_time(e1), k5_k6_ms=e1.elapsed_time(e2),
+                step_ms=e0.elapsed_time(e2), windows_per_s=2 * n5 / (e0.elapsed_time(e2) * 1e-3)))
             del sc
         del packed
 
@@ -169,6 +183,32 @@ if ONLY in ("", "wide"):
         ms = e0.elapsed_time(e1)
         print(f"    {tag}: w={w} span={dm.span} chunks={dm.info.n_chunks} R={dm.info.lut_replicas} smem={dm.info.smem_bytes}: K2 {ms:.2f} ms = "
               f"{nw / ms / 1e6:.1f} G k-mers/s, {16 * nw / ms / 1e6:.0f} GB/s; K5+K6 {e1.elapsed_time(e2):.2f} ms, {kept} hits")
+        RESULTS.setdefault("wide", []).append(dict(motif=tag, width=w, span=int(dm.span), chunk_bases=int(dm.info.chunk_bases), n_chunks=int(dm.info.n_chunks),
+            replicas=int(dm.info.lut_replicas), hist_global=int(dm.info.hist_global), smem_bytes=int(dm.info.smem_bytes), kmers=nw, k2_ms=ms,
+            kmers_per_s=nw / (ms * 1e-3), algorithmic_GBps=16 * nw / ms / 1e6, frac_of_measured_hbm_peak=16 * nw / ms / 1e6 / PEAK, hits=int(kept),
+            note="CUDA events around gb2_score on the context stream, third repetition; 16 B per k-mer (two packed words)"))
+        del packed, sc
+
+# ---------------------------------------------------------------- narrow motifs: one k-mer word, all widths' chunk plans
+if ONLY in ("", "narrow"):
+    print("narrow motifs (<= 32 bp): K2, thresholded, both strands, q-values on, 2^28 random k-mers")
+    nn = 1 << 28
+    for tag in ("synth_w8_meme__bgnt", "synth_w11_meme__bgnt", "ctcf_meme__unif", "synth_w25_meme__bgnt", "synth_w27_meme__bgnt", "synth_w30_meme__bgnt", "synth_w32_meme__bgnt"):
+        m = gu.load_motif(tag)
+        dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+        w = m["width"]
+        packed = torch.randint(0, 1 << 62, (nn,), dtype=torch.int64, device="cuda", generator=g) & ((1 << (2 * w)) - 1)
+        for rep in range(3):
+            sc = Scan(ctx, dm, strands=2, threshold=1e-4, hit_capacity=1 << 22)
+            e0, e1 = ev(), ev()
+            e0.record(ctx.stream)
+            sc.score(packed)
+            e1.record(ctx.stream); ctx.sync()
+        ms = e0.elapsed_time(e1)
+        print(f"    {tag}: w={w} span={dm.span} cb={dm.info.chunk_bases} chunks={dm.info.n_chunks} R={dm.info.lut_replicas}: K2 {ms:.3f} ms = {8 * nn / ms / 1e6:.0f} GB/s "
+              f"= {8 * nn / ms / 1e6 / PEAK:.3f} of the measured peak")
+        RESULTS.setdefault("narrow", []).append(dict(motif=tag, width=w, span=int(dm.span), chunk_bases=int(dm.info.chunk_bases), n_chunks=int(dm.info.n_chunks),
+            replicas=int(dm.info.lut_replicas), kmers=nn, k2_ms=ms, algorithmic_GBps=8 * nn / ms / 1e6, frac_of_measured_hbm_peak=8 * nn / ms / 1e6 / PEAK))
         del packed, sc
 
 # ---------------------------------------------------------------- K1
