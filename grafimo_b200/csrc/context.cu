@@ -224,7 +224,7 @@ bool plan_smem(int w, int64_t span, int64_t budget, bool allow_global_hist, int 
             if (copy + hb > budget) continue;
             int r = 32;
             while (r > 1 && copy * r + hb > budget) r >>= 1;
-            if (w <= GB2_NARROW_WIDTH && c == 3 && r < 8) continue;  // narrow 3-base kernels exist for R = 32, 16, 8
+            if (c == 3 && r < 8) continue;  // the 3-base kernels exist for R = 32, 16, 8 (wide: then the global histogram)
             // global-memory histogram updates are ~35x slower than shared-memory ones: only when nothing else fits
             const double cost = nch * lookup_wavefronts(r) + (hg ? 300.0 : 0.0);
             if (cost < best - 1e-9) { best = cost; cb = c; R = r; hist_global = hg; smem = copy * r + hb; found = true; }

@@ -186,98 +186,6 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_kernel(const ScoreParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Wide k-mers (32 < w <= 64, two packed words each): one 128-bit load = one k-mer.  3-base chunks (64-entry tables,
-// NCHUNK = ceil(w / 3) = 11..22 lookups): at 256 bytes per chunk the tables replicate 32x (16x at w >= 61 with the
-// largest spans) beside a histogram of up to 33 k bins, so a lookup stays at one or two wavefronts -- with 4-base
-// chunks (1 KB per chunk: R = 16 / 8 / 4 at w = 35 / 48 / 64) the shared-memory pipe was 88-96 % busy at 0.60 / 0.43 /
-// 0.34 of the HBM roofline (profiles/r02_wide_kernel_ncu_before.txt).  Same packed 16-bit fields, same histogram /
-// hit / dense semantics as the narrow kernel; when the histogram does not fit shared memory next to the tables
-// (hist_in_smem == 0) it is counted with 64-bit global atomics.  NCHUNK is a template parameter so that the lookups
-// are straight-line code; R is a run-time value.
-template <int NCHUNK>
-__global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int R, int hist_in_smem)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *lut_s = smem;                     // [NCHUNK*64][R]
-    uint32_t *hist_s = smem + NCHUNK * 64 * R;  // [span+1] when hist_in_smem
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
-    const bool do_hist = p.hist != nullptr;
-    const bool hist_smem = do_hist && hist_in_smem;
-
-    for (int i = tid; i < NCHUNK * 64 * R; i += 1024) lut_s[i] = p.lut[i / R];
-    if (hist_smem)
-        for (uint32_t i = tid; i <= p.span; i += 1024) hist_s[i] = 0u;
-    __syncthreads();
-
-    const uint32_t lut32 = smem_u32(lut_s) + 4u * (lane & (uint32_t)(R - 1));
-    const uint32_t hist32 = smem_u32(hist_s);
-    const uint32_t rstride = (uint32_t)R * 4u;
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.packed);
-    const uint32_t nsent = (p.span << 16) | p.span;
-    const bool two = p.two_strands != 0;
-    constexpr int U = 4;
-    constexpr int64_t TILE = 1024 * U;
-    const int64_t ntiles = (p.n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * TILE + tid;
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t row = r0 + u * 1024;
-            v[u] = row < p.n ? ld_stream_u4(src + row) : make_uint4(0, 0, 0, 0);
-        }
-        uint32_t acc[U];
-        bool any = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t wd[5] = {v[u].x, v[u].y, v[u].z, v[u].w, 0u};
-            uint32_t a = 0;
-#pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int bit = 6 * c, q = bit >> 5, sh = bit & 31;  // constants after unrolling
-                const uint32_t x = (sh + 6 <= 32) ? (wd[q] >> sh) : __funnelshift_r(wd[q], wd[q + 1], sh);
-                uint32_t e;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut32 + ((uint32_t)c * 64u + (x & 63u)) * rstride));
-                a += e;
-            }
-            const int64_t row = r0 + u * 1024;
-            const bool ok = row < p.n;
-            if (ok && p.nmask != nullptr && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) a = nsent;
-            acc[u] = a;
-            if (ok) {
-                const uint32_t bf = a & 0xFFFFu, br = a >> 16;
-                if (hist_smem) {
-                    red_shared_inc(hist32 + 4u * bf);
-                    if (two) red_shared_inc(hist32 + 4u * br);
-                } else if (do_hist) {
-                    atomicAdd(p.hist + bf, 1ull);
-                    if (two) atomicAdd(p.hist + br, 1ull);
-                }
-                if (p.dense != nullptr) p.dense[row] = (a == nsent) ? 0xFFFFFFFFu : a;
-                any |= (bf >= p.cut) | (two & (br >= p.cut));
-            }
-        }
-        if (p.hits != nullptr && __any_sync(0xFFFFFFFFu, any)) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t row = r0 + u * 1024;
-                const bool ok = row < p.n;
-                const uint32_t bf = acc[u] & 0xFFFFu, br = acc[u] >> 16;
-                append_hits(p, ok && bin_hits(p, bf), (uint64_t)row, bf, 0u, lane);
-                if (two) append_hits(p, ok && bin_hits(p, br), (uint64_t)row, br, 1u, lane);
-            }
-        }
-    }
-    if (hist_smem) {
-        __syncthreads();
-        for (uint32_t i = tid; i <= p.span; i += 1024) {
-            const uint32_t c = hist_s[i];
-            if (c) atomicAdd(p.hist + i, (unsigned long long)c);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 template <int CB, int NCHUNK, int R>
 static int launch_score(gb2_ctx *ctx, const ScoreParams &p, size_t smem, int grid)
 {
@@ -371,29 +279,7 @@ extern "C" int gb2_score(gb2_ctx *ctx, const gb2_motif *m, const uint64_t *d_pac
     }
 
     const size_t smem = (size_t)m->smem_bytes;
-    if (m->w > GB2_NARROW_WIDTH) {  // two packed words per k-mer, 3-base chunks
-        GB2_REQUIRE(ctx, m->chunk_bases == 3 && m->n_chunks >= 11 && m->n_chunks <= 22, "gb2_score: bad chunk plan of a wide motif");
-        const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(n, 4096)));
-        void (*kern)(const ScoreParams, int, int) = nullptr;
-        switch (m->n_chunks) {
-        case 11: kern = gb2_score_wide_kernel<11>; break;
-        case 12: kern = gb2_score_wide_kernel<12>; break;
-        case 13: kern = gb2_score_wide_kernel<13>; break;
-        case 14: kern = gb2_score_wide_kernel<14>; break;
-        case 15: kern = gb2_score_wide_kernel<15>; break;
-        case 16: kern = gb2_score_wide_kernel<16>; break;
-        case 17: kern = gb2_score_wide_kernel<17>; break;
-        case 18: kern = gb2_score_wide_kernel<18>; break;
-        case 19: kern = gb2_score_wide_kernel<19>; break;
-        case 20: kern = gb2_score_wide_kernel<20>; break;
-        case 21: kern = gb2_score_wide_kernel<21>; break;
-        default: kern = gb2_score_wide_kernel<22>; break;
-        }
-        GB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 1024, smem, ctx->stream>>>(p, m->replicas, m->hist_global ? 0 : 1);
-        GB2_LAUNCH_CHECK(ctx);
-        return GB2_OK;
-    }
+    if (m->w > GB2_NARROW_WIDTH) return gb2_launch_score_wide(ctx, m, p, n);  // two packed words per k-mer: score_wide.cu
     const int64_t npairs = n >> 1;
     int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, gb2_div_up(npairs, 4096)));
     if (m->chunk_bases == 3) {

@@ -124,3 +124,5 @@ __device__ __forceinline__ bool bin_hits(const ScoreParams &p, uint32_t bin)
 // Host side: the p-value cut-off of a launch as an integer test (hit <=> ptab[bin] < threshold, strict:
 // src/grafimo/resultsTmp.py:305-307) -> p.cut / p.bitmap, and the motif's tables -> p.lut / span / lo.
 int gb2_fill_score_params(gb2_ctx *ctx, const gb2_motif *m, double p_threshold, ScoreParams &p);
+// K2 for motifs wider than 32 bp (score_wide.cu)
+int gb2_launch_score_wide(gb2_ctx *ctx, const gb2_motif *m, const ScoreParams &p, int64_t n);

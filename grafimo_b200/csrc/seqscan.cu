@@ -608,6 +608,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     std::vector<Chunk> chunks;
     std::vector<Run> runs;
     int64_t n_windows = 0;
+    uint64_t overlap_n = 0, overlap_other = 0;  // non-ACGT bases inside the w-1 bases two pieces of a sequence share
     {
         Chunk cur;
         int64_t fill = 0;
@@ -641,6 +642,16 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                 pieces.push_back(p);
                 cur.n_pieces++;
                 fill += (take + 31) / 32 * 32;
+                if (ascii && take < rem) {  // the next piece re-reads the last w-1 bases of this one: count them once
+                    const uint8_t *t = (const uint8_t *)h_data + h_off[s] + a + take - (w - 1);
+                    for (int k = 0; k < w - 1; ++k) {
+                        const uint8_t u = t[k] & 0xDFu;
+                        if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) {
+                            ++overlap_n;
+                            if (u != 'N') ++overlap_other;
+                        }
+                    }
+                }
                 a += take - w + 1;
                 if (fill + MIN_PIECE > CHUNK_BASES) close();
             }
@@ -796,6 +807,10 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
         }
         rc = gb2_scan_tail_finish(ctx, m, b, (uint64_t)n_windows * (uint64_t)strands, (uint64_t)n_windows, p_threshold,
                                   q_filter, want_q, hit_capacity, o);
+        if (o.h_stats && (rc == GB2_OK || rc == GB2_ERR_CAPACITY)) {
+            o.h_stats[1] -= std::min<uint64_t>(o.h_stats[1], overlap_n);
+            o.h_stats[2] -= std::min<uint64_t>(o.h_stats[2], overlap_other);
+        }
     }
 done:
 #undef SH_CUDA

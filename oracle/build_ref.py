@@ -7,9 +7,10 @@ TEST / BENCH INFRASTRUCTURE ONLY.
 Outputs, all under oracle/_ref/ (git-ignored, NOT gpurun-ignored: it travels to the GPU box like our own .so):
   * motif_processing.<abi>.so   cythonized from /root/reference/src/grafimo/motif_processing.pyx (the reference's one
                                 native module, top-level name `motif_processing` as in its setup.py:53);
-  * grafimo/*.pyc               the reference's Python modules byte-compiled from the sources where they lie
-                                (sourceless layout: no reference source text is copied, nothing is written to
-                                /root/reference);
+  * grafimo_ref.zip             the reference's Python modules byte-compiled from the sources where they lie
+                                (grafimo/*.pyc inside one archive, imported through zipimport: no reference source
+                                text is copied, nothing is written to /root/reference; one binary file because loose
+                                *.pyc files are not shipped to the GPU box);
   * BUILD_INFO.json             versions + a self-check: the reference's compute_results on its own test fixture must
                                 reproduce its expected table.
 The two third-party modules the scoring path imports that are absent from this image (colorama; statsmodels.stats.multitest,
@@ -32,14 +33,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = "/root/reference"
 OUT = os.path.join(HERE, "_ref")
+ZIP = os.path.join(OUT, "grafimo_ref.zip")
 SHIMS = os.path.join(ROOT, "tests", "golden", "_shims")
 
 
 def activate():
     """Puts the built reference (and the shims) on sys.path; -> True when it is importable."""
-    if not os.path.isdir(os.path.join(OUT, "grafimo")) or not glob.glob(os.path.join(OUT, "motif_processing*.so")):
+    if not os.path.isfile(ZIP) or not glob.glob(os.path.join(OUT, "motif_processing*.so")):
         return False
-    for p in (SHIMS, OUT):
+    for p in (SHIMS, OUT, ZIP):
         if p not in sys.path:
             sys.path.insert(0, p)
     return True
@@ -52,7 +54,7 @@ def build(force=False):
     if os.path.exists(stamp) and not force:
         return activate()
     shutil.rmtree(OUT, ignore_errors=True)
-    os.makedirs(os.path.join(OUT, "grafimo"))
+    os.makedirs(OUT)
     scratch = tempfile.mkdtemp(prefix="gb2_refbuild_")
     pyx = os.path.join(REF, "src", "grafimo", "motif_processing.pyx")
     setup_py = os.path.join(scratch, "setup_mp.py")
@@ -62,9 +64,13 @@ def build(force=False):
                  f"setup(name='mp', ext_modules=cythonize([ext], build_dir={scratch!r}, language_level=3))\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REF, "src"), SHIMS, os.environ.get("PYTHONPATH", "")]))
     subprocess.check_call([sys.executable, setup_py, "build_ext", "--build-lib", OUT, "--build-temp", scratch, "-q"], cwd=scratch, env=env)
-    for src in sorted(glob.glob(os.path.join(REF, "src", "grafimo", "*.py"))):
-        name = os.path.basename(src)
-        py_compile.compile(src, cfile=os.path.join(OUT, "grafimo", name + "c"), dfile=f"grafimo/{name}", doraise=True)
+    import zipfile
+    with zipfile.ZipFile(ZIP, "w", zipfile.ZIP_DEFLATED) as zf:
+        for src in sorted(glob.glob(os.path.join(REF, "src", "grafimo", "*.py"))):
+            name = os.path.basename(src)
+            cfile = os.path.join(scratch, name + "c")
+            py_compile.compile(src, cfile=cfile, dfile=f"grafimo/{name}", doraise=True)
+            zf.write(cfile, f"grafimo/{name}c")
     shutil.rmtree(scratch, ignore_errors=True)
     info = {"reference": "pinellolab/GRAFIMO", "python": sys.version.split()[0]}
     try:
@@ -82,7 +88,7 @@ def self_check():
     """the reference's own test_scoring assertion (tests/grafimo_run_test.py:119-140) on the built copy, in a subprocess"""
     code = r'''
 import io, json, os, sys, tempfile, contextlib
-sys.path.insert(0, %r); sys.path.insert(0, %r)
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
 import pandas as pd
 from grafimo.motif_ops import build_motif_meme
 from grafimo.score_sequences import compute_results
@@ -99,7 +105,7 @@ key = ["start", "stop", "strand", "matched_sequence"]
 a = df.sort_values(key, kind="stable").reset_index(drop=True); b = exp.sort_values(key, kind="stable").reset_index(drop=True)
 ok = len(a) == len(b) == 704 and all((a[c] == b[c]).all() for c in ["score", "p-value", "q-value", "start", "stop", "haplotype_frequency"])
 print("SELFCHECK", "ok" if ok else "MISMATCH")
-''' % (SHIMS, OUT, os.path.join(ROOT, "tests", "golden", "fixtures.json"))
+''' % (SHIMS, OUT, ZIP, os.path.join(ROOT, "tests", "golden", "fixtures.json"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     if "SELFCHECK ok" not in r.stdout:
         raise SystemExit("oracle/_ref self-check failed:\n" + r.stdout[-1500:] + r.stderr[-3000:])

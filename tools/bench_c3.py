@@ -98,7 +98,7 @@ def main():
         sets[w] = torch.randint(0, 1 << (2 * w), (args.kmers,), dtype=torch.int64, device="cuda", generator=g)
     torch.cuda.synchronize()
     dms, prep = prepare(ctx, raw)
-    cap = 1 << 23
+    cap = 1 << 24
     best = None
     for rep in range(args.reps):
         if world > 1:
