@@ -116,12 +116,16 @@ def load_graphs(wf: Findmotif, debug: bool):
     seqs = read_fasta(wf.linear_genome)
     ctx = ss._context()
     out = []
+    parsed = None
+    if wf.vcf and len(regions) > 1:  # one pass over the VCF for all BED chromosomes, not one per chromosome
+        from .vgraph import read_vcf_device
+        parsed, _ = read_vcf_device(ctx, wf.vcf, None, by_chrom=True)
     for chrom, spans in regions.items():
         key = chrom[3:] if chrom.startswith("chr") else chrom
         name = wf.chroms_prefix + key
         if name not in seqs:
             exception_handler(KeyError, f"{name} is not a sequence of {wf.linear_genome}. Consider --chroms-prefix-find.\n", debug)
-        dg = DeviceGraph.from_files(ctx, seqs, wf.vcf, name, display_name=key)
+        dg = DeviceGraph.from_files(ctx, seqs, wf.vcf, name, display_name=key, parsed_vcf=parsed)
         out.append((dg, [(int(a), int(b)) for a, b in spans]))
     return out
 

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 
 #include "internal.cuh"
@@ -279,8 +280,8 @@ int motif_plan(gb2_ctx *ctx, const int64_t *sm, int w, int cb, MotifPlan &pl, co
 int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const double *d_pm, double *d_ctab, double *d_ptab,
                               double *d_totals);
 
-extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *h_score_mats,
-                                        const double *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
+extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *const *h_score_mats,
+                                        const double *const *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
                                         const double *h_offsets, gb2_motif **out)
 {
     if (!ctx || !out) return GB2_ERR_ARG;
@@ -290,10 +291,16 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
     GB2_REQUIRE(ctx, h_widths && h_score_mats && h_pval_mats && h_min_vals && h_scales && h_offsets,
                 "gb2_motif_create_batched: null argument");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool timing = getenv("GB2_MOTIF_TIMING") != nullptr;  // phase times of this call on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing) fprintf(stderr, "gb2_motif_create_batched[%d]: %-28s %.2f ms since entry\n", n_motifs, what,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     const int64_t budget = (int64_t)ctx->max_smem_optin - 1024;
     std::vector<MotifPlan> plans((size_t)n_motifs);
     std::vector<gb2_motif *> ms((size_t)n_motifs, nullptr);
-    std::vector<int64_t> sm_off((size_t)n_motifs + 1, 0), pm_off((size_t)n_motifs + 1, 0), sp_off((size_t)n_motifs + 1, 0);
+    std::vector<int64_t> sp_off((size_t)n_motifs + 1, 0);
     std::vector<size_t> lut_off((size_t)n_motifs + 1, 0), bm_off((size_t)n_motifs + 1, 0);
     int rc = GB2_OK;
     auto fail = [&](int code) {
@@ -306,13 +313,15 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
             GB2_SET_ERR(ctx, "gb2_motif_create: width %d outside [1,%d] (motif %d)", w, GB2_MAX_WIDTH, i);
             return fail(GB2_ERR_ARG);
         }
-        sm_off[(size_t)i + 1] = sm_off[(size_t)i] + 4 * (int64_t)w;
-        pm_off[(size_t)i + 1] = pm_off[(size_t)i] + (int64_t)GB2_RANGE * w + 1;
+        if (!h_score_mats[i] || !h_pval_mats[i]) {
+            GB2_SET_ERR(ctx, "gb2_motif_create: null matrix (motif %d)", i);
+            return fail(GB2_ERR_ARG);
+        }
         if (h_scales[i] <= 0) {
             GB2_SET_ERR(ctx, "gb2_motif_create: motif is not scaled (scale=%lld, motif %d)", (long long)h_scales[i], i);
             return fail(GB2_ERR_MOTIF);
         }
-        const int64_t *sm = h_score_mats + sm_off[(size_t)i];
+        const int64_t *sm = h_score_mats[i];
         MotifPlan probe;
         if ((rc = motif_plan(ctx, sm, w, 4, probe, "gb2_motif_create")) != GB2_OK) return fail(rc);
         const int64_t L = (int64_t)GB2_RANGE * w + 1;
@@ -334,7 +343,7 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         else if ((rc = motif_plan(ctx, sm, w, cb, plans[(size_t)i], "gb2_motif_create")) != GB2_OK) return fail(rc);
         const MotifPlan &pl = plans[(size_t)i];
         // mass outside the reachable range means the matrix and the p-value matrix do not belong together
-        const double *pm = h_pval_mats + pm_off[(size_t)i];
+        const double *pm = h_pval_mats[i];
         for (int64_t k = 0; k < L; ++k) {
             if ((k < pl.lo || k > pl.hi) && pm[k] != 0.0) {
                 GB2_SET_ERR(ctx, "gb2_motif_create: p-value matrix has mass at unreachable score %lld", (long long)k);
@@ -353,6 +362,7 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         lut_off[(size_t)i + 1] = lut_off[(size_t)i] + align256(pl.lut.size() * sizeof(uint32_t));
         bm_off[(size_t)i + 1] = bm_off[(size_t)i] + align256((size_t)gb2_div_up(pl.span + 1, 32) * sizeof(uint32_t));
     }
+    lap("plans + checks (host)");
     // ---- one allocation: [p-tables of all motifs][LUTs][bitmaps]; K4's two work arrays come from the scratch buffer
     const int64_t total_span = sp_off[(size_t)n_motifs];
     const size_t b_ptab = align256((size_t)total_span * sizeof(double));
@@ -378,13 +388,14 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
     for (int i = 0; i < n_motifs; ++i) {
         const MotifPlan &pl = plans[(size_t)i];
         memcpy(h_lut.data() + lut_off[(size_t)i], pl.lut.data(), pl.lut.size() * sizeof(uint32_t));
-        memcpy(h_pm.data() + sp_off[(size_t)i], h_pval_mats + pm_off[(size_t)i] + pl.lo, (size_t)pl.span * sizeof(double));
+        memcpy(h_pm.data() + sp_off[(size_t)i], h_pval_mats[i] + pl.lo, (size_t)pl.span * sizeof(double));
         gb2_motif *m = ms[(size_t)i];
         m->d_ptab = (double *)base + sp_off[(size_t)i];
         m->d_lut = (uint32_t *)(base + b_ptab + lut_off[(size_t)i]);
         m->d_bitmap = (uint32_t *)(base + b_ptab + b_lut + bm_off[(size_t)i]);
     }
     std::vector<double> h_ptab_all((size_t)total_span), h_tot((size_t)n_motifs);
+    lap("alloc + staging (host)");
     cudaError_t e = cudaMemcpyAsync(base + b_ptab, h_lut.data(), b_lut, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_pm, h_pm.data(), (size_t)total_span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
@@ -402,6 +413,7 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         delete blk;
         return fail(rc);
     }
+    lap("upload + K4 + download");
     for (int i = 0; i < n_motifs; ++i) {
         gb2_motif *m = ms[(size_t)i];
         m->total = h_tot[(size_t)i];
@@ -421,6 +433,7 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         blk->refs++;
         out[i] = ms[(size_t)i];
     }
+    lap("monotone checks (host)");
     return GB2_OK;
 }
 
@@ -431,7 +444,7 @@ extern "C" int gb2_motif_create(gb2_ctx *ctx, const int64_t *sm, int w, const do
     *out = nullptr;
     GB2_REQUIRE(ctx, sm && h_pval_mat, "gb2_motif_create: null matrix");
     const int32_t w32 = w;
-    return gb2_motif_create_batched(ctx, 1, &w32, sm, h_pval_mat, &min_val, &scale, &offset, out);
+    return gb2_motif_create_batched(ctx, 1, &w32, &sm, &h_pval_mat, &min_val, &scale, &offset, out);
 }
 
 extern "C" int gb2_motif_get_info(const gb2_motif *m, gb2_motif_info *info)

@@ -181,14 +181,18 @@ class DeviceGraph:
         return [DeviceGraph(ctx, None, handle=ctypes.c_void_p(outs[i]), chrom=items[i][0]) for i in range(n)]
 
     @staticmethod
-    def from_files(ctx, fasta, vcf, chrom, display_name=None, max_node_len=32, use_haplotypes=True):
+    def from_files(ctx, fasta, vcf, chrom, display_name=None, max_node_len=32, use_haplotypes=True, parsed_vcf=None):
         """Reference FASTA + phased VCF (the inputs of `grafimo buildvg`, src/grafimo/__main__.py:198-217) -> graph on
-        the device: the VCF is tokenised on the GPU (K9), the graph is built by the library (gb2_graph_build)."""
+        the device: the VCF is tokenised on the GPU (K9), the graph is built by the library (gb2_graph_build).
+        parsed_vcf: the {chromosome: (variants, genotype bits)} dict of read_vcf_device(..., by_chrom=True) -- callers
+        that build several chromosomes read the file ONCE instead of once per chromosome."""
         from .vgraph import read_fasta, read_vcf_device
         seqs = fasta if isinstance(fasta, dict) else read_fasta(fasta)  # a dict {name: sequence} is taken as is
         if chrom not in seqs:
             raise KeyError(f"{chrom} is not a sequence of {fasta}")
-        if vcf:
+        if parsed_vcf is not None:
+            variants, gtb = parsed_vcf.get(chrom, ([], None))
+        elif vcf:
             variants, gtb, _ = read_vcf_device(ctx, vcf, chrom)
         else:
             variants, gtb = [], None

@@ -502,7 +502,7 @@ def _host_genotype_rows(line: bytes, n_alts: int, ploidy: int, n_hap: int, words
     return rows, bad
 
 
-def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
+def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30, by_chrom=False):
     """Phased VCF -> ({pos int64, ref_len int32, alt_off int64[n+1], alt uint8}, (gt_bits uint32 [n, words], n_hap),
     samples): the arrays DeviceGraph.build / gb2_graph_build take, alleles reduced, one entry per ALT allele, in file
     order (stable-sorted by position).  The text is tokenised on the GPU (gb2_tsv_index_lines, gb2_vcf_parse_fields,
@@ -519,6 +519,7 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
     samples, ploidy = None, None
     want = None if chrom is None else np.frombuffer(str(chrom).encode("ascii"), dtype=np.uint8)
     out_pos, out_rlen, out_alt, out_bits, out_ref = [], [], [], [], []
+    out_chrom, chrom_ids = [], {}  # by_chrom: chromosome id of every kept row (names in order of first appearance)
     n_hap = words = 0
     skipped_many = bad_calls = 0
     ctx.enter()
@@ -632,26 +633,46 @@ def read_vcf_device(ctx, path, chrom=None, chunk_bytes=1 << 30):
                 pos0[row], rl[row], alts[row], keep[row] = s, len(r), a_.encode("ascii"), True
                 refs[row] = r.upper().encode("ascii")
         kept = np.nonzero(keep)[0]
+        if by_chrom:
+            cl = h["clen"][sel].astype(np.int64)
+            mx = int(cl.max())
+            col = np.arange(mx, dtype=np.int64)[None, :]
+            nm = host[np.minimum(off[:, None] + col, len(host) - 1)].copy()
+            nm[col >= cl[:, None]] = 0
+            uniq, inv = np.unique(np.ascontiguousarray(nm).view(f"S{mx}").ravel(), return_inverse=True)
+            gid = np.array([chrom_ids.setdefault(u.decode("ascii"), len(chrom_ids)) for u in uniq], dtype=np.int64)
+            out_chrom.append(np.repeat(gid[inv], counts_alt)[kept])
         out_pos.append(pos0[kept]); out_rlen.append(rl[kept]); out_alt.extend(alts[i] for i in kept.tolist())
         out_ref.extend(refs[i] for i in kept.tolist())
         out_bits.append(bits[kept])
     ctx.leave()
     if samples is None:
         samples = []
-    if not out_pos:
-        empty = {"pos": np.zeros(0, np.int64), "ref_len": np.zeros(0, np.int32), "alt_off": np.zeros(1, np.int64), "alt": np.zeros(0, np.uint8)}
-        return empty, (np.zeros((0, max(words, 4)), np.uint32), n_hap), samples
-    pos = np.concatenate(out_pos); rlen = np.concatenate(out_rlen); bits = np.concatenate(out_bits)
-    order = np.argsort(pos, kind="stable")
-    alt_list = [out_alt[i] for i in order.tolist()]
-    alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alt_list])]).astype(np.int64)
-    alt = np.frombuffer(b"".join(alt_list), dtype=np.uint8) if alt_list else np.zeros(0, np.uint8)
-    ref_cat = b"".join(out_ref[i] for i in order.tolist())  # REF alleles (reduced), back to back: checked against the FASTA
     if bad_calls:
         import warnings
         warnings.warn(f"{path}: {bad_calls} genotype calls name an allele the line does not have (or a haplotype beyond the "
                       "header's samples); they were read as the reference allele")
-    variants = {"pos": np.ascontiguousarray(pos[order]), "ref_len": np.ascontiguousarray(rlen[order]), "alt_off": alt_off,
-                "alt": alt, "ref": np.frombuffer(ref_cat, dtype=np.uint8), "lines_with_many_alts_read_on_host": skipped_many,
-                "calls_out_of_range": bad_calls}
-    return variants, (np.ascontiguousarray(bits[order]), n_hap), samples
+
+    def assemble(rows):
+        """variants dict + genotype bit rows of the kept rows `rows` (indices into the concatenated outputs; None = all)"""
+        if not out_pos or (rows is not None and len(rows) == 0):
+            empty = {"pos": np.zeros(0, np.int64), "ref_len": np.zeros(0, np.int32), "alt_off": np.zeros(1, np.int64),
+                     "alt": np.zeros(0, np.uint8), "ref": np.zeros(0, np.uint8)}
+            return empty, (np.zeros((0, max(words, 4)), np.uint32), n_hap)
+        pos = np.concatenate(out_pos); rlen = np.concatenate(out_rlen); bits = np.concatenate(out_bits)
+        idx = np.arange(len(pos)) if rows is None else rows
+        order = idx[np.argsort(pos[idx], kind="stable")]
+        alt_list = [out_alt[i] for i in order.tolist()]
+        alt_off = np.concatenate([[0], np.cumsum([len(a) for a in alt_list])]).astype(np.int64)
+        alt = np.frombuffer(b"".join(alt_list), dtype=np.uint8) if alt_list else np.zeros(0, np.uint8)
+        ref_cat = b"".join(out_ref[i] for i in order.tolist())  # REF alleles (reduced), back to back: checked against the FASTA
+        variants = {"pos": np.ascontiguousarray(pos[order]), "ref_len": np.ascontiguousarray(rlen[order]), "alt_off": alt_off,
+                    "alt": alt, "ref": np.frombuffer(ref_cat, dtype=np.uint8), "lines_with_many_alts_read_on_host": skipped_many,
+                    "calls_out_of_range": bad_calls}
+        return variants, (np.ascontiguousarray(bits[order]), n_hap)
+
+    if by_chrom:  # ONE pass over the file for all chromosomes: {name: (variants, (bits, n_hap))}
+        ids = np.concatenate(out_chrom) if out_chrom else np.zeros(0, np.int64)
+        return {name: assemble(np.nonzero(ids == k)[0]) for name, k in chrom_ids.items()}, samples
+    variants, gtb = assemble(None)
+    return variants, gtb, samples

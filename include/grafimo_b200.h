@@ -166,13 +166,14 @@ int gb2_pval_dp_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, con
 int gb2_motif_create(gb2_ctx *ctx, const int64_t *h_score_matrix, int w, const double *h_pval_mat,
                      int64_t min_val, int64_t scale, double offset, gb2_motif **out);
 /* The same for n_motifs motifs at once (a motif collection, BASELINE config 3; replaces the per-motif loop of
- * motif_ops.py:303-335 / 971-1022 on the device side): arrays as gb2_pval_dp_batched takes them (h_widths[m]; concatenated
- * int64[4][w_m] matrices; concatenated float64[1000*w_m+1] p-value matrices) plus min_val / scale / offset per motif.
+ * motif_ops.py:303-335 / 971-1022 on the device side): h_widths[m]; h_score_mats[m] -> int64[4][w_m]; h_pval_mats[m] ->
+ * float64[1000*w_m+1] (arrays of n_motifs host pointers: every Motif keeps its own arrays, nothing has to be
+ * concatenated) plus min_val / scale / offset per motif.
  * ONE device allocation, ONE upload, TWO kernel launches (K4 for every motif) and ONE synchronisation for the whole
  * collection; out[n_motifs] receives the handles (each destroyed with gb2_motif_destroy; the shared allocation goes
  * with the last one).  On failure no handle is returned. */
-int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *h_score_mats,
-                             const double *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
+int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *const *h_score_mats,
+                             const double *const *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
                              const double *h_offsets, gb2_motif **out);
 int gb2_motif_destroy(gb2_motif *motif);
 int gb2_motif_get_info(const gb2_motif *motif, gb2_motif_info *info);

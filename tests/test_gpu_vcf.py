@@ -65,6 +65,14 @@ def test_device_reader_equals_python_reader_and_source(ctx, tmp_path, fmt, gz):
     # no chromosome filter: the lines of the other chromosome come too
     dv2, _, _ = read_vcf_device(ctx, str(path), None, chunk_bytes=1 << 20)
     assert len(dv2["pos"]) > len(dv["pos"])
+    # one pass, split by chromosome (what the command line does for a BED file with several chromosomes)
+    parts, psamples2 = read_vcf_device(ctx, str(path), None, chunk_bytes=1 << 20, by_chrom=True)
+    assert sorted(parts) == ["7", "other"] and psamples2 == psamples
+    v7, (b7, nh7) = parts["7"]
+    assert nh7 == n_hap and np.array_equal(b7, bits)
+    assert all(np.array_equal(v7[k], dv[k]) for k in ("pos", "ref_len", "alt_off", "alt", "ref"))
+    vo, (bo, _) = parts["other"]
+    assert len(vo["pos"]) == len(dv2["pos"]) - len(dv["pos"]) and bo.shape[0] == len(vo["pos"])
 
 
 def test_device_reader_special_cases(ctx, tmp_path):

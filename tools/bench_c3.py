@@ -36,11 +36,12 @@ def prepare(ctx, raw):
     from grafimo_b200 import motif_ops as mo
     from grafimo_b200.score_sequences import device_motifs
     t0 = time.perf_counter()
-    for m in raw:
+    todo = [m for m in raw if not m.is_scaled]  # rank 0 prepares the rest of the collection later for the parity run
+    for m in todo:
         mo._scale_motif(m, True)
     t1 = time.perf_counter()
-    pvs = ctx.pval_dp_batched([m.score_matrix_acgt() for m in raw], [m.bg_acgt() for m in raw])
-    for m, pv in zip(raw, pvs):
+    pvs = ctx.pval_dp_batched([m.score_matrix_acgt() for m in todo], [m.bg_acgt() for m in todo])
+    for m, pv in zip(todo, pvs):
         m.set_motif_pval_matrix(pv)
     t2 = time.perf_counter()
     dms = device_motifs(raw, ctx)

@@ -26,6 +26,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chrom-len", type=int, default=50_818_468)
     ap.add_argument("--chroms-per-gpu", type=int, default=1)
+    ap.add_argument("--total-chroms", type=int, default=0,
+                    help="strong scaling: a FIXED genome of this many chromosomes dealt round-robin over the ranks (overrides --chroms-per-gpu)")
+    ap.add_argument("--out", default="", help="also write the JSON line to this file")
     ap.add_argument("--haplotypes", type=int, default=5008)
     ap.add_argument("--width", type=int, default=19)
     ap.add_argument("--threshold", type=float, default=1e-4)
@@ -42,6 +45,7 @@ def main():
     rank, world, local = info["rank"], info["world"], info["local"]
     torch.cuda.set_device(local)
     ctx = ss._context()
+    gdist.init_comm(ctx)  # histogram all-reduce + hit-column all-gather run inside the C ABI (csrc/comm.cu)
     tmp = tempfile.mkdtemp(prefix="gb2_genome_")
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
     open(os.path.join(tmp, "ctcf.meme"), "w").write(fx["ctcf_meme"])
@@ -55,8 +59,8 @@ def main():
     t = dict(gen=0.0, build=0.0, extract=0.0)
     rows, n_var, n_nodes, set_mb = [], 0, 0, 0.0
     items = []
-    for c in range(a.chroms_per_gpu):
-        idx = rank * a.chroms_per_gpu + c
+    mine = list(range(rank, a.total_chroms, world)) if a.total_chroms else [rank * a.chroms_per_gpu + c for c in range(a.chroms_per_gpu)]
+    for idx in mine:
         t0 = time.perf_counter()
         ref, variants, gtb = synth.variant_arrays(a.chrom_len, a.haplotypes, 5000 + idx, device=ctx.device)
         t["gen"] += time.perf_counter() - t0
@@ -86,16 +90,22 @@ def main():
     out = {k: gdist.allreduce_max(v, device=ctx.device) for k, v in t.items()}
     t_table = gdist.allreduce_max(t_table, device=ctx.device)
     if rank == 0:
-        L, H = a.chrom_len * a.chroms_per_gpu * world, a.haplotypes
-        print(json.dumps({
-            "workload": f"{world} GPU(s) x {a.chroms_per_gpu} synthetic chromosome(s) of {a.chrom_len} bp, {H} haplotypes, "
+        n_chroms = a.total_chroms or a.chroms_per_gpu * world
+        L, H = a.chrom_len * n_chroms, a.haplotypes
+        line = json.dumps({
+            "workload": f"{n_chroms} synthetic chromosome(s) of {a.chrom_len} bp over {world} GPU(s) ({'fixed genome: strong scaling' if a.total_chroms else 'per-GPU load fixed: weak scaling'}), {H} haplotypes, "
                         f"~1/40 bp variants (10 % indels), CTCF w=19, both strands, p<{a.threshold:g}, global q-values",
             "n_gpus": world, "genome_bp": L, "variants_rank0": n_var, "nodes_rank0": n_nodes, "haplotype_sets_mb_rank0": set_mb,
             "kmer_rows_total": tot_rows, "windows_scored_total": 2 * tot_rows,
             "haplotype_windows_equivalent": 2 * L * H,
             "synth_gen_s": out["gen"], "graph_build_s": out["build"], "graph_build_threads": threads, "extract_s": out["extract"], "score_to_table_s": t_table,
             "extract_rows_per_s": tot_rows / out["extract"], "scan_s": out["extract"] + t_table,
-            "haplotype_windows_equivalent_per_s": 2 * L * H / (out["extract"] + t_table), "hits": int(len(df))}))
+            "haplotype_windows_equivalent_per_s": 2 * L * H / (out["extract"] + t_table), "hits": int(len(df)),
+            "table_merge": "fixed-width hit columns all-gathered on the device (gb2_allgather_bytes), strings decoded once"})
+        print(line)
+        if a.out:
+            with open(a.out, "w") as fh:
+                fh.write(line + "\n")
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
