@@ -1,8 +1,11 @@
 // context.cu -- context / motif lifetime of the grafimo_b200 C ABI (include/grafimo_b200.h).
 #include <stdlib.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <new>
 
 #include "internal.cuh"
@@ -234,6 +237,40 @@ bool plan_smem(int w, int64_t span, int64_t budget, bool allow_global_hist, int 
     return found;
 }
 
+// K4 without the quadratic chain when floating-point addition cannot round on this data: every value of pv[0..span) is a
+// non-negative integer multiple of 2^L (L = the lowest set bit over all values) and the sum of all of them is at most
+// 2^53 such units.  Then every partial sum of ANY order is exactly representable, each fp64 addition of the reference's
+// sequential sums (score_sequences.py:390-391) is exact, and the integer suffix sums below are those sums, bit for bit.
+// -> false when the condition does not hold (the caller uses the order-preserving kernels instead).
+bool exact_ptable(const double *pv, int64_t span, double *ptab, double *total_out)
+{
+    int min_lsb = INT32_MAX;
+    for (int64_t k = 0; k < span; ++k) {
+        const double v = pv[k];
+        if (v == 0.0) continue;
+        uint64_t bits;
+        memcpy(&bits, &v, sizeof(bits));
+        const int e = (int)((bits >> 52) & 0x7FFu);
+        if ((bits >> 63) || e == 0 || e == 0x7FF) return false;  // negative, subnormal, inf/nan: not here
+        const uint64_t mant = (bits & ((1ull << 52) - 1ull)) | (1ull << 52);
+        min_lsb = std::min(min_lsb, e - 1075 + __builtin_ctzll(mant));  // v = mant * 2^(e-1075)
+    }
+    if (min_lsb == INT32_MAX) return false;
+    const double limit = 9007199254740992.0;  // 2^53
+    uint64_t acc = 0;
+    for (int64_t k = span - 1; k >= 0; --k) {
+        const double u = ldexp(pv[k], -min_lsb);  // exact scaling; an integer by construction
+        if (u > limit) return false;
+        acc += (uint64_t)u;
+        if (acc > (1ull << 53)) return false;
+        ptab[k] = (double)acc;  // exact: acc <= 2^53
+    }
+    const double tot_units = (double)acc;
+    for (int64_t k = 0; k < span; ++k) ptab[k] = ldexp(ptab[k], min_lsb) / ldexp(tot_units, min_lsb);  // IEEE division, as K4
+    *total_out = ldexp(tot_units, min_lsb);
+    return true;
+}
+
 int motif_plan(gb2_ctx *ctx, const int64_t *sm, int w, int cb, MotifPlan &pl, const char *who)
 {
     int64_t mincol[GB2_MAX_WIDTH], lo = 0, hi = 0;
@@ -277,8 +314,8 @@ int motif_plan(gb2_ctx *ctx, const int64_t *sm, int w, int cb, MotifPlan &pl, co
 }  // namespace
 
 // K4 over many motifs at once (pval.cu)
-int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const double *d_pm, double *d_ctab, double *d_ptab,
-                              double *d_totals);
+int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_in_off, const int64_t *h_out_off, const double *d_pm,
+                              double *d_ctab, double *d_ptab, double *d_totals);
 
 extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_t *h_widths, const int64_t *const *h_score_mats,
                                         const double *const *h_pval_mats, const int64_t *h_min_vals, const int64_t *h_scales,
@@ -292,6 +329,7 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
                 "gb2_motif_create_batched: null argument");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool timing = getenv("GB2_MOTIF_TIMING") != nullptr;  // phase times of this call on stderr
+    const bool force_chain = getenv("GB2_K4_FORCE_CHAIN") != nullptr;  // tests: every motif through the device kernels
     const auto t_begin = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         if (timing) fprintf(stderr, "gb2_motif_create_batched[%d]: %-28s %.2f ms since entry\n", n_motifs, what,
@@ -363,16 +401,10 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         bm_off[(size_t)i + 1] = bm_off[(size_t)i] + align256((size_t)gb2_div_up(pl.span + 1, 32) * sizeof(uint32_t));
     }
     lap("plans + checks (host)");
-    // ---- one allocation: [p-tables of all motifs][LUTs][bitmaps]; K4's two work arrays come from the scratch buffer
+    // ---- one allocation: [p-tables of all motifs][LUTs][bitmaps]
     const int64_t total_span = sp_off[(size_t)n_motifs];
     const size_t b_ptab = align256((size_t)total_span * sizeof(double));
     const size_t b_lut = lut_off[(size_t)n_motifs], b_bm = bm_off[(size_t)n_motifs];
-    const size_t b_work = align256((size_t)total_span * sizeof(double));
-    const size_t b_tot = align256((size_t)n_motifs * sizeof(double));
-    if ((rc = gb2_scratch_reserve(ctx, 2 * b_work + b_tot)) != GB2_OK) return fail(rc);
-    double *d_pm = (double *)ctx->scratch;
-    double *d_ctab = (double *)((char *)ctx->scratch + b_work);
-    double *d_tot = (double *)((char *)ctx->scratch + 2 * b_work);
     gb2_motif_block *blk = new (std::nothrow) gb2_motif_block();
     if (!blk) return fail(GB2_ERR_NOMEM);
     blk->device = ctx->device;
@@ -381,52 +413,91 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         delete blk;
         return fail(GB2_ERR_NOMEM);
     }
+    auto drop = [&](int code) {
+        cudaFree(blk->d_ptr);
+        delete blk;
+        return fail(code);
+    };
     char *base = (char *)blk->d_ptr;
-    // host staging of everything that goes up: one copy for the LUTs, one for the reachable slices of the p-value matrices
-    std::vector<uint8_t> h_lut(b_lut, 0);
-    std::vector<double> h_pm((size_t)total_span);
+    // K4, p[s] = seqsum(pv[s:]) / seqsum(pv) in the reference's summation order (score_sequences.py:390-391).
+    //  * EXACT motifs -- every partial sum is an integer multiple of one power of two and fits 53 bits (uniform background,
+    //    the reference's default, up to 26 bp: all values are multiples of 4^-w) -- are done here on the host with integer
+    //    suffix sums: fp64 addition cannot round on such data, so the order of the additions does not matter and the
+    //    O(span) suffix sum IS the reference's O(span^2) result, bit for bit (exact_ptable).
+    //  * the others keep the order-preserving device kernels (one dependent add chain per start score), batched.
+    std::unique_ptr<uint8_t[]> h_lut(new (std::nothrow) uint8_t[b_lut]);
+    std::unique_ptr<double[]> h_ptab_all(new (std::nothrow) double[(size_t)total_span]);
+    if (!h_lut || !h_ptab_all) return drop(GB2_ERR_NOMEM);
+    std::vector<int> slow;
+    std::vector<int64_t> slow_in((size_t)1, 0), slow_out;
     for (int i = 0; i < n_motifs; ++i) {
         const MotifPlan &pl = plans[(size_t)i];
-        memcpy(h_lut.data() + lut_off[(size_t)i], pl.lut.data(), pl.lut.size() * sizeof(uint32_t));
-        memcpy(h_pm.data() + sp_off[(size_t)i], h_pval_mats[i] + pl.lo, (size_t)pl.span * sizeof(double));
+        memcpy(h_lut.get() + lut_off[(size_t)i], pl.lut.data(), pl.lut.size() * sizeof(uint32_t));
         gb2_motif *m = ms[(size_t)i];
         m->d_ptab = (double *)base + sp_off[(size_t)i];
         m->d_lut = (uint32_t *)(base + b_ptab + lut_off[(size_t)i]);
         m->d_bitmap = (uint32_t *)(base + b_ptab + b_lut + bm_off[(size_t)i]);
+        if (!force_chain && exact_ptable(h_pval_mats[i] + pl.lo, pl.span, h_ptab_all.get() + sp_off[(size_t)i], &m->total)) continue;
+        slow.push_back(i);
+        slow_out.push_back(sp_off[(size_t)i]);
+        slow_in.push_back(slow_in.back() + pl.span);
     }
-    std::vector<double> h_ptab_all((size_t)total_span), h_tot((size_t)n_motifs);
-    lap("alloc + staging (host)");
-    cudaError_t e = cudaMemcpyAsync(base + b_ptab, h_lut.data(), b_lut, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pm, h_pm.data(), (size_t)total_span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        // K4 for every motif in two launches: p[s] = seqsum(pv[s:]) / seqsum(pv) -- mass outside [lo,hi] is exactly +0.0
-        rc = gb2_launch_ptable_batched(ctx, n_motifs, sp_off.data(), d_pm, d_ctab, (double *)base, d_tot);
-        if (rc == GB2_OK) {
-            e = cudaMemcpyAsync(h_ptab_all.data(), base, (size_t)total_span * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot.data(), d_tot, (size_t)n_motifs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    lap("LUT staging + exact p-tables (host)");
+    cudaError_t e = cudaMemcpyAsync(base + b_ptab, h_lut.get(), b_lut, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !slow.empty()) {
+        const int ns = (int)slow.size();
+        const int64_t slow_span = slow_in.back();
+        const size_t b_work = align256((size_t)slow_span * sizeof(double));
+        const size_t b_tot = align256((size_t)ns * sizeof(double));
+        if ((rc = gb2_scratch_reserve(ctx, 2 * b_work + b_tot)) != GB2_OK) return drop(rc);
+        double *d_pm = (double *)ctx->scratch;
+        double *d_ctab = (double *)((char *)ctx->scratch + b_work);
+        double *d_tot = (double *)((char *)ctx->scratch + 2 * b_work);
+        std::unique_ptr<double[]> h_pm(new (std::nothrow) double[(size_t)slow_span]);
+        std::vector<double> h_tot((size_t)ns);
+        if (!h_pm) return drop(GB2_ERR_NOMEM);
+        for (int k = 0; k < ns; ++k) {
+            const MotifPlan &pl = plans[(size_t)slow[(size_t)k]];
+            memcpy(h_pm.get() + slow_in[(size_t)k], h_pval_mats[slow[(size_t)k]] + pl.lo, (size_t)pl.span * sizeof(double));
+        }
+        e = cudaMemcpyAsync(d_pm, h_pm.get(), (size_t)slow_span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            rc = gb2_launch_ptable_batched(ctx, ns, slow_in.data(), slow_out.data(), d_pm, d_ctab, (double *)base, d_tot);
+            if (rc != GB2_OK) return drop(rc);
+            for (int k = 0; k < ns && e == cudaSuccess; ++k)
+                e = cudaMemcpyAsync(h_ptab_all.get() + slow_out[(size_t)k], (double *)base + slow_out[(size_t)k],
+                                    (size_t)(slow_in[(size_t)k + 1] - slow_in[(size_t)k]) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot.data(), d_tot, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_pm / h_tot are read by the copies above
+            for (int k = 0; k < ns; ++k) ms[(size_t)slow[(size_t)k]]->total = h_tot[(size_t)k];
         }
     }
-    if (e != cudaSuccess || rc != GB2_OK) {
-        if (e != cudaSuccess) { GB2_SET_ERR(ctx, "gb2_motif_create: upload / p-table failed: %s", cudaGetErrorString(e)); rc = GB2_ERR_CUDA; }
-        cudaFree(blk->d_ptr);
-        delete blk;
-        return fail(rc);
+    // the host-made tables go up in one copy per run of consecutive exact motifs (one copy when all are exact)
+    for (int i = 0; i < n_motifs && e == cudaSuccess;) {
+        if (std::binary_search(slow.begin(), slow.end(), i)) { ++i; continue; }
+        int j = i;
+        while (j + 1 < n_motifs && !std::binary_search(slow.begin(), slow.end(), j + 1)) ++j;
+        e = cudaMemcpyAsync((double *)base + sp_off[(size_t)i], h_ptab_all.get() + sp_off[(size_t)i],
+                            (size_t)(sp_off[(size_t)j + 1] - sp_off[(size_t)i]) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        i = j + 1;
     }
-    lap("upload + K4 + download");
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_lut / h_ptab_all are pageable: done with them here
+    if (e != cudaSuccess) {
+        GB2_SET_ERR(ctx, "gb2_motif_create: upload / p-table failed: %s", cudaGetErrorString(e));
+        return drop(GB2_ERR_CUDA);
+    }
+    lap("uploads + K4 of the inexact motifs");
     for (int i = 0; i < n_motifs; ++i) {
         gb2_motif *m = ms[(size_t)i];
-        m->total = h_tot[(size_t)i];
         if (!(m->total > 0.0)) {
             GB2_SET_ERR(ctx, "gb2_motif_create: empty p-value matrix (motif %d)", i);
-            cudaFree(blk->d_ptr);
-            delete blk;
-            return fail(GB2_ERR_MOTIF);
+            return drop(GB2_ERR_MOTIF);
         }
-        m->h_ptab.assign(h_ptab_all.begin() + sp_off[(size_t)i], h_ptab_all.begin() + sp_off[(size_t)i + 1]);
+        m->h_ptab.assign(h_ptab_all.get() + sp_off[(size_t)i], h_ptab_all.get() + sp_off[(size_t)i + 1]);
         m->monotone = 1;
         for (int64_t k = 1; k < m->span; ++k)
             if (m->h_ptab[(size_t)k] > m->h_ptab[(size_t)k - 1]) { m->monotone = 0; break; }
+        m->ptab_exact_host = std::binary_search(slow.begin(), slow.end(), i) ? 0 : 1;
     }
     for (int i = 0; i < n_motifs; ++i) {
         ms[(size_t)i]->block = blk;

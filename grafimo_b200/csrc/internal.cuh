@@ -48,6 +48,7 @@ struct gb2_motif {
     int replicas = 0;
     int monotone = 0;
     int hist_global = 0;           // 1: span too large for shared memory, K2 counts with global atomics
+    int ptab_exact_host = 0;       // 1: the p-value table came from the exact integer suffix sums on the host (context.cu)
     int64_t lo = 0, hi = 0, span = 0;
     int64_t min_val = 0, scale = 0;
     double offset = 0.0, total = 0.0;

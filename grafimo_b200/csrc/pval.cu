@@ -22,8 +22,9 @@
 // [off[m], off[m+1])); a CTA takes 128 consecutive start scores of one motif (tile -> motif by binary search over the
 // per-motif tile prefix).  Same dependent add chain per start score as above: bit-identical tables.
 struct PtabBatch {
-    const int64_t *off;       // [n+1] element offsets
+    const int64_t *off;       // [n+1] element offsets of the inputs (and of the cumulative sums)
     const int64_t *tile_off;  // [n+1] tiles before motif m
+    const int64_t *out_off;   // [n]   first element of motif m's p-value table in the output array
     int n;
 };
 
@@ -74,18 +75,19 @@ __global__ void __launch_bounds__(128) gb2_ptab_div_batched_kernel(const PtabBat
     const int64_t s = ((int64_t)blockIdx.x - b.tile_off[m]) * 128 + threadIdx.x;
     if (s >= span) return;
     const double tot = ctab_all[base];  // seqsum over the whole matrix (zeros outside [lo,hi])
-    ptab_all[base + s] = __ddiv_rn(ctab_all[base + s], tot);
+    ptab_all[b.out_off[m] + s] = __ddiv_rn(ctab_all[base + s], tot);
     if (s == 0) totals[m] = tot;
 }
 
-int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const double *d_pm, double *d_ctab, double *d_ptab,
-                              double *d_totals)
+int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const int64_t *h_out_off, const double *d_pm,
+                              double *d_ctab, double *d_ptab, double *d_totals)
 {
-    std::vector<int64_t> host((size_t)2 * (n + 1));
+    std::vector<int64_t> host((size_t)3 * (n + 1));
     int64_t tiles = 0;
     for (int m = 0; m <= n; ++m) {
         host[(size_t)m] = h_off[m];
         host[(size_t)(n + 1 + m)] = tiles;
+        host[(size_t)(2 * (n + 1) + m)] = m < n ? h_out_off[m] : 0;
         if (m < n) tiles += gb2_div_up(h_off[m + 1] - h_off[m], 128);
     }
     GB2_REQUIRE(ctx, tiles > 0 && tiles < ((int64_t)1 << 31), "gb2_motif_create: too many score bins for one launch");
@@ -95,6 +97,7 @@ int gb2_launch_ptable_batched(gb2_ctx *ctx, int n, const int64_t *h_off, const d
     PtabBatch b;
     b.off = d_idx;
     b.tile_off = d_idx + (n + 1);
+    b.out_off = d_idx + 2 * (n + 1);
     b.n = n;
     gb2_ctab_batched_kernel<<<(unsigned)tiles, 128, 0, ctx->stream>>>(b, d_pm, d_ctab);
     GB2_LAUNCH_CHECK(ctx);

@@ -34,6 +34,69 @@ struct WideSum<NCHUNK, NCHUNK, R> {
     static __device__ __forceinline__ uint32_t run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) { return 0u; }
 };
 
+// One tile of 1024 * U k-mers.  FULL: every row of the tile exists -- no per-row bounds test (the kernel is bound by the
+// integer ALU pipe, 80 % busy in profiles/r02_wide_kernel_ncu.txt, so the remainder logic stays out of the main loop).
+template <int NCHUNK, int R, int U, bool FULL>
+__device__ __forceinline__ void wide_tile(const ScoreParams &p, const uint4 *src, int64_t r0, uint32_t lut32, uint32_t hist32,
+                                          bool hist_smem, bool do_hist, bool two, uint32_t nsent, uint32_t cut_hi, unsigned lane)
+{
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t row = r0 + u * 1024;
+        v[u] = (FULL || row < p.n) ? ld_stream_u4(src + row) : make_uint4(0, 0, 0, 0);
+    }
+    uint32_t acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = WideSum<0, NCHUNK, R>::run(v[u].x, v[u].y, v[u].z, v[u].w, lut32);
+    if (p.nmask != nullptr) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = r0 + u * 1024;
+            if ((FULL || row < p.n) && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) acc[u] = nsent;
+        }
+    }
+    if (hist_smem) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (FULL || r0 + u * 1024 < p.n) {
+                red_shared_inc(hist32 + 4u * __byte_perm(acc[u], 0u, 0x4410u));
+                if (two) red_shared_inc(hist32 + 4u * (acc[u] >> 16));
+            }
+        }
+    } else if (do_hist) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (FULL || r0 + u * 1024 < p.n) {
+                atomicAdd(p.hist + (acc[u] & 0xFFFFu), 1ull);
+                if (two) atomicAdd(p.hist + (acc[u] >> 16), 1ull);
+            }
+        }
+    }
+    if (p.dense != nullptr) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (FULL || r0 + u * 1024 < p.n) p.dense[r0 + u * 1024] = (acc[u] == nsent) ? 0xFFFFFFFFu : acc[u];
+    }
+    if (p.hits != nullptr) {
+        // N rows carry bin `span` in both fields: above the cut, so they pass this screen and are rejected by bin_hits
+        uint32_t mx = FULL ? acc[0] : 0u;
+#pragma unroll
+        for (int u = FULL ? 1 : 0; u < U; ++u) mx = __vimax3_u16x2(mx, (FULL || r0 + u * 1024 < p.n) ? acc[u] : 0u, 0u);
+        const bool any = ((mx & 0xFFFFu) >= p.cut) | (two & (mx >= cut_hi));
+        if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t row = r0 + u * 1024;
+                const bool ok = FULL || row < p.n;
+                const uint32_t bf = acc[u] & 0xFFFFu, br = acc[u] >> 16;
+                append_hits(p, ok && bin_hits(p, bf), (uint64_t)row, bf, 0u, lane);
+                if (two) append_hits(p, ok && bin_hits(p, br), (uint64_t)row, br, 1u, lane);
+            }
+        }
+    }
+}
+
 template <int NCHUNK, int R>
 __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScoreParams p, int hist_in_smem)
 {
@@ -57,57 +120,11 @@ __global__ void __launch_bounds__(1024, 1) gb2_score_wide_kernel(const ScorePara
     const bool two = p.two_strands != 0;
     constexpr int U = 4;
     constexpr int64_t TILE = 1024 * U;
-    const int64_t ntiles = (p.n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * TILE + tid;
-        const bool full = (tile + 1) * TILE <= p.n;  // uniform over the CTA: no per-row bounds checks in full tiles
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t row = r0 + u * 1024;
-            v[u] = (full || row < p.n) ? ld_stream_u4(src + row) : make_uint4(0, 0, 0, 0);
-        }
-        uint32_t acc[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) acc[u] = WideSum<0, NCHUNK, R>::run(v[u].x, v[u].y, v[u].z, v[u].w, lut32);
-        if (p.nmask != nullptr) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t row = r0 + u * 1024;
-                if ((full || row < p.n) && ((__ldg(p.nmask + (row >> 5)) >> (row & 31)) & 1u)) acc[u] = nsent;
-            }
-        }
-        uint32_t mx = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t row = r0 + u * 1024;
-            const bool ok = full || row < p.n;
-            const uint32_t a = acc[u];
-            if (ok) {
-                const uint32_t bf = a & 0xFFFFu, br = a >> 16;
-                if (hist_smem) {
-                    red_shared_inc(hist32 + 4u * bf);
-                    if (two) red_shared_inc(hist32 + 4u * br);
-                } else if (do_hist) {
-                    atomicAdd(p.hist + bf, 1ull);
-                    if (two) atomicAdd(p.hist + br, 1ull);
-                }
-                if (p.dense != nullptr) p.dense[row] = (a == nsent) ? 0xFFFFFFFFu : a;
-                mx = __vimax3_u16x2(mx, a == nsent ? 0u : a, 0u);
-            }
-        }
-        const bool any = ((mx & 0xFFFFu) >= p.cut) | (two & (mx >= cut_hi));
-        if (p.hits != nullptr && __any_sync(0xFFFFFFFFu, any)) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t row = r0 + u * 1024;
-                const bool ok = full || row < p.n;
-                const uint32_t bf = acc[u] & 0xFFFFu, br = acc[u] >> 16;
-                append_hits(p, ok && bin_hits(p, bf), (uint64_t)row, bf, 0u, lane);
-                if (two) append_hits(p, ok && bin_hits(p, br), (uint64_t)row, br, 1u, lane);
-            }
-        }
-    }
+    const int64_t nfull = p.n / TILE;
+    for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x)
+        wide_tile<NCHUNK, R, U, true>(p, src, tile * TILE + tid, lut32, hist32, hist_smem, do_hist, two, nsent, cut_hi, lane);
+    if (nfull * TILE < p.n && (int64_t)blockIdx.x == nfull % gridDim.x)  // the remainder: one CTA, guarded
+        wide_tile<NCHUNK, R, U, false>(p, src, nfull * TILE + tid, lut32, hist32, hist_smem, do_hist, two, nsent, cut_hi, lane);
     if (hist_smem) {
         __syncthreads();
         for (uint32_t i = tid; i <= p.span; i += 1024) {

@@ -54,6 +54,25 @@ def test_comm_world_1_is_a_no_op(ctx):
         ctx.comm_init(None, 3, 2)
 
 
+def test_k4_exact_host_path_equals_chain_kernels(ctx, monkeypatch):
+    """K4 takes integer suffix sums on the host when no addition can round (uniform background: values are multiples of
+    4^-w and the total fits 53 bits) and the order-preserving device kernels otherwise; forcing every motif through the
+    kernels must give the same tables, and both are the oracle's (sequential sums per start score)"""
+    from grafimo_b200.engine import DeviceMotif
+    from oracle import oracle as orc
+    tags = ["ctcf_meme__unif", "gata1_meme__unif", "synth_w8_meme__unif", "ctcf_meme__bgnt", "synth_w35_meme__unif_norev", "synth_w30_meme__bgnt"]
+    ms = [gu.load_motif(t) for t in tags]
+    items = [(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"]) for m in ms]
+    monkeypatch.delenv("GB2_K4_FORCE_CHAIN", raising=False)
+    fast = DeviceMotif.create_many(ctx, items)
+    monkeypatch.setenv("GB2_K4_FORCE_CHAIN", "1")
+    chain = DeviceMotif.create_many(ctx, items)
+    for m, a, b in zip(ms, fast, chain):
+        tab = orc.pvalue_table(m["pval_mat"])[a.lo:a.hi + 1]
+        assert np.array_equal(a.ptable, b.ptable) and np.array_equal(a.ptable, tab), m["tag"]
+        assert a.info.total == b.info.total and a.info.monotone == b.info.monotone
+
+
 def test_batched_motif_create_equals_single(ctx):
     """gb2_motif_create_batched (one allocation / upload / K4 launch pair for the collection) == gb2_motif_create per motif:
     p-value tables bit-equal, same chunk plan; K4 stays pinned on the oracle for every golden motif"""
