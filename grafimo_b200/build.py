@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
                 if verbose and out:
                     print(out)
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-lpthread"]
         run(cmd)
     return LIB
 

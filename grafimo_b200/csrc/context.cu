@@ -4,9 +4,11 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <new>
+#include <thread>
 
 #include "internal.cuh"
 
@@ -256,19 +258,39 @@ bool exact_ptable(const double *pv, int64_t span, double *ptab, double *total_ou
         min_lsb = std::min(min_lsb, e - 1075 + __builtin_ctzll(mant));  // v = mant * 2^(e-1075)
     }
     if (min_lsb == INT32_MAX) return false;
-    const double limit = 9007199254740992.0;  // 2^53
+    if (min_lsb < -1000 || min_lsb > 1000) return false;  // the two scale factors below must be normal numbers
+    const double limit = 9007199254740992.0;                // 2^53
+    const double to_units = ldexp(1.0, -min_lsb), from_units = ldexp(1.0, min_lsb);  // powers of two: exact scaling
     uint64_t acc = 0;
     for (int64_t k = span - 1; k >= 0; --k) {
-        const double u = ldexp(pv[k], -min_lsb);  // exact scaling; an integer by construction
-        if (u > limit) return false;
+        const double u = pv[k] * to_units;  // an integer by construction
+        if (!(u <= limit)) return false;
         acc += (uint64_t)u;
         if (acc > (1ull << 53)) return false;
         ptab[k] = (double)acc;  // exact: acc <= 2^53
     }
-    const double tot_units = (double)acc;
-    for (int64_t k = 0; k < span; ++k) ptab[k] = ldexp(ptab[k], min_lsb) / ldexp(tot_units, min_lsb);  // IEEE division, as K4
-    *total_out = ldexp(tot_units, min_lsb);
+    const double total = (double)acc * from_units;
+    for (int64_t k = 0; k < span; ++k) ptab[k] = (ptab[k] * from_units) / total;  // IEEE division, as K4's div kernel
+    *total_out = total;
     return true;
+}
+
+// the per-motif host work of a collection (plans, checks, exact p-tables) is independent per motif: a few worker threads
+template <typename F>
+void parallel_for(int n, F &&fn)
+{
+    const int nt = std::max(1, std::min<int>({n / 16, (int)std::thread::hardware_concurrency(), 16}));
+    if (nt <= 1) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto &th : pool) th.join();
 }
 
 int motif_plan(gb2_ctx *ctx, const int64_t *sm, int w, int cb, MotifPlan &pl, const char *who)
@@ -380,14 +402,6 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         if (cb == 4) plans[(size_t)i] = std::move(probe);
         else if ((rc = motif_plan(ctx, sm, w, cb, plans[(size_t)i], "gb2_motif_create")) != GB2_OK) return fail(rc);
         const MotifPlan &pl = plans[(size_t)i];
-        // mass outside the reachable range means the matrix and the p-value matrix do not belong together
-        const double *pm = h_pval_mats[i];
-        for (int64_t k = 0; k < L; ++k) {
-            if ((k < pl.lo || k > pl.hi) && pm[k] != 0.0) {
-                GB2_SET_ERR(ctx, "gb2_motif_create: p-value matrix has mass at unreachable score %lld", (long long)k);
-                return fail(GB2_ERR_MOTIF);
-            }
-        }
         gb2_motif *m = new (std::nothrow) gb2_motif();
         if (!m) return fail(GB2_ERR_NOMEM);
         ms[(size_t)i] = m;
@@ -399,6 +413,23 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         sp_off[(size_t)i + 1] = sp_off[(size_t)i] + pl.span;
         lut_off[(size_t)i + 1] = lut_off[(size_t)i] + align256(pl.lut.size() * sizeof(uint32_t));
         bm_off[(size_t)i + 1] = bm_off[(size_t)i] + align256((size_t)gb2_div_up(pl.span + 1, 32) * sizeof(uint32_t));
+    }
+    {   // mass outside the reachable range means the matrix and the p-value matrix do not belong together
+        std::vector<int64_t> bad_at((size_t)n_motifs, -1);
+        parallel_for(n_motifs, [&](int i) {
+            const MotifPlan &pl = plans[(size_t)i];
+            const double *pm = h_pval_mats[i];
+            const int64_t L = (int64_t)GB2_RANGE * pl.w + 1;
+            for (int64_t k = 0; k < pl.lo; ++k)
+                if (pm[k] != 0.0) { bad_at[(size_t)i] = k; return; }
+            for (int64_t k = pl.hi + 1; k < L; ++k)
+                if (pm[k] != 0.0) { bad_at[(size_t)i] = k; return; }
+        });
+        for (int i = 0; i < n_motifs; ++i)
+            if (bad_at[(size_t)i] >= 0) {
+                GB2_SET_ERR(ctx, "gb2_motif_create: p-value matrix has mass at unreachable score %lld", (long long)bad_at[(size_t)i]);
+                return fail(GB2_ERR_MOTIF);
+            }
     }
     lap("plans + checks (host)");
     // ---- one allocation: [p-tables of all motifs][LUTs][bitmaps]
@@ -430,17 +461,21 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
     if (!h_lut || !h_ptab_all) return drop(GB2_ERR_NOMEM);
     std::vector<int> slow;
     std::vector<int64_t> slow_in((size_t)1, 0), slow_out;
-    for (int i = 0; i < n_motifs; ++i) {
+    std::vector<uint8_t> is_exact((size_t)n_motifs, 0);
+    parallel_for(n_motifs, [&](int i) {
         const MotifPlan &pl = plans[(size_t)i];
         memcpy(h_lut.get() + lut_off[(size_t)i], pl.lut.data(), pl.lut.size() * sizeof(uint32_t));
         gb2_motif *m = ms[(size_t)i];
         m->d_ptab = (double *)base + sp_off[(size_t)i];
         m->d_lut = (uint32_t *)(base + b_ptab + lut_off[(size_t)i]);
         m->d_bitmap = (uint32_t *)(base + b_ptab + b_lut + bm_off[(size_t)i]);
-        if (!force_chain && exact_ptable(h_pval_mats[i] + pl.lo, pl.span, h_ptab_all.get() + sp_off[(size_t)i], &m->total)) continue;
+        is_exact[(size_t)i] = !force_chain && exact_ptable(h_pval_mats[i] + pl.lo, pl.span, h_ptab_all.get() + sp_off[(size_t)i], &m->total);
+    });
+    for (int i = 0; i < n_motifs; ++i) {
+        if (is_exact[(size_t)i]) continue;
         slow.push_back(i);
         slow_out.push_back(sp_off[(size_t)i]);
-        slow_in.push_back(slow_in.back() + pl.span);
+        slow_in.push_back(slow_in.back() + plans[(size_t)i].span);
     }
     lap("LUT staging + exact p-tables (host)");
     cudaError_t e = cudaMemcpyAsync(base + b_ptab, h_lut.get(), b_lut, cudaMemcpyHostToDevice, ctx->stream);
@@ -487,18 +522,19 @@ extern "C" int gb2_motif_create_batched(gb2_ctx *ctx, int n_motifs, const int32_
         return drop(GB2_ERR_CUDA);
     }
     lap("uploads + K4 of the inexact motifs");
-    for (int i = 0; i < n_motifs; ++i) {
-        gb2_motif *m = ms[(size_t)i];
-        if (!(m->total > 0.0)) {
+    for (int i = 0; i < n_motifs; ++i)
+        if (!(ms[(size_t)i]->total > 0.0)) {
             GB2_SET_ERR(ctx, "gb2_motif_create: empty p-value matrix (motif %d)", i);
             return drop(GB2_ERR_MOTIF);
         }
+    parallel_for(n_motifs, [&](int i) {
+        gb2_motif *m = ms[(size_t)i];
         m->h_ptab.assign(h_ptab_all.get() + sp_off[(size_t)i], h_ptab_all.get() + sp_off[(size_t)i + 1]);
         m->monotone = 1;
         for (int64_t k = 1; k < m->span; ++k)
             if (m->h_ptab[(size_t)k] > m->h_ptab[(size_t)k - 1]) { m->monotone = 0; break; }
-        m->ptab_exact_host = std::binary_search(slow.begin(), slow.end(), i) ? 0 : 1;
-    }
+        m->ptab_exact_host = is_exact[(size_t)i];
+    });
     for (int i = 0; i < n_motifs; ++i) {
         ms[(size_t)i]->block = blk;
         blk->refs++;
