@@ -43,29 +43,71 @@ __global__ void gb2_bh_keys_kernel(const double *__restrict__ ptab, uint32_t spa
 //   count  one CTA: rank of every bin, cumulative row count C at every sorted position (block scan, exact integers)
 //   raw    grid:    raw = p / (C / float(N)) with IEEE div.rn, +inf for empty bins
 //   min    one CTA: reverse running minimum (block min-scan, exact), clip at 1, scatter to the bins
+// The one-CTA kernels walk the sorted positions in chunks of 1,024 CONSECUTIVE elements (thread t takes element
+// chunk * 1024 + t, the chunk total is carried): a thread-owns-a-contiguous-range layout makes every warp access touch 32
+// sectors and the single SM's load/store unit then bounds the kernel (measured 43 + 30 us at 22,806 bins; loads in flight
+// were not the limit -- batching them changed nothing).
+// inclusive scan over the 1,024 threads of the CTA (warp shuffles + one pass over the 32 warp totals), `carry` = what
+// came before this chunk; cub::BlockScan's default raking form costs ~2.5 us per call at 1,024 threads
+template <typename T, typename Op>
+__device__ __forceinline__ T bh_block_scan(T v, T identity, Op op, T *s_warp, T &carry)
+{
+    const unsigned lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T up = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= (unsigned)o) v = op(up, v);
+    }
+    if (lane == 31) s_warp[wp] = v;
+    __syncthreads();
+    if (wp == 0) {
+        T w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T up = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= (unsigned)o) w = op(up, w);
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const T before = op(carry, wp ? s_warp[wp - 1] : identity);
+    const T total = s_warp[BH_THREADS / 32 - 1];
+    __syncthreads();  // s_warp is reused by the next chunk
+    carry = op(carry, total);
+    return op(before, v);
+}
+
+struct BhAdd {
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; }
+};
+struct BhMin {
+    __device__ __forceinline__ double operator()(double a, double b) const { return fmin(a, b); }
+};
+
 __global__ void __launch_bounds__(BH_THREADS) gb2_bh_count_kernel(const uint32_t *__restrict__ sorted_bins,
                                                                   const unsigned long long *__restrict__ hist, uint32_t nbins,
                                                                   uint32_t *__restrict__ rank,
                                                                   unsigned long long *__restrict__ cum,
                                                                   unsigned long long *__restrict__ total_out)
 {
-    typedef cub::BlockScan<unsigned long long, BH_THREADS> ScanU64;
-    __shared__ typename ScanU64::TempStorage tmp;
+    static_assert(BH_THREADS == 1024, "bh_block_scan scans 32 warp totals with one warp");
+    __shared__ unsigned long long s_warp[32];
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
-    const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
-    for (uint32_t i = beg; i < end; ++i) rank[sorted_bins[i]] = i;  // position of every bin in p-ascending order
-    if (hist == nullptr) return;  // rank-only call (no q-values wanted)
-    unsigned long long local = 0;
-    for (uint32_t i = beg; i < end; ++i) local += hist[sorted_bins[i]];
-    unsigned long long prefix, total;
-    ScanU64(tmp).ExclusiveSum(local, prefix, total);
-    if (tid == 0) *total_out = total;
-    unsigned long long c = prefix;
-    for (uint32_t i = beg; i < end; ++i) {
-        c += hist[sorted_bins[i]];
-        cum[i] = c;
+    unsigned long long carry = 0ull;
+    uint32_t b_next = tid < nbins ? sorted_bins[tid] : 0u;
+    unsigned long long h_next = (hist != nullptr && tid < nbins) ? hist[b_next] : 0ull;
+    for (uint32_t base = 0; base < nbins; base += BH_THREADS) {
+        const uint32_t i = base + tid, b = b_next;
+        const unsigned long long h = h_next;
+        const uint32_t in = i + BH_THREADS;  // the next chunk's loads fly during this chunk's scan
+        b_next = in < nbins ? sorted_bins[in] : 0u;
+        h_next = (hist != nullptr && in < nbins) ? hist[b_next] : 0ull;
+        if (i < nbins) rank[b] = i;  // position of every bin in p-ascending order
+        if (hist == nullptr) continue;  // rank-only call (no q-values wanted)
+        const unsigned long long c = bh_block_scan(h, 0ull, BhAdd(), s_warp, carry);
+        if (i < nbins) cum[i] = c;
     }
+    if (hist != nullptr && tid == 0) *total_out = carry;
 }
 
 __global__ void gb2_bh_raw_kernel(const double *__restrict__ sorted_p, const unsigned long long *__restrict__ cum,
@@ -82,28 +124,22 @@ __global__ void __launch_bounds__(BH_THREADS) gb2_bh_min_kernel(const double *__
                                                                 const uint32_t *__restrict__ sorted_bins, uint32_t nbins,
                                                                 double *__restrict__ qtab)
 {
-    typedef cub::BlockScan<double, BH_THREADS> ScanF64;
-    __shared__ typename ScanF64::TempStorage tmp;
-    __shared__ double s_run[BH_THREADS];
+    __shared__ double s_warp[32];
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nbins + BH_THREADS - 1) / BH_THREADS;
-    const uint32_t beg = min(tid * per, nbins), end = min(beg + per, nbins);
-    double run_min = CUDART_INF;
-    for (uint32_t i = beg; i < end; ++i) run_min = fmin(run_min, raw[i]);
-    // suffix-min over threads: reverse the thread order and take an inclusive min-scan
-    double scanned;
-    s_run[BH_THREADS - 1 - tid] = run_min;
-    __syncthreads();
-    const double rev = s_run[tid];
-    ScanF64(tmp).InclusiveScan(rev, scanned, cub::Min());
-    __syncthreads();
-    s_run[tid] = scanned;  // s_run[j] = min over original threads >= BH_THREADS-1-j
-    __syncthreads();
-    // minimum over all runs strictly to the right of this thread's run, then right-to-left inside the run
-    double m = (tid + 1 < BH_THREADS) ? s_run[BH_THREADS - 2 - tid] : CUDART_INF;
-    for (uint32_t i = end; i > beg; --i) {
-        m = fmin(m, raw[i - 1]);
-        qtab[sorted_bins[i - 1]] = m > 1.0 ? 1.0 : m;
+    // right to left: thread t of a chunk takes the element t places before the chunk's right end, so an inclusive
+    // min-scan over the threads IS the running minimum from the right; the minimum of the chunks already done is carried
+    double carry = CUDART_INF;
+    double r_next = tid < nbins ? raw[nbins - 1u - tid] : CUDART_INF;
+    uint32_t b_next = tid < nbins ? sorted_bins[nbins - 1u - tid] : 0u;
+    for (uint32_t base = 0; base < nbins; base += BH_THREADS) {
+        const uint32_t k = base + tid;  // distance from the right end
+        const double r = r_next;
+        const uint32_t b = b_next;
+        const uint32_t kn = k + BH_THREADS;
+        r_next = kn < nbins ? raw[nbins - 1u - kn] : CUDART_INF;
+        b_next = kn < nbins ? sorted_bins[nbins - 1u - kn] : 0u;
+        const double m = bh_block_scan(r, (double)CUDART_INF, BhMin(), s_warp, carry);
+        if (k < nbins) qtab[b] = m > 1.0 ? 1.0 : m;
     }
 }
 
@@ -518,26 +554,27 @@ __global__ void gb2_dense_gather_kernel(const uint32_t *__restrict__ sorted_rank
     o_row[t] = row_base + (strands == 2 ? (i >> 1) : i);
     o_strand[t] = (uint8_t)(strands == 2 ? (i & 1ull) : 0ull);
     o_iscore[t] = sc;
-    o_score[t] = __dadd_rn(__ddiv_rn((double)sc, scale), __dmul_rn((double)w, offset));  // score_sequences.py:393
-    o_p[t] = ptab[bin];
+    if (o_score != nullptr) o_score[t] = __dadd_rn(__ddiv_rn((double)sc, scale), __dmul_rn((double)w, offset));  // score_sequences.py:393
+    if (o_p != nullptr) o_p[t] = ptab[bin];
     if (o_q != nullptr && qtab != nullptr) o_q[t] = qtab[bin];
 }
 
-extern "C" int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *m, const uint32_t *d_dense, uint64_t n_kmers, int strands,
+// library-sort form; gb2_finalize_dense (dense_sort.cu) is the product path, this one its checker (GB2_DENSE_CUB=1)
+int gb2_finalize_dense_cub(gb2_ctx *ctx, const gb2_motif *m, const uint32_t *d_dense, uint64_t n_kmers, int strands,
                                   uint64_t row_base, const double *d_qtab, const uint32_t *d_rank, double p_threshold,
                                   int q_filter, double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore,
                                   double *d_score, double *d_p, double *d_q, uint64_t *d_n_out)
 {
     if (!ctx || !m) return GB2_ERR_ARG;
-    GB2_REQUIRE(ctx, d_n_out != nullptr && d_rank != nullptr, "gb2_finalize_dense: null counter or rank table");
-    GB2_REQUIRE(ctx, strands == 1 || strands == 2, "gb2_finalize_dense: strands must be 1 or 2");
-    GB2_REQUIRE(ctx, !q_filter || d_qtab != nullptr, "gb2_finalize_dense: q filter needs the q table");
+    GB2_REQUIRE(ctx, d_n_out != nullptr && d_rank != nullptr, "gb2_finalize_dense_cub: null counter or rank table");
+    GB2_REQUIRE(ctx, strands == 1 || strands == 2, "gb2_finalize_dense_cub: strands must be 1 or 2");
+    GB2_REQUIRE(ctx, !q_filter || d_qtab != nullptr, "gb2_finalize_dense_cub: q filter needs the q table");
     const uint64_t n_windows = n_kmers * (uint64_t)strands;
-    GB2_REQUIRE(ctx, n_windows < ((uint64_t)1 << 31), "gb2_finalize_dense: at most 2^31-1 windows per call");
+    GB2_REQUIRE(ctx, n_windows < ((uint64_t)1 << 31), "gb2_finalize_dense_cub: at most 2^31-1 windows per call");
     GB2_CUDA(ctx, cudaSetDevice(ctx->device));
     GB2_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), ctx->stream));
     if (n_windows == 0) return GB2_OK;
-    GB2_REQUIRE(ctx, d_dense && d_row && d_strand && d_iscore && d_score && d_p, "gb2_finalize_dense: null buffer");
+    GB2_REQUIRE(ctx, d_dense && d_row && d_strand && d_iscore, "gb2_finalize_dense_cub: null buffer");
     const int n = (int)n_windows;
     int rank_bits = 1;
     while ((1ll << rank_bits) < m->span + 1) ++rank_bits;  // ranks are < span + 1 <= 2^rank_bits

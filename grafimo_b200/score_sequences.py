@@ -550,6 +550,19 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
     return df
 
 
+LAST_PHASES = {}  # GB2_PHASES=1: wall seconds of the phases of the last compute_results_rows call (stream-synchronised)
+
+
+def _phase(ctx, name, t_prev):
+    """Phase timer of compute_results_rows (only with GB2_PHASES=1: it synchronises the stream)."""
+    if not os.environ.get("GB2_PHASES"):
+        return t_prev
+    ctx.sync()
+    now = time.perf_counter()
+    LAST_PHASES[name] = LAST_PHASES.get(name, 0.0) + now - t_prev
+    return now
+
+
 def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmode: Optional[bool] = False) -> pd.DataFrame:
     """compute_results for k-mers that are already on the device: `rows` is a GraphRows (or a list of them, one per
     chromosome) from extract_regions.DeviceGraph.extract -- the forward walks of every region, with start/stop,
@@ -586,20 +599,27 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     import torch.distributed as tdist
     from . import dist as gdist
     world, rank = _dist_world()
+    ctx = batches[0].ctx if batches else _context()
+    LAST_PHASES.clear()
+    tp = time.perf_counter()
     if world > 1:
-        counts = [None] * world
-        tdist.all_gather_object(counts, n_kmers)
+        if getattr(ctx, "world", 1) == world:  # the context owns the communicator: 8 bytes per rank through the library
+            counts = ctx.allgather(torch.tensor([n_kmers], dtype=torch.int64, device=ctx.device)).view(-1).cpu().tolist()
+        else:
+            counts = [None] * world
+            tdist.all_gather_object(counts, n_kmers)
         rank_base, n_all = sum(counts[:rank]), sum(counts)
     else:
         rank_base, n_all = 0, n_kmers
+    tp = _phase(ctx, "row_counts", tp)
     n = n_all * strands
     if n == 0:  # score_sequences.py:189-192
         errmsg = "No result retrieved. Unable to proceed.\n"
         errmsg += "\nAre you using the correct VGs and searching on the right chromosomes?\n"
         exception_handler(ValueError, errmsg, debug)
     t0 = time.time()
-    ctx = batches[0].ctx if batches else _context()
     dm = device_motif(motif, ctx)
+    tp = _phase(ctx, "motif", tp)
     bases = (rank_base + np.concatenate([[0], np.cumsum([b.n for b in batches])])).astype(np.int64)
     n_local = n_kmers * strands
     cap = max(1, n_local if threshold >= 0.25 else min(n_local, max(1 << 20, n_local // 8)))
@@ -613,10 +633,13 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         if found <= cap:
             break
         cap = found
+    tp = _phase(ctx, "score", tp)
     if world > 1 and not no_qvalue:  # the one exchange step: global score histogram -> global q-values
         with torch.cuda.stream(ctx.stream):
             gdist.allreduce_histogram(scan.histogram(), ctx=ctx)
+    tp = _phase(ctx, "allreduce", tp)
     kept = scan.finalize_device(q_filter=bool(qval_t))
+    tp = _phase(ctx, "finalize", tp)
     if rank == 0:
         if verbose:
             print("Sequences scored in %.2fs" % (time.time() - t0))
@@ -653,10 +676,13 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         if not no_qvalue:
             dev["q"] = scan.out["q"][:kept]
     names = [b.region_name(r) for b in batches for r in range(len(b.regions))]
+    tp = _phase(ctx, "hit_columns", tp)
     if world > 1:
         dev, names = _gather_hit_columns(ctx, dev, names, kept, world)
+    tp = _phase(ctx, "gather_ranks", tp)
     with torch.cuda.stream(ctx.stream):
         host = {k: v.cpu().numpy() for k, v in dev.items()}
+    tp = _phase(ctx, "to_host", tp)
     minus = host["minus"].astype(bool)
     from .extract_regions import decode_kmers
     comp = np.zeros(256, np.uint8)
@@ -672,7 +698,9 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     ref = np.where(host["isref"].astype(bool) & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
     keep = np.ones(len(minus), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     strand = np.where(minus, "-", "+").astype(object)
+    tp = _phase(ctx, "strings", tp)
     df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, host["score"], host["p"], host.get("q"), seq, freq, ref, 1)
+    tp = _phase(ctx, "dataframe", tp)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
     return df
@@ -770,7 +798,7 @@ def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
         if found <= cap:
             break
         cap = found
-    kept = scan.finalize_device(q_filter=bool(qval_t))
+    kept = scan.finalize_device(q_filter=bool(qval_t), index_only=True)  # K8 prints score / p / q from per-bin tables
     if not no_qvalue:
         print("\nComputing q-values...\n")
     print(f"Scanned sequences:\t{n}")
@@ -991,7 +1019,7 @@ def scan_dir_device(motif: Motif, sequence_loc: str, debug: bool, args_obj):
         if found <= cap:
             break
         cap = found
-    kept = scan.finalize_device(q_filter=bool(qval_t))
+    kept = scan.finalize_device(q_filter=bool(qval_t), index_only=True)
     if not no_qvalue:
         print("\nComputing q-values...\n")
     print(f"Scanned sequences:\t{n}")

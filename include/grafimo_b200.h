@@ -239,9 +239,11 @@ int gb2_finalize_hits(gb2_ctx *ctx, const gb2_motif *motif, const gb2_hit *d_hit
 
 /* The same step for an unselective scan (`-t 1`, docs/paper_results/run_analysis.sh:43: every window with p < 1 is a
  * report row), from the dense scores gb2_score wrote for n_kmers consecutive k-mers (d_dense, see gb2_score) instead of
- * hit records: window i = (k-mer i / strands, strand i % strands) is already in (row, strand) order, so one stable radix
- * sort on the p-rank gives the same (p, row, strand) order with 4-byte keys.  Row indices = row_base + k-mer index.
- * Outputs need room for n_kmers * strands entries; n_kmers * strands < 2^31. */
+ * hit records: window i = (k-mer i / strands, strand i % strands) is already in (row, strand) order, so a stable sort on
+ * the <= 16-bit p-rank alone gives the same (p, row, strand) order: two hand-written partition passes (csrc/dense_sort.cu),
+ * the first reading the dense scores, the second writing the columns in place.  Row indices = row_base + k-mer index.
+ * d_score, d_p and d_q may be NULL (a caller that prints the rows on the device, gb2_report_*, needs only row, strand
+ * and integer score).  Outputs need room for n_kmers * strands entries; n_kmers * strands < 2^31. */
 int gb2_finalize_dense(gb2_ctx *ctx, const gb2_motif *motif, const uint32_t *d_dense, uint64_t n_kmers, int strands,
                        uint64_t row_base, const double *d_qtab, const uint32_t *d_rank, double p_threshold, int q_filter,
                        double q_threshold, uint64_t *d_row, uint8_t *d_strand, int32_t *d_iscore, double *d_score,

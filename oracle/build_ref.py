@@ -37,9 +37,14 @@ ZIP = os.path.join(OUT, "grafimo_ref.zip")
 SHIMS = os.path.join(ROOT, "tests", "golden", "_shims")
 
 
+def available():
+    """True when oracle/_ref holds the built reference (nothing is imported, sys.path is left alone)."""
+    return os.path.isfile(ZIP) and bool(glob.glob(os.path.join(OUT, "motif_processing*.so")))
+
+
 def activate():
     """Puts the built reference (and the shims) on sys.path; -> True when it is importable."""
-    if not os.path.isfile(ZIP) or not glob.glob(os.path.join(OUT, "motif_processing*.so")):
+    if not available():
         return False
     for p in (SHIMS, OUT, ZIP):
         if p not in sys.path:

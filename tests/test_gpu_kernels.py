@@ -235,6 +235,33 @@ def test_dense_finalize_equals_hit_path(ctx, tag):
         assert np.array_equal(np.asarray(got[k]), np.asarray(exp[k])), k
 
 
+@pytest.mark.parametrize("tag,n", [("synth_w25_meme__bgnt", 2_000_003), ("synth_w8_meme__bgnt", 300_001)])
+def test_dense_partition_passes_equal_library_sort(ctx, tag, n, monkeypatch):
+    """gb2_finalize_dense (two hand-written stable partition passes, csrc/dense_sort.cu) == the library-sort form it replaced
+    (GB2_DENSE_CUB=1), column for column, over many tiles: threshold 1, a threshold that drops windows, a q-value filter,
+    one strand, N rows."""
+    from grafimo_b200.engine import Scan
+    m = gu.load_motif(tag)
+    w = m["width"]
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    g = torch.Generator(device="cuda"); g.manual_seed(31)
+    packed = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device="cuda", generator=g) & ((1 << (2 * w)) - 1)
+    nmask = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    nmask[::97] = 0x00010400  # a few N rows
+    for strands, thr, qf in ((2, 1.0, False), (2, 0.4, False), (1, 1.0, False), (2, 0.97, True)):
+        out = {}
+        for form in ("cub", "passes", "passes+table"):  # "+table": bin -> rank through the shared-memory table even if p is monotone
+            monkeypatch.setenv("GB2_DENSE_CUB", "1" if form == "cub" else "0")
+            monkeypatch.setenv("GB2_DENSE_RANK_TABLE", "1" if form.endswith("table") else "0")
+            sc = Scan(ctx, dm, strands=strands, threshold=thr, dense_rows=n)
+            sc.score(packed, nmask, row_base=5)
+            out[form] = sc.finalize(q_filter=qf)
+        assert qf or len(out["cub"]["row"]) > n // 4
+        for form in ("passes", "passes+table"):
+            for k in out["cub"]:
+                assert np.array_equal(np.asarray(out[form][k]), np.asarray(out["cub"][k])), (tag, form, strands, thr, qf, k)
+
+
 def test_scan_host_wide_motif(ctx):
     """gb2_scan_host with a 48-bp motif: two packed words per k-mer through the chunked encode + score loop."""
     from grafimo_b200.engine import scan_host

@@ -143,7 +143,14 @@ if ONLY in ("", "c5"):
         dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
         w = m["width"]
         packed = torch.randint(0, 1 << 62, (n5,), dtype=torch.int64, device="cuda", generator=g) & ((1 << (2 * w)) - 1)
-        for mode in ("hit records + 41-bit keys", "dense scores + gb2_finalize_dense"):
+        modes = [("hit records + 41-bit keys", {}, False),
+                 ("dense scores + library sort (GB2_DENSE_CUB=1, round 1)", {"GB2_DENSE_CUB": "1"}, False),
+                 ("dense scores + gb2_finalize_dense (two partition passes)", {}, False),
+                 ("dense scores + gb2_finalize_dense, row / strand / integer score only (what the device report writer reads)", {}, True)]
+        for mode, env, index_only in modes:
+            for k in ("GB2_DENSE_CUB",):
+                os.environ.pop(k, None)
+            os.environ.update(env)
             for rep in range(3):
                 sc = Scan(ctx, dm, strands=2, threshold=1.0, hit_capacity=2 * n5, dense_rows=n5 if mode.startswith("dense") else 0)
                 e0, e1, e2 = ev(), ev(), ev()
@@ -151,7 +158,7 @@ if ONLY in ("", "c5"):
                 sc.score(packed)
                 e1.record(ctx.stream)
                 sc.qvalues()
-                kept = sc.finalize_device()
+                kept = sc.finalize_device(index_only=index_only)
                 e2.record(ctx.stream); ctx.sync()
             print(f"    {tag}: w={w} span={dm.span} R={dm.info.lut_replicas} [{mode}]: K2 {e0.elapsed_time(e1):.2f} ms, K5+K6 {e1.elapsed_time(e2):.2f} ms, "
                   f"{kept} rows reported of {2 * n5}; {2 * n5 / (e0.elapsed_time(e2) * 1e-3) / 1e9:.2f} G windows/s")
