@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "score_common.cuh"
 
@@ -603,6 +604,11 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     if (const char *t = getenv("GB2_SEQ_CHUNK_BASES")) CHUNK_BASES = std::max<int64_t>(1024, atoll(t));
     const int64_t MIN_PIECE = std::max<int64_t>(64 + w, std::min<int64_t>((int64_t)1 << 16, CHUNK_BASES / 4));
 
+    const bool timing = getenv("GB2_SCAN_TIMING") != nullptr;  // phase times of this call on stderr (events with timing)
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
+    double ms_plan = 0, ms_issue = 0, ms_tail0 = 0;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // loop start, first copy done, last copy done, last kernel done
     // ---- plan: pieces, chunks, copies
     std::vector<Piece> pieces;
     std::vector<Chunk> chunks;
@@ -766,6 +772,11 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
         if (rc != GB2_OK) goto done;
         sq.w = w;
 
+        if (timing) {
+            for (int i = 0; i < 4; ++i) SH_CUDA(cudaEventCreate(&tev[i]));
+            ms_plan = host_ms();
+            SH_CUDA(cudaEventRecord(tev[0], ctx->stream));
+        }
         int buf = 0;
         for (size_t c = 0; c < chunks.size(); ++c) {
             const Chunk &ch = chunks[c];
@@ -784,6 +795,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                 }
             }
             SH_CUDA(cudaEventRecord(copied[buf], ctx->copy_stream));
+            if (timing && (c == 0 || c + 1 == chunks.size())) SH_CUDA(cudaEventRecord(tev[c == 0 ? 1 : 2], ctx->copy_stream));
             SH_CUDA(cudaStreamWaitEvent(ctx->stream, copied[buf], 0));
             const int wb = ascii ? 0 : buf;
             if (ascii) {
@@ -805,8 +817,24 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             if (!ascii) SH_CUDA(cudaEventRecord(consumed[buf], ctx->stream));
             buf ^= 1;
         }
+        if (timing) {
+            SH_CUDA(cudaEventRecord(tev[3], ctx->stream));
+            ms_issue = host_ms();
+            SH_CUDA(cudaStreamSynchronize(ctx->stream));
+            ms_tail0 = host_ms();
+        }
         rc = gb2_scan_tail_finish(ctx, m, b, (uint64_t)n_windows * (uint64_t)strands, (uint64_t)n_windows, p_threshold,
                                   q_filter, want_q, hit_capacity, o);
+        if (timing && tev[2]) {
+            float first = 0, copies = 0, kernels = 0;
+            cudaEventElapsedTime(&first, tev[0], tev[1]);
+            cudaEventElapsedTime(&copies, tev[0], tev[2]);
+            cudaEventElapsedTime(&kernels, tev[0], tev[3]);
+            fprintf(stderr, "gb2_scan_host_sequences: %zu chunks, %zu copies; plan %.2f ms | all launches issued at %.2f ms | device: first copy done "
+                    "+%.2f ms, last copy done +%.2f ms, last kernel done +%.2f ms | host: loop drained at %.2f ms, K5 + K6 + table back "
+                    "%.2f ms, total %.2f ms\n", chunks.size(), runs.size(), ms_plan, ms_issue, first, copies, kernels, ms_tail0,
+                    host_ms() - ms_tail0, host_ms());
+        }
         if (o.h_stats && (rc == GB2_OK || rc == GB2_ERR_CAPACITY)) {
             o.h_stats[1] -= std::min<uint64_t>(o.h_stats[1], overlap_n);
             o.h_stats[2] -= std::min<uint64_t>(o.h_stats[2], overlap_other);
@@ -820,5 +848,7 @@ done:
         if (copied[i]) cudaEventDestroy(copied[i]);
         if (consumed[i]) cudaEventDestroy(consumed[i]);
     }
+    for (int i = 0; i < 4; ++i)
+        if (tev[i]) cudaEventDestroy(tev[i]);
     return rc;
 }

@@ -502,6 +502,18 @@ class Scan:
         if n > self.capacity:
             raise GrafimoB200Error(_lib.GB2_ERR_CAPACITY, "Scan.finalize", f"{n} hits exceed the capacity {self.capacity}")
         cap = max(n, 1)
+        if self.dense_rows and self.want_q and self.threshold < 0.5:
+            # dense scan under a selective threshold: the number of report rows is the histogram mass of the kept bins --
+            # size the output columns for that, not for every window (37 bytes each)
+            with torch.cuda.stream(ctx.stream):
+                pt = getattr(self.motif, "_ptab1_dev", None)
+                if pt is None:
+                    pt = torch.from_numpy(np.concatenate([np.asarray(self.motif.ptable, dtype=np.float64), [1.0]])).to(ctx.device)
+                    self.motif._ptab1_dev = pt
+                keep_bins = pt < self.threshold
+                if q_filter:
+                    keep_bins &= self.qtab < self.threshold
+                cap = max(int(self.hist[keep_bins].sum().item()), 1)
         index_only = bool(index_only) and bool(self.dense_rows)
         if getattr(self, "_out_cap", 0) < cap or getattr(self, "_out_index_only", False) != index_only:
             f64 = (lambda: None) if index_only else (lambda: ctx.empty(cap, torch.float64))
@@ -637,8 +649,8 @@ class ManyScan:
         return np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
 
 
-def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):
-    """gb2_scan_host: numpy/pinned-torch uint8 [n, w] host k-mers -> dict of numpy columns (+ stats)."""
+def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None, out=None):
+    """gb2_scan_host: numpy/pinned-torch uint8 [n, w] host k-mers -> dict of numpy columns (+ stats).  out: a HostTable."""
     if isinstance(ascii_rows, torch.Tensor):
         assert not ascii_rows.is_cuda
         base, n, stride = ascii_rows.data_ptr(), ascii_rows.shape[0], ascii_rows.stride(0)
@@ -647,23 +659,39 @@ def scan_host(ctx, motif, ascii_rows, strands=1, threshold=1e-4, q_filter=False,
         a = np.ascontiguousarray(ascii_rows, dtype=np.uint8)
         base, n, stride, w = a.ctypes.data, a.shape[0], a.strides[0], a.shape[1]
     cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n * strands, 1 << 26)))
-    row = np.empty(cap, np.uint64); strand = np.empty(cap, np.uint8); isc = np.empty(cap, np.int32)
-    score = np.empty(cap, np.float64); p = np.empty(cap, np.float64); q = np.empty(cap, np.float64) if want_q else None
+    row, strand, isc, score, p, q = _host_outputs(cap, want_q, out)
     nh = ctypes.c_uint64(0)
     stats = np.zeros(4, np.uint64)
     rc = ctx.lib.gb2_scan_host(ctx.h, motif.h, ctypes.c_void_p(base), n, w, stride, int(strands), float(threshold),
                                int(bool(q_filter)), int(bool(want_q)), cap, _np_ptr(row), _np_ptr(strand), _np_ptr(isc),
                                _np_ptr(score), _np_ptr(p), _np_ptr(q) if want_q else None, ctypes.byref(nh), _np_ptr(stats))
     check(rc, "gb2_scan_host", ctx.h)
-    k = int(nh.value)
-    out = {"row": row[:k], "strand": strand[:k], "int_score": isc[:k], "score": score[:k], "p-value": p[:k]}
-    if want_q:
-        out["q-value"] = q[:k]
-    out["stats"] = dict(windows=int(stats[0]), n_rows=int(stats[1]), bad_rows=int(stats[2]), hits=int(stats[3]))
-    return out
+    return _host_result(int(nh.value), row, strand, isc, score, p, q, want_q, stats, ("windows", "n_rows", "bad_rows", "hits"))
 
 
-def _host_outputs(cap, want_q):
+class HostTable:
+    """Reusable PINNED host buffers for the hit table of the host-buffer entry points (scan_host*, `out=`).  The table comes
+    back with one asynchronous copy per column at the PCIe rate; fresh pageable numpy arrays (the default) cost a staged
+    copy plus a page fault per 4 KB touched -- measured 4 ms of a 16 ms call for 489 k hits.  The arrays a scan returns are
+    views of these buffers: they are overwritten by the next scan that is given the same HostTable."""
+
+    def __init__(self, capacity, want_q=True):
+        self.capacity = int(capacity)
+        mk = lambda dt: torch.empty(self.capacity, dtype=dt, pin_memory=True)  # noqa: E731
+        self._t = [mk(torch.int64), mk(torch.uint8), mk(torch.int32), mk(torch.float64), mk(torch.float64),
+                   mk(torch.float64) if want_q else None]
+        self.want_q = bool(want_q)
+
+    def arrays(self):
+        row, strand, isc, score, p, q = [None if t is None else t.numpy() for t in self._t]
+        return row.view(np.uint64), strand, isc, score, p, q
+
+
+def _host_outputs(cap, want_q, out=None):
+    if out is not None:
+        if out.capacity < cap or (want_q and not out.want_q):
+            raise ValueError(f"HostTable of {out.capacity} rows given to a scan with hit capacity {cap}")
+        return out.arrays()
     row = np.empty(cap, np.uint64); strand = np.empty(cap, np.uint8); isc = np.empty(cap, np.int32)
     score = np.empty(cap, np.float64); p = np.empty(cap, np.float64); q = np.empty(cap, np.float64) if want_q else None
     return row, strand, isc, score, p, q
@@ -684,12 +712,12 @@ def _host_base(a):
     return a.ctypes.data
 
 
-def scan_host_packed(ctx, motif, packed, nmask=None, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None):
+def scan_host_packed(ctx, motif, packed, nmask=None, strands=1, threshold=1e-4, q_filter=False, want_q=True, hit_capacity=None, out=None):
     """gb2_scan_host_packed: 2-bit packed k-mers in host memory (numpy uint64/int64 or pinned torch int64; [n] or [n, 2]
     for a motif wider than 32) -> dict of numpy columns (+ stats)."""
     n = int(packed.shape[0])
     cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n * strands, 1 << 26)))
-    row, strand, isc, score, p, q = _host_outputs(cap, want_q)
+    row, strand, isc, score, p, q = _host_outputs(cap, want_q, out)
     nh = ctypes.c_uint64(0)
     stats = np.zeros(4, np.uint64)
     rc = ctx.lib.gb2_scan_host_packed(ctx.h, motif.h, ctypes.c_void_p(_host_base(packed)),
@@ -702,7 +730,7 @@ def scan_host_packed(ctx, motif, packed, nmask=None, strands=1, threshold=1e-4, 
 
 
 def scan_host_sequences(ctx, motif, data, offsets, lens, fmt="ascii", nbits=None, strands=1, threshold=1e-4, q_filter=False,
-                        want_q=True, hit_capacity=None):
+                        want_q=True, hit_capacity=None, out=None):
     """gb2_scan_host_sequences: whole sequences in host memory -> hit table.  fmt "ascii": data = uint8 bytes, offsets =
     byte offset of every sequence; fmt "2bit": data = uint64/int64 words (32 bases each), offsets = word offsets, nbits =
     optional uint32 per word.  Rows are window indices (sequence-major, see include/grafimo_b200.h)."""
@@ -710,7 +738,7 @@ def scan_host_sequences(ctx, motif, data, offsets, lens, fmt="ascii", nbits=None
     ln = np.ascontiguousarray(lens, dtype=np.int64)
     n_win = int(np.maximum(ln - motif.width + 1, 0).sum())
     cap = int(hit_capacity if hit_capacity is not None else max(1024, min(n_win * strands, 1 << 26)))
-    row, strand, isc, score, p, q = _host_outputs(cap, want_q)
+    row, strand, isc, score, p, q = _host_outputs(cap, want_q, out)
     nh = ctypes.c_uint64(0)
     stats = np.zeros(4, np.uint64)
     rc = ctx.lib.gb2_scan_host_sequences(ctx.h, motif.h, 0 if fmt == "ascii" else 1, ctypes.c_void_p(_host_base(data)),

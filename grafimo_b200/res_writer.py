@@ -209,7 +209,7 @@ class DeviceReport:
         n, w = self.n, self.width
         from .extract_regions import decode_kmers
         letters = decode_kmers(h["kmer"], w)
-        seq = np.char.decode(np.ascontiguousarray(letters).view(f"S{w}").ravel(), "ascii").astype(object) if n else np.array([], dtype=object)
+        seq = np.ascontiguousarray(letters).view(f"S{w}").ravel().astype(f"U{w}").astype(object) if n else np.array([], dtype=object)
         cols = {
             "motif_id": [self.motif.motif_id] * n, "motif_alt_id": [self.motif.motif_name] * n,
             "sequence_name": np.array(self.seqnames, dtype=object)[h["name"]] if n else np.array([], dtype=object),

@@ -173,10 +173,16 @@ def clear_parsed_cache():
     _PARSED.clear()
 
 
+_DENSE_FROM = 0.006  # p-value threshold from which the dense form is the faster one
+
+
 def _dense_rows(threshold, n_kmers, strands):
     """Unselective thresholds (`-t 1` in docs/paper_results/run_analysis.sh) report a large share of the windows: K2 then
-    writes dense scores and gb2_finalize_dense builds the rows (no hit records, 4-byte sort keys).  -> dense_rows of Scan."""
-    return int(n_kmers) if (threshold >= 0.25 and 0 < n_kmers * strands < (1 << 31)) else 0
+    writes dense scores (4 bytes per k-mer) and gb2_finalize_dense builds the rows -- no 16-byte hit records appended
+    through an atomic counter, no 41-bit sort keys.  Measured on 2^26 k-mers, both strands (tools/bench_configs.py, section
+    "midrange", profiles/r02_configs_midrange.json): the dense form costs 0.93 ms whatever the threshold, hit records
+    0.48 / 0.68 / 1.20 / 2.39 / 4.25 / 6.39 ms at p < 0.001 / 0.003 / 0.01 / 0.03 / 0.1 / 0.25.  -> dense_rows of Scan."""
+    return int(n_kmers) if (threshold >= _DENSE_FROM and 0 < n_kmers * strands < (1 << 31)) else 0
 
 
 _CHUNK_BYTES = 256 << 20  # TSV text goes to the device in chunks of at most 256 MiB (cut at line boundaries): two pinned
@@ -342,15 +348,18 @@ def _var_strings(text, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
     return out
 
 
-def _report_order(pval, start, stop, strand, seq):
+def _report_order(pval, start, stop, strand, seq, minus=None):
     """Row order of the report: p-value ascending, ties -- which the reference leaves undefined -- by (start, stop,
     strand, matched_sequence).  Numeric keys first; the sequence strings are only compared inside groups that tie on
-    all of them."""
+    all of them.  `minus` (bool array): the caller already knows which rows are on the '-' strand and every other row is '+'."""
     n = len(pval)
     if n < 2:
         return np.arange(n)
-    minus = (strand == "-")
-    other = ~minus & (strand != "+")
+    if minus is None:
+        minus = (strand == "-")
+        other = ~minus & (strand != "+")
+    else:
+        other = np.zeros(n, dtype=bool)
     scode = minus.astype(np.int8) * 2 + other.astype(np.int8) * 3  # '+' < '-' < anything else, like the characters
     order = np.lexsort((scode, stop, start, pval))
     p, a, b, c = pval[order], start[order], stop[order], scode[order]
@@ -366,18 +375,19 @@ def _report_order(pval, start, stop, strand, seq):
     return order
 
 
-def _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world):
+def _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, world, minus=None):
     """The 12-column table (resultsTmp.py:269-313) from per-hit arrays: filter, merge over ranks, order, DataFrame."""
     arrays = [seqname, start, stop, strand, score, pval, qval, seq, freq, ref]
     if not keep.all():
         arrays = [None if a is None else a[keep] for a in arrays]
+        minus = None if minus is None else minus[keep]
     if world > 1:  # every rank returns the whole table
         import torch.distributed as tdist
         parts = [None] * world
         tdist.all_gather_object(parts, arrays)
         arrays = [None if parts[0][k] is None else np.concatenate([p[k] for p in parts]) for k in range(len(arrays))]
     seqname, start, stop, strand, score, pval, qval, seq, freq, ref = arrays
-    order = _report_order(pval, start, stop, strand, seq)
+    order = _report_order(pval, start, stop, strand, seq, minus if world == 1 else None)
     n = len(order)
     cols = {
         "motif_id": np.full(n, motif.motif_id, dtype=object),
@@ -535,7 +545,7 @@ def compute_results(motif: Motif, sequence_loc: str, debug: bool, args_obj=None,
                 first = _gather_rows(text, off + lead, 1)[:, 0]
         seqname[m] = _var_strings(text, off + lead, g["name_len"].astype(np.int64))
         seq[m] = _fixed_strings(text, off + g["seq_off"].astype(np.int64), width)
-        strand[m] = np.char.decode(g["strand"].view("S1"), "ascii").astype(object)
+        strand[m] = g["strand"].view("S1").astype("U1").astype(object)
         start[m], stop[m], freq[m] = g["start"], g["stop"], g["freq"]
         r = np.where(g["ref"] == 1, "ref", "non.ref").astype(object)
         other = np.nonzero(g["ref"] == 2)[0]
@@ -689,7 +699,8 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
     asc = decode_kmers(host["packed"], width)
     asc = np.where(minus[:, None], comp[asc][:, ::-1], asc)
-    seq = np.char.decode(np.ascontiguousarray(asc).view(f"S{width}").ravel(), "ascii").astype(object) if len(minus) else np.array([], dtype=object)
+    # bytes -> str objects at C speed (np.char.decode is a per-element Python call: 0.21 s against 0.06 s for 229 k hits)
+    seq = np.ascontiguousarray(asc).view(f"S{width}").ravel().astype(f"U{width}").astype(object) if len(minus) else np.array([], dtype=object)
     seqname = np.array(names, dtype=object)[host["region"]] if len(minus) else np.array([], dtype=object)
     # the '-' row of a walk starts where the walk stops
     start = np.where(minus, host["stop"], host["start"])
@@ -699,7 +710,7 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
     keep = np.ones(len(minus), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
     strand = np.where(minus, "-", "+").astype(object)
     tp = _phase(ctx, "strings", tp)
-    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, host["score"], host["p"], host.get("q"), seq, freq, ref, 1)
+    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, host["score"], host["p"], host.get("q"), seq, freq, ref, 1, minus=minus)
     tp = _phase(ctx, "dataframe", tp)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))

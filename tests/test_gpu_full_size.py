@@ -75,3 +75,51 @@ def test_full_size_headline_workload_properties():
     qtab[order] = q
     assert np.array_equal(out["q-value"], qtab[out["int_score"] - dm.lo])
     ctx.close()
+
+
+def test_full_size_unselective_scan_properties():
+    """BASELINE config 5 at its full size (w = 25, 30 M k-mers, both strands, threshold 1: 60 M report rows) through the dense
+    form (K2 dense scores -> gb2_finalize_dense, two partition passes): the oracle cannot score that row by row, so the
+    table is checked through what the sort must guarantee -- every window with p < 1 is reported exactly once, the rows are
+    ordered by (p-rank, row, strand), p / q / score are functions of the integer score, the per-score row counts equal K2's
+    histogram -- plus an oracle check of a sample of rows."""
+    from grafimo_b200.engine import Context, Scan
+    from oracle import oracle as orc
+    free, total = torch.cuda.mem_get_info()
+    if free < 20e9:
+        pytest.skip("needs ~10 GB of free device memory")
+    ctx = Context(0)
+    m = gu.load_motif("synth_w25_meme__bgnt")
+    w = m["width"]
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    n = 30_000_000
+    g = torch.Generator(device="cuda"); g.manual_seed(55)
+    packed = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device="cuda", generator=g) & ((1 << (2 * w)) - 1)
+    sc = Scan(ctx, dm, strands=2, threshold=1.0, dense_rows=n)
+    sc.score(packed)
+    kept = sc.finalize_device()
+    hist = sc.histogram()
+    o = sc.out
+    with torch.cuda.stream(ctx.stream):
+        ptab = torch.from_numpy(np.concatenate([dm.ptable, [1.0]])).to(ctx.device)
+        reported_bins = ptab < 1.0
+        assert kept == int(hist[reported_bins].sum().item())  # every window with p < 1, nothing else
+        row, strand, isc, p, q, score = (o[k][:kept] for k in ("row", "strand", "iscore", "p", "q", "score"))
+        bins = (isc - int(dm.lo)).to(torch.int64)
+        assert torch.equal(torch.bincount(bins, minlength=dm.span + 1)[reported_bins], hist[reported_bins])
+        assert torch.equal(p, ptab[bins]) and torch.equal(q, sc.qtab[bins])
+        rank = sc.rank.to(torch.int64)[bins]
+        key = row * 2 + strand.to(torch.int64)
+        d_rank, d_key = rank[1:] - rank[:-1], key[1:] - key[:-1]
+        assert bool((d_rank >= 0).all()) and bool(((d_rank > 0) | (d_key > 0)).all())  # (p-rank, row, strand), strictly: no duplicates
+        assert bool((p[1:] >= p[:-1]).all()) and bool((q >= p).all())
+        sel = torch.arange(0, kept, 600_011, device=ctx.device)
+        rows_s, strand_s = row[sel].cpu().numpy(), strand[sel].cpu().numpy()
+        isc_s, p_s, score_s = isc[sel].cpu().numpy(), p[sel].cpu().numpy(), score[sel].cpu().numpy()
+        xs = packed[torch.from_numpy(rows_s).to(ctx.device)].cpu().numpy()
+    seqs = ["".join("ACGT"[(int(v) >> (2 * i)) & 3] for i in range(w)) for v in xs]
+    comp = str.maketrans("ACGT", "TGCA")
+    seqs = [s.translate(comp)[::-1] if st else s for s, st in zip(seqs, strand_s)]
+    e_isc, e_lo, e_p = orc.score_rows(orc.kmers_to_matrix(seqs, w), m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    assert np.array_equal(e_isc, isc_s) and np.array_equal(e_p, p_s) and np.array_equal(e_lo, score_s)
+    ctx.close()

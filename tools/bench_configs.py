@@ -168,6 +168,30 @@ if ONLY in ("", "c5"):
             del sc
         del packed
 
+# ---------------------------------------------------------------- mid-range thresholds: hit records or dense scores?
+if ONLY in ("", "midrange"):
+    print("mid-range thresholds (CTCF, 2^26 k-mers, both strands): hit-record form against the dense form")
+    nm = 1 << 26
+    m = gu.load_motif("ctcf_meme__unif")
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    packed = torch.randint(0, 1 << 62, (nm,), dtype=torch.int64, device="cuda", generator=g) & ((1 << 38) - 1)
+    for thr in (1e-3, 3e-3, 0.01, 0.03, 0.1, 0.25):
+        for dense in (False, True):
+            for rep in range(3):
+                sc = Scan(ctx, dm, strands=2, threshold=thr, hit_capacity=int(2 * nm * min(1.0, thr * 1.3)) + (1 << 16), dense_rows=nm if dense else 0)
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record(ctx.stream)
+                sc.score(packed)
+                e1.record(ctx.stream)
+                sc.qvalues()
+                kept = sc.finalize_device()
+                e2.record(ctx.stream); ctx.sync()
+            print(f"    t={thr:g} [{'dense' if dense else 'hits '}]: K2 {e0.elapsed_time(e1):.2f} ms, K5+K6 {e1.elapsed_time(e2):.2f} ms, step {e0.elapsed_time(e2):.2f} ms, {kept} rows")
+            RESULTS.setdefault("midrange", []).append(dict(threshold=thr, form="dense" if dense else "hit records", kmers=nm, rows_reported=int(kept),
+                k2_ms=e0.elapsed_time(e1), k5_k6_ms=e1.elapsed_time(e2), step_ms=e0.elapsed_time(e2)))
+            del sc
+    del packed
+
 # ---------------------------------------------------------------- wide motifs (two packed words per k-mer)
 if ONLY in ("", "wide"):
     print("wide motifs (33..64 bp): K2 wide kernel, thresholded, both strands, q-values on")
