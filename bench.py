@@ -528,11 +528,25 @@ def run_ours(args):
     if world == 1 and hits_kmers is not None:
         parity["e2e_table_equal"] = bool(all(np.array_equal(out[k], hits_kmers[k]) for k in ("row", "strand", "int_score", "p-value", "q-value")))
         parity["ok"] = bool(parity["ok"] and parity["e2e_table_equal"])
-    line["e2e"] = {"value": 2.0 * n * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(H * L), "d2h_bytes_per_step": hit_bytes(out),
+    moved = ctx.last_transfer()  # counted by the library from the copies it issued in the last step
+    line["e2e"] = {"value": 2.0 * n * world / dt, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],
+                   "input_bytes_per_step": int(H * L), "chunks_as_text": moved["chunks_as_given"], "chunks_packed_on_host": moved["chunks_host_packed"],
+                   "host_cpus": os.cpu_count(),
                    "windows_per_step_per_gpu": int(2 * n), "steps": e2e_steps, "ms_per_step": dt * 1e3,
                    "api": "gb2_scan_host_sequences(format=ASCII): haplotype sequences as text in pinned host memory, 1 byte per "
-                          "window over PCIe; windows formed on the device; hit table back into pinned buffers (engine.HostTable)", "hits": int(len(out["row"]))}
+                          "window in host memory; host threads re-code part of the chunks to 2 bits per base while the copy engine moves the others as text "
+                          "(transfer compression, csrc/host_pack.cpp; nothing is scored on the host); windows formed on the device; hit table back into "
+                          "pinned buffers (engine.HostTable)", "hits": int(len(out["row"]))}
     variants = {}
+    # (a) the same call with the host packers off: every base crosses PCIe as one byte of text -- the PCIe wall itself
+    os.environ["GB2_HOST_PACK_THREADS"] = "0"
+    dt0, out0 = time_host(lambda: engine.scan_host_sequences(ctx, dm, host_ascii.view(-1), offs, lens, fmt="ascii", strands=2,
+                                                             threshold=THRESHOLD, hit_capacity=1 << 23, out=host_out))
+    os.environ.pop("GB2_HOST_PACK_THREADS", None)
+    moved0 = ctx.last_transfer()
+    variants["sequences_ascii_copy_engine_only"] = {"value": 2.0 * n * world / dt0, "unit": UNIT, "ms_per_step": dt0 * 1e3,
+                                                    "h2d_bytes_per_step": moved0["h2d_bytes"], "d2h_bytes_per_step": moved0["d2h_bytes"],
+                                                    "api": "gb2_scan_host_sequences(format=ASCII), GB2_HOST_PACK_THREADS=0"}
     # (b) the same sequences already 2-bit packed on the host: 0.25 byte per window over PCIe
     host_words = torch.empty(seq_words.shape, dtype=torch.int64, pin_memory=True)
     with torch.cuda.stream(ctx.stream):

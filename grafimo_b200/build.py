@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libgrafimo_b200.so")
-SOURCES = ["context.cu", "encode.cu", "tsv.cu", "score.cu", "score_wide.cu", "pval.cu", "qvalue.cu", "dense_sort.cu", "scan_host.cu", "seqscan.cu", "graph.cu", "graph_build.cu", "vcf.cu", "report.cu", "comm.cu"]
+SOURCES = ["context.cu", "encode.cu", "tsv.cu", "score.cu", "score_wide.cu", "pval.cu", "qvalue.cu", "dense_sort.cu", "scan_host.cu", "seqscan.cu", "graph.cu", "graph_build.cu", "vcf.cu", "report.cu", "comm.cu", "host_pack.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--fmad=true", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [nvcc()] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]

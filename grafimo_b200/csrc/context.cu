@@ -79,6 +79,7 @@ extern "C" int gb2_ctx_destroy(gb2_ctx *ctx)
     for (auto &d : ctx->desc)
         if (d.d_ptr) cudaFree(d.d_ptr);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -140,6 +141,36 @@ int gb2_pool_reserve(gb2_ctx *ctx, size_t bytes, char **out)
         ctx->pool_bytes = bytes;
     }
     *out = (char *)ctx->pool;
+    return GB2_OK;
+}
+
+extern "C" int gb2_scan_last_transfer(const gb2_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *chunks_as_given,
+                                      uint64_t *chunks_host_packed)
+{
+    if (!ctx) return GB2_ERR_ARG;
+    if (h2d_bytes) *h2d_bytes = ctx->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->last_d2h_bytes;
+    if (chunks_as_given) *chunks_as_given = ctx->last_chunks_given;
+    if (chunks_host_packed) *chunks_host_packed = ctx->last_chunks_packed;
+    return GB2_OK;
+}
+
+int gb2_pinned_reserve(gb2_ctx *ctx, size_t bytes, char **out)
+{
+    *out = nullptr;
+    if (bytes > ctx->h_pin_bytes) {
+        GB2_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (ctx->h_pin) {
+            GB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            GB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            GB2_CUDA(ctx, cudaFreeHost(ctx->h_pin));
+            ctx->h_pin = nullptr;
+            ctx->h_pin_bytes = 0;
+        }
+        GB2_CUDA(ctx, cudaHostAlloc(&ctx->h_pin, bytes, cudaHostAllocDefault));
+        ctx->h_pin_bytes = bytes;
+    }
+    *out = (char *)ctx->h_pin;
     return GB2_OK;
 }
 

@@ -33,6 +33,11 @@ struct gb2_ctx {
         uint64_t hash = 0;
         int64_t n_seqs = -1, total_units = 0;
     } desc[2];
+    // grow-only pinned host staging of the host-side packer (gb2_scan_host_sequences, host_pack.cpp)
+    void *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    // what the last gb2_scan_host* call moved (gb2_scan_last_transfer)
+    uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0, last_chunks_given = 0, last_chunks_packed = 0;
     // NCCL communicator of a multi-GPU run (comm.cu); null on one GPU
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_world = 1;
@@ -92,6 +97,10 @@ struct gb2_motif {
 int gb2_scratch_reserve(gb2_ctx *ctx, size_t bytes);
 // grows the pool of the host-buffer entry points; *out = its base
 int gb2_pool_reserve(gb2_ctx *ctx, size_t bytes, char **out);
+int gb2_pinned_reserve(gb2_ctx *ctx, size_t bytes, char **out);  // grow-only pinned host buffer of the context
 void gb2_comm_release(gb2_ctx *ctx);  // comm.cu
+// host_pack.cpp: ASCII bases -> 2-bit words + N bits, the device encoder's output bit for bit
+void gb2_host_pack_bases(const uint8_t *text, int64_t n_bases, uint64_t *words, uint32_t *nbits, uint64_t *n_invalid, uint64_t *n_other);
+int gb2_host_pack_simd();
 
 static inline int64_t gb2_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -76,6 +76,7 @@ int gb2_scan_tail_finish(gb2_ctx *ctx, const gb2_motif *m, const gb2_scan_bufs &
     TAIL_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint64_t kept = ctx->h_mail[8];
     *o.h_n_hits = kept;
+    ctx->last_d2h_bytes = 6 * sizeof(uint64_t) + kept * (8 + 1 + 4 + 8 + 8 + (want_q ? 8 : 0));
     if (kept) {
         TAIL_CUDA(cudaMemcpyAsync(o.h_row, b.o_row, kept * 8, cudaMemcpyDeviceToHost, ctx->stream));
         TAIL_CUDA(cudaMemcpyAsync(o.h_strand, b.o_strand, kept, cudaMemcpyDeviceToHost, ctx->stream));
@@ -162,6 +163,9 @@ static int scan_host_kmers(gb2_ctx *ctx, const gb2_motif *m, const uint8_t *h_in
         SH_CUDA(cudaEventRecord(consumed[1], ctx->stream));
         int64_t done_rows = 0;
         int buf = 0;
+        ctx->last_h2d_bytes = 0;
+        ctx->last_chunks_given = 0;
+        ctx->last_chunks_packed = 0;
         while (done_rows < n) {
             const int64_t rows = std::min(chunk_rows, n - done_rows);
             const size_t bytes = packed_in ? (size_t)rows * (size_t)kbytes : (size_t)((rows - 1) * stride + w);
@@ -170,6 +174,8 @@ static int scan_host_kmers(gb2_ctx *ctx, const gb2_motif *m, const uint8_t *h_in
             if (packed_in && h_nmask)  // chunk starts are multiples of 32 rows: whole mask words
                 SH_CUDA(cudaMemcpyAsync(d_mask[buf], h_nmask + (done_rows >> 5), (size_t)gb2_div_up(rows, 32) * 4,
                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+            ctx->last_h2d_bytes += bytes + ((packed_in && h_nmask) ? (size_t)gb2_div_up(rows, 32) * 4 : 0);
+            ctx->last_chunks_given++;
             SH_CUDA(cudaEventRecord(copied[buf], ctx->copy_stream));
             SH_CUDA(cudaStreamWaitEvent(ctx->stream, copied[buf], 0));
             const uint64_t *d_kmers = d_packed;

@@ -19,7 +19,12 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "score_common.cuh"
 
@@ -609,6 +614,8 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
     double ms_plan = 0, ms_issue = 0, ms_tail0 = 0;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // loop start, first copy done, last copy done, last kernel done
+    bool tev_first_done = false;
+    uint64_t host_flagged[2] = {0, 0};  // N-or-other / other bases counted by the host packers
     // ---- plan: pieces, chunks, copies
     std::vector<Piece> pieces;
     std::vector<Chunk> chunks;
@@ -670,6 +677,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
 
     // per chunk: device word offsets, copy runs, unit counts; descriptor arrays for every chunk back to back
     std::vector<int64_t> desc_s, desc_e;  // SeqDesc / SeqEncDesc as 4 x int64 (+ one sentinel per chunk)
+    std::vector<int64_t> piece_words(pieces.size(), 0);  // first device word of every piece inside its chunk (ASCII input)
     std::vector<size_t> desc_pos(chunks.size());
     int64_t max_words = 0, max_text = 0;
     for (size_t c = 0; c < chunks.size(); ++c) {
@@ -694,6 +702,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             const int64_t in_dev = run.dst + (p.src - run.src);  // where the piece starts in the device copy
             const int64_t nwin = p.len - w + 1;
             if (ascii) {
+                piece_words[k] = words;
                 desc_s.insert(desc_s.end(), {words, p.len, p.row0, us});
                 desc_e.insert(desc_e.end(), {in_dev, p.len, words, ue});
             } else {
@@ -719,14 +728,25 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     const size_t b_words = al256_seq((size_t)max_words * 8 + 64);
     const size_t b_nbits = al256_seq((size_t)max_words * 4 + 64);
     const size_t b_desc = al256_seq(desc_s.size() * 8) + al256_seq(desc_e.size() * 8);
-    const int nwordbuf = ascii ? 1 : 2;
+    // Host-side packing (host_pack.cpp): worker threads re-code chunks from the BACK of the chunk list into 2-bit words in
+    // pinned staging while the copy engine moves the text of the chunks at the FRONT; both meet in the middle.
+    // GB2_HOST_PACK_THREADS overrides the thread count (0 = off); default: the host threads this rank can count on.
+    int pack_threads = 0;
+    if (ascii && chunks.size() >= 4) {
+        const int hw = (int)std::thread::hardware_concurrency();
+        pack_threads = std::max(0, std::min(16, hw / (2 * std::max(1, ctx->comm_world))));  // measured: no gain past the physical cores
+        if (const char *t = getenv("GB2_HOST_PACK_THREADS")) pack_threads = std::max(0, std::min(64, atoi(t)));
+    }
+    const int n_slots = pack_threads ? 6 : 0;  // pinned staging slots of one packed chunk each (a slot is busy from the first
+                                               // block packed until its copy has left the queue behind up to two text chunks)
+    const int nwordbuf = ascii ? (pack_threads ? 3 : 1) : 2;  // ASCII: [0] the device encoder's output, [1], [2] host-packed chunks
     const size_t total = 2 * b_text + nwordbuf * (b_words + b_nbits) + b_desc + gb2_scan_tail_bytes(m, hit_capacity);
     char *q = nullptr;
     rc = gb2_pool_reserve(ctx, total, &q);
     if (rc != GB2_OK) return rc;
     uint8_t *d_text[2] = {nullptr, nullptr};
-    uint64_t *d_words[2] = {nullptr, nullptr};
-    uint32_t *d_nb[2] = {nullptr, nullptr};
+    uint64_t *d_words[3] = {nullptr, nullptr, nullptr};
+    uint32_t *d_nb[3] = {nullptr, nullptr, nullptr};
     for (int i = 0; i < 2 && ascii; ++i) { d_text[i] = (uint8_t *)q; q += b_text; }
     for (int i = 0; i < nwordbuf; ++i) {
         d_words[i] = (uint64_t *)q; q += b_words;
@@ -746,6 +766,14 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             GB2_SET_ERR(ctx, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e));      \
             rc = GB2_ERR_CUDA;                                                                                \
             goto done;                                                                                        \
+        }                                                                                                     \
+    } while (0)
+#define SH_CUDA_RET(call)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t e2__ = (call);                                                                            \
+        if (e2__ != cudaSuccess) {                                                                            \
+            GB2_SET_ERR(ctx, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e2__));   \
+            return GB2_ERR_CUDA;                                                                              \
         }                                                                                                     \
     } while (0)
     {
@@ -777,26 +805,31 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             ms_plan = host_ms();
             SH_CUDA(cudaEventRecord(tev[0], ctx->stream));
         }
+        // ---- one chunk from the caller's buffer as it is (text or 2-bit words): copy, [encode], score
         int buf = 0;
-        for (size_t c = 0; c < chunks.size(); ++c) {
+        uint64_t h2d_bytes = desc_s.size() * 8 + (ascii ? desc_e.size() * 8 : 0);
+        size_t n_given = 0, n_packed = 0;
+        auto issue_raw = [&](size_t c) -> int {
             const Chunk &ch = chunks[c];
-            SH_CUDA(cudaStreamWaitEvent(ctx->copy_stream, consumed[buf], 0));
+            ++n_given;
+            SH_CUDA_RET(cudaStreamWaitEvent(ctx->copy_stream, consumed[buf], 0));
             for (size_t r = ch.run0; r < ch.run0 + ch.n_runs; ++r) {
                 const Run &run = runs[r];
+                h2d_bytes += ascii ? (uint64_t)run.count : (uint64_t)run.count * (h_nbits ? 12 : 8);
                 if (ascii) {
-                    SH_CUDA(cudaMemcpyAsync(d_text[buf] + run.dst, (const uint8_t *)h_data + run.src, (size_t)run.count,
-                                            cudaMemcpyHostToDevice, ctx->copy_stream));
-                } else {
-                    SH_CUDA(cudaMemcpyAsync(d_words[buf] + run.dst, (const uint64_t *)h_data + run.src, (size_t)run.count * 8,
-                                            cudaMemcpyHostToDevice, ctx->copy_stream));
-                    if (h_nbits)
-                        SH_CUDA(cudaMemcpyAsync(d_nb[buf] + run.dst, h_nbits + run.src, (size_t)run.count * 4,
+                    SH_CUDA_RET(cudaMemcpyAsync(d_text[buf] + run.dst, (const uint8_t *)h_data + run.src, (size_t)run.count,
                                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+                } else {
+                    SH_CUDA_RET(cudaMemcpyAsync(d_words[buf] + run.dst, (const uint64_t *)h_data + run.src, (size_t)run.count * 8,
+                                                cudaMemcpyHostToDevice, ctx->copy_stream));
+                    if (h_nbits)
+                        SH_CUDA_RET(cudaMemcpyAsync(d_nb[buf] + run.dst, h_nbits + run.src, (size_t)run.count * 4,
+                                                    cudaMemcpyHostToDevice, ctx->copy_stream));
                 }
             }
-            SH_CUDA(cudaEventRecord(copied[buf], ctx->copy_stream));
-            if (timing && (c == 0 || c + 1 == chunks.size())) SH_CUDA(cudaEventRecord(tev[c == 0 ? 1 : 2], ctx->copy_stream));
-            SH_CUDA(cudaStreamWaitEvent(ctx->stream, copied[buf], 0));
+            SH_CUDA_RET(cudaEventRecord(copied[buf], ctx->copy_stream));
+            if (timing && !tev_first_done) { SH_CUDA_RET(cudaEventRecord(tev[1], ctx->copy_stream)); tev_first_done = true; }
+            SH_CUDA_RET(cudaStreamWaitEvent(ctx->stream, copied[buf], 0));
             const int wb = ascii ? 0 : buf;
             if (ascii) {
                 const int64_t blocks = gb2_div_up(ch.units_enc, SEQENC_WARPS);
@@ -804,19 +837,199 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                     d_text[buf], ch.text_bytes, (const SeqEncDesc *)(d_desc_e + 4 * desc_pos[c]), (int64_t)ch.n_pieces,
                     ch.units_enc, d_words[0], d_nb[0], (unsigned long long *)b.d_cnt);
                 ctx->launches++;
-                SH_CUDA(cudaGetLastError());
-                SH_CUDA(cudaEventRecord(consumed[buf], ctx->stream));  // the text buffer is free once encoded
+                SH_CUDA_RET(cudaGetLastError());
+                SH_CUDA_RET(cudaEventRecord(consumed[buf], ctx->stream));  // the text buffer is free once encoded
             }
             sq.seq2 = d_words[wb];
             sq.nbits = (ascii || h_nbits) ? d_nb[wb] : nullptr;
             sq.desc = (const SeqDesc *)(d_desc_s + 4 * desc_pos[c]);
             sq.n_seqs = (int64_t)ch.n_pieces;
             sq.total_units = ch.units_score;
-            rc = gb2_launch_score_seq(ctx, m, sq);
-            if (rc != GB2_OK) goto done;
-            if (!ascii) SH_CUDA(cudaEventRecord(consumed[buf], ctx->stream));
+            int r2 = gb2_launch_score_seq(ctx, m, sq);
+            if (r2 != GB2_OK) return r2;
+            if (!ascii) SH_CUDA_RET(cudaEventRecord(consumed[buf], ctx->stream));
             buf ^= 1;
+            return GB2_OK;
+        };
+
+        if (!pack_threads) {
+            for (size_t c = 0; c < chunks.size() && rc == GB2_OK; ++c) rc = issue_raw(c);
+            if (rc != GB2_OK) goto done;
+        } else {
+            // ---- hybrid: raw chunks from the front, host-packed chunks from the back -----------------------------------
+            char *pin = nullptr;
+            const size_t slot_bytes = b_words + b_nbits;
+            rc = gb2_pinned_reserve(ctx, (size_t)n_slots * slot_bytes, &pin);
+            if (rc != GB2_OK) goto done;
+            struct Block { const uint8_t *src; int64_t n_bases; int64_t word; };
+            struct Job {
+                size_t chunk = 0;
+                int slot = 0;
+                std::vector<Block> blocks;
+                size_t next = 0;                 // guarded by mu
+                std::atomic<size_t> done{0};
+            };
+            std::mutex mu;
+            std::condition_variable cv;
+            size_t front = 0, back = chunks.size();  // chunks [front, back) are unclaimed
+            std::vector<int> free_slots;
+            for (int i = 0; i < n_slots; ++i) free_slots.push_back(i);
+            std::deque<Job *> ready;
+            Job *open = nullptr;
+            size_t jobs_claimed = 0, jobs_issued = 0;
+            bool stop = false;
+            std::atomic<uint64_t> host_invalid{0}, host_other{0};
+            const int64_t BLOCK_BASES = (int64_t)1 << 19;  // work unit of one packer thread (a multiple of 32)
+            auto worker = [&]() {
+                for (;;) {
+                    Job *job = nullptr;
+                    Block blk{};
+                    size_t n_blocks = 0;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        for (;;) {
+                            if (stop) return;
+                            if (open == nullptr) {
+                                if (front >= back) return;  // every chunk is claimed; jobs under way are finished by their workers
+                                if (free_slots.empty()) { cv.wait_for(lk, std::chrono::milliseconds(1)); continue; }
+                                Job *j = new Job();
+                                j->chunk = --back;
+                                j->slot = free_slots.back();
+                                free_slots.pop_back();
+                                const Chunk &ch = chunks[j->chunk];
+                                for (size_t k = ch.piece0; k < ch.piece0 + ch.n_pieces; ++k)
+                                    for (int64_t a = 0; a < pieces[k].len; a += BLOCK_BASES)
+                                        j->blocks.push_back(Block{(const uint8_t *)h_data + pieces[k].src + a,
+                                                                  std::min(BLOCK_BASES, pieces[k].len - a), piece_words[k] + (a >> 5)});
+                                ++jobs_claimed;
+                                open = j;
+                            }
+                            job = open;
+                            n_blocks = job->blocks.size();
+                            blk = job->blocks[job->next++];
+                            if (job->next == n_blocks) open = nullptr;
+                            break;
+                        }
+                    }
+                    uint64_t inv = 0, oth = 0;
+                    uint64_t *hw_ = reinterpret_cast<uint64_t *>(pin + (size_t)job->slot * slot_bytes);
+                    uint32_t *hn_ = reinterpret_cast<uint32_t *>(pin + (size_t)job->slot * slot_bytes + b_words);
+                    gb2_host_pack_bases(blk.src, blk.n_bases, hw_ + blk.word, hn_ + blk.word, &inv, &oth);
+                    if (inv) host_invalid.fetch_add(inv, std::memory_order_relaxed);
+                    if (oth) host_other.fetch_add(oth, std::memory_order_relaxed);
+                    if (job->done.fetch_add(1, std::memory_order_acq_rel) + 1 == n_blocks) {  // the main thread deletes the job once it is ready
+                        std::lock_guard<std::mutex> lk(mu);
+                        ready.push_back(job);
+                        cv.notify_all();
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            size_t raw_issued = 0, packed_chunks = 0;
+            for (; front < 2 && rc == GB2_OK; ++front, ++raw_issued) rc = issue_raw(front);  // the copy engine starts before the threads do
+            for (int t = 0; t < pack_threads && rc == GB2_OK; ++t) pool.emplace_back(worker);
+
+            cudaEvent_t slot_copied[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, pw_consumed[2] = {nullptr, nullptr};
+            std::vector<int> slots_in_flight;
+            int pbuf = 0;
+            auto fail_hybrid = [&](int code) {
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    stop = true;
+                    cv.notify_all();
+                }
+                for (auto &t : pool) t.join();
+                pool.clear();
+                return code;
+            };
+            for (int i = 0; i < n_slots && rc == GB2_OK; ++i)
+                if (cudaEventCreateWithFlags(&slot_copied[i], cudaEventDisableTiming) != cudaSuccess) rc = GB2_ERR_CUDA;
+            for (int i = 0; i < 2 && rc == GB2_OK; ++i) {
+                if (cudaEventCreateWithFlags(&pw_consumed[i], cudaEventDisableTiming) != cudaSuccess) rc = GB2_ERR_CUDA;
+                else if (cudaEventRecord(pw_consumed[i], ctx->stream) != cudaSuccess) rc = GB2_ERR_CUDA;
+            }
+            auto issue_packed = [&](Job *job) -> int {
+                const Chunk &ch = chunks[job->chunk];
+                const int wb = 1 + pbuf;
+                const char *src = pin + (size_t)job->slot * slot_bytes;
+                h2d_bytes += (uint64_t)ch.words * 12;
+                ++n_packed;
+                SH_CUDA_RET(cudaStreamWaitEvent(ctx->copy_stream, pw_consumed[pbuf], 0));
+                SH_CUDA_RET(cudaMemcpyAsync(d_words[wb], src, (size_t)ch.words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+                SH_CUDA_RET(cudaMemcpyAsync(d_nb[wb], src + b_words, (size_t)ch.words * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                SH_CUDA_RET(cudaEventRecord(slot_copied[job->slot], ctx->copy_stream));
+                SH_CUDA_RET(cudaStreamWaitEvent(ctx->stream, slot_copied[job->slot], 0));
+                sq.seq2 = d_words[wb];
+                sq.nbits = d_nb[wb];
+                sq.desc = (const SeqDesc *)(d_desc_s + 4 * desc_pos[job->chunk]);
+                sq.n_seqs = (int64_t)ch.n_pieces;
+                sq.total_units = ch.units_score;
+                int r2 = gb2_launch_score_seq(ctx, m, sq);
+                if (r2 != GB2_OK) return r2;
+                SH_CUDA_RET(cudaEventRecord(pw_consumed[pbuf], ctx->stream));
+                slots_in_flight.push_back(job->slot);
+                pbuf ^= 1;
+                return GB2_OK;
+            };
+            // raw copies are paced (at most two chunks queued on the copy engine) so that the packers get their share
+            while (rc == GB2_OK) {
+                Job *job = nullptr;
+                bool do_raw = false;
+                size_t raw_c = 0;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    // staging slots whose copy has finished go back to the packers
+                    for (size_t i = 0; i < slots_in_flight.size();) {
+                        if (cudaEventQuery(slot_copied[slots_in_flight[i]]) == cudaSuccess) {
+                            free_slots.push_back(slots_in_flight[i]);
+                            slots_in_flight.erase(slots_in_flight.begin() + (long)i);
+                            cv.notify_all();
+                        } else {
+                            ++i;
+                        }
+                    }
+                    if (!ready.empty()) {
+                        job = ready.front();
+                        ready.pop_front();
+                    } else {
+                        // a raw chunk goes into text buffer `buf`: at most two are queued on the copy engine
+                        if (front < back && cudaEventQuery(copied[buf]) == cudaSuccess) {
+                            raw_c = front++;
+                            do_raw = true;
+                        } else if (front >= back && jobs_issued == jobs_claimed && open == nullptr) {
+                            break;  // every chunk is on the device queues
+                        } else {
+                            cv.wait_for(lk, std::chrono::microseconds(50));
+                            continue;
+                        }
+                    }
+                }
+                if (job) {
+                    rc = issue_packed(job);
+                    delete job;
+                    ++jobs_issued;
+                    ++packed_chunks;
+                } else if (do_raw) {
+                    rc = issue_raw(raw_c);
+                    ++raw_issued;
+                }
+            }
+            rc = fail_hybrid(rc);  // stops and joins the packers (on success they have nothing left to do)
+            host_flagged[0] = host_invalid.load();  // the device encoder counts the flagged bases of the raw chunks, the packers theirs
+            host_flagged[1] = host_other.load();
+            if (timing) fprintf(stderr, "gb2_scan_host_sequences: %d packer threads (simd %d): %zu chunks as text, %zu packed on the host\n",
+                                pack_threads, gb2_host_pack_simd(), raw_issued, packed_chunks);
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (int i = 0; i < 8; ++i)
+                if (slot_copied[i]) cudaEventDestroy(slot_copied[i]);
+            for (int i = 0; i < 2; ++i)
+                if (pw_consumed[i]) cudaEventDestroy(pw_consumed[i]);
+            if (rc != GB2_OK) goto done;
         }
+        if (timing) SH_CUDA(cudaEventRecord(tev[2], ctx->copy_stream));
+        ctx->last_h2d_bytes = h2d_bytes;
+        ctx->last_chunks_given = n_given;
+        ctx->last_chunks_packed = n_packed;
         if (timing) {
             SH_CUDA(cudaEventRecord(tev[3], ctx->stream));
             ms_issue = host_ms();
@@ -836,12 +1049,15 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                     host_ms() - ms_tail0, host_ms());
         }
         if (o.h_stats && (rc == GB2_OK || rc == GB2_ERR_CAPACITY)) {
+            o.h_stats[1] += host_flagged[0];
+            o.h_stats[2] += host_flagged[1];
             o.h_stats[1] -= std::min<uint64_t>(o.h_stats[1], overlap_n);
             o.h_stats[2] -= std::min<uint64_t>(o.h_stats[2], overlap_other);
         }
     }
 done:
 #undef SH_CUDA
+#undef SH_CUDA_RET
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; ++i) {

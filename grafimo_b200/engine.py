@@ -84,6 +84,12 @@ class Context:
         with torch.cuda.stream(self.stream):
             return torch.zeros(int(n), dtype=dtype, device=self.device)
 
+    def last_transfer(self):
+        """Bytes the last scan_host* call on this context moved over PCIe and how its chunks travelled (gb2_scan_last_transfer)."""
+        v = [ctypes.c_uint64(0) for _ in range(4)]
+        check(self.lib.gb2_scan_last_transfer(self.h, *[ctypes.byref(x) for x in v]), "gb2_scan_last_transfer", self.h)
+        return dict(h2d_bytes=int(v[0].value), d2h_bytes=int(v[1].value), chunks_as_given=int(v[2].value), chunks_host_packed=int(v[3].value))
+
     # -- multi-GPU: NCCL communicator owned by the library context (csrc/comm.cu) -------------------
     world = 1
     rank = 0

@@ -331,7 +331,16 @@ int gb2_score_sequences(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_
  * per window for gb2_scan_host.  The batch is copied in chunks (long sequences are cut into pieces overlapping by w-1
  * bases) while the previous chunk is encoded and scored.  Outputs as gb2_scan_host; h_row = window index as defined
  * above; h_stats = {windows scored (both strands), non-ACGT bases, bases that are neither ACGT nor N, hits before the
- * q filter} (the two base counts are 0 for format 1). */
+ * q filter} (the two base counts are 0 for format 1).
+ * Transfer compression (format 0): the end-to-end rate of this call is the PCIe rate, so host threads that would idle
+ * during the copy re-code part of the chunks into the 2-bit layout (csrc/host_pack.cpp; AVX-512 / AVX2 / scalar) while
+ * the copy engine moves the text of the others; packed chunks cross PCIe at 0.375 byte per base.  Nothing is scored on the
+ * host and the result does not depend on which chunks were packed.  GB2_HOST_PACK_THREADS sets the thread count (0 = off;
+ * default: half the host's hardware threads divided by the ranks of the context's communicator, at most 16).
+ * gb2_scan_last_transfer: bytes the last gb2_scan_host* call of this context copied host->device and device->host, and
+ * how many of its chunks went as given / were packed on the host (any pointer may be NULL). */
+int gb2_scan_last_transfer(const gb2_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *chunks_as_given,
+                           uint64_t *chunks_host_packed);
 int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *motif, int format, const void *h_data, const uint32_t *h_nbits,
                             int64_t n_seqs, const int64_t *h_off, const int64_t *h_len, int strands, double p_threshold,
                             int q_filter, int want_q, uint64_t hit_capacity, uint64_t *h_row, uint8_t *h_strand,

@@ -189,6 +189,33 @@ def test_scan_host_sequences_equals_scan_host(ctx, fmt, chunk, monkeypatch):
         assert np.array_equal(got[k], exp[k]), k
 
 
+
+@pytest.mark.parametrize("threads", ["0", "1", "5"])
+def test_scan_host_sequences_host_packers(ctx, threads, monkeypatch):
+    """ASCII sequences with part of the chunks re-coded to 2-bit words by host threads (csrc/host_pack.cpp, transfer
+    compression) and the rest encoded on the device: table and counters are those of the device-only route (threads = 0),
+    which the test above ties to gb2_scan_host -- also into a reusable pinned HostTable, with N, lower case and other symbols."""
+    from grafimo_b200 import engine
+    monkeypatch.setenv("GB2_SEQ_CHUNK_BASES", "8192")
+    m = gu.load_motif("ctcf_meme__unif")
+    w = m["width"]
+    rng = np.random.default_rng(61)
+    seqs = _random_seqs(rng, [70001, 33, 18, 19, 50000, 4096, 12345, 99999], n_rate=0.002)
+    seqs[3] = "acgtnACGTRYKMacgtacgTT"[:19]
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    text, offs = _layout_text(rng, seqs)
+    lens = [len(s) for s in seqs]
+    monkeypatch.setenv("GB2_HOST_PACK_THREADS", "0")
+    exp = engine.scan_host_sequences(ctx, dm, text, offs, lens, fmt="ascii", strands=2, threshold=0.01)
+    monkeypatch.setenv("GB2_HOST_PACK_THREADS", threads)
+    table = engine.HostTable(1 << 16)
+    for rep in range(3):  # the schedule (which chunks the packers take) differs from call to call
+        got = engine.scan_host_sequences(ctx, dm, text, offs, lens, fmt="ascii", strands=2, threshold=0.01, hit_capacity=1 << 16, out=table)
+        assert got["stats"] == exp["stats"] and got["stats"]["hits"] > 0
+        for k in ("row", "strand", "int_score", "score", "p-value", "q-value"):
+            assert np.array_equal(got[k], exp[k]), (threads, rep, k)
+
+
 def test_scan_host_packed_equals_scan_host(ctx):
     from grafimo_b200 import engine
     for tag in ("ctcf_meme__unif", "synth_w35_meme__bgnt"):
