@@ -94,14 +94,18 @@ __global__ void __launch_bounds__(BH_THREADS) gb2_bh_count_kernel(const uint32_t
     __shared__ unsigned long long s_warp[32];
     const uint32_t tid = threadIdx.x;
     unsigned long long carry = 0ull;
-    uint32_t b_next = tid < nbins ? sorted_bins[tid] : 0u;
-    unsigned long long h_next = (hist != nullptr && tid < nbins) ? hist[b_next] : 0ull;
+    // software pipeline: the bin indices run two chunks ahead and the counts they address one chunk ahead, so that neither of
+    // the two dependent loads of an element waits inside the chunk that scans it
+    uint32_t b_cur = tid < nbins ? sorted_bins[tid] : 0u;
+    uint32_t b_next = tid + BH_THREADS < nbins ? sorted_bins[tid + BH_THREADS] : 0u;
+    unsigned long long h_cur = (hist != nullptr && tid < nbins) ? hist[b_cur] : 0ull;
     for (uint32_t base = 0; base < nbins; base += BH_THREADS) {
-        const uint32_t i = base + tid, b = b_next;
-        const unsigned long long h = h_next;
-        const uint32_t in = i + BH_THREADS;  // the next chunk's loads fly during this chunk's scan
-        b_next = in < nbins ? sorted_bins[in] : 0u;
-        h_next = (hist != nullptr && in < nbins) ? hist[b_next] : 0ull;
+        const uint32_t i = base + tid, b = b_cur;
+        const unsigned long long h = h_cur;
+        const uint32_t i1 = i + BH_THREADS, i2 = i + 2 * BH_THREADS;
+        h_cur = (hist != nullptr && i1 < nbins) ? hist[b_next] : 0ull;
+        b_cur = b_next;
+        b_next = i2 < nbins ? sorted_bins[i2] : 0u;
         if (i < nbins) rank[b] = i;  // position of every bin in p-ascending order
         if (hist == nullptr) continue;  // rank-only call (no q-values wanted)
         const unsigned long long c = bh_block_scan(h, 0ull, BhAdd(), s_warp, carry);
