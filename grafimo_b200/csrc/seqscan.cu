@@ -933,7 +933,13 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             std::vector<std::thread> pool;
             size_t raw_issued = 0, packed_chunks = 0;
             for (; front < 2 && rc == GB2_OK; ++front, ++raw_issued) rc = issue_raw(front);  // the copy engine starts before the threads do
-            for (int t = 0; t < pack_threads && rc == GB2_OK; ++t) pool.emplace_back(worker);
+            for (int t = 0; t < pack_threads && rc == GB2_OK; ++t) {
+                try {
+                    pool.emplace_back(worker);
+                } catch (...) {  // no more threads to be had: the chunks nobody packs go through the copy engine as text
+                    break;
+                }
+            }
 
             cudaEvent_t slot_copied[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, pw_consumed[2] = {nullptr, nullptr};
             std::vector<int> slots_in_flight;
