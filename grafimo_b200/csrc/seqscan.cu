@@ -735,9 +735,9 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     if (ascii && chunks.size() >= 4) {
         const int hw = (int)std::thread::hardware_concurrency();
         // measured on 16- and 24-thread hosts (tools/bench_e2e.py): the rate grows up to ~12 threads and is flat beyond
-        pack_threads = std::max(0, std::min(16, hw * 3 / (4 * std::max(1, ctx->comm_world))));
+        pack_threads = std::max(0, std::min(16, hw / std::max(1, ctx->comm_world)));
         // Packing pays while PCIe is the limit of this GPU's copies.  Measured (profiles/r02_e2e_packers.json): per step of the
-        // headline workload 46.6 -> 29.5 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 110 -> 130 ms with
+        // headline workload 46.6 -> 26.4 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 110 -> 130 ms with
         // eight: there the HOST memory system is the limit (raw copies reach 23 GB/s per GPU instead of 55, tools/h2d_probe.py)
         // and a packed base costs it 1.75 bytes of traffic instead of 1.
         if (ctx->comm_world > 2) pack_threads = 0;
@@ -874,6 +874,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                 std::vector<Block> blocks;
                 size_t next = 0;                 // guarded by mu
                 std::atomic<size_t> done{0};
+                std::atomic<uint64_t> flagged{0};  // bases of this chunk that are not A/C/G/T: 0 = its N bits need not travel
             };
             std::mutex mu;
             std::condition_variable cv;
@@ -921,7 +922,10 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                     uint64_t *hw_ = reinterpret_cast<uint64_t *>(pin + (size_t)job->slot * slot_bytes);
                     uint32_t *hn_ = reinterpret_cast<uint32_t *>(pin + (size_t)job->slot * slot_bytes + b_words);
                     gb2_host_pack_bases(blk.src, blk.n_bases, hw_ + blk.word, hn_ + blk.word, &inv, &oth);
-                    if (inv) host_invalid.fetch_add(inv, std::memory_order_relaxed);
+                    if (inv) {
+                        host_invalid.fetch_add(inv, std::memory_order_relaxed);
+                        job->flagged.fetch_add(inv, std::memory_order_relaxed);
+                    }
                     if (oth) host_other.fetch_add(oth, std::memory_order_relaxed);
                     if (job->done.fetch_add(1, std::memory_order_acq_rel) + 1 == n_blocks) {  // the main thread deletes the job once it is ready
                         std::lock_guard<std::mutex> lk(mu);
@@ -964,15 +968,18 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                 const Chunk &ch = chunks[job->chunk];
                 const int wb = 1 + pbuf;
                 const char *src = pin + (size_t)job->slot * slot_bytes;
-                h2d_bytes += (uint64_t)ch.words * 12;
                 ++n_packed;
                 SH_CUDA_RET(cudaStreamWaitEvent(ctx->copy_stream, pw_consumed[pbuf], 0));
+                // a chunk without a single N (the usual case) travels as 0.25 byte per base: its N-bit words are all zero
+                const bool has_n = job->flagged.load(std::memory_order_acquire) != 0;
                 SH_CUDA_RET(cudaMemcpyAsync(d_words[wb], src, (size_t)ch.words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-                SH_CUDA_RET(cudaMemcpyAsync(d_nb[wb], src + b_words, (size_t)ch.words * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                if (has_n)
+                    SH_CUDA_RET(cudaMemcpyAsync(d_nb[wb], src + b_words, (size_t)ch.words * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
                 SH_CUDA_RET(cudaEventRecord(slot_copied[job->slot], ctx->copy_stream));
                 SH_CUDA_RET(cudaStreamWaitEvent(ctx->stream, slot_copied[job->slot], 0));
+                h2d_bytes += (uint64_t)ch.words * (has_n ? 12 : 8);
                 sq.seq2 = d_words[wb];
-                sq.nbits = d_nb[wb];
+                sq.nbits = has_n ? d_nb[wb] : nullptr;
                 sq.desc = (const SeqDesc *)(d_desc_s + 4 * desc_pos[job->chunk]);
                 sq.n_seqs = (int64_t)ch.n_pieces;
                 sq.total_units = ch.units_score;

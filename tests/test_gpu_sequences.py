@@ -190,8 +190,9 @@ def test_scan_host_sequences_equals_scan_host(ctx, fmt, chunk, monkeypatch):
 
 
 
+@pytest.mark.parametrize("n_rate", [0.002, 0.00002])  # nearly every 8 Ki-base chunk holds an N / hardly any does (its N bits stay home)
 @pytest.mark.parametrize("threads", ["0", "1", "5"])
-def test_scan_host_sequences_host_packers(ctx, threads, monkeypatch):
+def test_scan_host_sequences_host_packers(ctx, threads, n_rate, monkeypatch):
     """ASCII sequences with part of the chunks re-coded to 2-bit words by host threads (csrc/host_pack.cpp, transfer
     compression) and the rest encoded on the device: table and counters are those of the device-only route (threads = 0),
     which the test above ties to gb2_scan_host -- also into a reusable pinned HostTable, with N, lower case and other symbols."""
@@ -200,7 +201,7 @@ def test_scan_host_sequences_host_packers(ctx, threads, monkeypatch):
     m = gu.load_motif("ctcf_meme__unif")
     w = m["width"]
     rng = np.random.default_rng(61)
-    seqs = _random_seqs(rng, [70001, 33, 18, 19, 50000, 4096, 12345, 99999], n_rate=0.002)
+    seqs = _random_seqs(rng, [70001, 33, 18, 19, 50000, 4096, 12345, 99999], n_rate=n_rate)
     seqs[3] = "acgtnACGTRYKMacgtacgTT"[:19]
     dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
     text, offs = _layout_text(rng, seqs)
