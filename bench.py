@@ -282,8 +282,8 @@ def mem_available_bytes():
 def kernel_label(info):
     """Name of the K2 instantiation a motif runs (template arguments follow from the motif: csrc/score.cu dispatch)."""
     if info.width > 32:
-        return f"gb2_score_wide_kernel<{info.n_chunks}> (R={info.lut_replicas})"
-    return f"gb2_score_kernel<{info.n_chunks},{info.lut_replicas},4>"
+        return f"gb2_score_wide_kernel<{info.n_chunks},{info.lut_replicas}>"
+    return f"gb2_score_kernel<{info.chunk_bases},{info.n_chunks},{info.lut_replicas},4>"
 
 
 def parity_multi_gpu(ctx, dm, rank, world):

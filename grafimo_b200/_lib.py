@@ -131,6 +131,7 @@ SIGNATURES = {
     "gb2_encode_sequences": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gb2_score_sequences": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _u64, _int, _dbl, _vp, _vp, _u64, _vp, _vp,
                                    ctypes.POINTER(_u64)]),
+    "gb2_pack_sequence_host": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "gb2_scan_last_transfer": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "gb2_scan_host_sequences": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _dbl, _int, _int, _u64, _vp, _vp, _vp,
                                        _vp, _vp, _vp, ctypes.POINTER(_u64), _vp]),

@@ -9,6 +9,8 @@
 // the end of the piece are code 0 without N bit; *n_invalid counts flagged bases, *n_other those that are not N/n.
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -122,6 +124,20 @@ bool have_avx2()
 
 }  // namespace
 
+// 2: AVX-512BW, 1: AVX2 + BMI2, 0: scalar.  GB2_HOST_PACK_ISA=scalar|avx2 caps it (the tests walk all the paths the CPU has).
+static int isa_level()
+{
+    int level = 0;
+#if defined(__x86_64__)
+    level = have_avx512() ? 2 : have_avx2() ? 1 : 0;
+    if (const char *cap = getenv("GB2_HOST_PACK_ISA")) {
+        if (!strcmp(cap, "scalar")) level = 0;
+        else if (!strcmp(cap, "avx2")) level = level < 1 ? level : 1;
+    }
+#endif
+    return level;
+}
+
 // `n_bases` bases at `text` -> ceil(n_bases / 32) words and N-bit words.
 void gb2_host_pack_bases(const uint8_t *text, int64_t n_bases, uint64_t *words, uint32_t *nbits, uint64_t *n_invalid, uint64_t *n_other)
 {
@@ -129,10 +145,11 @@ void gb2_host_pack_bases(const uint8_t *text, int64_t n_bases, uint64_t *words, 
     const int64_t full = n_bases >> 5;
     int64_t done = 0;
 #if defined(__x86_64__)
-    if (have_avx512()) {
+    const int level = isa_level();
+    if (level == 2) {
         pack_words_avx512(text, full, words, nbits, invalid, other);
         done = full;
-    } else if (have_avx2()) {
+    } else if (level == 1) {
         pack_words_avx2(text, full, words, nbits, invalid, other);
         done = full;
     }
@@ -144,10 +161,17 @@ void gb2_host_pack_bases(const uint8_t *text, int64_t n_bases, uint64_t *words, 
     *n_other += other;
 }
 
-int gb2_host_pack_simd() {
-#if defined(__x86_64__)
-    return have_avx512() ? 2 : have_avx2() ? 1 : 0;
-#else
+// C ABI (include/grafimo_b200.h): the same packer for callers that keep their sequences 2-bit packed (format 1 input)
+extern "C" int gb2_pack_sequence_host(const uint8_t *h_text, int64_t n_bases, uint64_t *h_words, uint32_t *h_nbits, uint64_t *h_counts)
+{
+    if (n_bases < 0 || (n_bases > 0 && (!h_text || !h_words || !h_nbits))) return 1;  // GB2_ERR_ARG
+    uint64_t invalid = 0, other = 0;
+    gb2_host_pack_bases(h_text, n_bases, h_words, h_nbits, &invalid, &other);
+    if (h_counts) {
+        h_counts[0] += invalid;
+        h_counts[1] += other;
+    }
     return 0;
-#endif
 }
+
+int gb2_host_pack_simd() { return isa_level(); }

@@ -325,6 +325,29 @@ def pack_sequences_2bit(seqs):
     return words, nbits, word_off, lens
 
 
+def pack_sequences_host(seqs):
+    """The library's host packer (gb2_pack_sequence_host: AVX-512 / AVX2 / scalar, no GPU involved) on a list of str / bytes /
+    uint8 arrays -> (words uint64, nbits uint32, word_off int64, lens int64, counts uint64[2] = bases that are not ACGT / that
+    are not N either): the layout of pack_sequences_2bit, which is its independent numpy check."""
+    lib = _lib.load()
+    bufs = [np.frombuffer(x.encode("ascii") if isinstance(x, str) else bytes(x) if not isinstance(x, np.ndarray) else x, dtype=np.uint8)
+            for x in seqs]
+    lens = np.array([len(b) for b in bufs], dtype=np.int64)
+    nwords = (lens + 31) // 32
+    word_off = np.concatenate([[0], np.cumsum(nwords)[:-1]]).astype(np.int64) if len(bufs) else np.zeros(0, np.int64)
+    total = int(nwords.sum())
+    words = np.zeros(max(total, 1), dtype=np.uint64)
+    nbits = np.zeros(max(total, 1), dtype=np.uint32)
+    counts = np.zeros(2, dtype=np.uint64)
+    for b, off, n in zip(bufs, word_off, lens):
+        if n:
+            b = np.ascontiguousarray(b)
+            rc = lib.gb2_pack_sequence_host(b.ctypes.data, int(n), words[off:].ctypes.data, nbits[off:].ctypes.data, counts.ctypes.data)
+            if rc != 0:
+                raise GrafimoB200Error(rc, "gb2_pack_sequence_host", "bad argument")
+    return words, nbits, word_off, lens, counts
+
+
 class DeviceMotif:
     """Device-resident motif: chunk LUTs + the score -> p-value table (K4)."""
 

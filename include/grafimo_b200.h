@@ -340,6 +340,11 @@ int gb2_score_sequences(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_
  * none when more than two ranks share the host: the host memory system, not PCIe, limits the copies then).
  * gb2_scan_last_transfer: bytes the last gb2_scan_host* call of this context copied host->device and device->host, and
  * how many of its chunks went as given / were packed on the host (any pointer may be NULL). */
+/* The host packer on its own, for callers that keep their sequences 2-bit packed (format 1 above, gb2_score_sequences): n_bases
+ * ASCII bases -> ceil(n_bases / 32) words and as many N-bit words, exactly what gb2_encode_sequences writes for them (invalid
+ * bases: code 0 + N bit; bases past the end: code 0, no N bit).  h_counts (may be NULL): [0] += bases that are not ACGTacgt,
+ * [1] += those that are not N/n either.  No GPU involved; thread-safe (call it from as many threads as there are sequences). */
+int gb2_pack_sequence_host(const uint8_t *h_text, int64_t n_bases, uint64_t *h_words, uint32_t *h_nbits, uint64_t *h_counts);
 int gb2_scan_last_transfer(const gb2_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *chunks_as_given,
                            uint64_t *chunks_host_packed);
 int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *motif, int format, const void *h_data, const uint32_t *h_nbits,

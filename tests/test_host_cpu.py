@@ -240,3 +240,32 @@ def test_string_column_helpers_on_host_text():
     g = _gather_rows(text, np.array([len(text) - 3], dtype=np.int64), 8)  # indices beyond the text are clamped
     assert g.shape == (1, 8) and bytes(g[0, :3]) == b"\tw\n" and set(g[0, 3:].tolist()) == {10}
     assert _fixed_strings(text, np.zeros(0, np.int64), 7).tolist() == [] and _var_strings(text, np.zeros(0, np.int64), np.zeros(0, np.int64)).tolist() == []
+
+
+@pytest.mark.parametrize("isa", ["", "avx2", "scalar"])
+def test_host_packer_equals_numpy_packer(isa, monkeypatch):
+    """gb2_pack_sequence_host (csrc/host_pack.cpp: the transfer compression of gb2_scan_host_sequences and a public utility;
+    AVX-512 / AVX2 / scalar by what the CPU has) against the plain numpy packer: words, N bits and counters, for lengths around
+    the 32- and 64-base steps, lower case, N and other symbols.  No GPU involved."""
+    from grafimo_b200 import engine
+    if isa:
+        monkeypatch.setenv("GB2_HOST_PACK_ISA", isa)
+    else:
+        monkeypatch.delenv("GB2_HOST_PACK_ISA", raising=False)
+    rng = np.random.default_rng(77)
+    letters = np.array(list("ACGTacgt"))
+    seqs = []
+    for n in [0, 1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 4096, 70001]:
+        s = rng.choice(letters, size=n)
+        if n:
+            s = np.where(rng.random(n) < 0.01, "N", s)
+            s = np.where(rng.random(n) < 0.003, "n", s)
+            s = np.where(rng.random(n) < 0.002, rng.choice(np.array(list("RYKMxz-*"))), s)
+        seqs.append("".join(s))
+    words, nbits, off, lens, counts = engine.pack_sequences_host(seqs)
+    e_words, e_nbits, e_off, e_lens = engine.pack_sequences_2bit(seqs)
+    assert np.array_equal(off, e_off) and np.array_equal(lens, e_lens)
+    assert np.array_equal(words, e_words) and np.array_equal(nbits, e_nbits)
+    flat = "".join(seqs)
+    assert int(counts[0]) == sum(ch not in "ACGTacgt" for ch in flat) > 0
+    assert int(counts[1]) == sum(ch not in "ACGTacgtNn" for ch in flat) > 0
