@@ -737,9 +737,9 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
         // measured on 16- and 24-thread hosts (tools/bench_e2e.py): the rate grows up to ~12 threads and is flat beyond
         pack_threads = std::max(0, std::min(16, hw / std::max(1, ctx->comm_world)));
         // Packing pays while PCIe is the limit of this GPU's copies.  Measured (profiles/r02_e2e_packers.json): per step of the
-        // headline workload 46.6 -> 26.4 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 110 -> 130 ms with
-        // eight: there the HOST memory system is the limit (raw copies reach 23 GB/s per GPU instead of 55, tools/h2d_probe.py)
-        // and a packed base costs it 1.75 bytes of traffic instead of 1.
+        // headline workload 46.6 -> 26.4 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 51 -> 67 ms with four
+        // and 110 -> 130 ms with eight: there the HOST memory system is the limit (a packed base costs it ~1.6 bytes of traffic
+        // instead of 1; on the 8-GPU box raw copies reach 23 GB/s per GPU instead of 55, tools/h2d_probe.py).
         if (ctx->comm_world > 2) pack_threads = 0;
         if (const char *t = getenv("GB2_HOST_PACK_THREADS")) pack_threads = std::max(0, std::min(64, atoi(t)));
     }
