@@ -1034,6 +1034,9 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                 }
             }
             rc = fail_hybrid(rc);  // stops and joins the packers (on success they have nothing left to do)
+            for (Job *j : ready) delete j;  // only after an error: jobs nobody issued
+            ready.clear();
+            if (open) { delete open; open = nullptr; }
             host_flagged[0] = host_invalid.load();  // the device encoder counts the flagged bases of the raw chunks, the packers theirs
             host_flagged[1] = host_other.load();
             if (timing) fprintf(stderr, "gb2_scan_host_sequences: %d packer threads (simd %d): %zu chunks as text, %zu packed on the host\n",
