@@ -604,8 +604,25 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     GB2_REQUIRE(ctx, format == 1 || h_nbits == nullptr, "gb2_scan_host_sequences: N bits are derived from ASCII input");
     const int w = m->w;
     const bool ascii = format == 0;
-    // chunk size in bases (GB2_SEQ_CHUNK_BASES overrides it: the tests use small chunks to exercise the piece logic)
-    int64_t CHUNK_BASES = (int64_t)1 << 26;
+    // Host-side packing (host_pack.cpp): worker threads re-code chunks from the BACK of the chunk list into 2-bit words in
+    // pinned staging while the copy engine moves the text of the chunks at the FRONT; both meet in the middle.
+    // GB2_HOST_PACK_THREADS overrides the thread count (0 = off); default: the host threads this rank can count on.
+    int pack_threads = 0;
+    if (ascii) {
+        const int hw = (int)std::thread::hardware_concurrency();
+        // measured on 16- and 24-thread hosts (tools/bench_e2e.py): the rate grows up to ~12 threads and is flat beyond
+        pack_threads = std::max(0, std::min(16, hw / std::max(1, ctx->comm_world)));
+        // Packing pays while PCIe is the limit of this GPU's copies.  Measured (profiles/r02_e2e_packers.json): per step of the
+        // headline workload 46.6 -> 25 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 51 -> 67 ms with four
+        // and 110 -> 130 ms with eight: there the HOST memory system is the limit (a packed base costs it ~1.6 bytes of traffic
+        // instead of 1; on the 8-GPU box raw copies reach 23 GB/s per GPU instead of 55, tools/h2d_probe.py).
+        if (ctx->comm_world > 2) pack_threads = 0;
+        if (const char *t = getenv("GB2_HOST_PACK_THREADS")) pack_threads = std::max(0, std::min(64, atoi(t)));
+    }
+    // chunk size in bases (GB2_SEQ_CHUNK_BASES overrides it: the tests use small chunks to exercise the piece logic).  With the
+    // packers a finer grain wins -- the two sides meet with less idle time at the end (measured per step, 16 threads: 27.1 /
+    // 27.2 / 25.1 / 25.0 ms at 64 / 32 / 16 / 8 Mi bases); the copy engine alone prefers the coarse one (46.5 / 46.8 / 47.2 / 47.7).
+    int64_t CHUNK_BASES = pack_threads ? (int64_t)1 << 24 : (int64_t)1 << 26;
     if (const char *t = getenv("GB2_SEQ_CHUNK_BASES")) CHUNK_BASES = std::max<int64_t>(1024, atoll(t));
     const int64_t MIN_PIECE = std::max<int64_t>(64 + w, std::min<int64_t>((int64_t)1 << 16, CHUNK_BASES / 4));
 
@@ -728,22 +745,8 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     const size_t b_words = al256_seq((size_t)max_words * 8 + 64);
     const size_t b_nbits = al256_seq((size_t)max_words * 4 + 64);
     const size_t b_desc = al256_seq(desc_s.size() * 8) + al256_seq(desc_e.size() * 8);
-    // Host-side packing (host_pack.cpp): worker threads re-code chunks from the BACK of the chunk list into 2-bit words in
-    // pinned staging while the copy engine moves the text of the chunks at the FRONT; both meet in the middle.
-    // GB2_HOST_PACK_THREADS overrides the thread count (0 = off); default: the host threads this rank can count on.
-    int pack_threads = 0;
-    if (ascii && chunks.size() >= 4) {
-        const int hw = (int)std::thread::hardware_concurrency();
-        // measured on 16- and 24-thread hosts (tools/bench_e2e.py): the rate grows up to ~12 threads and is flat beyond
-        pack_threads = std::max(0, std::min(16, hw / std::max(1, ctx->comm_world)));
-        // Packing pays while PCIe is the limit of this GPU's copies.  Measured (profiles/r02_e2e_packers.json): per step of the
-        // headline workload 46.6 -> 26.4 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 51 -> 67 ms with four
-        // and 110 -> 130 ms with eight: there the HOST memory system is the limit (a packed base costs it ~1.6 bytes of traffic
-        // instead of 1; on the 8-GPU box raw copies reach 23 GB/s per GPU instead of 55, tools/h2d_probe.py).
-        if (ctx->comm_world > 2) pack_threads = 0;
-        if (const char *t = getenv("GB2_HOST_PACK_THREADS")) pack_threads = std::max(0, std::min(64, atoi(t)));
-    }
-    const int n_slots = pack_threads ? 6 : 0;  // pinned staging slots of one packed chunk each (a slot is busy from the first
+    if (chunks.size() < 4) pack_threads = 0;  // nothing to overlap
+    const int n_slots = pack_threads ? 8 : 0;  // pinned staging slots of one packed chunk each (a slot is busy from the first
                                                // block packed until its copy has left the queue behind up to two text chunks)
     const int nwordbuf = ascii ? (pack_threads ? 3 : 1) : 2;  // ASCII: [0] the device encoder's output, [1], [2] host-packed chunks
     const size_t total = 2 * b_text + nwordbuf * (b_words + b_nbits) + b_desc + gb2_scan_tail_bytes(m, hit_capacity);
