@@ -75,33 +75,69 @@ __attribute__((target("avx2,bmi2,popcnt"))) void pack_words_avx2(const uint8_t *
 
 // 64 bases per step: the 2-bit codes of four neighbouring bytes are folded into one byte with two multiply-adds
 // (c0 + 4 c1 per 16-bit lane, then lo + 16 hi per 32-bit lane) and the 16 result bytes leave through vpmovdb.
-__attribute__((target("avx512f,avx512bw,popcnt"))) void pack_words_avx512(const uint8_t *t, int64_t n_words, uint64_t *words,
-                                                                          uint32_t *nbits, uint64_t &invalid, uint64_t &other)
+struct Avx512Step {
+    __m128i words;  // 64 bases
+    uint64_t bad;   // their N bits
+};
+
+__attribute__((target("avx512f,avx512bw,popcnt"), always_inline)) inline Avx512Step pack_step_avx512(const uint8_t *t, uint64_t &inv, uint64_t &oth)
 {
     const __m512i m_df = _mm512_set1_epi8((char)0xDF), m_3 = _mm512_set1_epi8(3), m_1 = _mm512_set1_epi8(1);
     const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T'),
                   cN = _mm512_set1_epi8('N');
     const __m512i f1 = _mm512_set1_epi16(0x0401), f2 = _mm512_set1_epi32(0x00100001);
+    const __m512i v = _mm512_loadu_si512(reinterpret_cast<const void *>(t));
+    const __m512i u = _mm512_and_si512(v, m_df);
+    const __m512i x = _mm512_and_si512(_mm512_srli_epi16(v, 1), m_3);                  // A 0, C 1, G 3, T 2
+    __m512i c = _mm512_xor_si512(x, _mm512_and_si512(_mm512_srli_epi16(x, 1), m_1));   // A 0, C 1, G 2, T 3
+    const __mmask64 ok = _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) | _mm512_cmpeq_epi8_mask(u, cG) |
+                         _mm512_cmpeq_epi8_mask(u, cT);
+    const uint64_t bad = ~(uint64_t)ok;
+    if (bad) {
+        c = _mm512_maskz_mov_epi8(ok, c);
+        const uint64_t is_n = (uint64_t)_mm512_cmpeq_epi8_mask(u, cN);
+        inv += (uint64_t)_mm_popcnt_u64(bad);
+        oth += (uint64_t)_mm_popcnt_u64(bad & ~is_n);
+    }
+    const __m512i q = _mm512_madd_epi16(_mm512_maddubs_epi16(c, f1), f2);  // one byte of four codes per 32-bit lane
+    return Avx512Step{_mm512_cvtepi32_epi8(q), bad};
+}
+
+// The output is written once and read by the copy engine (or a later pass), never by this core again: whole cache lines
+// leave through streaming stores -- 512 bases = 16 words (two lines) + 16 N-bit words (one line) per round -- which spares
+// the read-for-ownership of every line (a quarter of the packer's memory traffic; the packers are bound by that traffic).
+__attribute__((target("avx512f,avx512bw,popcnt"))) void pack_words_avx512(const uint8_t *t, int64_t n_words, uint64_t *words,
+                                                                          uint32_t *nbits, uint64_t &invalid, uint64_t &other)
+{
     uint64_t inv = 0, oth = 0;
     int64_t k = 0;
+    // head: up to the first word whose two output arrays both start a cache line
+    while (k + 2 <= n_words && (((uintptr_t)(words + k) & 63u) != 0 || ((uintptr_t)(nbits + k) & 63u) != 0)) {
+        const Avx512Step r = pack_step_avx512(t + 32 * k, inv, oth);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(words + k), r.words);
+        nbits[k] = (uint32_t)r.bad;
+        nbits[k + 1] = (uint32_t)(r.bad >> 32);
+        k += 2;
+    }
+    for (; k + 16 <= n_words; k += 16) {
+        Avx512Step r[8];
+#pragma GCC unroll 8
+        for (int j = 0; j < 8; ++j) r[j] = pack_step_avx512(t + 32 * k + 64 * j, inv, oth);
+        __m512i w0 = _mm512_castsi128_si512(r[0].words), w1 = _mm512_castsi128_si512(r[4].words);
+        w0 = _mm512_inserti32x4(w0, r[1].words, 1); w0 = _mm512_inserti32x4(w0, r[2].words, 2); w0 = _mm512_inserti32x4(w0, r[3].words, 3);
+        w1 = _mm512_inserti32x4(w1, r[5].words, 1); w1 = _mm512_inserti32x4(w1, r[6].words, 2); w1 = _mm512_inserti32x4(w1, r[7].words, 3);
+        const __m512i nb = _mm512_set_epi64((long long)r[7].bad, (long long)r[6].bad, (long long)r[5].bad, (long long)r[4].bad,
+                                            (long long)r[3].bad, (long long)r[2].bad, (long long)r[1].bad, (long long)r[0].bad);
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(words + k), w0);
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(words + k + 8), w1);
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(nbits + k), nb);
+    }
+    _mm_sfence();
     for (; k + 2 <= n_words; k += 2) {
-        const __m512i v = _mm512_loadu_si512(reinterpret_cast<const void *>(t + 32 * k));
-        const __m512i u = _mm512_and_si512(v, m_df);
-        const __m512i x = _mm512_and_si512(_mm512_srli_epi16(v, 1), m_3);                  // A 0, C 1, G 3, T 2
-        __m512i c = _mm512_xor_si512(x, _mm512_and_si512(_mm512_srli_epi16(x, 1), m_1));   // A 0, C 1, G 2, T 3
-        const __mmask64 ok = _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) | _mm512_cmpeq_epi8_mask(u, cG) |
-                             _mm512_cmpeq_epi8_mask(u, cT);
-        const uint64_t bad = ~(uint64_t)ok;
-        if (bad) {
-            c = _mm512_maskz_mov_epi8(ok, c);
-            const uint64_t is_n = (uint64_t)_mm512_cmpeq_epi8_mask(u, cN);
-            inv += (uint64_t)_mm_popcnt_u64(bad);
-            oth += (uint64_t)_mm_popcnt_u64(bad & ~is_n);
-        }
-        const __m512i q = _mm512_madd_epi16(_mm512_maddubs_epi16(c, f1), f2);  // one byte of four codes per 32-bit lane
-        _mm_storeu_si128(reinterpret_cast<__m128i *>(words + k), _mm512_cvtepi32_epi8(q));
-        nbits[k] = (uint32_t)bad;
-        nbits[k + 1] = (uint32_t)(bad >> 32);
+        const Avx512Step r = pack_step_avx512(t + 32 * k, inv, oth);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(words + k), r.words);
+        nbits[k] = (uint32_t)r.bad;
+        nbits[k + 1] = (uint32_t)(r.bad >> 32);
     }
     invalid += inv;
     other += oth;

@@ -1,7 +1,5 @@
-# round 2, GPU call Q (1 GPU): chunk size of gb2_scan_host_sequences against the end-to-end step (packers on, 16 threads)
+# round 2, GPU call Q (1 GPU): streaming stores in the host packer -- parity and e2e rate
 set -x
 mkdir -p gpurun_out
-for cb in 67108864 33554432 16777216 8388608; do
-  echo "chunk bases $cb"
-  GB2_SEQ_CHUNK_BASES=$cb timeout 300 python tools/bench_e2e.py --threads 16,0 2>/dev/null | cut -c1-110
-done
+timeout 600 python -m pytest tests/test_gpu_sequences.py tests/test_host_cpu.py -x -q > gpurun_out/q_pytest.log 2>&1; tail -2 gpurun_out/q_pytest.log
+timeout 300 python tools/bench_e2e.py --threads 16,12,8,16 --out gpurun_out/q_e2e.json 2>/dev/null | cut -c1-110
