@@ -84,6 +84,32 @@ def test_compute_results_equals_reference_table(tag, tmp_path, capsys):
     assert f"Scoring hits for motif +{m.motif_id}." in out
 
 
+
+@pytest.mark.parametrize("threshold", [0.001, 0.005, 0.006, 0.02, 0.2])
+@pytest.mark.parametrize("qval_t", [False, True])
+def test_compute_results_across_the_dense_switch(threshold, qval_t, tmp_path, capsys):
+    """compute_results on the reference's 704-row fixture for p-value thresholds on both sides of the point where the scan
+    switches from hit records to dense scores + partition passes (score_sequences._DENSE_FROM = 0.006), with and without
+    --qvalueT: every table == the oracle's (the oracle is pinned on the reference's own golden at threshold 1)."""
+    from grafimo_b200.score_sequences import compute_results
+    from oracle import oracle as orc
+    fx = gu.fixtures()
+    m, g = _build("ctcf_meme__unif", tmp_path)
+    d = tmp_path / "input" / "width_19"
+    d.mkdir(parents=True)
+    (d / "scoring_test_input.tsv").write_text(fx["scoring_input_tsv"])
+    opts = dict(threshold=threshold, noqvalue=False, qvalueT=qval_t, noreverse=False, recomb=True)
+    if qval_t:
+        opts["threshold"] = max(threshold, 0.5)  # q-values of this fixture start at 0.47
+    df = compute_results(m, str(tmp_path / "input") + "/", True, _Args(opts))
+    lines = fx["scoring_input_tsv"].strip("\n").split("\n")
+    exp = orc.compute_results(g, lines, **opts)
+    cols = ["sequence_name", "start", "stop", "strand", "score", "p-value", "q-value", "matched_sequence", "haplotype_frequency", "reference"]
+    got = {c: df[c].to_numpy() for c in df.columns}
+    assert len(df) == len(exp["start"]) and (len(df) > 0 or threshold < 0.002)
+    gu.assert_tables_equal(got, exp, cols)
+
+
 def test_compute_results_reference_own_golden(tmp_path):
     """The reference's test_scoring: CTCF on width_19/scoring_test_input.tsv == expected_results/scoring_results.tsv."""
     from grafimo_b200.score_sequences import compute_results
