@@ -611,7 +611,7 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
     if (ascii) {
         const int hw = (int)std::thread::hardware_concurrency();
         // measured on 16- and 24-thread hosts (tools/bench_e2e.py): the rate grows up to ~12 threads and is flat beyond
-        pack_threads = std::max(0, std::min(16, hw / std::max(1, ctx->comm_world)));
+        pack_threads = std::max(0, std::min(16, ctx->comm_world <= 1 ? hw : hw / (2 * ctx->comm_world)));  // 2 ranks: 6 each of 24 (measured)
         // Packing pays while PCIe is the limit of this GPU's copies.  Measured (profiles/r02_e2e_packers.json): per step of the
         // headline workload 46.6 -> 25 ms on one GPU, 46.5 -> 39.7 ms with two ranks on the host, but 51 -> 67 ms with four
         // and 110 -> 130 ms with eight: there the HOST memory system is the limit (a packed base costs it ~1.6 bytes of traffic

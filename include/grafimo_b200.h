@@ -336,7 +336,7 @@ int gb2_score_sequences(gb2_ctx *ctx, const gb2_motif *motif, const uint64_t *d_
  * during the copy re-code part of the chunks into the 2-bit layout (csrc/host_pack.cpp; AVX-512 / AVX2 / scalar) while
  * the copy engine moves the text of the others; packed chunks cross PCIe at 0.25 byte per base (0.375 when they hold an N).  Nothing is scored on the
  * host and the result does not depend on which chunks were packed.  GB2_HOST_PACK_THREADS sets the thread count (0 = off;
- * default: the host's hardware threads divided by the ranks of the context's communicator, at most 16, and
+ * default: the host's hardware threads, at most 16; half of them shared out when two ranks of the context's communicator use the host, and
  * none when more than two ranks share the host: the host memory system, not PCIe, limits the copies then).
  * gb2_scan_last_transfer: bytes the last gb2_scan_host* call of this context copied host->device and device->host, and
  * how many of its chunks went as given / were packed on the host (any pointer may be NULL). */
