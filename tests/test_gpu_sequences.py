@@ -217,6 +217,31 @@ def test_scan_host_sequences_host_packers(ctx, threads, n_rate, monkeypatch):
             assert np.array_equal(got[k], exp[k]), (threads, rep, k)
 
 
+
+def test_scan_host_sequences_random_schedules(ctx, monkeypatch):
+    """Random batches x random chunk sizes x random packer thread counts: the table and the counters never depend on how the
+    batch was cut into chunks / pieces or on which chunks the host packers took."""
+    from grafimo_b200 import engine
+    m = gu.load_motif("ctcf_meme__unif")
+    dm = ctx.motif(m["score_matrix"], m["pval_mat"], m["min_val"], m["scale"], m["offset"])
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        lens = [int(x) for x in rng.integers(0, 60000, size=int(rng.integers(3, 12)))] + [int(rng.integers(100000, 250000))]
+        seqs = _random_seqs(rng, lens, n_rate=float(rng.choice([0.0, 0.00005, 0.003])), bad=bool(trial & 1))
+        text, offs = _layout_text(rng, seqs)
+        ln = [len(x) for x in seqs]
+        monkeypatch.setenv("GB2_HOST_PACK_THREADS", "0")
+        monkeypatch.delenv("GB2_SEQ_CHUNK_BASES", raising=False)
+        exp = engine.scan_host_sequences(ctx, dm, text, offs, ln, fmt="ascii", strands=2, threshold=0.004)
+        for rep in range(3):
+            monkeypatch.setenv("GB2_HOST_PACK_THREADS", str(int(rng.integers(0, 8))))
+            monkeypatch.setenv("GB2_SEQ_CHUNK_BASES", str(int(rng.choice([1024, 3000, 8192, 40000, 1 << 17]))))
+            got = engine.scan_host_sequences(ctx, dm, text, offs, ln, fmt="ascii", strands=2, threshold=0.004)
+            assert got["stats"] == exp["stats"], (trial, rep)
+            for k in ("row", "strand", "int_score", "score", "p-value", "q-value"):
+                assert np.array_equal(got[k], exp[k]), (trial, rep, k)
+
+
 def test_scan_host_packed_equals_scan_host(ctx):
     from grafimo_b200 import engine
     for tag in ("ctcf_meme__unif", "synth_w35_meme__bgnt"):
