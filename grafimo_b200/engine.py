@@ -542,7 +542,7 @@ class Scan:
                 keep_bins = pt < self.threshold
                 if q_filter:
                     keep_bins &= self.qtab < self.threshold
-                cap = max(int(self.hist[keep_bins].sum().item()), 1)
+                cap = max(min(int(self.hist[keep_bins].sum().item()), n), 1)  # an all-reduced histogram counts the other ranks' rows too
         index_only = bool(index_only) and bool(self.dense_rows)
         if getattr(self, "_out_cap", 0) < cap or getattr(self, "_out_index_only", False) != index_only:
             f64 = (lambda: None) if index_only else (lambda: ctx.empty(cap, torch.float64))
