@@ -544,6 +544,9 @@ def run_ours(args):
                                                              threshold=THRESHOLD, hit_capacity=1 << 23, out=host_out))
     os.environ.pop("GB2_HOST_PACK_THREADS", None)
     moved0 = ctx.last_transfer()
+    # the same call without any host-side help, next to the headline so that nobody has to look for it
+    line["e2e"]["value_without_host_packers"] = 2.0 * n * world / dt0
+    line["e2e"]["ms_per_step_without_host_packers"] = dt0 * 1e3
     variants["sequences_ascii_copy_engine_only"] = {"value": 2.0 * n * world / dt0, "unit": UNIT, "ms_per_step": dt0 * 1e3,
                                                     "h2d_bytes_per_step": moved0["h2d_bytes"], "d2h_bytes_per_step": moved0["d2h_bytes"],
                                                     "api": "gb2_scan_host_sequences(format=ASCII), GB2_HOST_PACK_THREADS=0"}
