@@ -269,3 +269,23 @@ def test_host_packer_equals_numpy_packer(isa, monkeypatch):
     flat = "".join(seqs)
     assert int(counts[0]) == sum(ch not in "ACGTacgt" for ch in flat) > 0
     assert int(counts[1]) == sum(ch not in "ACGTacgtNn" for ch in flat) > 0
+
+
+def test_header_is_plain_c_and_the_example_compiles(tmp_path):
+    """include/grafimo_b200.h must be consumable by a C compiler on its own (the boundary is a C ABI: plain pointers and sizes, no
+    C++ / CUDA / torch types), and examples/c_abi_scan.c must compile and link against the built library (it is RUN on a GPU box by
+    tests/test_gpu_c_abi.py)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tu = tmp_path / "only_the_header.c"
+    tu.write_text('#include "grafimo_b200.h"\nint main(void) { return GB2_ABI_VERSION == 3 ? 0 : 1; }\n')
+    for std in ("-std=c99", "-std=c11"):
+        subprocess.run(["gcc", std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(tu)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", os.path.join(root, "include"), str(tu)], check=True)
+    lib = os.path.join(root, "grafimo_b200")
+    if os.path.exists(os.path.join(lib, "libgrafimo_b200.so")):
+        subprocess.run(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_scan.c"), "-o",
+                        str(tmp_path / "c_abi_scan"), "-L", lib, "-lgrafimo_b200", f"-Wl,-rpath,{lib}", "-lm"], check=True)
