@@ -348,7 +348,7 @@ def _var_strings(text, offs: np.ndarray, lens: np.ndarray) -> np.ndarray:
     return out
 
 
-def _report_order(pval, start, stop, strand, seq, minus=None):
+def _report_order(pval, start, stop, strand, seq, minus=None, presorted=False):
     """Row order of the report: p-value ascending, ties -- which the reference leaves undefined -- by (start, stop,
     strand, matched_sequence).  Numeric keys first; the sequence strings are only compared inside groups that tie on
     all of them.  `minus` (bool array): the caller already knows which rows are on the '-' strand and every other row is '+'."""
@@ -358,10 +358,11 @@ def _report_order(pval, start, stop, strand, seq, minus=None):
     if minus is None:
         minus = (strand == "-")
         other = ~minus & (strand != "+")
-    else:
+    else:  # the caller knows the strands (strand may be None)
         other = np.zeros(n, dtype=bool)
     scode = minus.astype(np.int8) * 2 + other.astype(np.int8) * 3  # '+' < '-' < anything else, like the characters
-    order = np.lexsort((scode, stop, start, pval))
+    # presorted: the rows already come in (p, start, stop, strand) order (sorted on the device); only the ties remain
+    order = np.arange(n) if presorted else np.lexsort((scode, stop, start, pval))
     p, a, b, c = pval[order], start[order], stop[order], scode[order]
     same = (p[1:] == p[:-1]) & (a[1:] == a[:-1]) & (b[1:] == b[:-1]) & (c[1:] == c[:-1])
     if same.any():
@@ -404,6 +405,73 @@ def _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pv
     cols["matched_sequence"] = seq[order]
     cols["haplotype_frequency"] = freq[order]
     cols["reference"] = ref[order]
+    return pd.DataFrame(cols)
+
+
+def _arrow_string_dtype():
+    """The dtype pandas gives a column of Python strings when it is left to infer it: an Arrow-backed string dtype from
+    pandas 3 on (then the string columns of a table can be built from byte buffers, without a Python object per cell), or
+    None where it is still `object`."""
+    try:
+        dt = pd.Series(np.array(["a"], dtype=object)).dtype
+        if dt == object:
+            return None
+        import pyarrow  # noqa: F401
+        return dt
+    except Exception:
+        return None
+
+
+def _build_table_rows(motif, no_qvalue, keep, names, region, start, stop, minus, score, pval, qval, asc, freq, isref_fixed, presorted=False):
+    """_build_table for rows that come from the device (graph path): the same table, but where pandas backs string columns by
+    Arrow (pandas >= 3) they are assembled from byte buffers -- the k-mer letters, one byte per strand, dictionary look-ups for
+    region names and the ref flag -- instead of 4 Python string objects per row that pandas would then convert again
+    (229 k rows: 0.32 s -> ~0.05 s; with eight ranks building the table at once the saving is larger)."""
+    dt = _arrow_string_dtype()
+    n_all = len(minus)
+    width = asc.shape[1] if asc.ndim == 2 else 0
+    if dt is None or n_all == 0:
+        seq = np.ascontiguousarray(asc).view(f"S{width}").ravel().astype(f"U{width}").astype(object) if n_all else np.array([], dtype=object)
+        seqname = np.array(names, dtype=object)[region] if n_all else np.array([], dtype=object)
+        ref = np.where(isref_fixed, "ref", "non.ref").astype(object)
+        strand = np.where(minus, "-", "+").astype(object)
+        return _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, score, pval, qval, seq, freq, ref, 1, minus=minus)
+    import pyarrow as pa
+    if not keep.all():
+        region, start, stop, minus, score, pval, asc, freq, isref_fixed = (a[keep] for a in (region, start, stop, minus, score, pval, asc, freq, isref_fixed))
+        qval = None if qval is None else qval[keep]
+    seq_bytes = np.ascontiguousarray(asc).view(f"S{width}").ravel()
+    order = _report_order(pval, start, stop, None, seq_bytes, minus, presorted=presorted)
+    n = len(order)
+
+    def fixed(rows_u8):  # [n, k] bytes -> Arrow strings of k characters
+        k = rows_u8.shape[1]
+        off = np.arange(0, (n + 1) * k, k, dtype=np.int64)
+        return pa.Array.from_buffers(pa.large_string(), n, [None, pa.py_buffer(off), pa.py_buffer(np.ascontiguousarray(rows_u8))])
+
+    def const(text):
+        b = np.frombuffer(text.encode("utf-8"), dtype=np.uint8)
+        return fixed(np.broadcast_to(b, (n, len(b))))
+
+    def take(values, idx):
+        return pa.array(list(values), type=pa.large_string()).take(pa.array(np.ascontiguousarray(idx, dtype=np.int64)))
+
+    col = lambda arr: pd.array(arr, dtype=dt)  # noqa: E731
+    cols = {
+        "motif_id": col(const(str(motif.motif_id))),
+        "motif_alt_id": col(const(str(motif.motif_name))),
+        "sequence_name": col(take(names, region[order])),
+        "start": start[order],
+        "stop": stop[order],
+        "strand": col(fixed(np.where(minus[order], np.uint8(45), np.uint8(43)).astype(np.uint8)[:, None])),
+        "score": score[order],
+        "p-value": pval[order],
+    }
+    if not no_qvalue:
+        cols["q-value"] = qval[order]
+    cols["matched_sequence"] = col(fixed(asc[order]))
+    cols["haplotype_frequency"] = freq[order]
+    cols["reference"] = col(take(["non.ref", "ref"], isref_fixed[order].astype(np.int64)))
     return pd.DataFrame(cols)
 
 
@@ -691,26 +759,31 @@ def compute_results_rows(motif: Motif, rows, debug: bool, args_obj=None, testmod
         dev, names = _gather_hit_columns(ctx, dev, names, kept, world)
     tp = _phase(ctx, "gather_ranks", tp)
     with torch.cuda.stream(ctx.stream):
+        # report order (p, start, stop, strand) on the device: four stable sorts of the (merged) hit columns, least significant
+        # key first -- the host then only looks at rows that tie on all four (np.lexsort took 70-80 ms per rank for 229 k rows)
+        n_rows = int(dev["p"].shape[0])
+        if n_rows > 1:
+            mi = dev["minus"].to(torch.bool)
+            r_start = torch.where(mi, dev["stop"], dev["start"])
+            r_stop = torch.where(mi, dev["start"], dev["stop"])
+            idx = torch.arange(n_rows, device=ctx.device)
+            for key in (dev["minus"].to(torch.int16), r_stop, r_start, dev["p"]):
+                idx = idx[torch.sort(key[idx], stable=True).indices]
+            dev = {k: v[idx] for k, v in dev.items()}
+        dev["letters"] = _letters_device(dev.pop("packed"), dev["minus"], width) if n_rows else torch.zeros((0, width), dtype=torch.uint8, device=ctx.device)
         host = {k: v.cpu().numpy() for k, v in dev.items()}
     tp = _phase(ctx, "to_host", tp)
     minus = host["minus"].astype(bool)
-    from .extract_regions import decode_kmers
-    comp = np.zeros(256, np.uint8)
-    comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
-    asc = decode_kmers(host["packed"], width)
-    asc = np.where(minus[:, None], comp[asc][:, ::-1], asc)
-    # bytes -> str objects at C speed (np.char.decode is a per-element Python call: 0.21 s against 0.06 s for 229 k hits)
-    seq = np.ascontiguousarray(asc).view(f"S{width}").ravel().astype(f"U{width}").astype(object) if len(minus) else np.array([], dtype=object)
-    seqname = np.array(names, dtype=object)[host["region"]] if len(minus) else np.array([], dtype=object)
+    asc = host["letters"]
     # the '-' row of a walk starts where the walk stops
     start = np.where(minus, host["stop"], host["start"])
     stop = np.where(minus, host["start"], host["stop"])
     freq = host["freq"]
-    ref = np.where(host["isref"].astype(bool) & (np.abs(stop - start) == width), "ref", "non.ref").astype(object)  # score_sequences.py:305-307
+    isref = host["isref"].astype(bool) & (np.abs(stop - start) == width)  # score_sequences.py:305-307
     keep = np.ones(len(minus), dtype=bool) if recomb else freq > 0  # resultsTmp.py:309-310
-    strand = np.where(minus, "-", "+").astype(object)
     tp = _phase(ctx, "strings", tp)
-    df = _build_table(motif, no_qvalue, keep, seqname, start, stop, strand, host["score"], host["p"], host.get("q"), seq, freq, ref, 1, minus=minus)
+    df = _build_table_rows(motif, no_qvalue, keep, names, host["region"], start, stop, minus, host["score"], host["p"], host.get("q"),
+                           asc, freq, isref, presorted=True)
     tp = _phase(ctx, "dataframe", tp)
     if verbose and rank == 0:
         print("\nResults summary built in %.2fs" % (time.time() - t1))
@@ -772,6 +845,18 @@ def _revcomp_packed(packed, width):
         j = width - 1 - i
         out[j >> 5] |= (3 - ((words[i >> 5] >> (2 * (i & 31))) & 3)) << (2 * (j & 31))
     return torch.stack(out, dim=1) if wide else out[0]
+
+
+def _letters_device(packed, minus, width):
+    """Packed k-mers of the reported rows -> uint8 [n, width] ASCII on the device, the '-' rows as the reverse complement
+    (what the report prints as matched_sequence): one small gather instead of a host pass over every hit."""
+    import torch
+    wide = packed.dim() == 2
+    words = [packed[:, 0], packed[:, 1]] if wide else [packed]
+    fwd = torch.stack([(words[int(i) >> 5] >> (2 * (int(i) & 31))) & 3 for i in range(width)], dim=1)  # [n, width] codes 0..3
+    rc = 3 - fwd.flip(1)
+    codes = torch.where(minus.to(torch.bool)[:, None], rc, fwd)
+    return torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=packed.device)[codes]
 
 
 def scan_rows_device(motif: Motif, rows, debug: bool, args_obj):
