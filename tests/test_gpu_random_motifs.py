@@ -80,3 +80,10 @@ def test_random_motifs_all_widths(ctx, seed):
         assert sorted(idx.tolist()) == np.nonzero(p_all < thr)[0].tolist(), (w, kind, thr)
         assert np.array_equal(out["int_score"], is_all[idx]) and np.array_equal(out["score"], lo_all[idx])
         assert np.array_equal(out["p-value"], p_all[idx]) and np.array_equal(out["q-value"], q_all[idx])
+        # the dense form (K2 dense scores -> two partition passes) must give the same table, row for row: degenerate score
+        # distributions (one bin, tied p-values, non-monotone p-tables) and both k-mer forms included
+        den = Scan(ctx, dm, strands=2, threshold=thr, dense_rows=n)
+        den.score(packed, nmask)
+        dout = den.finalize()
+        for k in ("row", "strand", "int_score", "score", "p-value", "q-value"):
+            assert np.array_equal(dout[k], out[k]), (w, kind, thr, k)
