@@ -890,7 +890,8 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             bool stop = false;
             std::atomic<uint64_t> host_invalid{0}, host_other{0};
             const int64_t BLOCK_BASES = (int64_t)1 << 19;  // work unit of one packer thread (a multiple of 32)
-            auto worker = [&]() {
+            std::atomic<bool> worker_failed{false};
+            auto worker_body = [&]() {
                 for (;;) {
                     Job *job = nullptr;
                     Block blk{};
@@ -935,6 +936,16 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
                         ready.push_back(job);
                         cv.notify_all();
                     }
+                }
+            };
+            auto worker = [&]() {  // an exception must not leave a thread (std::terminate): report it and stop everybody
+                try {
+                    worker_body();
+                } catch (...) {
+                    worker_failed.store(true);
+                    std::lock_guard<std::mutex> lk(mu);
+                    stop = true;
+                    cv.notify_all();
                 }
             };
             std::vector<std::thread> pool;
@@ -995,6 +1006,11 @@ extern "C" int gb2_scan_host_sequences(gb2_ctx *ctx, const gb2_motif *m, int for
             };
             // raw copies are paced (at most two chunks queued on the copy engine) so that the packers get their share
             while (rc == GB2_OK) {
+                if (worker_failed.load()) {
+                    GB2_SET_ERR(ctx, "gb2_scan_host_sequences: a host packer thread failed (out of memory?)");
+                    rc = GB2_ERR_NOMEM;
+                    break;
+                }
                 Job *job = nullptr;
                 bool do_raw = false;
                 size_t raw_c = 0;
