@@ -537,6 +537,31 @@ def run_ours(args):
                           "window in host memory; host threads re-code part of the chunks to 2 bits per base while the copy engine moves the others as text "
                           "(transfer compression, csrc/host_pack.cpp; nothing is scored on the host); windows formed on the device; hit table back into "
                           "pinned buffers (engine.HostTable)", "hits": int(len(out["row"]))}
+    # what the host can deliver to this GPU while every rank copies at once: a bare pinned host -> device copy of 1 GiB of the same
+    # input (no library code) -- the wall the copy-engine-only rate sits on (55 GB/s alone, ~23 GB/s with eight ranks on this pool's hosts)
+    try:
+        probe_bytes = int(min(host_ascii.numel(), 1 << 30))
+        with torch.cuda.stream(ctx.stream):
+            probe_dst = torch.empty(probe_bytes, dtype=torch.uint8, device=ctx.device)
+        ctx.sync()
+        best = None
+        for rep in range(3):
+            if world > 1:
+                torch.distributed.barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ctx.stream):
+                ea.record(ctx.stream)
+                probe_dst.copy_(host_ascii.view(-1)[:probe_bytes], non_blocking=True)
+                eb.record(ctx.stream)
+            ctx.sync()
+            ms = ea.elapsed_time(eb)
+            best = ms if best is None or (rep and ms < best) else best
+        worst_rank_ms = ctx.allreduce_max([best])[0]
+        line["e2e"]["raw_h2d_GBps_per_gpu_all_ranks_copying"] = probe_bytes / (worst_rank_ms * 1e-3) / 1e9
+        line["e2e"]["copy_engine_only_fraction_of_raw_h2d"] = None  # filled below
+        del probe_dst
+    except Exception as e:  # informational
+        line["e2e"]["raw_h2d_GBps_per_gpu_all_ranks_copying"] = repr(e)
     variants = {}
     # (a) the same call with the host packers off: every base crosses PCIe as one byte of text -- the PCIe wall itself
     os.environ["GB2_HOST_PACK_THREADS"] = "0"
@@ -547,6 +572,9 @@ def run_ours(args):
     # the same call without any host-side help, next to the headline so that nobody has to look for it
     line["e2e"]["value_without_host_packers"] = 2.0 * n * world / dt0
     line["e2e"]["ms_per_step_without_host_packers"] = dt0 * 1e3
+    raw = line["e2e"].get("raw_h2d_GBps_per_gpu_all_ranks_copying")
+    if isinstance(raw, float) and raw > 0:
+        line["e2e"]["copy_engine_only_fraction_of_raw_h2d"] = (H * L / dt0 / 1e9) / raw
     variants["sequences_ascii_copy_engine_only"] = {"value": 2.0 * n * world / dt0, "unit": UNIT, "ms_per_step": dt0 * 1e3,
                                                     "h2d_bytes_per_step": moved0["h2d_bytes"], "d2h_bytes_per_step": moved0["d2h_bytes"],
                                                     "api": "gb2_scan_host_sequences(format=ASCII), GB2_HOST_PACK_THREADS=0"}
