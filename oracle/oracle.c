@@ -9,7 +9,7 @@
  * against (a) the reference's own golden table tests/test_data/expected_results/
  * scoring_results.tsv (704 rows: score, p-value, q-value) and integer matrices, and
  * (b) vectors produced by running the unmodified reference in the dev container
- * (tests/golden/make_golden.py -> tests/golden/cases/*.npz).
+ * (tests/golden/make_golden.py -> tests/golden/cases/<case>.npz).
  *
  * Each function cites the reference lines (paths relative to /root/reference) it restates.
  * The arithmetic ORDER is part of the contract (fp64, no FMA contraction, no reassociation):
