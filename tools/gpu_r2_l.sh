@@ -1,11 +1,13 @@
-# round 2, GPU call L (2 GPUs): do the host packers still pay when two ranks share the host?  e2e with 6 packer threads per rank against the
-# copy-engine-only variant of the same run
+# round 2, GPU call L (2 GPUs): packer threads per rank with two ranks on the host (6 = the default: a quarter of the hardware threads)
 set -x
 mkdir -p gpurun_out
-GB2_HOST_PACK_THREADS=6 timeout 500 python bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/l_bench_2gpu.json 2> gpurun_out/l_bench_2gpu.err; tail -2 gpurun_out/l_bench_2gpu.err | cut -c1-300
-python - <<'P'
+nproc
+for t in 9 12; do
+GB2_HOST_PACK_THREADS=$t timeout 300 python bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline --no-graph-path --no-kmer-e2e > gpurun_out/l_bench_2gpu_$t.json 2> gpurun_out/l_bench_2gpu_$t.err
+python - <<P
 import json
-for ln in open('gpurun_out/l_bench_2gpu.json'):
+for ln in open('gpurun_out/l_bench_2gpu_$t.json'):
     if ln.startswith('{'):
-        d=json.loads(ln); print(d['value'], d['ms_per_step'], {k:v for k,v in d['e2e'].items() if k!='api'}, {k:(v['ms_per_step']) for k,v in d['e2e_variants'].items()}, d['parity'].get('ok'))
+        d=json.loads(ln); e=d['e2e']; print($t, e['ms_per_step'], e['ms_per_step_without_host_packers'], e['chunks_as_text'], e['chunks_packed_on_host'], e['host_cpus'], d['parity'].get('ok'))
 P
+done
