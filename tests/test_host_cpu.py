@@ -289,3 +289,42 @@ def test_header_is_plain_c_and_the_example_compiles(tmp_path):
     if os.path.exists(os.path.join(lib, "libgrafimo_b200.so")):
         subprocess.run(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_scan.c"), "-o",
                         str(tmp_path / "c_abi_scan"), "-L", lib, "-lgrafimo_b200", f"-Wl,-rpath,{lib}", "-lm"], check=True)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5000])
+def test_arrow_backed_table_equals_generic_table(n):
+    """score_sequences._build_table_rows (string columns assembled from byte buffers where pandas backs them by Arrow, report
+    order optionally pre-computed) == the generic _build_table on the same rows: values, order, dtypes -- with ties on
+    (p, start, stop, strand) that only the sequence resolves, the frequency filter and an empty input."""
+    from grafimo_b200 import score_sequences as ss
+    rng = np.random.default_rng(5 + n)
+    w = 11
+
+    class M:
+        motif_id, motif_name = "MA0000.1", "TEST"
+
+    pval = np.round(rng.random(n) * 1e-3, 5)  # many ties
+    start = rng.integers(0, 40, n).astype(np.int64)
+    stop = start + w
+    minus = rng.random(n) < 0.5
+    asc = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(n, w))
+    names = [f"chr{c}:0-1000" for c in range(3)]
+    region = rng.integers(0, 3, n).astype(np.int64)
+    freq = rng.integers(0, 6, n).astype(np.int64)
+    isref = rng.random(n) < 0.5
+    score, q = rng.random(n), rng.random(n)
+    for keep in (np.ones(n, dtype=bool), freq > 0):
+        seq = np.ascontiguousarray(asc).view(f"S{w}").ravel().astype(f"U{w}").astype(object) if n else np.array([], dtype=object)
+        generic = ss._build_table(M, False, keep, np.array(names, dtype=object)[region] if n else np.array([], dtype=object), start, stop,
+                                  np.where(minus, "-", "+").astype(object), score, pval, q, seq, freq,
+                                  np.where(isref, "ref", "non.ref").astype(object), 1)
+        fast = ss._build_table_rows(M, False, keep, names, region, start, stop, minus, score, pval, q, asc, freq, isref)
+        assert list(fast.columns) == list(generic.columns) and fast.dtypes.equals(generic.dtypes)
+        assert fast.equals(generic)
+        if n > 1:  # rows handed over in (p, start, stop, strand) order, as the device leaves them
+            o = np.lexsort((minus.astype(np.int8), stop, start, pval))
+            pre = ss._build_table_rows(M, False, keep[o], names, region[o], start[o], stop[o], minus[o], score[o], pval[o], q[o], asc[o],
+                                       freq[o], isref[o], presorted=True)
+            assert pre.equals(generic)
+        noq = ss._build_table_rows(M, True, keep, names, region, start, stop, minus, score, pval, None, asc, freq, isref)
+        assert "q-value" not in noq.columns and len(noq) == len(generic)
